@@ -1,0 +1,175 @@
+/* nfb200.h -- C ABI of libnfb200.so, the B200 (sm_100a) implementation of the
+ * itxtx/normalizing-flows-study transform hot path.
+ *
+ * The reference has no FFI/plugin boundary of its own: its hot path is nn.Module code calling ATen
+ * eager ops.  This header is therefore the boundary *we* define underneath the
+ * reference's Python class surface; each entry point names the reference function whose arithmetic
+ * it replaces (paths relative to the reference repository root).
+ *
+ * Conventions (every function):
+ *   - plain device pointers + sizes; no torch types.  All tensors are dense, row-major, contiguous.
+ *   - the caller owns every buffer (outputs and workspaces included); the library never allocates
+ *     device memory, never synchronises, keeps no per-call global state and launches on `stream`
+ *     (a cudaStream_t passed as void*).  Calls on distinct streams may run concurrently.
+ *   - `dtype` selects the arithmetic type of all floating buffers of the call (NF_F32 / NF_F64).
+ *   - returns NF_OK (0) or a negative nf_status; nothing is launched when an argument check fails.
+ *   - built for sm_100a only; there is no CPU path.
+ */
+#ifndef NFB200_H
+#define NFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nf_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define NF_API __attribute__((visibility("default")))
+#else
+#define NF_API
+#endif
+
+enum nf_status {
+    NF_OK = 0,
+    NF_ERR_BAD_SHAPE = -1,   /* negative / inconsistent sizes, unsupported bin count, ... */
+    NF_ERR_UNSUPPORTED = -2, /* dtype or configuration without a kernel */
+    NF_ERR_MISALIGNED = -3,  /* a pointer that must be 16-byte aligned is not */
+    NF_ERR_CUDA = -4,        /* a CUDA runtime call failed: see nf_last_cuda_error() */
+    NF_ERR_NULL = -5,        /* required pointer is NULL */
+    NF_ERR_WORKSPACE = -6    /* workspace / packed-weight buffer too small */
+};
+enum nf_dtype { NF_F32 = 0, NF_F64 = 1 };
+
+/* affine autoregressive modes (nf_affine_ar_*, nf_ar_sequential_*) */
+enum nf_ar_mode {
+    NF_AR_MAF_INVERSE = 0, /* masked_autoregressive_flow.py:18-44  (parallel, density) */
+    NF_AR_IAF_FORWARD = 1, /* inverse_autoregressive_flow.py:30-63 (parallel, sampling) */
+    NF_AR_MAF_FORWARD = 2, /* masked_autoregressive_flow.py:46-78  (sequential, sampling) */
+    NF_AR_IAF_INVERSE = 3  /* inverse_autoregressive_flow.py:65-103 (sequential, density) */
+};
+
+NF_API int nf_abi_version(void);
+NF_API const char* nf_status_string(int status);
+NF_API const char* nf_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+NF_API int64_t nf_launch_count(void);
+
+/* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------
+ * src/flows/spline/rational_quadratic_spline.py:4-104.  x,y,ld: [n]; w,h: [n,K]; d: [n,K-1].
+ * Per-element outputs and per-element log|dy/dx| (no row sum), domain [0,1], epsilon 1e-6. */
+NF_API int nf_rqs_unit_forward(const void* x, const void* w, const void* h, const void* d, void* y, void* ld, int64_t n,
+                        int num_bins, int inverse, double min_bin_width, double min_bin_height, double min_derivative,
+                        int dtype, nf_stream_t stream);
+/* reverse mode of the above: gx [n], gw/gh [n,K], gd [n,K-1] are overwritten. */
+NF_API int nf_rqs_unit_backward(const void* x, const void* w, const void* h, const void* d, const void* gy, const void* gld,
+                         void* gx, void* gw, void* gh, void* gd, int64_t n, int num_bins, int inverse,
+                         double min_bin_width, double min_bin_height, double min_derivative, int dtype,
+                         nf_stream_t stream);
+
+/* ---- a5/a6: SplineCouplingLayer.forward/.inverse minus the conditioner ------------------------------
+ * src/flows/spline/spline_coupling_layer.py:96-309.  x,y: [B,D]; params: [B, D*(3K-1)] = param_net output
+ * (row d*P+j = parameter j of dim d, :71); mask: [D] float {0,1}; tidx: [Dt] int32 indices with mask==0;
+ * ld: [B] = row sum over transformed dims, NaN/Inf scrubbed (:130-135).  rescale_in/rescale_lo/rescale_out:
+ * NULL, or [D] arrays a,lo,c with x_spline = a*(x-lo)-bound and x_out = (y+bound)*c+lo (:78-94). */
+NF_API int nf_spline_transform_forward(const void* x, const void* params, const void* mask, const int32_t* tidx, void* y,
+                                void* ld, int64_t B, int D, int Dt, int num_bins, int inverse, double bound,
+                                double min_bin_width, double min_bin_height, double min_derivative,
+                                const void* rescale_in, const void* rescale_lo, const void* rescale_out, int dtype,
+                                nf_stream_t stream);
+/* gx: [B,D] overwritten; gparams: [B, D*(3K-1)] -- only the transformed dims' entries are written, the
+ * caller zero-fills the buffer beforehand. */
+NF_API int nf_spline_transform_backward(const void* x, const void* params, const void* mask, const int32_t* tidx,
+                                 const void* gy, const void* gld, void* gx, void* gparams, int64_t B, int D, int Dt,
+                                 int num_bins, int inverse, double bound, double min_bin_width, double min_bin_height,
+                                 double min_derivative, const void* rescale_in, const void* rescale_lo,
+                                 const void* rescale_out, int dtype, nf_stream_t stream);
+
+/* ---- a1/a2: CouplingLayer.forward/.inverse minus the conditioners ---------------------------------
+ * src/flows/coupling/coupling_layer.py:47-66 / :76-94.  s_raw,b_raw: [B,D] un-clamped s_net/b_net outputs. */
+NF_API int nf_affine_coupling_forward(const void* x, const void* s_raw, const void* b_raw, const void* mask, void* y,
+                               void* ld, int64_t B, int D, int inverse, int dtype, nf_stream_t stream);
+NF_API int nf_affine_coupling_backward(const void* x, const void* s_raw, const void* b_raw, const void* mask, const void* gy,
+                                const void* gld, void* gx, void* gs, void* gb, int64_t B, int D, int inverse,
+                                int dtype, nf_stream_t stream);
+
+/* ---- a11/a13 (parallel directions): MAF.inverse / IAF.forward minus MADE ----------------------------
+ * params: [B,2D] = [mu_0..mu_{D-1}, alpha_0..alpha_{D-1}] (made.py:67-78).  ld clamped to +-100 / +-50. */
+NF_API int nf_affine_ar_forward(const void* v, const void* params, void* out, void* ld, int64_t B, int D, int mode,
+                         int dtype, nf_stream_t stream);
+/* ld_saved: the forward's ld output (decides whether the +-100/+-50 clamp passes gradient). */
+NF_API int nf_affine_ar_backward(const void* v, const void* params, const void* ld_saved, const void* gout, const void* gld,
+                          void* gv, void* gparams, int64_t B, int D, int mode, int dtype, nf_stream_t stream);
+
+/* ---- a8/a10 and the conditioner MLPs: dense building block ---------------------------------------------
+ * C[M,N] (+)= A[M,K] * Bm[K,N] (+ bias[N]) (ReLU), with element strides for A and Bm so that
+ *   Y = X W^T + b   (F.linear, masked_linear.py:18)      : sam=K, sak=1, sbk=1, sbn=K
+ *   dX = dY W       (backward wrt input)                    : A=dY, Bm=W  -> sbk=K_w, sbn=1
+ *   dW = dY^T X     (backward wrt weight)                   : A=dY^T      -> sam=1, sak=N_dy
+ * k_extent: NULL, or int32[ceil(N/64)]: output columns [64t, 64t+64) only accumulate k < k_extent[t]
+ * (zero-tile skipping for mask-folded, degree-sorted MADE weights, whose masks are block lower-triangular).
+ * Weight-gradient shapes (few output tiles, K>=4096) are split along K and combined with atomics. */
+NF_API int nf_gemm(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K, int64_t sam,
+            int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate, const int32_t* k_extent,
+            int dtype, nf_stream_t stream);
+
+/* elementwise helpers of the training path (so that it never leaves this library):
+ *   out = a * b (broadcast b over rows if b_rows==1): mask folding W*mask (masked_linear.py:17-18)
+ *   relu backward: gx = gy * (y > 0);  column sum: out[N] = sum_m a[m,n] (bias gradient) */
+NF_API int nf_mul_rows(const void* a, const void* b, void* out, int64_t rows, int64_t cols, int64_t b_rows, int dtype,
+                nf_stream_t stream);
+NF_API int nf_relu_backward(const void* y, const void* gy, void* gx, int64_t n, int dtype, nf_stream_t stream);
+NF_API int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, int dtype, nf_stream_t stream);
+
+/* nn.BatchNorm1d inside the coupling conditioners (coupling_layer.py:20,23), fused with the following ReLU.
+ * training!=0: batch statistics normalise (biased variance), running stats are updated in place with
+ * `momentum` (unbiased variance), save_mean/save_rstd [H] receive the batch statistics for backward.
+ * training==0: running statistics normalise.  y = relu?(gamma*(x-mean)*rstd+beta). */
+NF_API int nf_batchnorm_forward(const void* x, const void* gamma, const void* beta, void* running_mean, void* running_var,
+                         void* y, void* save_mean, void* save_rstd, int64_t B, int H, int training, double momentum,
+                         double eps, int relu, int dtype, nf_stream_t stream);
+/* y is the forward output (post-ReLU when relu!=0).  gx [B,H], ggamma/gbeta [H] overwritten.  training
+ * selects the batch-statistics Jacobian (training!=0) or the plain affine one (eval). */
+NF_API int nf_batchnorm_backward(const void* x, const void* y, const void* gamma, const void* save_mean,
+                          const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta, int64_t B, int H,
+                          int relu, int training, int dtype, nf_stream_t stream);
+
+/* ---- fused inference stacks (small data_dim): whole NormalizingFlowModel in one launch --------------------
+ * a4-a6 + a14/a15: L SplineCouplingLayers (+ optional between-layer BatchNorm affine using running stats,
+ * normalizing_flow_model.py:25-128) for data_dim<=8, hidden_dim<=128, num_bins<=16; fp32 only.
+ * `packed` is the float32 device buffer laid out by the host side (csrc/stack_small.cuh documents the layout);
+ * `hdr_host` is a HOST copy of its first 16 words (so the library never reads device memory on the host).
+ * Returns NF_ERR_UNSUPPORTED when the configuration does not fit one SM's shared memory (caller uses the
+ * layer-wise path: nf_gemm + nf_spline_transform_forward). */
+NF_API int nf_spline_stack_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
+                            void* ld, int64_t B, int inverse, nf_stream_t stream);
+/* a1/a2 + a14/a15: L CouplingLayers in eval mode (conditioner BatchNorm folded into the Linears at pack time). */
+NF_API int nf_coupling_stack_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
+                              void* ld, int64_t B, int inverse, nf_stream_t stream);
+/* upper bound (in 32-bit words) of the packed buffer for a configuration; -1 if the fused path cannot take it */
+NF_API int64_t nf_spline_stack_packed_floats(int D, int H, int K, int L);
+NF_API int64_t nf_coupling_stack_packed_floats(int D, int H, int L);
+
+/* ---- a10-a13 fused: MADE chain + affine autoregressive transform --------------------------------------
+ * Parallel directions (MAF.inverse, IAF.forward).  w0..w3: mask-folded weights W*mask ([H,D],[H,H],[H,H],[2D,H]),
+ * b0..b3 biases; kext1/kext2/kext3: optional int32 k-extent arrays for layers 1..3 (see nf_gemm).
+ * workspace: 2*B*max(H,2D) elements of `dtype`.  fp32/fp64. */
+NF_API int nf_made_affine_forward(const void* v, const void* w0, const void* b0, const void* w1, const void* b1,
+                           const void* w2, const void* b2, const void* w3, const void* b3, const int32_t* kext1,
+                           const int32_t* kext2, const int32_t* kext3, void* workspace, void* out, void* ld, int64_t B,
+                           int D, int H, int mode, int dtype, nf_stream_t stream);
+/* Sequential directions (MAF.forward, IAF.inverse) computed incrementally: one masked MADE evaluation in
+ * total instead of D (masked_autoregressive_flow.py:55-67 re-evaluates MADE D times).  Hidden units must be
+ * ordered by non-decreasing degree (made.py:25-41; the host permutes them for D==2); gstart: int32[D+1],
+ * gstart[g] = index of the first hidden unit with degree >= g.  fp32 only.  NF_ERR_UNSUPPORTED when the
+ * (D+3H)*32 activation tile does not fit shared memory. */
+NF_API int nf_ar_sequential_forward(const void* v, const void* w0, const void* b0, const void* w1, const void* b1,
+                             const void* w2, const void* b2, const void* w3, const void* b3, const int32_t* gstart,
+                             void* out, void* ld, int64_t B, int D, int H, int mode, nf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFB200_H */

@@ -1,0 +1,454 @@
+// dense_kernels.cu -- dense building blocks of the general / training path:
+//   nf_gemm              strided SIMT GEMM with bias/ReLU epilogue, zero-tile skipping (k_extent) and split-K
+//                        (F.linear of the conditioners and of MaskedLinear, masked_linear.py:14-18, + its backward)
+//   nf_mul_rows, nf_relu_backward, nf_col_sum     small elementwise / reduction helpers
+//   nf_batchnorm_*       nn.BatchNorm1d (+ReLU) of the coupling conditioners (coupling_layer.py:20-24)
+// fp32 accumulate in fp32 FFMA (bit-level parity class of the reference's sgemm); fp64 for gradcheck.
+// The tcgen05 GEMM for the large shapes lives in gemm_tcgen05.cu; this kernel is the exact-fp32 fallback
+// for every shape and the only path for fp64.
+#include "nf_common.cuh"
+
+namespace nf {
+
+// ------------------------------------------------------------------------------------------------
+// GEMM: C[M,N] (+)= A[M,K] * B[K,N], element strides (sam,sak) / (sbk,sbn).
+//   float : 128x128x16 tile, 256 threads, 8x8 micro-tile split as 2x2 blocks of 4x4 (conflict-free LDS.128)
+//   double:  64x64x16 tile, 256 threads, 4x4 micro-tile
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct GemmCfg;
+template <> struct GemmCfg<float>  { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; };
+template <> struct GemmCfg<double> { static constexpr int BM = 64,  BN = 64,  BK = 16, TM = 4, TN = 4; };
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+gemm_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C, const T* __restrict__ bias,
+            int64_t M, int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc,
+            int relu, int accumulate, const int32_t* __restrict__ k_extent, int ksplit_len) {
+    using Cfg = GemmCfg<T>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN;
+    constexpr int PADM = BM + 4, PADN = BN + 4;
+    constexpr int NT = 256;
+    constexpr int LA = BM * BK / NT, LB = BN * BK / NT;
+    __shared__ __align__(16) T As[BK][PADM];
+    __shared__ __align__(16) T Bs[BK][PADN];
+
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;   // M tiles on x (2^31 limit)
+    int64_t k_begin = 0, k_end = K;
+    if (k_extent) {                         // entries are per 64 output columns
+        int e = 0;
+        for (int64_t c = n0 / 64; c <= (n0 + BN - 1) / 64 && c * 64 < N; ++c) e = max(e, k_extent[c]);
+        k_end = (K < (int64_t)e) ? K : (int64_t)e;
+    }
+    if (ksplit_len > 0) {
+        k_begin = (int64_t)blockIdx.z * ksplit_len;
+        k_end = (k_end < k_begin + ksplit_len) ? k_end : k_begin + ksplit_len;
+    }
+    const bool a_kfast = (sak == 1);
+    const bool b_nfast = (sbn == 1);
+    const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+    T ra[LA], rb[LB];
+    auto load_tile = [&](int64_t kt) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int idx = tid + i * NT;
+            const int kk = a_kfast ? idx % BK : idx / BM;
+            const int mm = a_kfast ? idx / BK : idx % BM;
+            const int64_t gm = m0 + mm, gk = kt + kk;
+            ra[i] = (gm < M && gk < k_end) ? A[gm * sam + gk * sak] : T(0);
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int idx = tid + i * NT;
+            const int nn = b_nfast ? idx % BN : idx / BK;
+            const int kk = b_nfast ? idx / BN : idx % BK;
+            const int64_t gn = n0 + nn, gk = kt + kk;
+            rb[i] = (gn < N && gk < k_end) ? Bm[gk * sbk + gn * sbn] : T(0);
+        }
+    };
+    auto store_tile = [&]() {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int idx = tid + i * NT;
+            const int kk = a_kfast ? idx % BK : idx / BM;
+            const int mm = a_kfast ? idx / BK : idx % BM;
+            As[kk][mm] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int idx = tid + i * NT;
+            const int nn = b_nfast ? idx % BN : idx / BK;
+            const int kk = b_nfast ? idx / BN : idx % BK;
+            Bs[kk][nn] = rb[i];
+        }
+    };
+
+    if (k_begin < k_end) load_tile(k_begin);
+    for (int64_t kt = k_begin; kt < k_end; kt += BK) {
+        __syncthreads();
+        store_tile();
+        __syncthreads();
+        if (kt + BK < k_end) load_tile(kt + BK);       // prefetch next tile into registers
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[TM], b[TN];
+            if constexpr (sizeof(T) == 4) {
+                float4 v0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                float4 v1 = *reinterpret_cast<const float4*>(&As[kk][BM / 2 + ty * 4]);
+                a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+                float4 w0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                float4 w1 = *reinterpret_cast<const float4*>(&Bs[kk][BN / 2 + tx * 4]);
+                b[0] = w0.x; b[1] = w0.y; b[2] = w0.z; b[3] = w0.w; b[4] = w1.x; b[5] = w1.y; b[6] = w1.z; b[7] = w1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+        }
+    }
+
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int64_t gm;
+        if constexpr (sizeof(T) == 4) gm = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+        else gm = m0 + ty * TM + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int64_t gn;
+            if constexpr (sizeof(T) == 4) gn = n0 + (j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4));
+            else gn = n0 + tx * TN + j;
+            if (gn >= N) continue;
+            T v = acc[i][j];
+            T* cp = C + gm * ldc + gn;
+            if (ksplit_len > 0) { atomicAdd(cp, v); continue; }
+            if (bias) v += bias[gn];
+            if (accumulate) v += *cp;
+            if (relu) v = relu_nan(v);
+            *cp = v;
+        }
+    }
+}
+
+template <typename T>
+static int gemm_launch(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K,
+                       int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate,
+                       const int32_t* k_extent, cudaStream_t st) {
+    using Cfg = GemmCfg<T>;
+    const int64_t tm = cdiv(M, Cfg::BM), tn = cdiv(N, Cfg::BN);
+    if (tn > 65535 || tm > 2147483647LL) return NF_ERR_BAD_SHAPE;
+    int splits = 1;
+    if (!bias && !relu && !k_extent && tm * tn < kNumSMs && K >= 4096) {   // weight-gradient shape: split K
+        { int64_t a_ = cdiv(2 * kNumSMs, tm * tn), b_ = K / 1024; splits = (int)(a_ < b_ ? a_ : b_); }
+        if (splits < 1) splits = 1;
+    }
+    int ksplit_len = 0;
+    if (splits > 1) {
+        ksplit_len = (int)(cdiv(cdiv(K, splits), Cfg::BK) * Cfg::BK);
+        splits = (int)cdiv(K, ksplit_len);
+        if (!accumulate) {
+            if (ldc == N) NF_CUDA(cudaMemsetAsync(C, 0, sizeof(T) * M * N, st));
+            else NF_CUDA(cudaMemset2DAsync(C, sizeof(T) * ldc, 0, sizeof(T) * N, M, st));
+        }
+    }
+    dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
+    gemm_kernel<T><<<grid, 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, N, K, sam, sak, sbk, sbn,
+                                         ldc, relu, accumulate, k_extent, ksplit_len);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mul_rows_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t rows,
+                                int64_t cols, int64_t b_rows) {
+    const int64_t n = rows * cols, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = a[i] * (b_rows == 1 ? b[i % cols] : b[i]);
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gx, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        gx[i] = (y[i] > T(0)) ? gy[i] : T(0);
+}
+
+// column sums of a[rows, cols]: block = 32 columns x 8 row-lanes; grid.y row chunks combine with atomics
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_sum_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t rows, int64_t cols, int64_t rows_per_chunk) {
+    __shared__ double red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t col = (int64_t)blockIdx.x * 32 + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = (rows < r0 + rows_per_chunk) ? rows : r0 + rows_per_chunk;
+    double s = 0.0;
+    if (col < cols)
+        for (int64_t r = r0 + ry; r < r1; r += 8) s += (double)a[r * cols + col];
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && col < cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cx];
+        if (gridDim.y == 1) out[col] = (T)t; else atomicAdd(out + col, (T)t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d (+ReLU).  stats: per-column mean / biased variance in double accumulators.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ x, T* __restrict__ running_mean, T* __restrict__ running_var,
+                T* __restrict__ save_mean, T* __restrict__ save_rstd, int64_t B, int H, double momentum, double eps) {
+    __shared__ double s1[8][33], s2[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    double a = 0.0, b = 0.0;
+    if (col < H)
+        for (int64_t r = ry; r < B; r += 8) { const double v = (double)x[r * H + col]; a += v; b += v * v; }
+    s1[ry][cx] = a; s2[ry][cx] = b;
+    __syncthreads();
+    if (ry == 0 && col < H) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ta += s1[i][cx]; tb += s2[i][cx]; }
+        const double mean = ta / (double)B;
+        double var = tb / (double)B - mean * mean;
+        if (var < 0.0) var = 0.0;
+        save_mean[col] = (T)mean;
+        save_rstd[col] = (T)(1.0 / sqrt(var + eps));
+        if (running_mean) {
+            const double unb = (B > 1) ? var * (double)B / (double)(B - 1) : var;
+            running_mean[col] = (T)((1.0 - momentum) * (double)running_mean[col] + momentum * mean);
+            running_var[col] = (T)((1.0 - momentum) * (double)running_var[col] + momentum * unb);
+        }
+    }
+}
+
+template <typename T>
+__global__ void bn_eval_stats_kernel(const T* __restrict__ running_mean, const T* __restrict__ running_var,
+                                     T* __restrict__ save_mean, T* __restrict__ save_rstd, int H, double eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < H) { save_mean[c] = running_mean[c]; save_rstd[c] = (T)(1.0 / sqrt((double)running_var[c] + eps)); }
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta,
+                                const T* __restrict__ mean, const T* __restrict__ rstd, T* __restrict__ y, int64_t B,
+                                int H, int relu) {
+    const int64_t n = B * H, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)(i % H);
+        T v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+        y[i] = relu ? relu_nan(v) : v;
+    }
+}
+
+// ggamma = sum gy_eff*xhat ; gbeta = sum gy_eff   (gy_eff = gy * (y>0) when relu)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ mean,
+                     const T* __restrict__ rstd, const T* __restrict__ gy, T* __restrict__ ggamma,
+                     T* __restrict__ gbeta, int64_t B, int H, int relu) {
+    __shared__ double s1[8][33], s2[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    double a = 0.0, b = 0.0;
+    if (col < H) {
+        const double mu = (double)mean[col], rs = (double)rstd[col];
+        for (int64_t r = ry; r < B; r += 8) {
+            const int64_t o = r * H + col;
+            double g = (double)gy[o];
+            if (relu && !(y[o] > T(0))) g = 0.0;
+            a += g * ((double)x[o] - mu) * rs;
+            b += g;
+        }
+    }
+    s1[ry][cx] = a; s2[ry][cx] = b;
+    __syncthreads();
+    if (ry == 0 && col < H) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ta += s1[i][cx]; tb += s2[i][cx]; }
+        ggamma[col] = (T)ta; gbeta[col] = (T)tb;
+    }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ gamma,
+                                    const T* __restrict__ mean, const T* __restrict__ rstd, const T* __restrict__ gy,
+                                    const T* __restrict__ ggamma, const T* __restrict__ gbeta, T* __restrict__ gx,
+                                    int64_t B, int H, int relu, int training) {
+    const int64_t n = B * H, stride = (int64_t)gridDim.x * blockDim.x;
+    const T invB = T(1) / (T)B;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)(i % H);
+        T g = gy[i];
+        if (relu && !(y[i] > T(0))) g = T(0);
+        if (training) {
+            const T xhat = (x[i] - mean[c]) * rstd[c];
+            gx[i] = gamma[c] * rstd[c] * (g - invB * (gbeta[c] + xhat * ggamma[c]));
+        } else {
+            gx[i] = gamma[c] * rstd[c] * g;
+        }
+    }
+}
+
+static inline int ew_grid(int64_t n) {
+    int64_t need = cdiv(n, 256);
+    int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+template <typename T>
+static int bn_forward(const void* x, const void* gamma, const void* beta, void* rm, void* rv, void* y, void* sm,
+                      void* sr, int64_t B, int H, int training, double momentum, double eps, int relu, cudaStream_t st) {
+    if (training) {
+        bn_stats_kernel<T><<<(H + 31) / 32, 256, 0, st>>>((const T*)x, (T*)rm, (T*)rv, (T*)sm, (T*)sr, B, H, momentum, eps);
+    } else {
+        bn_eval_stats_kernel<T><<<(H + 255) / 256, 256, 0, st>>>((const T*)rm, (const T*)rv, (T*)sm, (T*)sr, H, eps);
+    }
+    count_launch();
+    NF_LAUNCH_CHECK();
+    bn_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)gamma, (const T*)beta, (const T*)sm,
+                                                       (const T*)sr, (T*)y, B, H, relu);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+template <typename T>
+static int bn_backward(const void* x, const void* y, const void* gamma, const void* sm, const void* sr, const void* gy,
+                       void* gx, void* gg, void* gb, int64_t B, int H, int relu, int training, cudaStream_t st) {
+    bn_bwd_reduce_kernel<T><<<(H + 31) / 32, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr,
+                                                           (const T*)gy, (T*)gg, (T*)gb, B, H, relu);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
+                                                           (const T*)sr, (const T*)gy, (const T*)gg, (const T*)gb,
+                                                           (T*)gx, B, H, relu, training);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+}  // namespace nf
+
+using namespace nf;
+#define NF_REQ(p) do { if ((p) == nullptr) return NF_ERR_NULL; } while (0)
+
+extern "C" int nf_gemm(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K,
+                       int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate,
+                       const int32_t* k_extent, int dtype, nf_stream_t stream) {
+    if (M < 0 || N < 0 || K < 0 || ldc < N) return NF_ERR_BAD_SHAPE;
+    if (M == 0 || N == 0) return NF_OK;
+    NF_REQ(C);
+    if (K > 0) { NF_REQ(A); NF_REQ(Bm); }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32)
+        return gemm_launch<float>(A, Bm, C, bias, M, N, K, sam, sak, sbk, sbn, ldc, relu, accumulate, k_extent, st);
+    if (dtype == NF_F64)
+        return gemm_launch<double>(A, Bm, C, bias, M, N, K, sam, sak, sbk, sbn, ldc, relu, accumulate, k_extent, st);
+    return NF_ERR_UNSUPPORTED;
+}
+
+extern "C" int nf_mul_rows(const void* a, const void* b, void* out, int64_t rows, int64_t cols, int64_t b_rows,
+                           int dtype, nf_stream_t stream) {
+    if (rows < 0 || cols < 0 || (b_rows != 1 && b_rows != rows)) return NF_ERR_BAD_SHAPE;
+    if (rows * cols == 0) return NF_OK;
+    NF_REQ(a); NF_REQ(b); NF_REQ(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32)
+        mul_rows_kernel<float><<<ew_grid(rows * cols), 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, rows, cols, b_rows);
+    else if (dtype == NF_F64)
+        mul_rows_kernel<double><<<ew_grid(rows * cols), 256, 0, st>>>((const double*)a, (const double*)b, (double*)out, rows, cols, b_rows);
+    else return NF_ERR_UNSUPPORTED;
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+extern "C" int nf_relu_backward(const void* y, const void* gy, void* gx, int64_t n, int dtype, nf_stream_t stream) {
+    if (n < 0) return NF_ERR_BAD_SHAPE;
+    if (n == 0) return NF_OK;
+    NF_REQ(y); NF_REQ(gy); NF_REQ(gx);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32) relu_bwd_kernel<float><<<ew_grid(n), 256, 0, st>>>((const float*)y, (const float*)gy, (float*)gx, n);
+    else if (dtype == NF_F64) relu_bwd_kernel<double><<<ew_grid(n), 256, 0, st>>>((const double*)y, (const double*)gy, (double*)gx, n);
+    else return NF_ERR_UNSUPPORTED;
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+extern "C" int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, int dtype, nf_stream_t stream) {
+    if (rows < 0 || cols < 0) return NF_ERR_BAD_SHAPE;
+    if (cols == 0) return NF_OK;
+    NF_REQ(out);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = dtype == NF_F64 ? 8 : 4;
+    const int64_t rows1 = rows > 1 ? rows : 1;
+    int chunks = (int)(rows / 4096 < 1 ? 1 : (rows / 4096 > 64 ? 64 : rows / 4096));
+    const int64_t rpc = cdiv(rows1, chunks);
+    chunks = (int)cdiv(rows1, rpc);
+    if (chunks > 1 || rows == 0) NF_CUDA(cudaMemsetAsync(out, 0, es * cols, st));
+    if (rows == 0) return NF_OK;
+    NF_REQ(a);
+    dim3 grid((unsigned)cdiv(cols, 32), (unsigned)chunks);
+    if (dtype == NF_F32) col_sum_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (float*)out, rows, cols, rpc);
+    else if (dtype == NF_F64) col_sum_kernel<double><<<grid, 256, 0, st>>>((const double*)a, (double*)out, rows, cols, rpc);
+    else return NF_ERR_UNSUPPORTED;
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+extern "C" int nf_batchnorm_forward(const void* x, const void* gamma, const void* beta, void* running_mean,
+                                    void* running_var, void* y, void* save_mean, void* save_rstd, int64_t B, int H,
+                                    int training, double momentum, double eps, int relu, int dtype,
+                                    nf_stream_t stream) {
+    if (B < 0 || H < 1) return NF_ERR_BAD_SHAPE;
+    if (B == 0) return NF_OK;
+    NF_REQ(x); NF_REQ(gamma); NF_REQ(beta); NF_REQ(y); NF_REQ(save_mean); NF_REQ(save_rstd);
+    if (!training) { NF_REQ(running_mean); NF_REQ(running_var); }
+    if ((running_mean == nullptr) != (running_var == nullptr)) return NF_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32)
+        return bn_forward<float>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, B, H, training, momentum, eps, relu, st);
+    if (dtype == NF_F64)
+        return bn_forward<double>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, B, H, training, momentum, eps, relu, st);
+    return NF_ERR_UNSUPPORTED;
+}
+
+extern "C" int nf_batchnorm_backward(const void* x, const void* y, const void* gamma, const void* save_mean,
+                                     const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
+                                     int64_t B, int H, int relu, int training, int dtype, nf_stream_t stream) {
+    if (B < 0 || H < 1) return NF_ERR_BAD_SHAPE;
+    if (B == 0) return NF_OK;
+    NF_REQ(x); NF_REQ(y); NF_REQ(gamma); NF_REQ(save_mean); NF_REQ(save_rstd); NF_REQ(gy); NF_REQ(gx); NF_REQ(ggamma); NF_REQ(gbeta);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32)
+        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, B, H, relu, training, st);
+    if (dtype == NF_F64)
+        return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, B, H, relu, training, st);
+    return NF_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,525 @@
+// nf_math.cuh -- scalar math of the flow transforms, shared by every kernel.
+//
+// Every function is __host__ __device__ so that tests/hostcheck can compile the *same* source
+// for the CPU and compare it with the oracle / torch autograd before any GPU time is spent.
+// The product library (libnfb200.so) only instantiates the __device__ side.
+//
+// Semantics follow the reference (paths relative to the reference repo root):
+//   * torch.clamp / torch.relu propagate NaN  -> clamp_* / relu_nan below never use fmin/fmax
+//   * NaN/Inf scrubs after every transform     (coupling_layer.py:61-66, spline_coupling_layer.py:306-307,
+//                                               masked_autoregressive_flow.py:35-42, inverse_autoregressive_flow.py:53-61)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NF_HD __host__ __device__ __forceinline__
+#else
+#define NF_HD inline
+#endif
+
+// Loop unrolling of the per-bin loops.  The register kernels unroll fully (arrays stay in registers);
+// transform_generic.cu compiles the same source with `unroll 1` for the rarely used num_bins>16 path.
+#ifndef NF_UNROLL
+#define NF_UNROLL _Pragma("unroll")
+#endif
+
+namespace nf {
+
+// ------------------------------------------------------------------------------------------
+// type-generic libm
+// ------------------------------------------------------------------------------------------
+NF_HD float  t_exp(float x)    { return expf(x); }
+NF_HD double t_exp(double x)   { return exp(x); }
+NF_HD float  t_log(float x)    { return logf(x); }
+NF_HD double t_log(double x)   { return log(x); }
+NF_HD float  t_log1p(float x)  { return log1pf(x); }
+NF_HD double t_log1p(double x) { return log1p(x); }
+NF_HD float  t_sqrt(float x)   { return sqrtf(x); }
+NF_HD double t_sqrt(double x)  { return sqrt(x); }
+NF_HD float  t_abs(float x)    { return fabsf(x); }
+NF_HD double t_abs(double x)   { return fabs(x); }
+
+template <typename T> NF_HD bool is_finite(T x) { return (x - x) == T(0); }       // false for NaN and +-Inf
+template <typename T> NF_HD T clamp_min(T x, T lo) { return x < lo ? lo : x; }    // NaN stays NaN (torch.clamp)
+template <typename T> NF_HD T clamp_mm(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+template <typename T> NF_HD T relu_nan(T x) { return x < T(0) ? T(0) : x; }       // torch.relu(NaN) = NaN
+template <typename T> NF_HD bool pass_min(T x, T lo) { return x >= lo; }          // clamp backward mask
+template <typename T> NF_HD bool pass_mm(T x, T lo, T hi) { return x >= lo && x <= hi; }
+template <typename T> NF_HD T scrub0(T x) { return is_finite(x) ? x : T(0); }
+// F.softplus, beta=1, threshold=20
+template <typename T> NF_HD T softplus(T x) { return x > T(20) ? x : t_log1p(t_exp(x)); }
+template <typename T> NF_HD T softplus_grad(T x) {
+    if (x > T(20)) return T(1);
+    T z = t_exp(x);
+    return z / (z + T(1));
+}
+
+// ------------------------------------------------------------------------------------------
+// a1/a2  affine coupling, one element          (src/flows/coupling/coupling_layer.py:47-58,76-86)
+//   m is the float mask value of this column; s_raw/b_raw are the un-clamped net outputs.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+NF_HD void affine_coupling_elem(T x, T m, T s_raw, T b_raw, bool inverse, T& y, T& ld_term) {
+    const T s = clamp_mm(s_raw, T(-10), T(10));
+    const T b = clamp_mm(b_raw, T(-10), T(10));
+    const T xa = x * m;
+    const T om = T(1) - m;
+    if (!inverse) {
+        y = xa + om * (x * t_exp(s) + b);
+        ld_term = om * s;
+    } else {
+        y = xa + om * ((x - b) * t_exp(-s));
+        ld_term = om * (-s);
+    }
+}
+
+// reverse mode of the above (gy already zeroed where the output was scrubbed, gld likewise)
+template <typename T>
+NF_HD void affine_coupling_elem_bwd(T x, T m, T s_raw, T b_raw, bool inverse, T gy, T gld,
+                                    T& gx, T& gs_raw, T& gb_raw) {
+    const T s = clamp_mm(s_raw, T(-10), T(10));
+    const T b = clamp_mm(b_raw, T(-10), T(10));
+    const T om = T(1) - m;
+    const bool ps = pass_mm(s_raw, T(-10), T(10)), pb = pass_mm(b_raw, T(-10), T(10));
+    if (!inverse) {
+        const T e = t_exp(s);
+        gx = gy * (m + om * e);
+        gs_raw = ps ? (gy * om * x * e + gld * om) : T(0);
+        gb_raw = pb ? gy * om : T(0);
+    } else {
+        const T e = t_exp(-s);
+        gx = gy * (m + om * e);
+        gs_raw = ps ? (-(gy * om * (x - b) * e) - gld * om) : T(0);
+        gb_raw = pb ? -(gy * om * e) : T(0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a11/a13  affine autoregressive transform, one element (parallel directions)
+//   mode 0: MAF.inverse  (masked_autoregressive_flow.py:24-33)  z=(x-mu)exp(clamp(-clamp(a,3),5)), ld-=a
+//   mode 1: IAF.forward  (inverse_autoregressive_flow.py:36-50)  x=z exp(clamp(clamp(a,2),3))+clamp(mu,10), ld+=a
+//   mode 2: MAF.forward step (:59-67)                            x=z exp(clamp(clamp(a,3),5))+mu, ld+=a
+//   mode 3: IAF.inverse step (:80-91)                            z=(x-clamp(mu,10)) exp(clamp(-clamp(a,2),3)), ld-=a
+// ------------------------------------------------------------------------------------------
+enum { AR_MAF_INV = 0, AR_IAF_FWD = 1, AR_MAF_FWD = 2, AR_IAF_INV = 3 };
+
+template <typename T>
+NF_HD void affine_ar_elem(int mode, T v, T mu_raw, T al_raw, T& out, T& ld_term) {
+    const bool iaf = (mode == AR_IAF_FWD || mode == AR_IAF_INV);
+    const T ca = iaf ? T(2) : T(3), cs = iaf ? T(3) : T(5);
+    const T al = clamp_mm(al_raw, -ca, ca);
+    const T mu = iaf ? clamp_mm(mu_raw, T(-10), T(10)) : mu_raw;
+    if (mode == AR_MAF_INV || mode == AR_IAF_INV) {
+        out = (v - mu) * t_exp(clamp_mm(-al, -cs, cs));
+        ld_term = -al;
+    } else {
+        out = v * t_exp(clamp_mm(al, -cs, cs)) + mu;
+        ld_term = al;
+    }
+}
+
+template <typename T>
+NF_HD void affine_ar_elem_bwd(int mode, T v, T mu_raw, T al_raw, T gout, T gld,
+                              T& gv, T& gmu_raw, T& gal_raw) {
+    const bool iaf = (mode == AR_IAF_FWD || mode == AR_IAF_INV);
+    const T ca = iaf ? T(2) : T(3), cs = iaf ? T(3) : T(5);
+    const T al = clamp_mm(al_raw, -ca, ca);
+    const bool pa = pass_mm(al_raw, -ca, ca);
+    const bool pm = iaf ? pass_mm(mu_raw, T(-10), T(10)) : true;
+    const T mu = iaf ? clamp_mm(mu_raw, T(-10), T(10)) : mu_raw;
+    if (mode == AR_MAF_INV || mode == AR_IAF_INV) {
+        const T ls = -al;
+        const T e = t_exp(clamp_mm(ls, -cs, cs));
+        const bool pl = pass_mm(ls, -cs, cs);
+        gv = gout * e;
+        gmu_raw = pm ? -(gout * e) : T(0);
+        T g_al = -gld;
+        if (pl) g_al -= gout * (v - mu) * e;
+        gal_raw = pa ? g_al : T(0);
+    } else {
+        const T e = t_exp(clamp_mm(al, -cs, cs));
+        const bool pl = pass_mm(al, -cs, cs);
+        gv = gout * e;
+        gmu_raw = pm ? gout : T(0);
+        T g_al = gld;
+        if (pl) g_al += gout * v * e;
+        gal_raw = pa ? g_al : T(0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Rational-quadratic splines.
+//   BOUNDED=true : SplineCouplingLayer._rational_quadratic_spline   (spline_coupling_layer.py:182-309)
+//                  domain [-B,B], identity tails, eps=1e-8, end knots pinned, widths re-differenced.
+//   BOUNDED=false: public rational_quadratic_spline                 (rational_quadratic_spline.py:4-104)
+//                  domain [0,1], eps=1e-6, no tails, no pinning, per-bin width = normalised width.
+// Raw parameters of one element: uw[K], uh[K], ud[K-1].  KMAX is the register-array extent; K<=KMAX
+// is the live bin count (K==KMAX lets every guard fold at compile time).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct RqsCfg {
+    T lo, hi;        // domain: (-B, B) or (0, 1)
+    T span;          // 2*B (bounded) or 1
+    T min_w, min_h, min_d;
+    T scale_w, scale_h;   // 1 - min_w*K, 1 - min_h*K (computed on the host in double, like the python scalars)
+    T eps;
+};
+
+// softmax -> floor -> clamp -> cumulative knots.  wn: normalised widths (post clamp); kn: K+1 knots.
+template <typename T, int KMAX, bool BOUNDED>
+NF_HD void rqs_knots(const T* u, int K, T floor_, T scale, const RqsCfg<T>& c, T* wn, T* kn) {
+    T mx = u[0];
+NF_UNROLL
+    for (int j = 1; j < KMAX; ++j) if (j < K) mx = (u[j] > mx) ? u[j] : mx;
+    T sum = T(0);
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) { wn[j] = t_exp(u[j] - mx); sum += wn[j]; }
+    T run = T(0);
+    kn[0] = BOUNDED ? c.lo : T(0);
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) {
+        T w = floor_ + scale * (wn[j] / sum);
+        w = clamp_min(w, c.eps);
+        wn[j] = w;
+        run += w;
+        kn[j + 1] = BOUNDED ? (c.span * run + c.lo) : run;
+    }
+    if (BOUNDED) {
+NF_UNROLL
+        for (int j = 0; j < KMAX; ++j) if (j + 1 == K) kn[j + 1] = c.hi;
+    }
+}
+
+// Quantities of the bin an input falls in.
+template <typename T>
+struct RqsBin {
+    int k;
+    T xk, xk1, yk, yk1;   // knots bracketing the bin on both axes
+    T wn, hn;             // normalised width/height of the bin (used by the unit variant)
+    T udk, udk1;          // raw derivative params at the two knots (ignored when edge flag set)
+    bool lo_edge, hi_edge;// derivative pinned to 1 at k==0 / k==K-1
+};
+
+// searchsorted(right=True)-1, clamped to [0,K-1]: the last j<K with knot_j <= v (j=0 always taken).
+template <typename T, int KMAX>
+NF_HD void rqs_select(T v, const T* sk /*search knots*/, const T* cw, const T* ch, const T* wn, const T* hn,
+                      const T* ud, int K, RqsBin<T>& b) {
+    b.k = 0; b.xk = cw[0]; b.xk1 = cw[1]; b.yk = ch[0]; b.yk1 = ch[1]; b.wn = wn[0]; b.hn = hn[0];
+    b.udk = T(0); b.udk1 = ud[0];
+NF_UNROLL
+    for (int j = 1; j < KMAX; ++j) if (j < K) {
+        if (sk[j] <= v) {
+            b.k = j; b.xk = cw[j]; b.xk1 = cw[j + 1]; b.yk = ch[j]; b.yk1 = ch[j + 1];
+            b.wn = wn[j]; b.hn = hn[j]; b.udk = ud[j - 1];
+            b.udk1 = (j < KMAX - 1) ? ud[j] : T(0);     // unused when j==K-1 (hi_edge)
+        }
+    }
+    b.lo_edge = (b.k == 0);
+    b.hi_edge = (b.k == K - 1);
+}
+
+// value + log|derivative| inside the selected bin.  (x_k, y_k, w_k, h_k, d_k, d_k1) as in the reference.
+template <typename T, bool BOUNDED>
+NF_HD void rqs_bin_eval(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, T eps, T& out, T& lad) {
+    const T wkc = clamp_min(wk, eps);
+    const T s = hk / wkc;
+    if (!inverse) {
+        const T xi = clamp_mm((v - xk) / wkc, T(0), T(1));
+        const T om = T(1) - xi;
+        const T A = dk1 + dk - T(2) * s;
+        const T den0 = s + A * xi * om;
+        const T denc = clamp_min(den0, eps);
+        const T N1 = s * (xi * xi) + dk * xi * om;
+        out = yk + hk * N1 / denc;
+        const T num = (s * s) * (dk1 * (xi * xi) + T(2) * s * xi * om + dk * (om * om));
+        const T den2 = BOUNDED ? denc * denc : den0 * den0;
+        const T der = num / clamp_min(den2, eps);
+        lad = t_log(clamp_min(der, eps));
+    } else {
+        const T t0 = v - yk;
+        const T A = dk + dk1 - T(2) * s;
+        const T t = t0 * A;
+        const T a = BOUNDED ? (t + hk * (s - dk)) : (hk * (s - dk) + t);
+        const T b = hk * dk - t;
+        const T c = -s * t0;
+        const T disc = clamp_min(b * b - T(4) * a * c, T(0));
+        T q = -b - t_sqrt(disc);
+        if (BOUNDED) { if (t_abs(q) < eps) q = eps; }
+        const T xi = clamp_mm((T(2) * c) / q, T(0), T(1));
+        out = xi * wk + xk;
+        const T om = T(1) - xi;
+        const T Q = dk1 * (xi * xi) + (BOUNDED ? T(2) * s * xi * om : T(2) * s * (xi * om)) + dk * (om * om);
+        const T num = (s * s) * Q;
+        if (BOUNDED) {
+            const T den0 = s + (dk1 + dk - T(2) * s) * xi * om;
+            lad = -t_log(clamp_min(num, eps)) + T(2) * t_log(clamp_min(den0, eps));
+        } else {
+            const T den0 = s + A * (xi * om);
+            const T der = num / clamp_min(den0 * den0, eps);
+            lad = -t_log(clamp_min(der, eps));
+        }
+    }
+}
+
+// Full element evaluation from raw parameters.
+template <typename T, int KMAX, bool BOUNDED>
+NF_HD void rqs_eval(T v, const T* uw, const T* uh, const T* ud, int K, bool inverse, const RqsCfg<T>& c,
+                    T& out, T& lad) {
+    if (BOUNDED) {
+        const bool inside = (v >= c.lo) && (v <= c.hi);
+        if (!inside) { out = v; lad = T(0); return; }       // identity tails (:192-197); NaN lands here too
+    }
+    T wn[KMAX], hn[KMAX], cw[KMAX + 1], ch[KMAX + 1];
+    rqs_knots<T, KMAX, BOUNDED>(uw, K, c.min_w, c.scale_w, c, wn, cw);
+    rqs_knots<T, KMAX, BOUNDED>(uh, K, c.min_h, c.scale_h, c, hn, ch);
+    RqsBin<T> b;
+    rqs_select<T, KMAX>(v, inverse ? ch : cw, cw, ch, wn, hn, ud, K, b);
+    const T dk  = b.lo_edge ? T(1) : clamp_min(c.min_d + softplus(b.udk), c.eps);
+    const T dk1 = b.hi_edge ? T(1) : clamp_min(c.min_d + softplus(b.udk1), c.eps);
+    T wk, hk;
+    if (BOUNDED) { wk = clamp_min(b.xk1 - b.xk, c.eps); hk = clamp_min(b.yk1 - b.yk, c.eps); }
+    else         { wk = b.wn; hk = b.hn; }
+    rqs_bin_eval<T, BOUNDED>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, out, lad);
+    if (BOUNDED) {                                          // :306-307
+        if (!is_finite(out)) out = v;
+        if (!is_finite(lad)) lad = T(0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reverse mode.  Given upstream (g_out, g_lad) of one element, produce g_v and ACCUMULATE the
+// raw-parameter gradients into guw[K], guh[K], gud[K-1] (caller zero-initialises).
+// Forward intermediates are recomputed (the element is 3K-1 parameters; nothing is stashed).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct RqsBinGrad { T gv, gxk, gyk, gwk, ghk, gdk, gdk1; };
+
+template <typename T, bool BOUNDED>
+NF_HD void rqs_bin_eval_bwd(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, T eps,
+                            T g_out, T g_lad, RqsBinGrad<T>& g) {
+    const T wkc = clamp_min(wk, eps);
+    const bool p_wkc = pass_min(wk, eps);
+    const T s = hk / wkc;
+    T g_s = T(0), g_xi = T(0), g_om = T(0), g_A = T(0), g_wkc = T(0);
+    g.gv = g.gxk = g.gyk = g.gwk = g.ghk = g.gdk = g.gdk1 = T(0);
+    if (!inverse) {
+        const T xi0 = (v - xk) / wkc;
+        const T xi = clamp_mm(xi0, T(0), T(1));
+        const T om = T(1) - xi;
+        const T A = dk1 + dk - T(2) * s;
+        const T den0 = s + A * xi * om;
+        const T denc = clamp_min(den0, eps);
+        const T N1 = s * (xi * xi) + dk * xi * om;
+        const T Q = dk1 * (xi * xi) + T(2) * s * xi * om + dk * (om * om);
+        const T num = (s * s) * Q;
+        const T den2 = BOUNDED ? denc * denc : den0 * den0;
+        const T den2c = clamp_min(den2, eps);
+        const T der = num / den2c;
+        const T derc = clamp_min(der, eps);
+        // lad = log(derc)
+        const T g_der = pass_min(der, eps) ? g_lad / derc : T(0);
+        const T g_num = g_der / den2c;
+        const T g_den2 = pass_min(den2, eps) ? -g_der * num / (den2c * den2c) : T(0);
+        T g_denc = T(0), g_den0 = T(0);
+        if (BOUNDED) g_denc += T(2) * denc * g_den2; else g_den0 += T(2) * den0 * g_den2;
+        // num = s^2 Q
+        g_s += T(2) * s * Q * g_num;
+        const T g_Q = (s * s) * g_num;
+        g.gdk1 += (xi * xi) * g_Q;
+        g.gdk += (om * om) * g_Q;
+        g_s += T(2) * xi * om * g_Q;
+        g_xi += (T(2) * dk1 * xi + T(2) * s * om) * g_Q;
+        g_om += (T(2) * s * xi + T(2) * dk * om) * g_Q;
+        // out = yk + hk*N1/denc
+        g.gyk += g_out;
+        g.ghk += N1 / denc * g_out;
+        const T g_N1 = hk / denc * g_out;
+        g_denc += -hk * N1 / (denc * denc) * g_out;
+        g_s += (xi * xi) * g_N1;
+        g_xi += (T(2) * s * xi + dk * om) * g_N1;
+        g.gdk += xi * om * g_N1;
+        g_om += dk * xi * g_N1;
+        // denc = clamp(den0)
+        if (pass_min(den0, eps)) g_den0 += g_denc;
+        g_s += g_den0;
+        g_A += xi * om * g_den0;
+        g_xi += A * om * g_den0;
+        g_om += A * xi * g_den0;
+        g.gdk1 += g_A; g.gdk += g_A; g_s += -T(2) * g_A;
+        g_xi += -g_om;
+        const T g_xi0 = pass_mm(xi0, T(0), T(1)) ? g_xi : T(0);
+        g.gv += g_xi0 / wkc;
+        g.gxk += -g_xi0 / wkc;
+        g_wkc += -xi0 / wkc * g_xi0;
+    } else {
+        const T t0 = v - yk;
+        const T A = dk + dk1 - T(2) * s;
+        const T t = t0 * A;
+        const T a = t + hk * (s - dk);
+        const T b = hk * dk - t;
+        const T c = -s * t0;
+        const T disc0 = b * b - T(4) * a * c;
+        const T disc = clamp_min(disc0, T(0));
+        const T sq = t_sqrt(disc);
+        const T q0 = -b - sq;
+        const bool q_small = BOUNDED && (t_abs(q0) < eps);
+        const T q = q_small ? eps : q0;
+        const T xi0 = (T(2) * c) / q;
+        const T xi = clamp_mm(xi0, T(0), T(1));
+        const T om = T(1) - xi;
+        const T Q = dk1 * (xi * xi) + T(2) * s * (xi * om) + dk * (om * om);
+        const T num = (s * s) * Q;
+        const T den0 = s + A * xi * om;
+        T g_num = T(0), g_den0 = T(0);
+        if (BOUNDED) {
+            const T numc = clamp_min(num, eps), denc = clamp_min(den0, eps);
+            if (pass_min(num, eps)) g_num = -g_lad / numc;
+            if (pass_min(den0, eps)) g_den0 = T(2) * g_lad / denc;
+        } else {
+            const T den2 = den0 * den0;
+            const T den2c = clamp_min(den2, eps);
+            const T der = num / den2c;
+            const T derc = clamp_min(der, eps);
+            const T g_der = pass_min(der, eps) ? -g_lad / derc : T(0);
+            g_num = g_der / den2c;
+            if (pass_min(den2, eps)) g_den0 = T(2) * den0 * (-g_der * num / (den2c * den2c));
+        }
+        g_s += T(2) * s * Q * g_num;
+        const T g_Q = (s * s) * g_num;
+        g.gdk1 += (xi * xi) * g_Q;
+        g.gdk += (om * om) * g_Q;
+        g_s += T(2) * xi * om * g_Q;
+        g_xi += (T(2) * dk1 * xi + T(2) * s * om) * g_Q;
+        g_om += (T(2) * s * xi + T(2) * dk * om) * g_Q;
+        g_s += g_den0;
+        g_A += xi * om * g_den0;
+        g_xi += A * om * g_den0;
+        g_om += A * xi * g_den0;
+        // out = xi*wk + xk
+        g_xi += wk * g_out;
+        g.gwk += xi * g_out;
+        g.gxk += g_out;
+        g_xi += -g_om;
+        const T g_xi0 = pass_mm(xi0, T(0), T(1)) ? g_xi : T(0);
+        T g_c = T(2) / q * g_xi0;
+        const T g_q = -xi0 / q * g_xi0;
+        const T g_q0 = q_small ? T(0) : g_q;
+        T g_b = -g_q0;
+        const T g_sq = -g_q0;
+        const T g_disc = (sq > T(0)) ? g_sq / (T(2) * sq) : T(0);
+        const T g_disc0 = pass_min(disc0, T(0)) ? g_disc : T(0);
+        g_b += T(2) * b * g_disc0;
+        const T g_a = -T(4) * c * g_disc0;
+        g_c += -T(4) * a * g_disc0;
+        g_s += -t0 * g_c;
+        T g_t0 = -s * g_c;
+        g.ghk += dk * g_b;
+        g.gdk += hk * g_b;
+        T g_t = -g_b;
+        g_t += g_a;
+        g.ghk += (s - dk) * g_a;
+        g_s += hk * g_a;
+        g.gdk += -hk * g_a;
+        g_t0 += A * g_t;
+        g_A += t0 * g_t;
+        g.gdk += g_A; g.gdk1 += g_A; g_s += -T(2) * g_A;
+        g.gv += g_t0;
+        g.gyk += -g_t0;
+    }
+    // s = hk / wkc
+    g.ghk += g_s / wkc;
+    g_wkc += -s / wkc * g_s;
+    if (p_wkc) g.gwk += g_wkc;
+}
+
+// push d(loss)/d(normalised bin sizes) through floor+clamp and the softmax:  gu += J^T gw
+template <typename T, int KMAX>
+NF_HD void rqs_softmax_bwd(const T* u, int K, T floor_, T scale, T eps, const T* gw, T* gu) {
+    T mx = u[0];
+NF_UNROLL
+    for (int j = 1; j < KMAX; ++j) if (j < K) mx = (u[j] > mx) ? u[j] : mx;
+    T e[KMAX];
+    T sum = T(0);
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) { e[j] = t_exp(u[j] - mx); sum += e[j]; }
+    T dot = T(0);
+    T gs[KMAX];
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) {
+        const T sm = e[j] / sum;
+        const T w = floor_ + scale * sm;
+        gs[j] = pass_min(w, eps) ? scale * gw[j] : T(0);
+        e[j] = sm;
+        dot += gs[j] * sm;
+    }
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) gu[j] += e[j] * (gs[j] - dot);
+}
+
+template <typename T, int KMAX, bool BOUNDED>
+NF_HD void rqs_eval_bwd(T v, const T* uw, const T* uh, const T* ud, int K, bool inverse, const RqsCfg<T>& c,
+                        T g_out, T g_lad, T& g_v, T* guw, T* guh, T* gud) {
+    if (BOUNDED) {
+        const bool inside = (v >= c.lo) && (v <= c.hi);
+        if (!inside) { g_v = g_out; return; }
+    }
+    T wn[KMAX], hn[KMAX], cw[KMAX + 1], ch[KMAX + 1];
+    rqs_knots<T, KMAX, BOUNDED>(uw, K, c.min_w, c.scale_w, c, wn, cw);
+    rqs_knots<T, KMAX, BOUNDED>(uh, K, c.min_h, c.scale_h, c, hn, ch);
+    RqsBin<T> b;
+    rqs_select<T, KMAX>(v, inverse ? ch : cw, cw, ch, wn, hn, ud, K, b);
+    const T dk_pre  = c.min_d + softplus(b.udk);
+    const T dk1_pre = c.min_d + softplus(b.udk1);
+    const T dk  = b.lo_edge ? T(1) : clamp_min(dk_pre, c.eps);
+    const T dk1 = b.hi_edge ? T(1) : clamp_min(dk1_pre, c.eps);
+    T wk, hk;
+    if (BOUNDED) { wk = clamp_min(b.xk1 - b.xk, c.eps); hk = clamp_min(b.yk1 - b.yk, c.eps); }
+    else         { wk = b.wn; hk = b.hn; }
+    T gv_direct = T(0);
+    if (BOUNDED) {                       // scrubs (:306-307): a replaced output passes its gradient to the input
+        T out, lad;
+        rqs_bin_eval<T, BOUNDED>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, out, lad);
+        if (!is_finite(lad)) g_lad = T(0);
+        if (!is_finite(out)) { gv_direct = g_out; g_out = T(0); }
+    }
+    RqsBinGrad<T> g;
+    rqs_bin_eval_bwd<T, BOUNDED>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, g_out, g_lad, g);
+    g_v = g.gv + gv_direct;
+    // derivatives
+    if (!b.lo_edge && pass_min(dk_pre, c.eps)) {
+NF_UNROLL
+        for (int j = 0; j < KMAX - 1; ++j) if (j == b.k - 1) gud[j] += g.gdk * softplus_grad(b.udk);
+    }
+    if (!b.hi_edge && pass_min(dk1_pre, c.eps)) {
+NF_UNROLL
+        for (int j = 0; j < KMAX - 1; ++j) if (j == b.k) gud[j] += g.gdk1 * softplus_grad(b.udk1);
+    }
+    // bin sizes: map (gxk, gwk) / (gyk, ghk) onto d/d(normalised widths / heights)
+    T gw[KMAX], gh[KMAX];
+    if (BOUNDED) {
+        // wk = clamp(xk1 - xk): gxk1 = +gwk', gxk -= gwk';  knots j (1..K-1) = span*cumsum_{i<j} + lo
+        T gxk = g.gxk, gxk1 = T(0), gyk = g.gyk, gyk1 = T(0);
+        if (pass_min(b.xk1 - b.xk, c.eps)) { gxk1 += g.gwk; gxk -= g.gwk; }
+        if (pass_min(b.yk1 - b.yk, c.eps)) { gyk1 += g.ghk; gyk -= g.ghk; }
+        const T aw = (b.k >= 1) ? c.span * gxk : T(0);           // knot k interior?
+        const T bw = (b.k + 1 <= K - 1) ? c.span * gxk1 : T(0);   // knot k+1 interior?
+        const T ah = (b.k >= 1) ? c.span * gyk : T(0);
+        const T bh = (b.k + 1 <= K - 1) ? c.span * gyk1 : T(0);
+NF_UNROLL
+        for (int j = 0; j < KMAX; ++j) if (j < K) {
+            gw[j] = (j <= b.k - 1 ? aw : T(0)) + (j <= b.k ? bw : T(0));
+            gh[j] = (j <= b.k - 1 ? ah : T(0)) + (j <= b.k ? bh : T(0));
+        }
+    } else {
+NF_UNROLL
+        for (int j = 0; j < KMAX; ++j) if (j < K) {
+            gw[j] = (j < b.k ? g.gxk : T(0)) + (j == b.k ? g.gwk : T(0));
+            gh[j] = (j < b.k ? g.gyk : T(0)) + (j == b.k ? g.ghk : T(0));
+        }
+    }
+    rqs_softmax_bwd<T, KMAX>(uw, K, c.min_w, c.scale_w, c.eps, gw, guw);
+    rqs_softmax_bwd<T, KMAX>(uh, K, c.min_h, c.scale_h, c.eps, gh, guh);
+}
+
+}  // namespace nf

@@ -1,0 +1,35 @@
+// stack_small.cuh -- packed-weight layout of the fused small-data_dim inference stacks.
+// Shared by stack_small.cu (device) and mirrored by the Python packer (nfb200/packing.py), which asks
+// nf_*_stack_packed_floats() for sizes and fills the buffer following the offsets documented here.
+//
+// All words are 32-bit; integers are stored as int32 bit patterns inside the float buffer.
+//
+//   header (NF_STACK_HDR words):
+//     [0] magic   [1] D   [2] H (true hidden_dim)   [3] HP (padded: 64 or 128)   [4] K (spline) / 0 (affine)
+//     [5] L       [6] W1S (words per hidden unit in W1k: 4 if D<=3 else 12)      [7] NO (padded #outputs of the head)
+//     [8] layer_stride (words)   [9] bn_between (0/1)   [10] bound   [11] min_w  [12] min_h  [13] min_d
+//     [14] scale_w = 1-min_w*K   [15] scale_h
+//   per layer (layer_stride words, 16-byte aligned sections):
+//     mask[8] | tdim[8] (int) | meta[8]: {Dt, rescale, bn_on, bn_ld(float), 0..} | r_in[8] | r_lo[8] | r_out[8]
+//     | bn_mean[8] | bn_sd[8] | bn_gamma[8] | bn_beta[8]                      (NF_LAYER_HDR = 80 words)
+//     then `nets` conditioner blocks (1 for spline: param_net; 2 for affine: s_net, b_net), each:
+//       W1k [HP][W1S]   : {W1[k][0..D-1], zero pad.., b1[k] at slot W1S-1}
+//       W2t [HP][HP]    : W2t[k][j] = W2[j][k]
+//       b2  [HP]
+//       W3c [NO/4][HP][4]: W3c[c][j][q] = W3[out(c*4+q)][j]
+//       b3  [NO]
+//   spline head outputs are ordered t*P + p for transformed dim t (P = 3K-1); affine head outputs are d.
+#pragma once
+#include <stdint.h>
+
+#define NF_STACK_MAGIC_SPLINE 0x4e465331  /* 'NFS1' */
+#define NF_STACK_MAGIC_AFFINE 0x4e464131  /* 'NFA1' */
+#define NF_STACK_HDR 16
+#define NF_LAYER_HDR 80
+#define NF_STACK_DMAX 8
+
+static inline int nf_stack_hp(int H) { return H <= 64 ? 64 : 128; }
+static inline int nf_stack_w1s(int D) { return D <= 3 ? 4 : 12; }
+static inline int64_t nf_stack_net_words(int HP, int W1S, int NO) {
+    return (int64_t)HP * W1S + (int64_t)HP * HP + HP + (int64_t)NO * HP + NO;
+}

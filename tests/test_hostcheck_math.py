@@ -1,0 +1,185 @@
+"""CPU: the product's scalar transform math (csrc/nf_math.cuh, compiled for the host by
+tests/hostcheck) against the oracle (values) and torch autograd of the oracle (gradients)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flows_oracle as O
+from tests import golden_util as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "normalizing-flows-study_b200", "csrc")
+SRC = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+LIB = os.path.join(ROOT, "tests", "hostcheck", "_hostcheck.so")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    deps = [SRC, os.path.join(CSRC, "nf_math.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-I", CSRC, SRC, "-o", LIB])
+    return ctypes.CDLL(LIB)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _cfg(bounded, K, bound=5.0, mw=1e-3, mh=1e-3, md=1e-3):
+    if bounded:
+        v = [-bound, bound, 2 * bound, mw, mh, md, 1 - mw * K, 1 - mh * K, 1e-8]
+    else:
+        v = [0.0, 1.0, 1.0, mw, mh, md, 1 - mw * K, 1 - mh * K, 1e-6]
+    return torch.tensor(v, dtype=torch.float64)
+
+
+def run_rqs(hc, bounded, x, w, h, d, inverse, gy=None, gld=None, **kw):
+    K = w.shape[-1]
+    n = x.numel()
+    f = hc.hc_rqs_f32 if x.dtype == torch.float32 else hc.hc_rqs_f64
+    x, w, h, d = (t.contiguous() for t in (x, w, h, d))
+    y, ld = torch.empty_like(x), torch.empty_like(x)
+    cfg = _cfg(bounded, K, **kw)
+    if gy is None:
+        f(int(bounded), _p(x), _p(w), _p(h), _p(d), ctypes.c_long(n), K, int(inverse), _p(cfg), _p(y), _p(ld),
+          None, None, None, None, None, None)
+        return y, ld
+    gx, gw, gh, gd = torch.empty_like(x), torch.empty_like(w), torch.empty_like(h), torch.empty_like(d)
+    f(int(bounded), _p(x), _p(w), _p(h), _p(d), ctypes.c_long(n), K, int(inverse), _p(cfg), _p(y), _p(ld),
+      _p(gy.contiguous()), _p(gld.contiguous()), _p(gx), _p(gw), _p(gh), _p(gd))
+    return y, ld, gx, gw, gh, gd
+
+
+def _close(a, b, atol, rtol):
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    m = ~torch.isnan(a)
+    err = (a[m] - b[m]).abs() - (atol + rtol * b[m].abs())
+    assert bool((err <= 0).all()), f"max excess {err.max().item():.3e}"
+
+
+def _close64(mine, ref32, ref64, atol, rtol):
+    """fp32 parity judged against the fp64 oracle: the reference's own fp32 result is up to 1e-4 away from
+    fp64 on ill-conditioned elements, so allow 2x its per-element error + half its worst."""
+    assert torch.equal(torch.isnan(mine), torch.isnan(ref32))
+    m = ~torch.isnan(mine)
+    e_ref = (ref32.double() - ref64).abs()[m]
+    thr = atol + rtol * ref64[m].abs() + 2 * e_ref + 0.5 * e_ref.max()
+    err = (mine.double()[m] - ref64[m]).abs()
+    assert bool((err <= thr).all()), f"max excess {(err - thr).max().item():.3e}"
+
+
+@pytest.mark.parametrize("name", G.golden_names("rqs_unit"))
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rqs_unit_values_vs_golden(hc, name, inverse):
+    g = G.load(name)
+    y, ld = run_rqs(hc, False, g["x"], g["w"], g["h"], g["d"], inverse)
+    key = "inv" if inverse else "fwd"
+    y64, l64 = O.rqs_unit(g["x"].double(), g["w"].double(), g["h"].double(), g["d"].double(), inverse)
+    _close64(y, g[key], y64, 2e-6, 2e-6)
+    _close64(ld, g[key + "_ld"], l64, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("name", [n for n in G.golden_names("spline_") if n.endswith("_rqs")])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rqs_bounded_values_vs_golden(hc, name, inverse):
+    g = G.load(name)
+    K = g["K"]
+    x = g["x"].reshape(-1)
+    y, ld = run_rqs(hc, True, x, g["uw"].reshape(-1, K), g["uh"].reshape(-1, K), g["ud"].reshape(-1, K - 1), inverse)
+    key = "inv" if inverse else "fwd"
+    y64, l64 = O.rqs_bounded(g["x"].double(), g["uw"].double(), g["uh"].double(), g["ud"].double(), inverse)
+    _close64(y, g[key].reshape(-1), y64.reshape(-1), 5e-6, 2e-6)
+    _close64(ld, g[key + "_ld"].reshape(-1), l64.reshape(-1), 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("bounded", [True, False])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("K", [4, 8, 10])
+def test_rqs_gradients_vs_autograd_f64(hc, bounded, inverse, K):
+    g = torch.Generator().manual_seed(K + 10 * bounded + inverse)
+    n = 200
+    w = (torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5).requires_grad_()
+    h = (torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5).requires_grad_()
+    d = (torch.randn(n, K - 1, generator=g, dtype=torch.float64) * 1.5).requires_grad_()
+    if bounded:
+        x = torch.rand(n, generator=g, dtype=torch.float64) * 11 - 5.5     # a few land in the tails
+    else:
+        x = torch.rand(n, generator=g, dtype=torch.float64) * 0.98 + 0.01
+    x.requires_grad_()
+    gy = torch.randn(n, generator=g, dtype=torch.float64)
+    gld = torch.randn(n, generator=g, dtype=torch.float64)
+    if bounded:
+        yo, lo = O.rqs_bounded(x.view(n, 1), w.view(n, 1, K), h.view(n, 1, K), d.view(n, 1, K - 1), inverse)
+        yo, lo = yo.view(n), lo.view(n)
+    else:
+        yo, lo = O.rqs_unit(x, w, h, d, inverse)
+    (yo * gy + lo * gld).sum().backward()
+    y, ld, gx, gw, gh, gd = run_rqs(hc, bounded, x.detach(), w.detach(), h.detach(), d.detach(), inverse, gy, gld)
+    _close(y, yo.detach(), 1e-11, 1e-11)
+    _close(ld, lo.detach(), 1e-10, 1e-10)
+    _close(gx, x.grad, 1e-8, 1e-8)
+    _close(gw, w.grad, 1e-8, 1e-8)
+    _close(gh, h.grad, 1e-8, 1e-8)
+    _close(gd, d.grad, 1e-8, 1e-8)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_affine_coupling_elem_vs_autograd(hc, inverse):
+    g = torch.Generator().manual_seed(3)
+    n = 400
+    x = torch.randn(n, generator=g, dtype=torch.float64).requires_grad_()
+    s = (torch.randn(n, generator=g, dtype=torch.float64) * 6).requires_grad_()   # some beyond the +-10 clamp
+    b = (torch.randn(n, generator=g, dtype=torch.float64) * 6).requires_grad_()
+    m = (torch.rand(n, generator=g) > 0.5).double()
+    gy = torch.randn(n, generator=g, dtype=torch.float64)
+    gld = torch.randn(n, generator=g, dtype=torch.float64)
+    sc, bc = torch.clamp(s, -10, 10), torch.clamp(b, -10, 10)
+    if not inverse:
+        yo = x * m + (1 - m) * (x * torch.exp(sc) + bc)
+        lo = (1 - m) * sc
+    else:
+        yo = x * m + (1 - m) * ((x - bc) * torch.exp(-sc))
+        lo = (1 - m) * -sc
+    (yo * gy + lo * gld).sum().backward()
+    y, ldt, gx, gs, gb = (torch.empty(n, dtype=torch.float64) for _ in range(5))
+    hc.hc_affine_coupling_f64(_p(x.detach()), _p(m), _p(s.detach()), _p(b.detach()), ctypes.c_long(n), int(inverse),
+                              _p(y), _p(ldt), _p(gy), _p(gld), _p(gx), _p(gs), _p(gb))
+    _close(y, yo.detach(), 1e-12, 1e-12)
+    _close(ldt, lo.detach(), 1e-12, 1e-12)
+    _close(gx, x.grad, 1e-10, 1e-10)
+    _close(gs, s.grad, 1e-10, 1e-10)
+    _close(gb, b.grad, 1e-10, 1e-10)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_affine_ar_elem_vs_autograd(hc, mode):
+    g = torch.Generator().manual_seed(mode)
+    n = 400
+    v = torch.randn(n, generator=g, dtype=torch.float64).requires_grad_()
+    mu = (torch.randn(n, generator=g, dtype=torch.float64) * 6).requires_grad_()
+    al = (torch.randn(n, generator=g, dtype=torch.float64) * 2.5).requires_grad_()
+    gout = torch.randn(n, generator=g, dtype=torch.float64)
+    gld = torch.randn(n, generator=g, dtype=torch.float64)
+    iaf = mode in (1, 3)
+    a = torch.clamp(al, -2, 2) if iaf else torch.clamp(al, -3, 3)
+    mm = torch.clamp(mu, -10, 10) if iaf else mu
+    cs = 3 if iaf else 5
+    if mode in (0, 3):
+        yo = (v - mm) * torch.exp(torch.clamp(-a, -cs, cs))
+        lo = -a
+    else:
+        yo = v * torch.exp(torch.clamp(a, -cs, cs)) + mm
+        lo = a
+    (yo * gout + lo * gld).sum().backward()
+    out, ldt, gv, gmu, gal = (torch.empty(n, dtype=torch.float64) for _ in range(5))
+    hc.hc_affine_ar_f64(mode, _p(v.detach()), _p(mu.detach()), _p(al.detach()), ctypes.c_long(n), _p(out), _p(ldt),
+                        _p(gout), _p(gld), _p(gv), _p(gmu), _p(gal))
+    _close(out, yo.detach(), 1e-12, 1e-12)
+    _close(ldt, lo.detach(), 1e-12, 1e-12)
+    _close(gv, v.grad, 1e-10, 1e-10)
+    _close(gmu, mu.grad, 1e-10, 1e-10)
+    _close(gal, al.grad, 1e-10, 1e-10)
