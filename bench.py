@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Headline benchmark: log_prob + sample throughput (samples/s, inverse/forward + log-det) of the flow hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference] [--workload c2|c3]
+
+Workload at every N (weak scaling: fixed rows per GPU, no data-path collective -- rows are independent):
+  c2 (default, BASELINE.json configs[1]): 8 SplineCouplingLayers, data_dim=2, hidden 64, 8 RQ-spline bins,
+      synthetic checkerboard, 2^20 rows per GPU; one step = one log_prob pass (inverse + log-det + N(0,I) head)
+      over the batch + one sample pass (forward + log-det of a N(0,I) batch).
+  c3 (configs[2]): MaskedAutoregressiveFlow(64, 512), 262144 rows, log_prob + sequential-direction sampling.
+`value` counts rows through either pass (2 x batch per step), inputs resident in HBM; `e2e` is the same step
+through the public nn.Module API from pinned HOST buffers with H2D/D2H copies inside the timed region.
+One JSON line on stdout (rank 0).  The product arm never touches oracle/; the `cpu_baseline` leg and
+`--impl reference` time the CPU oracle (a port: the Python reference cannot travel to the GPU box).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "log_prob+sample samples/sec (inverse/forward + log-det)"
+UNIT = "samples/s"
+WORKLOADS = {
+    "c2": dict(name="RealNVPSpline-style stack: 8 x SplineCouplingLayer(2, 64, num_bins=8), checkerboard, 2^20 rows/GPU, "
+                    "log_prob + sample",
+               rows=1 << 20, D=2, H=64, K=8, L=8),
+    "c3": dict(name="MaskedAutoregressiveFlow(64, 512), 8-component Gaussian mixture, 262144 rows/GPU, "
+                    "log_prob + sequential-direction sample",
+               rows=262144, D=64, H=512),
+}
+# dense GEMM FLOPs per row of one direction: c2 8 layers x 2*(D*H + H*H + H*D*(3K-1)); c3 one MADE pass
+FLOPS_DENSE = {"c2": 8 * 2 * (2 * 64 + 64 * 64 + 64 * 2 * 23), "c3": 2 * (64 * 512 + 2 * 512 * 512 + 512 * 128)}
+# executed by the fused kernels: c2 drops the provably-unused half of the last GEMM;
+# c3 skips the masked-out 64-column weight tiles
+FLOPS_EXEC = {"c2": 8 * 2 * (2 * 64 + 64 * 64 + 64 * 23), "c3": None}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data + weights (no oracle imports here)
+# ------------------------------------------------------------------------------------------------
+def checkerboard(n, seed):
+    """plots/_common.py:121-128 recipe: uniform(-2,2)^2, keep (floor(x)+floor(y)) even, standardise."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((0, 2), dtype=np.float32)
+    while out.shape[0] < n:
+        p = rng.uniform(-2, 2, size=(2 * n, 2))
+        keep = (np.floor(p[:, 0]) + np.floor(p[:, 1])) % 2 == 0
+        out = np.concatenate([out, p[keep].astype(np.float32)])
+    out = out[:n]
+    return (out - out.mean(0)) / out.std(0)
+
+
+def gaussian_mixture(n, D, seed):
+    rng = np.random.default_rng(seed)
+    means = 3.0 * np.random.default_rng(0).standard_normal((8, D))
+    comp = rng.integers(0, 8, size=n)
+    return (means[comp] + 0.5 * rng.standard_normal((n, D))).astype(np.float32)
+
+
+def build_model(wl, N):
+    """Reference-layout module with reference init + N(0, sigma^2) perturbation so no layer is the identity."""
+    cfg = WORKLOADS[wl]
+    torch.manual_seed(0)
+    if wl == "c2":
+        masks = []
+        for i in range(cfg["L"]):
+            m = torch.zeros(cfg["D"])
+            if i % 2 == 0:
+                m[: cfg["D"] // 2] = 1
+            else:
+                m[cfg["D"] // 2:] = 1
+            masks.append(m)
+        model = N.NormalizingFlowModel([N.SplineCouplingLayer(cfg["D"], cfg["H"], m, num_bins=cfg["K"]) for m in masks])
+        sigma = 0.05
+    else:
+        model = N.MaskedAutoregressiveFlow(cfg["D"], cfg["H"])
+        sigma = 0.02
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(sigma * torch.randn(p.shape, generator=g))
+    model.eval()
+    return model
+
+
+def make_inputs(wl, rows, seed):
+    cfg = WORKLOADS[wl]
+    x = checkerboard(rows, seed) if wl == "c2" else gaussian_mixture(rows, cfg["D"], seed)
+    z = np.random.default_rng(seed + 7919).standard_normal((rows, cfg["D"])).astype(np.float32)
+    return torch.from_numpy(x), torch.from_numpy(z)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for l in rows:
+            f = [c.strip() for c in l.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(f) > col and f[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm; the only place bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(wl, model_cpu):
+    from oracle import flows_oracle as O
+    sd = {k: v.detach().clone() for k, v in model_cpu.state_dict().items()}
+    cfg = WORKLOADS[wl]
+    if wl == "c2":
+        specs = [dict(kind="spline", num_bins=cfg["K"])] * cfg["L"]
+
+        def step(x, z):
+            with torch.no_grad():
+                zz, ld = O.flow_model(sd, "", specs, x, True)
+                lp = O.std_normal_log_prob(zz) + ld
+                xs, ld2 = O.flow_model(sd, "", specs, z, False)
+            return lp, xs
+    else:
+        def step(x, z):
+            with torch.no_grad():
+                zz, ld = O.maf_inverse(sd, "", x)
+                lp = O.std_normal_log_prob(zz) + ld
+                xs, ld2 = O.maf_forward(sd, "", z)
+            return lp, xs
+    return step
+
+
+def time_cpu(wl, model_cpu, sample_rows, reps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_oracle_step_fn(wl, model_cpu)
+    x, z = make_inputs(wl, sample_rows, 123)
+    step(x[:1024], z[:1024])
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        step(x, z)
+        ts.append(time.perf_counter() - t)
+    return 2 * sample_rows / (sum(ts) / len(ts)), sum(ts) / len(ts)
+
+
+def cpu_sample_rows(wl):
+    # bounded sample: ~10-30 s of host work in total
+    return 262144 if wl == "c2" else 2048
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import nfb200 as N
+    wl = args.workload
+    model = build_model(wl, N)
+    rows = cpu_sample_rows(wl)
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_oracle_step_fn(wl, model)
+    x, z = make_inputs(wl, rows, 123)
+    for _ in range(max(args.warmup, 1)):
+        step(x, z)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step(x, z)
+    dt = (time.perf_counter() - t) / args.steps
+    val = 2 * rows / dt
+    sample = f"{rows} rows per step of the {WORKLOADS[wl]['rows']}-row workload, log_prob + sample, fp32 ATen eager"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl]["name"], "rows_per_step": rows},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def run_product(args):
+    import torch.distributed as dist
+    import nfb200 as N
+    ops = N.ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (product arm) needs a CUDA device: libnfb200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    rows, D = cfg["rows"], cfg["D"]
+    model_cpu = build_model(wl, N)
+    import copy
+    model = copy.deepcopy(model_cpu).to(dev).eval()
+
+    # ring of distinct input sets so that no step finds its inputs in the 126 MB L2
+    step_bytes = rows * D * 4 * 2
+    ring = max(2, min(32, math.ceil(3 * 126e6 / step_bytes)))
+    host_sets = []
+    for i in range(ring):
+        x, z = make_inputs(wl, rows, seed=1000 * rank + i)
+        host_sets.append((x.pin_memory(), z.pin_memory()))
+    dev_sets = [(x.to(dev), z.to(dev)) for x, z in host_sets]
+
+    def step_resident(i, ev=None):
+        x, z = dev_sets[i % ring]
+        if ev:
+            ev[0].record()
+        zz, ld = model.inverse(x)
+        if ev:
+            ev[1].record()
+        lp = ops.std_normal_log_prob(zz, ld)
+        if ev:
+            ev[2].record()
+        xs, ld2 = model.forward(z)
+        if ev:
+            ev[3].record()
+        return lp, xs
+
+    lp_host = torch.empty(rows, dtype=torch.float32).pin_memory()
+    xs_host = torch.empty(rows, D, dtype=torch.float32).pin_memory()
+    x_in = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    z_in = torch.empty(rows, D, dtype=torch.float32, device=dev)
+
+    def step_e2e(i):
+        xh, zh = host_sets[i % ring]
+        x_in.copy_(xh, non_blocking=True)
+        zz, ld = model.inverse(x_in)
+        lp = ops.std_normal_log_prob(zz, ld)
+        lp_host.copy_(lp, non_blocking=True)
+        z_in.copy_(zh, non_blocking=True)
+        xs, _ = model.forward(z_in)
+        xs_host.copy_(xs, non_blocking=True)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            step_resident(i)
+        barrier()
+        clocks = ClockSampler(local)
+        clocks.start()
+        time.sleep(0.3)
+        # ---- timed region: exactly K steps ------------------------------------------------------
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        launches0 = N._lib.launch_count()
+        barrier()
+        t0 = time.time()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record()
+        for i in range(args.steps):
+            step_resident(i, evs[i])
+        e_end.record()
+        barrier()
+        t1 = time.time()
+        launches = N._lib.launch_count() - launches0
+        ms_total = e_start.elapsed_time(e_end)
+        clk = clocks.stop(t0, t1)
+        # ---- end-to-end through the public API from pinned host buffers ----------------------
+        for i in range(2):
+            step_e2e(i)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for i in range(args.steps):
+            step_e2e(i)
+        e2.record()
+        barrier()
+        ms_e2e = s2.elapsed_time(e2)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / args.steps
+    value = 2.0 * rows * world / (ms_step * 1e-3)
+    e2e_val = 2.0 * rows * world / (ms_e2e / args.steps * 1e-3)
+
+    # dominant kernel: the fused inverse/forward launches (events 0->1 and 2->3 of every step)
+    ms_inv = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_fwd = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    ms_head = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    which = "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback 1.59 PFLOP/s"
+    ms_dom = 0.5 * (ms_inv + ms_fwd) if wl == "c2" else ms_inv
+    flops_launch = FLOPS_DENSE[wl] * rows
+    achieved = flops_launch / (ms_dom * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        "traffic": None,
+        "kernel": "spline_stack_kernel (one launch = all 8 layers of one direction)" if wl == "c2"
+                  else "gemm_kernel chain of MAF.inverse (4 launches + affine_ar)",
+        "flops_per_row": FLOPS_DENSE[wl], "flops_per_row_executed": FLOPS_EXEC[wl], "peak_source": which,
+        "ms_per_launch": {"inverse": ms_inv, "forward": ms_fwd, "log_prob_head": ms_head},
+        "hbm_gbs_algorithmic": (rows * (2 * D + 1) * 4) / (ms_dom * 1e-3) / 1e9,
+        "note": "GEMM FLOPs on the dense accounting of SURVEY 8d; the kernel runs them on the FP32 FFMA pipe "
+                "(fp32 parity), so the tensor-peak fraction is the headroom a tcgen05 3xTF32 path would address",
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": cfg["name"], "rows_per_gpu": rows, "passes_per_step": "log_prob(inverse)+sample(forward)",
+                   "l2": f"ring of {ring} distinct input sets ({ring * step_bytes / 1e6:.0f} MB) cycled between steps",
+                   "sharding": "rows sharded across ranks, no data-path collective"},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * rows * D * 4,
+                "d2h_bytes_per_step": rows * 4 + rows * D * 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n = cpu_sample_rows(wl)
+        v, secs = time_cpu(wl, model_cpu, n, reps=3)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{n} rows of the workload, log_prob + sample, {secs:.2f} s per pass pair, "
+                                         "oracle port (fp32 ATen eager, same op sequence as the reference)"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1 and args.impl == "product":
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

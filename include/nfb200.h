@@ -169,6 +169,43 @@ NF_API int nf_ar_sequential_forward(const void* v, const void* w0, const void* b
                              const void* w2, const void* b2, const void* w3, const void* b3, const int32_t* gstart,
                              void* out, void* ld, int64_t B, int D, int H, int mode, nf_stream_t stream);
 
+/* ---- a14: between-layer BatchNorm as an invertible per-feature affine, and the spline layer's rescale -------
+ * y[b,d] = (x[b,d] - sub[d]) / div[d] * mul[d] + add[d]; sub/div/mul/add are [D] arrays or NULL (0, 1, 1,
+ * add_scalar).  normalizing_flow_model.py:67-85 is (sub,div,mul,add) = (running_mean, sqrt(var+eps), gamma, beta);
+ * its inverse :110-128 is (beta, gamma, sqrt(var+eps), running_mean); spline_coupling_layer.py:78-94 is
+ * (data_min, NULL, scale, -bound). */
+NF_API int nf_feature_affine_forward(const void* x, const void* sub, const void* div, const void* mul, const void* add,
+                              double add_scalar, void* y, int64_t B, int D, int dtype, nf_stream_t stream);
+/* gx [B,D] overwritten; gsub/gdiv/gmul/gadd: [D] outputs or NULL (skipped); workspace: 2*D doubles. */
+NF_API int nf_feature_affine_backward(const void* x, const void* sub, const void* div, const void* mul, const void* gy,
+                               void* gx, void* gsub, void* gdiv, void* gmul, void* gadd, void* workspace, int64_t B,
+                               int D, int dtype, nf_stream_t stream);
+/* per-feature batch mean and biased variance (running-stat update of normalizing_flow_model.py:74-79).
+ * workspace: 2*D doubles. */
+NF_API int nf_col_stats(const void* x, void* mean, void* var, void* workspace, int64_t B, int D, int dtype,
+                 nf_stream_t stream);
+
+/* ---- a12/a13 sequential directions, layered route (autograd / float64 / configurations the incremental kernel
+ * does not take): loop body of masked_autoregressive_flow.py:55-67 / inverse_autoregressive_flow.py:76-91.
+ * out = cur with column `col` replaced by the transform of v[:,col] under params[:, col], params[:, D+col];
+ * ld_out = ld_in (NULL = 0) +- alpha.  mode: NF_AR_MAF_FORWARD or NF_AR_IAF_INVERSE. */
+NF_API int nf_ar_step_forward(const void* cur, const void* v, const void* params, const void* ld_in, void* out,
+                       void* ld_out, int64_t B, int D, int col, int mode, int dtype, nf_stream_t stream);
+NF_API int nf_ar_step_backward(const void* v, const void* params, const void* gout, const void* gld, void* gcur, void* gv,
+                        void* gparams, int64_t B, int D, int col, int mode, int dtype, nf_stream_t stream);
+/* closing scrubs + log-det clamp of the loop (:69-76 / :93-101) */
+NF_API int nf_ar_finish_forward(const void* cur, const void* v, const void* ld_sum, void* out, void* ld, int64_t B, int D,
+                         int mode, int dtype, nf_stream_t stream);
+NF_API int nf_ar_finish_backward(const void* cur, const void* ld_sum, const void* gout, const void* gld, void* gcur,
+                          void* gv, void* gld_sum, int64_t B, int D, int mode, int dtype, nf_stream_t stream);
+
+/* ---- a16: Flow.log_prob head for a standard-normal base (flow.py:56-73) ---------------------------------
+ * lp[b] = sum_d(-z[b,d]^2/2) - D/2*log(2*pi) + ld[b]   (ld may be NULL).  backward: gz = -z*glp[b]; gld = glp. */
+NF_API int nf_std_normal_log_prob_forward(const void* z, const void* ld, void* lp, int64_t B, int D, int dtype,
+                                   nf_stream_t stream);
+NF_API int nf_std_normal_log_prob_backward(const void* z, const void* glp, void* gz, int64_t B, int D, int dtype,
+                                    nf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,461 @@
+"""Flow layers of the hot path: same class names, constructor arguments, attributes and state_dict
+layout as the reference's `src.flows`, with every [B, *]-sized computation running in
+libnfb200.so (sm_100a).  Reference files, relative to the reference repository root:
+
+    Flow / SequentialFlow               src/flows/flow/flow.py:4-73, src/flows/flow/sequential_flow.py:5-34
+    CouplingLayer                       src/flows/coupling/coupling_layer.py:5-111
+    SplineCouplingLayer                 src/flows/spline/spline_coupling_layer.py:6-323
+    rational_quadratic_spline           src/flows/spline/rational_quadratic_spline.py:4-104
+    MaskedLinear / MADE                 src/flows/autoregressive/masked_linear.py:4-18, made.py:6-140
+    MaskedAutoregressiveFlow            src/flows/autoregressive/masked_autoregressive_flow.py:5-78
+    InverseAutoregressiveFlow           src/flows/autoregressive/inverse_autoregressive_flow.py:5-103
+
+Two execution routes per layer, chosen per call:
+  * fused   (no autograd needed, float32): one launch for the whole layer -- or the whole stack when the
+            caller is a container, see ChainPlan -- conditioner included;
+  * layered (training, float64, wide layers): conditioner GEMMs + BatchNorm + transform kernels, each an
+            autograd Function with a hand-written backward kernel (ops.py).
+There is no CPU route: tensors and modules must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops, packing
+
+
+def wants_grad(module: nn.Module, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def _module_tensors(module: nn.Module):
+    return list(module.parameters()) + list(module.buffers())
+
+
+class _PackCache:
+    """Derived weight layouts keyed on (parameter versions, storage, device)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, tensors, build):
+        key = packing.tensors_key(tensors)
+        if key != self._key:
+            self._val = build()
+            self._key = key
+        return self._val
+
+
+# ------------------------------------------------------------------------------------------------
+# base classes
+# ------------------------------------------------------------------------------------------------
+class Flow(nn.Module):
+    """Base class: `forward(z) -> (x, log_det)`, `inverse(x) -> (z, log_det)` (flow.py:4-38)."""
+
+    def __init__(self):
+        super().__init__()
+        self.data_dim = None
+
+    def forward(self, z):
+        raise NotImplementedError
+
+    def inverse(self, x):
+        raise NotImplementedError
+
+    def sample(self, num_samples, base_dist, device="cpu"):
+        """flow.py:40-54."""
+        z = base_dist.sample((num_samples,)).to(device)
+        x, _ = self.forward(z)
+        return x
+
+    def log_prob(self, x, base_dist):
+        """flow.py:56-73: log p(z) (summed over the event axis if the base is factorised) + log|det J_inv|."""
+        z, log_det_inv = self.inverse(x)
+        log_p_z = base_dist.log_prob(z)
+        if log_p_z.dim() > 1:
+            log_p_z = log_p_z.sum(dim=1)
+        return log_p_z + log_det_inv
+
+
+class SequentialFlow(Flow):
+    """Flows applied in order; inverse walks them backwards (sequential_flow.py:5-34)."""
+
+    def __init__(self, flows):
+        super().__init__()
+        if not isinstance(flows, (list, nn.ModuleList)):
+            raise ValueError("flows must be a list or nn.ModuleList")
+        self.flows = nn.ModuleList(flows)
+        self._chain = ChainPlan()
+
+    def _run(self, v, inverse):
+        fused = self._chain.run(self.flows, None, self.training, v, inverse)
+        if fused is not None:
+            return fused
+        total = torch.zeros(v.size(0), device=v.device)         # float32 accumulator, as the reference
+        for flow in (reversed(self.flows) if inverse else self.flows):
+            v, ld = flow.inverse(v) if inverse else flow.forward(v)
+            total += ld
+        return v, total
+
+    def forward(self, z):
+        return self._run(z, False)
+
+    def inverse(self, x):
+        return self._run(x, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# affine coupling
+# ------------------------------------------------------------------------------------------------
+def _coupling_net(data_dim, hidden_dim):
+    return nn.Sequential(
+        nn.Linear(data_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(),
+        nn.Linear(hidden_dim, hidden_dim), nn.BatchNorm1d(hidden_dim), nn.ReLU(),
+        nn.Linear(hidden_dim, data_dim))
+
+
+class CouplingLayer(Flow):
+    """RealNVP affine coupling layer (coupling_layer.py:5-111).
+
+    s = clamp(s_net(x*mask), +-10), b = clamp(b_net(x*mask), +-10);
+    forward  x = z*mask + (1-mask)*(z*exp(s)+b),     log_det =  sum((1-mask)*s)
+    inverse  z = x*mask + (1-mask)*((x-b)*exp(-s)),  log_det = -sum((1-mask)*s);  NaN/Inf -> 0.
+    """
+
+    def __init__(self, data_dim, hidden_dim, mask):
+        super().__init__()
+        self.data_dim = data_dim
+        self.register_buffer("mask", mask)
+        self.s_net = _coupling_net(data_dim, hidden_dim)
+        self.b_net = _coupling_net(data_dim, hidden_dim)
+        self._initialize_weights()
+        self._pack = _PackCache()
+
+    def _initialize_weights(self):
+        """xavier-normal hidden layers with zero bias, zero final layer => identity at init (:98-111)."""
+        for net in (self.s_net, self.b_net):
+            for layer in list(net)[:-1]:
+                if isinstance(layer, nn.Linear):
+                    nn.init.xavier_normal_(layer.weight, gain=1.0)
+                    nn.init.zeros_(layer.bias)
+        for net in (self.s_net, self.b_net):
+            nn.init.zeros_(net[-1].weight)
+            nn.init.zeros_(net[-1].bias)
+
+    # -- layered route -------------------------------------------------------------------------
+    def _conditioner(self, net, v):
+        # x*mask is folded into the first weight's columns (same zero/NaN propagation as the product x*mask)
+        h = ops.linear(v, net[0].weight, net[0].bias, mask=self.mask)
+        h = ops.batchnorm_relu(h, net[1])
+        h = ops.linear(h, net[3].weight, net[3].bias)
+        h = ops.batchnorm_relu(h, net[4])
+        return ops.linear(h, net[6].weight, net[6].bias)
+
+    def fusable(self, v):
+        return (not self.training and v.dtype == torch.float32 and self.s_net[0].weight.dtype == torch.float32
+                and self.data_dim <= packing.DMAX and self.s_net[0].out_features <= 128)
+
+    def _run(self, v, inverse):
+        if not wants_grad(self, v) and self.fusable(v):
+            pk = self._pack.get(_module_tensors(self), lambda: packing.pack_coupling_stack([self], None))
+            if pk is not None:
+                out = ops.coupling_stack(pk[0], pk[1], v, inverse)
+                if out is not None:
+                    return out
+        s_raw = self._conditioner(self.s_net, v)
+        b_raw = self._conditioner(self.b_net, v)
+        return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
+
+    def forward(self, z):
+        return self._run(z, False)
+
+    def inverse(self, x):
+        return self._run(x, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# rational-quadratic spline coupling
+# ------------------------------------------------------------------------------------------------
+class SplineCouplingLayer(Flow):
+    """Neural-spline coupling layer on [-bound, bound] with identity tails (spline_coupling_layer.py:6-323)."""
+
+    def __init__(self, data_dim, hidden_dim, mask, num_bins=10, bound=5.0, min_bin_width=1e-3, min_bin_height=1e-3,
+                 min_derivative=1e-3, data_min=None, data_max=None):
+        super().__init__()
+        self.data_dim = data_dim
+        self.num_bins = num_bins
+        self.bound = bound
+        self.min_bin_width = min_bin_width
+        self.min_bin_height = min_bin_height
+        self.min_derivative = min_derivative
+        self.data_min = data_min
+        self.data_max = data_max
+        self.register_buffer("mask", mask)
+        self.param_net = nn.Sequential(
+            nn.Linear(data_dim, hidden_dim), nn.ReLU(),
+            nn.Linear(hidden_dim, hidden_dim), nn.ReLU(),
+            nn.Linear(hidden_dim, data_dim * (3 * num_bins - 1)))
+        self._initialize_weights()
+        self._pack = _PackCache()
+        self._aux = _PackCache()
+
+    def _initialize_weights(self):
+        """:311-323."""
+        for layer in list(self.param_net)[:-1]:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_normal_(layer.weight, gain=1.0)
+                nn.init.zeros_(layer.bias)
+        nn.init.zeros_(self.param_net[-1].weight)
+        nn.init.zeros_(self.param_net[-1].bias)
+
+    @property
+    def _mins(self):
+        return (self.min_bin_width, self.min_bin_height, self.min_derivative)
+
+    def _aux_tensors(self, v):
+        """(tidx int32 [Dt], rescale (a, lo, c) or None) on v's device/dtype."""
+        def build():
+            m = self.mask.detach().to("cpu")
+            tidx = torch.nonzero(m == 0).flatten().to(torch.int32).to(v.device)
+            return tidx, packing.rescale_tensors(self, self.data_dim, v.dtype, v.device)
+        return self._aux.get([self.mask, torch.empty(0, dtype=v.dtype, device=v.device)], build)
+
+    def fusable(self, v):
+        return (v.dtype == torch.float32 and self.param_net[0].weight.dtype == torch.float32
+                and self.data_dim <= packing.DMAX and self.param_net[0].out_features <= 128
+                and 2 <= self.num_bins <= 16)
+
+    def _run(self, v, inverse):
+        if not wants_grad(self, v) and self.fusable(v):
+            pk = self._pack.get(_module_tensors(self), lambda: packing.pack_spline_stack([self], None))
+            if pk is not None:
+                out = ops.spline_stack(pk[0], pk[1], v, inverse)
+                if out is not None:
+                    return out
+        tidx, rescale = self._aux_tensors(v)
+        net = self.param_net
+        vin = v
+        if rescale is not None:                       # conditioner sees the rescaled input (:101-102)
+            vin = ops.feature_affine(v, rescale[1], None, rescale[0], -float(self.bound))
+        h = ops.linear(vin, net[0].weight, net[0].bias, mask=self.mask, relu=True)
+        h = ops.linear(h, net[2].weight, net[2].bias, relu=True)
+        params = ops.linear(h, net[4].weight, net[4].bias)
+        return ops.spline_transform(v, params, self.mask, tidx, self.num_bins, inverse, self.bound, self._mins,
+                                    rescale)
+
+    def forward(self, z):
+        return self._run(z, False)
+
+    def inverse(self, x):
+        return self._run(x, True)
+
+
+def rational_quadratic_spline(inputs, widths, heights, derivatives, inverse=False, min_bin_width=1e-3,
+                              min_bin_height=1e-3, min_derivative=1e-3, epsilon=1e-6):
+    """Public spline on [0,1] (rational_quadratic_spline.py:4-104): per-element outputs and log|dy/dx|.
+    `epsilon` is accepted and ignored, as in the reference (it is overwritten with 1e-6, :19)."""
+    K = widths.shape[-1]
+    x = inputs.reshape(-1)
+    y, ld = ops.rqs_unit(x, widths.reshape(-1, K), heights.reshape(-1, K), derivatives.reshape(-1, K - 1), inverse,
+                         (min_bin_width, min_bin_height, min_derivative))
+    return y.view(inputs.shape), ld.view(inputs.shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# MADE / MAF / IAF
+# ------------------------------------------------------------------------------------------------
+class MaskedLinear(nn.Linear):
+    """nn.Linear whose weight is multiplied by a fixed binary mask (masked_linear.py:4-18)."""
+
+    def __init__(self, in_features, out_features, mask, bias=True):
+        super().__init__(in_features, out_features, bias)
+        self.register_buffer("mask", mask)
+
+    def forward(self, input):
+        return ops.linear(input, self.weight, self.bias, mask=self.mask)
+
+
+def made_degrees(input_dim, hidden_dim):
+    """Hidden-unit degrees (made.py:25-41): interleaved [0,0,1,1,...] for D==2, floor(linspace) for D>2."""
+    if input_dim > 1:
+        if input_dim == 2:
+            return np.array([0, 0, 1, 1] * (hidden_dim // 4 + 1))[:hidden_dim]
+        return np.floor(np.linspace(0, input_dim - 1, hidden_dim)).astype(int)
+    return np.zeros(hidden_dim, dtype=int)
+
+
+class MADE(nn.Module):
+    """Masked autoencoder conditioner: in->H, H->H, H->H, H->mult*D masked linears with ReLUs (made.py:6-140)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim_multiplier=2, use_batch_norm=False):
+        super().__init__()
+        self.input_dim = input_dim
+        self.hidden_dim = hidden_dim
+        self.output_dim_multiplier = output_dim_multiplier
+        self.use_batch_norm = use_batch_norm
+        self.m = {-1: np.arange(input_dim), 0: made_degrees(input_dim, hidden_dim), 1: np.arange(input_dim)}
+        self.masks = self.create_masks()
+        self.net = self.create_network()
+        self._fold = _PackCache()
+
+    def create_masks(self):
+        """in->h: deg(j) <= deg(a); h->h: deg(b) <= deg(a); h->out: deg(a) < i, strict (made.py:47-79)."""
+        d_in, d_h, d_out = self.m[-1], self.m[0], self.m[1]
+        m_in = (d_in[None, :] <= d_h[:, None]).astype(np.float32)                  # [H, D]
+        m_hh = (d_h[None, :] <= d_h[:, None]).astype(np.float32)                   # [H, H]
+        m_out = np.tile((d_h[None, :] < d_out[:, None]).astype(np.float32), (self.output_dim_multiplier, 1))
+        return [torch.from_numpy(m_in), torch.from_numpy(m_hh), torch.from_numpy(m_out)]
+
+    def create_network(self):
+        """made.py:81-134 (xavier-normal gain 0.5 hidden layers, N(0, 0.01^2) final layer, zero biases)."""
+        H = self.hidden_dim
+        linears = [MaskedLinear(self.input_dim, H, mask=self.masks[0]),
+                   MaskedLinear(H, H, mask=self.masks[1]),
+                   MaskedLinear(H, H, mask=self.masks[1]),
+                   MaskedLinear(H, self.input_dim * self.output_dim_multiplier, mask=self.masks[2])]
+        layers = []
+        for lin in linears[:-1]:
+            layers.append(lin)
+            if self.use_batch_norm:
+                layers.append(nn.BatchNorm1d(H))
+            layers.append(nn.ReLU())
+        layers.append(linears[-1])
+        for lin in linears[:-1]:
+            nn.init.xavier_normal_(lin.weight, gain=0.5)
+            nn.init.zeros_(lin.bias)
+        nn.init.normal_(linears[-1].weight, mean=0.0, std=0.01)
+        nn.init.zeros_(linears[-1].bias)
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        """Layered route: masked linears with the ReLU (or BatchNorm+ReLU) fused into the producing kernel."""
+        mods = list(self.net)
+        i, h = 0, x
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, MaskedLinear):
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if isinstance(nxt, nn.ReLU):
+                    h = ops.linear(h, m.weight, m.bias, mask=m.mask, relu=True)
+                    i += 2
+                elif isinstance(nxt, nn.BatchNorm1d) and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU):
+                    h = ops.batchnorm_relu(ops.linear(h, m.weight, m.bias, mask=m.mask), nxt)
+                    i += 3
+                else:
+                    h = ops.linear(h, m.weight, m.bias, mask=m.mask)
+                    i += 1
+            else:
+                h = m(h)
+                i += 1
+        return h
+
+    def folded(self):
+        """Mask-folded, degree-sorted weights for the fused kernels (None when BatchNorm / mult != 2)."""
+        return self._fold.get(_module_tensors(self), lambda: packing.fold_made(self))
+
+
+class _AffineAutoregressive(Flow):
+    """Shared driver of MAF and IAF: one direction is a single MADE pass, the other is D-step sequential."""
+    _parallel_is_inverse = True
+    _mode_parallel = L.AR_MAF_INVERSE
+    _mode_sequential = L.AR_MAF_FORWARD
+
+    def __init__(self, dim, hidden_dim=64, use_batch_norm=False):
+        super().__init__()
+        self.data_dim = dim
+        self.dim = dim
+        self.conditioner = MADE(dim, hidden_dim, 2, use_batch_norm=use_batch_norm)
+
+    def _parallel(self, v):
+        if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
+            f = self.conditioner.folded()
+            if f is not None and f.w[0].dtype == v.dtype:
+                return ops.made_affine(v, f, self._mode_parallel)
+        return ops.affine_ar(v, self.conditioner(v), self._mode_parallel)
+
+    def _sequential(self, v):
+        if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
+            f = self.conditioner.folded()
+            if f is not None and f.w[0].dtype == v.dtype:
+                out = ops.ar_sequential(v, f, self._mode_sequential)
+                if out is not None:
+                    return out
+        # D dependent steps, each re-evaluating the conditioner on the partially filled output
+        # (masked_autoregressive_flow.py:55-67 / inverse_autoregressive_flow.py:76-91)
+        cur = torch.zeros_like(v)
+        ld = None
+        for i in range(self.dim):
+            cur, ld = ops.ar_step(cur, v, self.conditioner(cur), ld, i, self._mode_sequential)
+        return ops.ar_finish(cur, v, ld, self._mode_sequential)
+
+
+class MaskedAutoregressiveFlow(_AffineAutoregressive):
+    """MAF: `inverse` (density) is one parallel pass, `forward` (sampling) is sequential
+    (masked_autoregressive_flow.py:5-78)."""
+
+    def inverse(self, x):
+        return self._parallel(x)
+
+    def forward(self, z):
+        return self._sequential(z)
+
+
+class InverseAutoregressiveFlow(_AffineAutoregressive):
+    """IAF: `forward` (sampling) is one parallel pass, `inverse` (density) is sequential
+    (inverse_autoregressive_flow.py:5-103)."""
+    _mode_parallel = L.AR_IAF_FORWARD
+    _mode_sequential = L.AR_IAF_INVERSE
+
+    def __init__(self, dim, hidden_dim=64, use_batch_norm=False):
+        super().__init__(dim, hidden_dim, use_batch_norm)
+        final = self.conditioner.net[-1]                 # re-drawn N(0, 0.01^2) final layer (:21-28)
+        nn.init.normal_(final.weight, mean=0.0, std=0.01)
+        nn.init.zeros_(final.bias)
+
+    def forward(self, z):
+        return self._parallel(z)
+
+    def inverse(self, x):
+        return self._sequential(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-stack fusion used by the containers (SequentialFlow, models.NormalizingFlowModel)
+# ------------------------------------------------------------------------------------------------
+class ChainPlan:
+    """Runs a homogeneous stack of coupling layers (+ optional between-layer BatchNorm affines on running
+    statistics, normalizing_flow_model.py:25-128) as ONE kernel launch when no autograd graph is needed:
+    a row is a few bytes, so keeping it in registers across all layers removes every intermediate HBM trip."""
+
+    def __init__(self):
+        self._pack = _PackCache()
+
+    def run(self, flows, bns, training, v, inverse):
+        """(y, log_det) from one fused launch, or None when the chain must be walked layer by layer."""
+        flows = list(flows)
+        if not flows or not v.is_cuda or v.dim() != 2:
+            return None
+        if bns is not None and training:          # train mode moves the running statistics layer by layer
+            return None
+        kind = type(flows[0])
+        if kind not in (CouplingLayer, SplineCouplingLayer) or any(type(f) is not kind for f in flows):
+            return None
+        if not all(f.fusable(v) for f in flows):
+            return None
+        mods = flows + (list(bns) if bns is not None else [])
+        if torch.is_grad_enabled() and (v.requires_grad or any(p.requires_grad for m in mods for p in m.parameters())):
+            return None
+        tensors = [t for m in mods for t in _module_tensors(m)]
+        if kind is CouplingLayer:
+            pk = self._pack.get(tensors, lambda: packing.pack_coupling_stack(flows, bns))
+            return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse)
+        pk = self._pack.get(tensors, lambda: packing.pack_spline_stack(flows, bns))
+        return None if pk is None else ops.spline_stack(pk[0], pk[1], v, inverse)

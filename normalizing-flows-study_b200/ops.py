@@ -1,0 +1,474 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (include/nfb200.h).
+
+Two families:
+  * layer-wise ops with hand-written backward kernels (training / general path):
+      linear (F.linear incl. MaskedLinear's W*mask, masked_linear.py:14-18), batchnorm_relu
+      (nn.BatchNorm1d+ReLU of coupling_layer.py:18-35), affine_coupling, spline_transform,
+      affine_ar, rqs_unit;
+  * fused inference launches (no autograd): spline_stack, coupling_stack, made_affine,
+    ar_sequential.
+Every op allocates its outputs with torch (device memory plumbing) and launches on the
+current CUDA stream.  Nothing here has a CPU implementation.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib as L
+
+ptr, call, stream = L.ptr, L.call, L.stream
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _same_dtype(ref, *ts):
+    return [None if t is None else (t if t.dtype == ref.dtype else t.to(ref.dtype)) for t in ts]
+
+
+# --------------------------------------------------------------------------------------------
+# raw kernels (no autograd)
+# --------------------------------------------------------------------------------------------
+def gemm(A, Bm, M, N, K, sam, sak, sbk, sbn, bias=None, relu=False, out=None, accumulate=False, k_extent=None):
+    """C[M,N] (+)= A[M,K]*B[K,N] with element strides; see nf_gemm in include/nfb200.h."""
+    if out is None:
+        out = torch.empty((M, N), dtype=A.dtype, device=A.device)
+    call("nf_gemm", ptr(A), ptr(Bm), ptr(out), ptr(bias), M, N, K, sam, sak, sbk, sbn, N, int(relu), int(accumulate),
+         ptr(k_extent), L.dtype_code(A), stream())
+    return out
+
+
+def linear_raw(x, w, bias=None, relu=False, k_extent=None):
+    """y = relu?(x @ w.T + bias) for contiguous x [M,K], w [N,K]."""
+    M, K = x.shape
+    N = w.shape[0]
+    return gemm(x, w, M, N, K, K, 1, 1, K, bias=bias, relu=relu, k_extent=k_extent)
+
+
+def mul_rows(a, b):
+    """a * b where b has a's shape or is a single row broadcast over a's rows."""
+    a2 = a.view(-1, a.shape[-1])
+    out = torch.empty_like(a2)
+    b_rows = 1 if b.dim() == 1 else a2.shape[0]
+    call("nf_mul_rows", ptr(a2), ptr(_c(b)), ptr(out), a2.shape[0], a2.shape[1], b_rows, L.dtype_code(a), stream())
+    return out.view_as(a)
+
+
+def col_sum(a):
+    out = torch.empty(a.shape[1], dtype=a.dtype, device=a.device)
+    call("nf_col_sum", ptr(a), ptr(out), a.shape[0], a.shape[1], L.dtype_code(a), stream())
+    return out
+
+
+def relu_backward(y, gy):
+    gx = torch.empty_like(gy)
+    call("nf_relu_backward", ptr(y), ptr(gy), ptr(gx), gy.numel(), L.dtype_code(gy), stream())
+    return gx
+
+
+# --------------------------------------------------------------------------------------------
+# Linear (+ optional weight mask, + optional fused ReLU)
+# --------------------------------------------------------------------------------------------
+class _LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mask, relu):
+        x = _c(x)
+        w_eff = _c(weight) if mask is None else mul_rows(_c(weight), mask)
+        y = linear_raw(x, w_eff, None if bias is None else _c(bias), relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w_eff, mask, y if relu else None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w_eff, mask, y = ctx.saved_tensors
+        g = _c(gy)
+        if ctx.relu:
+            g = relu_backward(y, g)
+        M, K = x.shape
+        N = w_eff.shape[0]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(g, w_eff, M, K, N, N, 1, K, 1)                 # dX = dY W
+        if ctx.needs_input_grad[1]:
+            gw = gemm(g, x, N, K, M, 1, N, K, 1)                     # dW = dY^T X
+            if mask is not None:
+                gw = mul_rows(gw, mask)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = col_sum(g)
+        return gx, gw, gb, None, None
+
+
+def linear(x, weight, bias=None, mask=None, relu=False):
+    """F.linear(x, weight*mask, bias) (+ReLU).  mask: None, [in] (column mask, broadcast) or [out,in]."""
+    weight, bias, mask = _same_dtype(x, weight, bias, mask)
+    return _LinearFn.apply(x, weight, bias, mask, relu)
+
+
+# --------------------------------------------------------------------------------------------
+# BatchNorm1d (+ReLU)
+# --------------------------------------------------------------------------------------------
+class _BatchNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu):
+        x = _c(x)
+        B, H = x.shape
+        y = torch.empty_like(x)
+        sm = torch.empty(H, dtype=x.dtype, device=x.device)
+        sr = torch.empty(H, dtype=x.dtype, device=x.device)
+        call("nf_batchnorm_forward", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
+             ptr(y), ptr(sm), ptr(sr), B, H, int(training), float(momentum), float(eps), int(relu),
+             L.dtype_code(x), stream())
+        ctx.relu, ctx.training = relu, training
+        ctx.save_for_backward(x, y, gamma, sm, sr)
+        ctx.mark_non_differentiable(sm, sr)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, y, gamma, sm, sr = ctx.saved_tensors
+        B, H = x.shape
+        gx = torch.empty_like(x)
+        gg = torch.empty_like(sm)
+        gb = torch.empty_like(sm)
+        call("nf_batchnorm_backward", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(_c(gy)), ptr(gx), ptr(gg),
+             ptr(gb), B, H, int(ctx.relu), int(ctx.training), L.dtype_code(x), stream())
+        return gx, gg, gb, None, None, None, None, None, None
+
+
+def batchnorm_relu(x, bn: torch.nn.BatchNorm1d, relu=True):
+    """nn.BatchNorm1d forward (train: batch stats + running-stat update, eval: running stats) fused with ReLU."""
+    training = bn.training or bn.running_mean is None
+    momentum = 0.0
+    if training and bn.track_running_stats and bn.running_mean is not None:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        momentum = (1.0 / float(bn.num_batches_tracked)) if bn.momentum is None else bn.momentum
+    rm, rv = bn.running_mean, bn.running_var
+    if rm is not None and rm.dtype != x.dtype:       # mixed dtypes: keep the module's buffers authoritative
+        rm32, rv32 = rm.to(x.dtype), rv.to(x.dtype)
+        y = _BatchNormFn.apply(x, bn.weight.to(x.dtype), bn.bias.to(x.dtype), rm32, rv32, training, momentum, bn.eps, relu)
+        if training:
+            rm.copy_(rm32)
+            rv.copy_(rv32)
+        return y
+    return _BatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, training, momentum, bn.eps, relu)
+
+
+# --------------------------------------------------------------------------------------------
+# transforms
+# --------------------------------------------------------------------------------------------
+class _AffineCouplingFn(Function):
+    @staticmethod
+    def forward(ctx, x, s_raw, b_raw, mask, inverse):
+        x, s_raw, b_raw = _c(x), _c(s_raw), _c(b_raw)
+        B, D = x.shape
+        y = torch.empty_like(x)
+        ld = torch.empty(B, dtype=x.dtype, device=x.device)
+        call("nf_affine_coupling_forward", ptr(x), ptr(s_raw), ptr(b_raw), ptr(mask), ptr(y), ptr(ld), B, D,
+             int(inverse), L.dtype_code(x), stream())
+        ctx.inverse = inverse
+        ctx.save_for_backward(x, s_raw, b_raw, mask)
+        return y, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gld):
+        x, s_raw, b_raw, mask = ctx.saved_tensors
+        B, D = x.shape
+        gx, gs, gb = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        call("nf_affine_coupling_backward", ptr(x), ptr(s_raw), ptr(b_raw), ptr(mask), ptr(_c(gy)), ptr(_c(gld)),
+             ptr(gx), ptr(gs), ptr(gb), B, D, int(ctx.inverse), L.dtype_code(x), stream())
+        return gx, gs, gb, None, None
+
+
+def affine_coupling(x, s_raw, b_raw, mask, inverse):
+    return _AffineCouplingFn.apply(x, s_raw, b_raw, _c(mask.to(x.dtype)), inverse)
+
+
+class _SplineTransformFn(Function):
+    @staticmethod
+    def forward(ctx, x, params, mask, tidx, K, inverse, bound, mins, rescale):
+        x, params = _c(x), _c(params)
+        B, D = x.shape
+        y = torch.empty_like(x)
+        ld = torch.empty(B, dtype=x.dtype, device=x.device)
+        r = rescale if rescale is not None else (None, None, None)
+        call("nf_spline_transform_forward", ptr(x), ptr(params), ptr(mask), ptr(tidx), ptr(y), ptr(ld), B, D,
+             tidx.numel(), K, int(inverse), bound, mins[0], mins[1], mins[2], ptr(r[0]), ptr(r[1]), ptr(r[2]),
+             L.dtype_code(x), stream())
+        ctx.cfg = (K, inverse, bound, mins)
+        ctx.rescale = rescale
+        ctx.save_for_backward(x, params, mask, tidx)
+        return y, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gld):
+        x, params, mask, tidx = ctx.saved_tensors
+        K, inverse, bound, mins = ctx.cfg
+        B, D = x.shape
+        r = ctx.rescale if ctx.rescale is not None else (None, None, None)
+        gx = torch.empty_like(x)
+        gp = torch.zeros_like(params)
+        call("nf_spline_transform_backward", ptr(x), ptr(params), ptr(mask), ptr(tidx), ptr(_c(gy)), ptr(_c(gld)),
+             ptr(gx), ptr(gp), B, D, tidx.numel(), K, int(inverse), bound, mins[0], mins[1], mins[2], ptr(r[0]),
+             ptr(r[1]), ptr(r[2]), L.dtype_code(x), stream())
+        return gx, gp, None, None, None, None, None, None, None
+
+
+def spline_transform(x, params, mask, tidx, K, inverse, bound, mins, rescale=None):
+    return _SplineTransformFn.apply(x, params, _c(mask.to(x.dtype)), tidx, K, inverse, float(bound),
+                                    tuple(float(m) for m in mins), rescale)
+
+
+class _AffineARFn(Function):
+    @staticmethod
+    def forward(ctx, v, params, mode):
+        v, params = _c(v), _c(params)
+        B, D = v.shape
+        out = torch.empty_like(v)
+        ld = torch.empty(B, dtype=v.dtype, device=v.device)
+        call("nf_affine_ar_forward", ptr(v), ptr(params), ptr(out), ptr(ld), B, D, mode, L.dtype_code(v), stream())
+        ctx.mode = mode
+        ctx.save_for_backward(v, params, ld)
+        return out, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gld):
+        v, params, ld = ctx.saved_tensors
+        B, D = v.shape
+        gv, gp = torch.empty_like(v), torch.empty_like(params)
+        call("nf_affine_ar_backward", ptr(v), ptr(params), ptr(ld), ptr(_c(gout)), ptr(_c(gld)), ptr(gv), ptr(gp), B, D,
+             ctx.mode, L.dtype_code(v), stream())
+        return gv, gp, None
+
+
+def affine_ar(v, params, mode):
+    return _AffineARFn.apply(v, params, mode)
+
+
+class _RqsUnitFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, h, d, inverse, mins):
+        x, w, h, d = _c(x), _c(w), _c(h), _c(d)
+        n, K = x.numel(), w.shape[-1]
+        y, ld = torch.empty_like(x), torch.empty_like(x)
+        call("nf_rqs_unit_forward", ptr(x), ptr(w), ptr(h), ptr(d), ptr(y), ptr(ld), n, K, int(inverse), mins[0],
+             mins[1], mins[2], L.dtype_code(x), stream())
+        ctx.cfg = (inverse, mins)
+        ctx.save_for_backward(x, w, h, d)
+        return y, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gld):
+        x, w, h, d = ctx.saved_tensors
+        inverse, mins = ctx.cfg
+        n, K = x.numel(), w.shape[-1]
+        gx, gw, gh, gd = torch.empty_like(x), torch.empty_like(w), torch.empty_like(h), torch.empty_like(d)
+        call("nf_rqs_unit_backward", ptr(x), ptr(w), ptr(h), ptr(d), ptr(_c(gy)), ptr(_c(gld)), ptr(gx), ptr(gw),
+             ptr(gh), ptr(gd), n, K, int(inverse), mins[0], mins[1], mins[2], L.dtype_code(x), stream())
+        return gx, gw, gh, gd, None, None
+
+
+def rqs_unit(x, w, h, d, inverse, mins):
+    return _RqsUnitFn.apply(x, w, h, d, bool(inverse), tuple(float(m) for m in mins))
+
+
+class _FeatureAffineFn(Function):
+    """y = (x - sub) / div * mul + add, per feature; any of sub/div/mul/add may be None (add: python float ok)."""
+
+    @staticmethod
+    def forward(ctx, x, sub, div, mul, add):
+        x = _c(x)
+        B, D = x.shape
+        y = torch.empty_like(x)
+        add_t = add if isinstance(add, torch.Tensor) else None
+        add_s = 0.0 if add is None or add_t is not None else float(add)
+        call("nf_feature_affine_forward", ptr(x), ptr(sub), ptr(div), ptr(mul), ptr(add_t), add_s, ptr(y), B, D,
+             L.dtype_code(x), stream())
+        ctx.save_for_backward(x, sub, div, mul)
+        ctx.add_is_tensor = add_t is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, sub, div, mul = ctx.saved_tensors
+        B, D = x.shape
+        need = [sub is not None and ctx.needs_input_grad[1], div is not None and ctx.needs_input_grad[2],
+                mul is not None and ctx.needs_input_grad[3], ctx.add_is_tensor and ctx.needs_input_grad[4]]
+        outs = [torch.empty(D, dtype=x.dtype, device=x.device) if n else None for n in need]
+        ws = torch.empty(2 * D, dtype=torch.float64, device=x.device) if any(need) else None
+        gx = torch.empty_like(x)
+        call("nf_feature_affine_backward", ptr(x), ptr(sub), ptr(div), ptr(mul), ptr(_c(gy)), ptr(gx), ptr(outs[0]),
+             ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), ptr(ws), B, D, L.dtype_code(x), stream())
+        return gx, outs[0], outs[1], outs[2], outs[3]
+
+
+def feature_affine(x, sub=None, div=None, mul=None, add=None):
+    sub, div, mul = _same_dtype(x, sub, div, mul)
+    if isinstance(add, torch.Tensor):
+        add, = _same_dtype(x, add)
+    return _FeatureAffineFn.apply(x, sub, div, mul, add)
+
+
+def col_stats(x):
+    """Per-feature batch mean and biased variance of x [B,D] (no autograd)."""
+    x = _c(x.detach())
+    B, D = x.shape
+    mean = torch.empty(D, dtype=x.dtype, device=x.device)
+    var = torch.empty(D, dtype=x.dtype, device=x.device)
+    ws = torch.empty(2 * D, dtype=torch.float64, device=x.device)
+    call("nf_col_stats", ptr(x), ptr(mean), ptr(var), ptr(ws), B, D, L.dtype_code(x), stream())
+    return mean, var
+
+
+class _ArStepFn(Function):
+    @staticmethod
+    def forward(ctx, cur, v, params, ld_in, col, mode):
+        cur, v, params = _c(cur), _c(v), _c(params)
+        B, D = v.shape
+        out = torch.empty_like(v)
+        ld = torch.empty(B, dtype=v.dtype, device=v.device)
+        call("nf_ar_step_forward", ptr(cur), ptr(v), ptr(params), ptr(None if ld_in is None else _c(ld_in)), ptr(out),
+             ptr(ld), B, D, col, mode, L.dtype_code(v), stream())
+        ctx.cfg = (col, mode, ld_in is not None)
+        ctx.save_for_backward(v, params)
+        return out, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gld):
+        v, params = ctx.saved_tensors
+        col, mode, has_ld = ctx.cfg
+        B, D = v.shape
+        gcur, gv, gp = torch.empty_like(v), torch.empty_like(v), torch.empty_like(params)
+        gld = _c(gld)
+        call("nf_ar_step_backward", ptr(v), ptr(params), ptr(_c(gout)), ptr(gld), ptr(gcur), ptr(gv), ptr(gp), B, D,
+             col, mode, L.dtype_code(v), stream())
+        return gcur, gv, gp, (gld if has_ld else None), None, None
+
+
+def ar_step(cur, v, params, ld_in, col, mode):
+    return _ArStepFn.apply(cur, v, params, ld_in, col, mode)
+
+
+class _ArFinishFn(Function):
+    @staticmethod
+    def forward(ctx, cur, v, ld_sum, mode):
+        cur, v, ld_sum = _c(cur), _c(v), _c(ld_sum)
+        B, D = v.shape
+        out = torch.empty_like(v)
+        ld = torch.empty_like(ld_sum)
+        call("nf_ar_finish_forward", ptr(cur), ptr(v), ptr(ld_sum), ptr(out), ptr(ld), B, D, mode, L.dtype_code(v),
+             stream())
+        ctx.mode = mode
+        ctx.save_for_backward(cur, ld_sum)
+        return out, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gld):
+        cur, ld_sum = ctx.saved_tensors
+        B, D = cur.shape
+        gcur, gv, gls = torch.empty_like(cur), torch.empty_like(cur), torch.empty_like(ld_sum)
+        call("nf_ar_finish_backward", ptr(cur), ptr(ld_sum), ptr(_c(gout)), ptr(_c(gld)), ptr(gcur), ptr(gv), ptr(gls),
+             B, D, ctx.mode, L.dtype_code(cur), stream())
+        return gcur, gv, gls, None
+
+
+def ar_finish(cur, v, ld_sum, mode):
+    return _ArFinishFn.apply(cur, v, ld_sum, mode)
+
+
+class _StdNormalLogProbFn(Function):
+    @staticmethod
+    def forward(ctx, z, ld):
+        z = _c(z)
+        B, D = z.shape
+        lp = torch.empty(B, dtype=z.dtype, device=z.device)
+        call("nf_std_normal_log_prob_forward", ptr(z), ptr(None if ld is None else _c(ld)), ptr(lp), B, D,
+             L.dtype_code(z), stream())
+        ctx.has_ld = ld is not None
+        ctx.save_for_backward(z)
+        return lp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, glp):
+        z, = ctx.saved_tensors
+        B, D = z.shape
+        glp = _c(glp)
+        gz = torch.empty_like(z)
+        call("nf_std_normal_log_prob_backward", ptr(z), ptr(glp), ptr(gz), B, D, L.dtype_code(z), stream())
+        return gz, (glp if ctx.has_ld else None)
+
+
+def std_normal_log_prob(z, log_det=None):
+    """log N(z; 0, I) + log_det per row: the Flow.log_prob head (flow.py:56-73) for a standard-normal base."""
+    if log_det is not None and log_det.dtype != z.dtype:
+        log_det = log_det.to(z.dtype)
+    return _StdNormalLogProbFn.apply(z, log_det)
+
+
+# --------------------------------------------------------------------------------------------
+# fused inference launches
+# --------------------------------------------------------------------------------------------
+def spline_stack(packed, hdr_host, x, inverse):
+    """Whole spline-coupling stack in one launch; returns None if the configuration is unsupported."""
+    x = _c(x)
+    B, D = x.shape
+    y = torch.empty_like(x)
+    ld = torch.empty(B, dtype=x.dtype, device=x.device)
+    ok = L.try_call("nf_spline_stack_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
+                    ptr(ld), B, int(inverse), stream())
+    return (y, ld) if ok else None
+
+
+def coupling_stack(packed, hdr_host, x, inverse):
+    x = _c(x)
+    B, D = x.shape
+    y = torch.empty_like(x)
+    ld = torch.empty(B, dtype=x.dtype, device=x.device)
+    ok = L.try_call("nf_coupling_stack_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x),
+                    ptr(y), ptr(ld), B, int(inverse), stream())
+    return (y, ld) if ok else None
+
+
+def made_affine(v, folded, mode):
+    """MADE chain + MAF.inverse / IAF.forward.  folded: packing.FoldedMade."""
+    v = _c(v)
+    B, D = v.shape
+    H = folded.H
+    ws = torch.empty(2 * B * max(H, 2 * D), dtype=v.dtype, device=v.device)
+    out = torch.empty_like(v)
+    ld = torch.empty(B, dtype=v.dtype, device=v.device)
+    w, b = folded.w, folded.b
+    call("nf_made_affine_forward", ptr(v), ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(w[2]), ptr(b[2]),
+         ptr(w[3]), ptr(b[3]), ptr(folded.kext[0]), ptr(folded.kext[1]), ptr(folded.kext[2]), ptr(ws), ptr(out),
+         ptr(ld), B, D, H, mode, L.dtype_code(v), stream())
+    return out, ld
+
+
+def ar_sequential(v, folded, mode):
+    """MAF.forward / IAF.inverse incremental kernel; returns None when unsupported (H too large, fp64)."""
+    if v.dtype != torch.float32:
+        return None
+    v = _c(v)
+    B, D = v.shape
+    out = torch.empty_like(v)
+    ld = torch.empty(B, dtype=v.dtype, device=v.device)
+    w, b = folded.w, folded.b
+    ok = L.try_call("nf_ar_sequential_forward", ptr(v), ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(w[2]),
+                    ptr(b[2]), ptr(w[3]), ptr(b[3]), ptr(folded.gstart), ptr(out), ptr(ld), B, D, folded.H, mode,
+                    stream())
+    return (out, ld) if ok else None

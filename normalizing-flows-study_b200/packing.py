@@ -1,0 +1,243 @@
+"""Host-side weight packing for the fused kernels (derived caches of the nn.Module parameters).
+
+The modules keep the reference's parameter/buffer names and shapes (state_dict compatible);
+the kernels want other layouts: transposed / chunked / zero-padded conditioner weights with eval-mode
+BatchNorm folded in (stack_small.cuh), and mask-folded, degree-sorted MADE weights.  Packs are rebuilt
+whenever a parameter's version counter or storage changes.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MAGIC_SPLINE = 0x4E465331
+MAGIC_AFFINE = 0x4E464131
+HDR, LAYER_HDR, DMAX = 16, 80, 8
+
+
+def tensors_key(tensors):
+    """Cache key that changes when any tensor is modified in place, re-assigned or moved."""
+    return tuple((t.data_ptr(), t._version, t.device.index, t.dtype) for t in tensors if t is not None)
+
+
+def _np(t, dtype=np.float64):
+    return t.detach().to("cpu").numpy().astype(dtype)
+
+
+def _hp(H):
+    return 64 if H <= 64 else 128
+
+
+def _w1s(D):
+    return 4 if D <= 3 else 12
+
+
+def _net_words(HP, W1S, NO):
+    return HP * W1S + HP * HP + HP + NO * HP + NO
+
+
+def _pack_net(W1, b1, W2, b2, W3, b3, out_rows, D, H, HP, W1S, NO):
+    """One conditioner block: W1k | W2t | b2 | W3c | b3 (float64 numpy in, float32 words out)."""
+    w1k = np.zeros((HP, W1S))
+    w1k[:H, :D] = W1
+    w1k[:H, W1S - 1] = b1
+    w2t = np.zeros((HP, HP))
+    w2t[:H, :H] = W2.T
+    b2p = np.zeros(HP)
+    b2p[:H] = b2
+    w3 = np.zeros((NO, HP))
+    b3p = np.zeros(NO)
+    n = len(out_rows)
+    w3[:n, :H] = W3[out_rows]
+    b3p[:n] = b3[out_rows]
+    w3c = w3.reshape(NO // 4, 4, HP).transpose(0, 2, 1)          # [c][j][q]
+    return np.concatenate([w1k.ravel(), w2t.ravel(), b2p, w3c.ravel(), b3p]).astype(np.float32)
+
+
+def _layer_header(mask, tdims, rescale, bn):
+    """80-word per-layer header; ints are stored as raw int32 bit patterns."""
+    h = np.zeros(LAYER_HDR, dtype=np.float32)
+    hi = h.view(np.int32)
+    D = len(mask)
+    h[0:D] = mask
+    hi[8:8 + len(tdims)] = tdims
+    hi[16] = len(tdims)
+    if rescale is not None:
+        hi[17] = 1
+        h[24:24 + D], h[32:32 + D], h[40:40 + D] = rescale
+    if bn is not None:
+        hi[18] = 1
+        mean, sd, gamma, beta, bn_ld = bn
+        h[19] = bn_ld
+        h[48:48 + D], h[56:56 + D], h[64:64 + D], h[72:72 + D] = mean, sd, gamma, beta
+    else:
+        h[56:64] = 1.0
+        h[64:72] = 1.0
+    return h
+
+
+def _bn_between_consts(bn: torch.nn.BatchNorm1d):
+    """Between-layer BatchNorm as an affine on running stats (normalizing_flow_model.py:67-128), computed with the
+    same float32 torch expressions as the reference so the constants match bit for bit."""
+    with torch.no_grad():
+        sd = torch.sqrt(bn.running_var.float() + bn.eps)
+        ld = (torch.log(torch.abs(bn.weight.float())) - 0.5 * torch.log(bn.running_var.float() + bn.eps)).sum()
+    return (_np(bn.running_mean, np.float32), _np(sd, np.float32), _np(bn.weight, np.float32),
+            _np(bn.bias, np.float32), float(ld))
+
+
+def _rescale_arrays(layer, D):
+    if layer.data_min is None or layer.data_max is None:
+        return None
+    lo = np.broadcast_to(_np(torch.as_tensor(layer.data_min)), (D,)).astype(np.float64)
+    hi = np.broadcast_to(_np(torch.as_tensor(layer.data_max)), (D,)).astype(np.float64)
+    return ((2 * layer.bound) / (hi - lo)).astype(np.float32), lo.astype(np.float32), \
+        ((hi - lo) / (2 * layer.bound)).astype(np.float32)
+
+
+def rescale_tensors(layer, D, dtype, device):
+    r = None
+    if layer.data_min is not None and layer.data_max is not None:
+        lo = np.broadcast_to(_np(torch.as_tensor(layer.data_min)), (D,)).astype(np.float64)
+        hi = np.broadcast_to(_np(torch.as_tensor(layer.data_max)), (D,)).astype(np.float64)
+        r = tuple(torch.tensor(a, dtype=dtype, device=device)
+                  for a in ((2 * layer.bound) / (hi - lo), lo, (hi - lo) / (2 * layer.bound)))
+    return r
+
+
+def _stack_header(magic, D, H, HP, K, L_, W1S, NO, stride, bn, bound=0.0, mins=(0.0, 0.0, 0.0)):
+    h = np.zeros(HDR, dtype=np.float32)
+    hi = h.view(np.int32)
+    hi[0:10] = [magic, D, H, HP, K, L_, W1S, NO, stride, int(bn)]
+    h[10] = bound
+    h[11], h[12], h[13] = mins
+    h[14] = np.float32(1.0 - mins[0] * K)
+    h[15] = np.float32(1.0 - mins[1] * K)
+    return h
+
+
+def pack_spline_stack(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
+    """layers: SplineCouplingLayer modules (same D/H/K/bound/minimums).  Returns (packed_device, hdr_host) or None
+    when the stack cannot use the fused kernel."""
+    l0 = layers[0]
+    D, K = l0.data_dim, l0.num_bins
+    H = l0.param_net[0].out_features
+    key = (l0.num_bins, l0.bound, l0.min_bin_width, l0.min_bin_height, l0.min_derivative)
+    for l in layers:
+        if (l.data_dim != D or l.param_net[0].out_features != H
+                or (l.num_bins, l.bound, l.min_bin_width, l.min_bin_height, l.min_derivative) != key):
+            return None
+    if D > DMAX or H > 128 or K < 2 or K > 16 or l0.param_net[0].weight.dtype != torch.float32:
+        return None
+    if L.lib().nf_spline_stack_packed_floats(D, H, K, len(layers)) < 0:
+        return None
+    P = 3 * K - 1
+    HP, W1S = _hp(H), _w1s(D)
+    masks = [_np(l.mask) for l in layers]
+    max_dt = max(int((m == 0).sum()) for m in masks)
+    NO = 4 * ((max_dt * P + 3) // 4)
+    if NO == 0:
+        return None
+    stride = LAYER_HDR + _net_words(HP, W1S, NO)
+    words = [_stack_header(MAGIC_SPLINE, D, H, HP, K, len(layers), W1S, NO, stride, bns is not None, l0.bound,
+                           (l0.min_bin_width, l0.min_bin_height, l0.min_derivative))]
+    for i, (l, m) in enumerate(zip(layers, masks)):
+        tdims = [d for d in range(D) if m[d] == 0]
+        bn = _bn_between_consts(bns[i]) if (bns is not None and i < len(layers) - 1) else None
+        words.append(_layer_header(m.astype(np.float32), tdims, _rescale_arrays(l, D), bn))
+        net = l.param_net
+        rows = [d * P + p for d in tdims for p in range(P)]
+        words.append(_pack_net(_np(net[0].weight), _np(net[0].bias), _np(net[2].weight), _np(net[2].bias),
+                               _np(net[4].weight), _np(net[4].bias), rows, D, H, HP, W1S, NO))
+    flat = np.concatenate(words)
+    assert flat.size == HDR + len(layers) * stride
+    dev = l0.param_net[0].weight.device
+    return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)
+
+
+def _fold_bn(W, b, bn: torch.nn.BatchNorm1d):
+    """Linear followed by eval-mode BatchNorm1d == Linear with scaled rows (coupling_layer.py:19-24)."""
+    s = _np(bn.weight) / np.sqrt(_np(bn.running_var) + bn.eps)
+    return W * s[:, None], (b - _np(bn.running_mean)) * s + _np(bn.bias)
+
+
+def pack_coupling_stack(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
+    """layers: CouplingLayer modules in eval mode."""
+    l0 = layers[0]
+    D = l0.data_dim
+    H = l0.s_net[0].out_features
+    for l in layers:
+        if l.data_dim != D or l.s_net[0].out_features != H:
+            return None
+    if D > DMAX or H > 128 or l0.s_net[0].weight.dtype != torch.float32:
+        return None
+    HP, W1S = _hp(H), _w1s(D)
+    NO = 4 if D <= 3 else 8
+    stride = LAYER_HDR + 2 * _net_words(HP, W1S, NO)
+    words = [_stack_header(MAGIC_AFFINE, D, H, HP, 0, len(layers), W1S, NO, stride, bns is not None)]
+    for i, l in enumerate(layers):
+        m = _np(l.mask)
+        bn = _bn_between_consts(bns[i]) if (bns is not None and i < len(layers) - 1) else None
+        words.append(_layer_header(m.astype(np.float32), [d for d in range(D) if m[d] == 0], None, bn))
+        for net in (l.s_net, l.b_net):
+            W1, b1 = _fold_bn(_np(net[0].weight), _np(net[0].bias), net[1])
+            W2, b2 = _fold_bn(_np(net[3].weight), _np(net[3].bias), net[4])
+            words.append(_pack_net(W1, b1, W2, b2, _np(net[6].weight), _np(net[6].bias), list(range(D)), D, H, HP,
+                                   W1S, NO))
+    flat = np.concatenate(words)
+    assert flat.size == HDR + len(layers) * stride
+    dev = l0.s_net[0].weight.device
+    return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)
+
+
+@dataclass
+class FoldedMade:
+    """Mask-folded MADE weights with hidden units sorted by degree (made.py:25-79)."""
+    D: int
+    H: int
+    w: list
+    b: list
+    kext: list          # per-layer int32 k-extent arrays for layers 1..3 (None entries allowed)
+    gstart: torch.Tensor
+
+
+def fold_made(made) -> Optional[FoldedMade]:
+    if made.use_batch_norm or made.output_dim_multiplier != 2:
+        return None
+    lin = [m for m in made.net if hasattr(m, "mask")]
+    D, H = made.input_dim, made.hidden_dim
+    deg = np.asarray(made.m[0]).astype(np.int64)
+    perm = np.argsort(deg, kind="stable")
+    sdeg = deg[perm]
+    dev = lin[0].weight.device
+    p = torch.as_tensor(perm, device=dev)
+    with torch.no_grad():
+        eff = [l.weight * l.mask.to(l.weight.dtype) for l in lin]
+        w = [eff[0][p].contiguous(), eff[1][p][:, p].contiguous(), eff[2][p][:, p].contiguous(),
+             eff[3][:, p].contiguous()]
+        b = [lin[0].bias[p].contiguous(), lin[1].bias[p].contiguous(), lin[2].bias[p].contiguous(),
+             lin[3].bias.detach().contiguous()]
+    gstart = np.searchsorted(sdeg, np.arange(D + 1), side="left").astype(np.int32)   # #units with degree < g
+    # k-extents per 64 output columns
+    def hh_ext():
+        out = []
+        for t in range(0, H, 64):
+            last = sdeg[min(t + 63, H - 1)]
+            out.append(int(np.searchsorted(sdeg, last, side="right")))
+        return torch.tensor(out, dtype=torch.int32, device=dev)
+
+    def out_ext():
+        out = []
+        for t in range(0, 2 * D, 64):
+            cols = np.arange(t, min(t + 64, 2 * D)) % D
+            out.append(int(gstart[cols.max()]))
+        return torch.tensor(out, dtype=torch.int32, device=dev)
+
+    kext = [hh_ext(), hh_ext(), out_ext()]
+    return FoldedMade(D, H, w, b, kext, torch.as_tensor(gstart, device=dev))

@@ -1,0 +1,109 @@
+"""CPU: the drop-in nn.Module surface (names, constructor arguments, state_dict layout, shims) and the
+C-ABI library's exported symbols.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import nfb200 as N
+from tests import golden_util as G
+from tests.build_util import MODULE_KINDS, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nfb200.h")).read()
+    declared = set(re.findall(r"NF_API\s+[\w\s\*]+?\b(nf_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(N._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/nfb200.h but not exported"
+    assert declared == set(N._lib.EXPORTED_SYMBOLS), declared ^ set(N._lib.EXPORTED_SYMBOLS)
+    assert N._lib.lib().nf_abi_version() == 1
+    assert N._lib.lib().nf_status_string(-2).decode().startswith("unsupported")
+
+
+@pytest.mark.parametrize("name", [n for n in G.golden_names() if G.load(n)["kind"] in MODULE_KINDS])
+def test_reference_state_dict_loads_strictly(name):
+    g = G.load(name)
+    m = build(g)                      # load_state_dict(strict=True) inside
+    ours = {k: (tuple(v.shape), v.dtype) for k, v in m.state_dict().items()}
+    ref = {k: (tuple(v.shape), v.dtype) for k, v in g["sd"].items()}
+    assert ours == ref
+    assert list(m.state_dict().keys()) == list(g["sd"].keys())
+
+
+def test_made_masks_match_reference():
+    for name in G.golden_names("maf_") + G.golden_names("iaf_"):
+        g = G.load(name)
+        made = N.MADE(g["D"], g["H"])
+        assert torch.equal(torch.as_tensor(made.m[0]), g["degrees"])
+        for idx in (0, 2, 4, 6):
+            assert torch.equal(made.net[idx].mask, g["sd"][f"conditioner.net.{idx}.mask"])
+
+
+def test_initialisation_draws_match_reference():
+    """Same seed => same initial weights as the reference constructors (tests/golden/init_parity.pt)."""
+    g = G.load("init_parity")
+    ctors = {
+        "coupling": lambda: N.CouplingLayer(4, 16, torch.tensor([1., 0., 1., 0.])),
+        "spline": lambda: N.SplineCouplingLayer(4, 16, torch.tensor([1., 1., 0., 0.]), num_bins=6),
+        "maf": lambda: N.MaskedAutoregressiveFlow(5, 32),
+        "iaf": lambda: N.InverseAutoregressiveFlow(5, 32),
+        "made_bn": lambda: N.MADE(3, 8, 2, use_batch_norm=True),
+        "realnvp_bn": lambda: N.RealNVP(4, 4, 16, batch_norm_between_layers=True),
+        "realnvpspline": lambda: N.RealNVPSpline(6, 2, 32),
+    }
+    for key, ctor in ctors.items():
+        torch.manual_seed(g["seed"])
+        sd = ctor().state_dict()
+        assert list(sd.keys()) == list(g[key].keys()), key
+        for k, v in g[key].items():
+            assert torch.equal(sd[k], v), f"{key}.{k}"
+
+
+def test_constructor_contracts():
+    with pytest.raises(AssertionError):
+        N.RealNVP(2, 3, 8)
+    with pytest.raises(AssertionError):
+        N.RealNVPSpline(2, 3, 8)
+    with pytest.raises(ValueError):
+        N.SequentialFlow(tuple())
+    with pytest.raises(ValueError):
+        N.NormalizingFlowModel([torch.nn.Identity()], batch_norm_between_layers=True)
+    m = N.RealNVP(6, 4, 8)
+    masks = [f.mask.tolist() for f in m.flow.flows]
+    assert masks[0] == [1, 1, 1, 0, 0, 0] and masks[1] == [0, 0, 0, 1, 1, 1] and masks[2] == masks[0]
+    s = N.SplineCouplingLayer(4, 8, torch.tensor([1., 0., 1., 0.]))
+    assert (s.num_bins, s.bound, s.data_dim) == (10, 5.0, 4)
+    assert s.param_net[-1].out_features == 4 * 29
+    f = N.MaskedAutoregressiveFlow(3)
+    assert (f.dim, f.data_dim, f.conditioner.hidden_dim) == (3, 3, 64)
+    assert isinstance(f.conditioner.net[-1], N.MaskedLinear)
+    with pytest.raises(NotImplementedError):
+        N.Flow().forward(torch.zeros(1, 1))
+
+
+def test_src_shims_resolve_to_product():
+    import src.flows as SF
+    import src.models as SM
+    assert SF.CouplingLayer is N.CouplingLayer and SM.RealNVP is N.RealNVP
+    assert SF.rational_quadratic_spline is N.rational_quadratic_spline
+
+
+def test_no_cpu_route():
+    layer = N.CouplingLayer(2, 8, torch.tensor([1., 0.]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer.forward(torch.zeros(4, 2))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "normalizing-flows-study_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("flows_oracle", "oracle") or fn == "build.py" or "import oracle" not in src
+            assert "import oracle" not in src and "from oracle" not in src
