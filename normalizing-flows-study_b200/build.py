@@ -56,6 +56,14 @@ def build(force=False, verbose=True):
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(PKG, "..", "include", "*.h"))
     hd = _digest(headers)
+    # the object directory does not travel to the GPU box (.gpurunignore) but the library does: a digest of all
+    # sources stored beside it says whether the shipped library is current
+    whole = _digest(headers + srcs) + " ".join(ARCH + FLAGS)
+    lib_stamp = LIB + ".digest"
+    if not force and os.path.exists(LIB) and os.path.exists(lib_stamp) and open(lib_stamp).read() == whole:
+        if verbose:
+            print(f"  up to date: {LIB}", flush=True)
+        return LIB
     objs = []
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         for obj, dt in ex.map(lambda s: _compile(s, hd, force), srcs):
@@ -70,6 +78,8 @@ def build(force=False, verbose=True):
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(f"  linked {LIB}", flush=True)
+    with open(lib_stamp, "w") as f:
+        f.write(whole)
     return LIB
 
 
