@@ -206,6 +206,11 @@ NF_API int nf_std_normal_log_prob_forward(const void* z, const void* ld, void* l
 NF_API int nf_std_normal_log_prob_backward(const void* z, const void* glp, void* gz, int64_t B, int D, int dtype,
                                     nf_stream_t stream);
 
+/* ---- unit-test hook of the tcgen05 tile primitive (csrc/tc_common.cuh): D[128,N] = A[128,64] * W[N,64]^T.
+ * w_images: the hi then the lo K-major SWIZZLE_128B image of W (packing.umma_sw128_images); N % 16 == 0, <= 128;
+ * passes: 3 = 3xTF32 (fp32-accurate), 1 = single TF32 pass. */
+NF_API int nf_debug_tc_gemm128(const void* a, const void* w_images, void* d, int N, int passes, nf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "nf_ar_finish_backward": [_P] * 7 + [_L, _I, _I, _I, _P],
     "nf_std_normal_log_prob_forward": [_P] * 3 + [_L, _I, _I, _P],
     "nf_std_normal_log_prob_backward": [_P] * 3 + [_L, _I, _I, _P],
+    "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P],
 }
 _RESTYPES = {
     "nf_status_string": _c.c_char_p,

@@ -1,0 +1,127 @@
+// tc_common.cuh -- sm_100a tensor-core plumbing shared by the tcgen05 kernels: mbarrier, TMEM allocation,
+// tcgen05.mma (kind::tf32, A from TMEM or shared memory, B from shared memory), tcgen05.ld/st, descriptors.
+//
+// Conventions used by every kernel here:
+//   * operands are fp32 containers read as TF32 by the tensor core; fp32 accuracy comes from the 3xTF32 split
+//       a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   x_hi = x & 0xffffe000 (exact TF32), x_lo = x - x_hi (exact fp32)
+//     (the dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22) relative);
+//   * B (weights, [N][K] row-major = K-major) lives in shared memory in the canonical UMMA K-major SWIZZLE_128B
+//     layout: K is cut into atoms of 32 floats (128 B); inside an atom block row n occupies 128 B at
+//     (n/8)*1024 + (n%8)*128 and its eight 16-byte chunks are XOR-swizzled with (n%8); the host packs that image;
+//   * A (activations) is written by its owning thread into TMEM: lane = tile row, column = k (M = 128).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nf {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// generic-proxy writes to shared memory (st.shared / cp.async) -> visible to the async proxy (tcgen05.mma, TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared through the TMA unit (async proxy), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -----------------------------------------------------------------------------------------------
+// one full warp; writes the base address (lane 0, column c0) to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// MMA completion -> mbarrier (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// warp-collective: thread (lane l of warp w) reads / writes 16 consecutive columns of TMEM lane 32*(w%4)+l
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major SWIZZLE_128B (sm_100 version 1): start address >> 4 in bits [0,14),
+// LBO (unused for swizzled K-major) bits [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in bits [32,46),
+// version = 1 at bit 46, layout type SWIZZLE_128B = 2 at bits [61,64).  The tile base must be 1024-byte aligned;
+// advancing K inside an atom adds the byte offset to the start address.
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_byte_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_byte_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32_m128(uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : one elected thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- 3xTF32 split -----------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(a) & 0xffffe000u;
+    lo = __float_as_uint(a - __uint_as_float(hi));
+}
+
+// byte offset of element (n, k) inside a K-major SWIZZLE_128B image of an [rows][K] fp32 matrix (K % 32 == 0, rows % 8 == 0)
+__host__ __device__ constexpr uint32_t sw128_offset(uint32_t n, uint32_t k, uint32_t rows) {
+    return (k >> 5) * (rows * 128u) + (n >> 3) * 1024u + (n & 7u) * 128u + ((((k & 31u) >> 2) ^ (n & 7u)) << 4) + (k & 3u) * 4u;
+}
+
+}  // namespace tc
+}  // namespace nf

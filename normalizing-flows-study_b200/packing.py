@@ -241,3 +241,33 @@ def fold_made(made) -> Optional[FoldedMade]:
 
     kext = [hh_ext(), hh_ext(), out_ext()]
     return FoldedMade(D, H, w, b, kext, torch.as_tensor(gstart, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core operand images (csrc/tc_common.cuh)
+# ------------------------------------------------------------------------------------------------
+def split_tf32(w: np.ndarray):
+    """w = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = w - hi (exact)."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    hi = (w.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    return hi, (w - hi).astype(np.float32)
+
+
+def umma_sw128_image(w: np.ndarray) -> np.ndarray:
+    """[rows, K] fp32 (rows % 8 == 0, K % 32 == 0) -> flat float32 array in the UMMA K-major SWIZZLE_128B layout:
+    K atoms of 32 floats; inside an atom block row n sits at (n/8)*1024 + (n%8)*128 bytes with its eight 16-byte
+    chunks XOR-swizzled by (n%8)."""
+    rows, K = w.shape
+    assert rows % 8 == 0 and K % 32 == 0
+    n = np.arange(rows)[:, None]
+    k = np.arange(K)[None, :]
+    off = (k >> 5) * (rows * 128) + (n >> 3) * 1024 + (n & 7) * 128 + ((((k & 31) >> 2) ^ (n & 7)) << 4) + (k & 3) * 4
+    out = np.zeros(rows * K, dtype=np.float32)
+    out[(off // 4).ravel()] = np.ascontiguousarray(w, dtype=np.float32).ravel()
+    return out
+
+
+def umma_sw128_images(w: np.ndarray) -> np.ndarray:
+    """hi image followed by lo image (3xTF32 operands)."""
+    hi, lo = split_tf32(w)
+    return np.concatenate([umma_sw128_image(hi), umma_sw128_image(lo)])
