@@ -206,10 +206,20 @@ NF_API int nf_std_normal_log_prob_forward(const void* z, const void* ld, void* l
 NF_API int nf_std_normal_log_prob_backward(const void* z, const void* glp, void* gz, int64_t B, int D, int dtype,
                                     nf_stream_t stream);
 
+/* ---- fused inference stacks on the tensor cores (tcgen05 + TMEM, 3xTF32 = fp32-accurate): same contract as
+ * nf_spline_stack_forward, for hidden_dim <= 64, num_bins <= 10 and at most 2 transformed dims per layer; `packed`
+ * follows the tensor-core layout (csrc/stack_tc.cu; magic 'NFS2').  NF_ERR_UNSUPPORTED otherwise. */
+NF_API int nf_spline_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
+                               void* ld, int64_t B, int inverse, nf_stream_t stream);
+/* words per layer block of that layout (-1 if the configuration is not supported) */
+NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
+
 /* ---- unit-test hook of the tcgen05 tile primitive (csrc/tc_common.cuh): D[128,N] = A[128,64] * W[N,64]^T.
  * w_images: the hi then the lo K-major SWIZZLE_128B image of W (packing.umma_sw128_images); N % 16 == 0, <= 128;
- * passes: 3 = 3xTF32 (fp32-accurate), 1 = single TF32 pass. */
-NF_API int nf_debug_tc_gemm128(const void* a, const void* w_images, void* d, int N, int passes, nf_stream_t stream);
+ * passes: 3 = 3xTF32 (fp32-accurate), 1 = single TF32 pass; > 3 and nacc > 1 (independent accumulators) are for
+ * timing only.  timing: NULL or 2 x int64 device words receiving (issue cycles, issue-to-completion cycles). */
+NF_API int nf_debug_tc_gemm128(const void* a, const void* w_images, void* d, int N, int passes, void* timing, int nacc,
+                        nf_stream_t stream);
 
 #ifdef __cplusplus
 }

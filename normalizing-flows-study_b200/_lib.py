@@ -13,7 +13,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libnfb200.so")
+LIB_PATH = os.environ.get("NFB200_LIB") or os.path.join(_PKG, "lib", "libnfb200.so")   # override: debug builds
 
 NF_F32, NF_F64 = 0, 1
 NF_ERR_UNSUPPORTED = -2
@@ -57,7 +57,9 @@ _SIGNATURES = {
     "nf_ar_finish_backward": [_P] * 7 + [_L, _I, _I, _I, _P],
     "nf_std_normal_log_prob_forward": [_P] * 3 + [_L, _I, _I, _P],
     "nf_std_normal_log_prob_backward": [_P] * 3 + [_L, _I, _I, _P],
-    "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P],
+    "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P, _I, _P],
+    "nf_spline_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
+    "nf_spline_stack_tc_block_words": [_I, _I, _I],
 }
 _RESTYPES = {
     "nf_status_string": _c.c_char_p,
@@ -65,6 +67,7 @@ _RESTYPES = {
     "nf_launch_count": _L,
     "nf_spline_stack_packed_floats": _L,
     "nf_coupling_stack_packed_floats": _L,
+    "nf_spline_stack_tc_block_words": _L,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

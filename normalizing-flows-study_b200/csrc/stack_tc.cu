@@ -1,0 +1,386 @@
+// stack_tc.cu -- whole-model fused inference kernels on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-accurate:
+//   nf_spline_stack_tc_forward     L x SplineCouplingLayer (+ between-layer BatchNorm affine), hidden_dim <= 64
+//   nf_coupling_stack_tc_forward   L x CouplingLayer in eval mode (conditioner BatchNorm folded at pack time)
+// (spline_coupling_layer.py:96-309, coupling_layer.py:40-96, normalizing_flow_model.py:25-128)
+//
+// Mapping.  CTA = 128 threads; thread t owns row t of a 128-row sub-tile and keeps its x / log-det in registers for
+// the whole stack (a row is 8..32 bytes: HBM traffic is 4D in + 4D+4 out).  Per layer and sub-tile:
+//   (a) layer 1 (K = data_dim <= 8) on the FP32 pipe, ReLU, 3xTF32 split, written by the owning thread straight
+//       into TMEM as the A operand (lane = row, column = k) with tcgen05.st          -- no activation in smem
+//   (b) layer 2: D2[128x64] = A1 * W2^T on tcgen05 (kind::tf32, M=128, N=64, 8 k-steps x 3 split passes),
+//       W2 hi/lo images resident in shared memory (K-major SWIZZLE_128B, packed on the host)
+//   (c) bias + ReLU + split of D2 (tcgen05.ld -> registers -> tcgen05.st) = A operand of the head
+//   (d) head: D3[128 x 32*Dt] = A2 * W3^T on tcgen05 (every transformed dim's 3K-1 parameters padded to 32 columns)
+//   (e) tcgen05.ld of the thread's own parameters, rational-quadratic spline / affine transform, row log-det.
+// One elected thread issues the MMAs; completion comes back through an mbarrier (tcgen05.commit).  Layer weights
+// (~50 KB) are double-buffered in shared memory with cp.async and shared by T sub-tiles; two CTAs per SM overlap
+// one CTA's tensor phase with the other's FP32 phase.  TMEM: A_hi | A_lo | D2 | D3 = 64+64+64+<=64 columns.
+#include <stdio.h>
+#include "nf_common.cuh"
+#include "stack_small.cuh"
+#include "tc_common.cuh"
+
+namespace nf {
+
+#ifdef NF_TC_PROFILE
+__device__ long long g_tc_prof[8];
+#endif
+constexpr int kTcThreads = 128;
+constexpr int kTcSub = 4;            // sub-tiles (of 128 rows) per weight staging
+constexpr int kColAhi = 0, kColAlo = 64, kColD2 = 128, kColD3 = 192;
+constexpr int kTmemCols = 256;
+
+struct TcHdr {
+    int D, H, K, L, W1S, NO3, blk_words, bn_between, nets, aux_words;
+    float bound, min_w, min_h, min_d, scale_w, scale_h;
+};
+
+__device__ __forceinline__ TcHdr read_tc_hdr(const float* __restrict__ p) {
+    const int* q = reinterpret_cast<const int*>(p);
+    TcHdr h;
+    h.D = q[1]; h.H = q[2]; h.nets = q[3]; h.K = q[4]; h.L = q[5]; h.W1S = q[6]; h.NO3 = q[7];
+    h.blk_words = q[8]; h.bn_between = q[9];
+    h.bound = p[10]; h.min_w = p[11]; h.min_h = p[12]; h.min_d = p[13]; h.scale_w = p[14]; h.scale_h = p[15];
+    h.aux_words = 0;
+    return h;
+}
+
+__device__ __forceinline__ float relu_keepnan(float x) {      // torch.relu: NaN stays NaN
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void stage_block(float* dst, const float* __restrict__ src, int n_words) {
+    for (int i = threadIdx.x * 4; i < n_words; i += kTcThreads * 4) cp_async16(dst + i, src + i);
+}
+
+// between-layer BatchNorm as an invertible affine on running stats (normalizing_flow_model.py:67-128)
+template <int DM>
+__device__ __forceinline__ void bn_between_tc(const float* __restrict__ sL, int D, bool inverse, float (&xv)[DM], float& tot) {
+    const float* mean = sL + 48; const float* sd = sL + 56; const float* gm = sL + 64; const float* bt = sL + 72;
+    const float bn_ld = sL[16 + 3];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) if (d < D) {
+        if (!inverse) xv[d] = (xv[d] - mean[d]) / sd[d] * gm[d] + bt[d];
+        else          xv[d] = (xv[d] - bt[d]) / gm[d] * sd[d] + mean[d];
+    }
+    tot = inverse ? tot - bn_ld : tot + bn_ld;
+}
+
+// (a): hidden layer 1 of one conditioner for this thread's row -> TMEM A operand (hi at kColAhi, lo at kColAlo)
+template <int DM>
+__device__ __forceinline__ void layer1_to_tmem(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], uint32_t lane_addr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float* w1 = sW1k + (c * 16 + j) * W1S;
+            float t;
+            if constexpr (DM <= 4) {
+                const float4 v = *reinterpret_cast<const float4*>(w1);     // {w0, w1, w2, b1}
+                t = v.w;
+                t = fmaf(v.x, xa[0], t);
+                if constexpr (DM > 1) t = fmaf(v.y, xa[1], t);
+                if constexpr (DM > 2) t = fmaf(v.z, xa[2], t);
+            } else {
+                const float4 v0 = *reinterpret_cast<const float4*>(w1);
+                const float4 v1 = *reinterpret_cast<const float4*>(w1 + 4);
+                t = w1[W1S - 1];
+                t = fmaf(v0.x, xa[0], t); t = fmaf(v0.y, xa[1], t); t = fmaf(v0.z, xa[2], t); t = fmaf(v0.w, xa[3], t);
+                t = fmaf(v1.x, xa[4], t); t = fmaf(v1.y, xa[5], t); t = fmaf(v1.z, xa[6], t); t = fmaf(v1.w, xa[7], t);
+            }
+            tc::split_tf32(relu_keepnan(t), hi[j], lo[j]);
+        }
+        tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
+        tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
+    }
+}
+
+// (c): D2 + b2 -> ReLU -> split -> A operand
+__device__ __forceinline__ void hidden2_to_tmem(const float* __restrict__ sb2, uint32_t lane_addr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[16], hi[16], lo[16];
+        tc::tmem_ld16(lane_addr + kColD2 + c * 16, v);
+        tc::wait_ld();
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb2 + c * 16 + j4 * 4);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+        }
+        tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
+        tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
+    }
+}
+
+// layout of one layer block in shared memory (words)
+struct BlkOff { int w1k, b2, b3, w2hi, w2lo, w3hi, w3lo, net_words; };
+__host__ __device__ inline int pad256(int x) { return (x + 255) & ~255; }
+// nets conditioner blocks follow the 80-word layer header; every block is a multiple of 256 words so that the
+// weight images stay 1024-byte aligned
+__host__ __device__ inline BlkOff blk_offsets(int W1S, int NO3) {
+    BlkOff o;
+    o.w1k = 0; o.b2 = 64 * W1S; o.b3 = o.b2 + 64;
+    o.w2hi = pad256(NF_LAYER_HDR + o.b3 + NO3) - NF_LAYER_HDR;       // first net: header shares the leading pad
+    o.w2lo = o.w2hi + 4096; o.w3hi = o.w2lo + 4096; o.w3lo = o.w3hi + NO3 * 64;
+    o.net_words = o.w3lo + NO3 * 64;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// spline stack
+// ------------------------------------------------------------------------------------------------
+// KS > 0: num_bins known at compile time (== KMAX), every per-bin guard folds away; KS == 0: runtime num_bins <= KMAX
+template <int DM, int KMAX, int KS>
+__global__ void __launch_bounds__(kTcThreads, 2)
+spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
+                       float* __restrict__ ld, int64_t B, int inverse) {
+    // dynamic shared memory only (no static __shared__), so its base is the CTA's 1024-byte aligned window start:
+    // [2 x layer block | row state | mbarrier | tmem base]
+    extern __shared__ __align__(1024) float sbuf[];
+    const TcHdr hd = read_tc_hdr(packed);
+    const int D = hd.D, K = (KS > 0) ? KS : hd.K, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, BW = hd.blk_words;
+    float* sx = sbuf + (size_t)2 * BW;                         // [kTcSub][DM+1][128] row state
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(sx + kTcSub * (DM + 1) * kTcThreads);
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sx + kTcSub * (DM + 1) * kTcThreads + 2);
+    const BlkOff off = blk_offsets(W1S, NO3);
+
+    RqsCfg<float> cfg;
+    cfg.lo = -hd.bound; cfg.hi = hd.bound; cfg.span = 2.0f * hd.bound; cfg.eps = 1e-8f;
+    cfg.min_w = hd.min_w; cfg.min_h = hd.min_h; cfg.min_d = hd.min_d; cfg.scale_w = hd.scale_w; cfg.scale_h = hd.scale_h;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+#ifdef NF_TC_PROFILE
+    long long pt[6] = {0, 0, 0, 0, 0, 0}, pt0 = clock64(), ptk = clock64();
+#define NF_TICK(i) do { long long n__ = clock64(); pt[i] += n__ - pt0; pt0 = n__; } while (0)
+#else
+#define NF_TICK(i) do { } while (0)
+#endif
+
+    constexpr int ROWS = kTcThreads * kTcSub;
+    const int64_t ntiles = (B + ROWS - 1) / ROWS;
+    const float* layers = packed + NF_STACK_HDR;
+
+    // prefetch the first layer of the first tile
+    int buf = 0;
+    if ((int64_t)blockIdx.x < ntiles) {
+        stage_block(sbuf, layers + (size_t)(inverse ? L - 1 : 0) * BW, BW);
+        cp_async_commit();
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // per-row state (x, running log-det) of the kTcSub sub-tiles: one shared-memory column per thread
+#pragma unroll
+        for (int s = 0; s < kTcSub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+#pragma unroll
+            for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = (d < D && r < B) ? ld_stream(x + r * D + d) : 0.f;
+            sx[(s * (DM + 1) + DM) * kTcThreads + tid] = 0.f;
+        }
+        for (int li = 0; li < L; ++li) {
+            // this layer's block has landed; everyone is done with the other buffer -> prefetch the next layer into it
+            cp_async_wait<0>();
+            tc::fence_proxy_async_smem();
+            __syncthreads();
+            {
+                const bool last = (li == L - 1);
+                const bool more = !last || (tile + gridDim.x < ntiles);
+                if (more) {
+                    const int nli = last ? 0 : li + 1;
+                    stage_block(sbuf + (size_t)(buf ^ 1) * BW, layers + (size_t)(inverse ? L - 1 - nli : nli) * BW, BW);
+                }
+                cp_async_commit();
+            }
+            const float* sL = sbuf + (size_t)buf * BW;
+            const float* net = sL + NF_LAYER_HDR;
+            const int* meta = reinterpret_cast<const int*>(sL + 16);
+            const bool rescale = meta[1] != 0, bn_on = meta[2] != 0;
+            const float* mask = sL;
+            const uint32_t w2hi = tc::smem_u32(net + off.w2hi), w2lo = tc::smem_u32(net + off.w2lo);
+            const uint32_t w3hi = tc::smem_u32(net + off.w3hi), w3lo = tc::smem_u32(net + off.w3lo);
+
+#pragma unroll 1
+            for (int s = 0; s < kTcSub; ++s) {
+                float xv[DM], tot;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                if (inverse && bn_on) bn_between_tc<DM>(sL, D, true, xv, tot);
+                float xs[DM], xa[DM];
+#pragma unroll
+                for (int d = 0; d < DM; ++d) {
+                    float v = xv[d];
+                    if (rescale && d < D) v = sL[24 + d] * (v - sL[32 + d]) - hd.bound;
+                    xs[d] = v;
+                    xa[d] = (d < D) ? v * mask[d] : 0.f;
+                }
+                NF_TICK(5);
+                layer1_to_tmem<DM>(net + off.w1k, W1S, xa, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                NF_TICK(0);
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, 64u, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                NF_TICK(1);
+                hidden2_to_tmem(net + off.b2, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                NF_TICK(2);
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD3, kColAhi, kColAlo, w3hi, w3lo, (uint32_t)NO3, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                NF_TICK(3);
+
+                // (e) this row's spline parameters: 32 columns per transformed dim
+                float lsum = 0.f;
+                int t = 0;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) {
+                    if (d < D && mask[d] == 0.f) {
+                        uint32_t p0[16], p1[16];
+                        tc::tmem_ld16(lane_addr + kColD3 + t * 32, p0);
+                        if constexpr (3 * KMAX - 1 <= 24) {
+                            uint32_t q[8];
+                            tc::tmem_ld8(lane_addr + kColD3 + t * 32 + 16, q);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) p1[j] = q[j];
+#pragma unroll
+                            for (int j = 8; j < 16; ++j) p1[j] = 0u;
+                        } else {
+                            tc::tmem_ld16(lane_addr + kColD3 + t * 32 + 16, p1);
+                        }
+                        tc::wait_ld();
+                        const float* b3 = net + off.b3 + t * 32;
+                        float prm[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { prm[j] = __uint_as_float(p0[j]) + b3[j]; prm[16 + j] = __uint_as_float(p1[j]) + b3[16 + j]; }
+                        // columns of one transformed dim: [uw: KMAX slots | uh: KMAX slots | ud: KMAX-1 slots] (host packing)
+                        float uw[KMAX], uh[KMAX], ud[KMAX];
+#pragma unroll
+                        for (int j = 0; j < KMAX; ++j) {
+                            uw[j] = prm[j];
+                            uh[j] = prm[KMAX + j];
+                            ud[j] = (j < KMAX - 1) ? prm[2 * KMAX + j] : 0.f;
+                        }
+                        float out, lad;
+                        rqs_eval<float, KMAX, true>(xs[d], uw, uh, ud, K, inverse != 0, cfg, out, lad);
+                        if (rescale) out = (out + hd.bound) * sL[40 + d] + sL[32 + d];
+                        xv[d] = out;
+                        lsum += lad;
+                        ++t;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = scrub0(xv[d]);      // layer-level scrub (:130-135)
+                tot += scrub0(lsum);
+                if (!inverse && bn_on) bn_between_tc<DM>(sL, D, false, xv, tot);
+#pragma unroll
+                for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = xv[d];
+                sx[(s * (DM + 1) + DM) * kTcThreads + tid] = tot;
+                NF_TICK(4);
+            }
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int s = 0; s < kTcSub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+            if (r < B) {
+#pragma unroll
+                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + tid]);
+                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + tid]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, kTmemCols);
+#ifdef NF_TC_PROFILE
+    if (blockIdx.x == 0 && tid == 0) {
+        for (int i = 0; i < 6; ++i) g_tc_prof[i] = pt[i];
+        g_tc_prof[6] = (long long)clock64() - ptk;
+    }
+#endif
+}
+
+}  // namespace nf
+
+using namespace nf;
+#define NF_REQ(p) do { if ((p) == nullptr) return NF_ERR_NULL; } while (0)
+
+extern "C" int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt) {
+    if (D < 1 || D > NF_STACK_DMAX || K < 2 || K > 10 || max_dt < 1 || max_dt > 2) return -1;
+    const int W1S = nf_stack_w1s(D), NO3 = 32 * max_dt;
+    return NF_LAYER_HDR + blk_offsets(W1S, NO3).net_words;
+}
+
+extern "C" int nf_spline_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
+                                          void* y, void* ld, int64_t B, int inverse, nf_stream_t stream) {
+    if (B < 0) return NF_ERR_BAD_SHAPE;
+    NF_REQ(hdr_host);
+    if (B == 0) return NF_OK;
+    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    if (!aligned16(packed)) return NF_ERR_MISALIGNED;
+    const int32_t* h = (const int32_t*)hdr_host;
+    if (h[0] != NF_STACK_MAGIC_SPLINE_TC) return NF_ERR_BAD_SHAPE;
+    const int D = h[1], H = h[2], K = h[4], L = h[5], W1S = h[6], NO3 = h[7], BW = h[8];
+    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 64 || L < 1 || K < 2 || K > 10) return NF_ERR_UNSUPPORTED;
+    if (NO3 != 32 && NO3 != 64) return NF_ERR_UNSUPPORTED;
+    if (W1S != nf_stack_w1s(D) || BW != NF_LAYER_HDR + blk_offsets(W1S, NO3).net_words) return NF_ERR_BAD_SHAPE;
+    if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)L * BW)) return NF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
+    const size_t smem = sizeof(float) * ((size_t)2 * BW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 4);
+    if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
+    const int rows = kTcThreads * kTcSub;
+    const int64_t ntiles = cdiv(B, rows);
+#define NF_TC(DMv, KMv, KSv)                                                                                         \
+    do {                                                                                                             \
+        auto kern = spline_stack_tc_kernel<DMv, KMv, KSv>;                                                           \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        int per_sm = 0;                                                                                              \
+        NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTcThreads, smem));                     \
+        if (per_sm < 1) return NF_ERR_UNSUPPORTED;                                                                   \
+        if (per_sm > 512 / kTmemCols) per_sm = 512 / kTmemCols;   /* TMEM: 512 columns per SM */                     \
+        const int64_t cap = (int64_t)kNumSMs * per_sm;                                                               \
+        const int grid = (int)(ntiles < cap ? ntiles : cap);                                                         \
+        kern<<<grid, kTcThreads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, inverse); \
+    } while (0)
+#define NF_TC_K(DMv)                                      \
+    do {                                                  \
+        if (K == 8) NF_TC(DMv, 8, 8);                     \
+        else if (K == 10) NF_TC(DMv, 10, 10);             \
+        else if (K < 8) NF_TC(DMv, 8, 0);                 \
+        else NF_TC(DMv, 10, 0);                           \
+    } while (0)
+    if (D <= 2) NF_TC_K(2);
+    else if (D <= 3) NF_TC_K(4);
+    else NF_TC_K(8);
+#undef NF_TC_K
+#undef NF_TC
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+#ifdef NF_TC_PROFILE
+// debug builds only (-DNF_TC_PROFILE): per-phase cycle counters of CTA 0 / thread 0 of the last launch
+extern "C" __attribute__((visibility("default"))) int nf_debug_tc_profile(long long* out) {
+    return cudaMemcpyFromSymbol(out, nf::g_tc_prof, sizeof(long long) * 8) == cudaSuccess ? 0 : -4;
+}
+#endif

@@ -112,6 +112,38 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// warp-convergent election of one lane (the MMA issuer); the whole warp must execute this
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// 3xTF32 GEMM over K = 64 of the CTA's TMEM-resident A operand (hi columns a_hi_col.., lo columns a_lo_col..) with a
+// [N][64] weight whose hi / lo SWIZZLE_128B images sit at shared-memory byte addresses w_hi / w_lo; result (overwritten)
+// in TMEM columns d_col.. .  Must be executed by ONE WHOLE WARP with convergent control flow: descriptors are then
+// computed once in uniform registers and the 24 tcgen05.mma issue back to back from the elected lane (issuing from a
+// divergent `if (tid == 0)` costs ~70 cycles per MMA in R2UR transfers).  Ends with tcgen05.commit -> bar.
+__device__ __forceinline__ void warp_issue_gemm_k64_3xtf32(uint32_t tmem_base, uint32_t d_col, uint32_t a_hi_col, uint32_t a_lo_col,
+                                                           uint32_t w_hi, uint32_t w_lo, uint32_t N, uint64_t* bar) {
+    const uint32_t idesc = idesc_tf32_m128(N);
+    const uint32_t atom16 = (N * 128u) >> 4;                  // K-atom block stride in 16-byte units
+    const uint64_t d_hi = smem_desc_k_sw128(w_hi), d_lo = smem_desc_k_sw128(w_lo);
+    const bool leader = elect_one();
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a_col = (pass == 1) ? a_lo_col : a_hi_col;
+        const uint64_t wd = (pass == 2) ? d_lo : d_hi;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t bd = wd + (uint64_t)((uint32_t)(k >> 2) * atom16 + (uint32_t)(k & 3) * 2u);
+            if (leader) mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + k * 8, bd, idesc, (pass | k) != 0 ? 1u : 0u);
+        }
+    }
+    if (leader) mma_commit(bar);
+    __syncwarp();
+}
+
 // ---- 3xTF32 split -----------------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(a) & 0xffffe000u;

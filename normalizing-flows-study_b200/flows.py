@@ -235,11 +235,9 @@ class SplineCouplingLayer(Flow):
 
     def _run(self, v, inverse):
         if not wants_grad(self, v) and self.fusable(v):
-            pk = self._pack.get(_module_tensors(self), lambda: packing.pack_spline_stack([self], None))
-            if pk is not None:
-                out = ops.spline_stack(pk[0], pk[1], v, inverse)
-                if out is not None:
-                    return out
+            out = run_spline_stack(self._pack, _module_tensors(self), [self], None, v, inverse)
+            if out is not None:
+                return out
         tidx, rescale = self._aux_tensors(v)
         net = self.param_net
         vin = v
@@ -427,6 +425,29 @@ class InverseAutoregressiveFlow(_AffineAutoregressive):
         return self._sequential(x)
 
 
+USE_TENSOR_CORES = True      # tcgen05 stack kernels (3xTF32, fp32-accurate); False forces the FP32-pipe kernels
+
+
+def run_spline_stack(cache: _PackCache, tensors, flows, bns, v, inverse):
+    """Spline-coupling stack in one launch: tcgen05 kernel when the configuration fits it, FP32-pipe kernel otherwise."""
+    def build():
+        tcp = packing.pack_spline_stack_tc(flows, bns) if USE_TENSOR_CORES else None
+        return ("tc", tcp) if tcp is not None else ("simt", packing.pack_spline_stack(flows, bns))
+    kind, pk = cache.get(tensors + [_TC_FLAG[USE_TENSOR_CORES]], build)
+    if pk is None:
+        return None
+    if kind == "tc":
+        out = ops.spline_stack_tc(pk[0], pk[1], v, inverse)
+        if out is not None:
+            return out
+        pk = packing.pack_spline_stack(flows, bns)
+        return None if pk is None else ops.spline_stack(pk[0], pk[1], v, inverse)
+    return ops.spline_stack(pk[0], pk[1], v, inverse)
+
+
+_TC_FLAG = {True: torch.zeros(1), False: torch.zeros(2)}     # distinct cache-key tensors for the two settings
+
+
 # ------------------------------------------------------------------------------------------------
 # whole-stack fusion used by the containers (SequentialFlow, models.NormalizingFlowModel)
 # ------------------------------------------------------------------------------------------------
@@ -457,5 +478,4 @@ class ChainPlan:
         if kind is CouplingLayer:
             pk = self._pack.get(tensors, lambda: packing.pack_coupling_stack(flows, bns))
             return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse)
-        pk = self._pack.get(tensors, lambda: packing.pack_spline_stack(flows, bns))
-        return None if pk is None else ops.spline_stack(pk[0], pk[1], v, inverse)
+        return run_spline_stack(self._pack, tensors, flows, bns, v, inverse)

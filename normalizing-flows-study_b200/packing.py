@@ -18,6 +18,8 @@ from . import _lib as L
 
 MAGIC_SPLINE = 0x4E465331
 MAGIC_AFFINE = 0x4E464131
+MAGIC_SPLINE_TC = 0x4E465332
+MAGIC_AFFINE_TC = 0x4E464132
 HDR, LAYER_HDR, DMAX = 16, 80, 8
 
 
@@ -271,3 +273,77 @@ def umma_sw128_images(w: np.ndarray) -> np.ndarray:
     """hi image followed by lo image (3xTF32 operands)."""
     hi, lo = split_tf32(w)
     return np.concatenate([umma_sw128_image(hi), umma_sw128_image(lo)])
+
+
+def _pad256(n):
+    return (n + 255) & ~255
+
+
+def _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, lead_words):
+    """One conditioner block of the tensor-core stack layout (csrc/stack_tc.cu: blk_offsets):
+    W1k[64][W1S] | b2[64] | b3[NO3] | pad to a 256-word boundary (counting `lead_words` in front) |
+    W2 hi image | W2 lo image | W3 hi image | W3 lo image.  W3rows/b3rows: [NO3, H] / [NO3] already in head-column order."""
+    w1k = np.zeros((64, W1S))
+    w1k[:H, :D] = W1
+    w1k[:H, W1S - 1] = b1
+    b2p = np.zeros(64)
+    b2p[:H] = b2
+    small = np.concatenate([w1k.ravel(), b2p, b3rows]).astype(np.float32)
+    pad = _pad256(lead_words + small.size) - lead_words - small.size
+    w2 = np.zeros((64, 64), dtype=np.float32)
+    w2[:H, :H] = W2
+    w3 = np.zeros((NO3, 64), dtype=np.float32)
+    w3[:, :H] = W3rows
+    return np.concatenate([small, np.zeros(pad, dtype=np.float32), umma_sw128_images(w2), umma_sw128_images(w3)])
+
+
+def pack_spline_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
+    """Tensor-core layout of a spline-coupling stack; None when the configuration is outside the kernel's envelope
+    (hidden_dim <= 64, num_bins <= 10, <= 2 transformed dims per layer, data_dim <= 8)."""
+    l0 = layers[0]
+    D, K = l0.data_dim, l0.num_bins
+    H = l0.param_net[0].out_features
+    key = (l0.num_bins, l0.bound, l0.min_bin_width, l0.min_bin_height, l0.min_derivative)
+    for l in layers:
+        if (l.data_dim != D or l.param_net[0].out_features != H
+                or (l.num_bins, l.bound, l.min_bin_width, l.min_bin_height, l.min_derivative) != key):
+            return None
+    if D > DMAX or H > 64 or K < 2 or K > 10 or l0.param_net[0].weight.dtype != torch.float32:
+        return None
+    masks = [_np(l.mask) for l in layers]
+    max_dt = max(int((m == 0).sum()) for m in masks)
+    if max_dt < 1 or max_dt > 2:
+        return None
+    bw = L.lib().nf_spline_stack_tc_block_words(D, K, max_dt)
+    if bw < 0:
+        return None
+    P = 3 * K - 1
+    GS = 8 if K <= 8 else 10                       # slots per parameter group inside a dim's 32 columns
+    W1S, NO3 = _w1s(D), 32 * max_dt
+    hdr = np.zeros(HDR, dtype=np.float32)
+    hi = hdr.view(np.int32)
+    hi[0:10] = [MAGIC_SPLINE_TC, D, H, 1, K, len(layers), W1S, NO3, bw, int(bns is not None)]
+    hdr[10] = l0.bound
+    hdr[11], hdr[12], hdr[13] = l0.min_bin_width, l0.min_bin_height, l0.min_derivative
+    hdr[14] = np.float32(1.0 - l0.min_bin_width * K)
+    hdr[15] = np.float32(1.0 - l0.min_bin_height * K)
+    words = [hdr]
+    for i, (l, m) in enumerate(zip(layers, masks)):
+        tdims = [d for d in range(D) if m[d] == 0]
+        bn = _bn_between_consts(bns[i]) if (bns is not None and i < len(layers) - 1) else None
+        words.append(_layer_header(m.astype(np.float32), tdims, _rescale_arrays(l, D), bn))
+        net = l.param_net
+        W3, b3 = _np(net[4].weight), _np(net[4].bias)
+        W3rows = np.zeros((NO3, H))
+        b3rows = np.zeros(NO3)
+        for t, d in enumerate(tdims):
+            for g, cnt in enumerate((K, K, K - 1)):
+                for j in range(cnt):
+                    W3rows[t * 32 + g * GS + j] = W3[d * P + g * K + j]
+                    b3rows[t * 32 + g * GS + j] = b3[d * P + g * K + j]
+        words.append(_tc_net_block(_np(net[0].weight), _np(net[0].bias), _np(net[2].weight), _np(net[2].bias),
+                                   W3rows, b3rows, D, H, W1S, NO3, LAYER_HDR))
+    flat = np.concatenate(words).astype(np.float32)
+    assert flat.size == HDR + len(layers) * bw, (flat.size, bw)
+    dev = l0.param_net[0].weight.device
+    return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)

@@ -108,9 +108,11 @@ def _compare(g, y, ld, key, tag, name):
         assert torch.equal(torch.isfinite(ld[wild]), torch.isfinite(ref_ld[wild]))
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("name", MODULE_CASES)
-def test_fused_route_matches_reference_golden(name):
-    """no_grad + eval: single-launch kernels (stack / MADE chain / incremental sequential)."""
+def test_fused_route_matches_reference_golden(name, tensor_cores, monkeypatch):
+    """no_grad + eval: single-launch kernels (tcgen05 / FP32-pipe stacks, MADE chain, incremental sequential)."""
+    monkeypatch.setattr(N.flows, "USE_TENSOR_CORES", tensor_cores)
     g = G.load(name)
     m = build(g).to(_dev())
     x = g["x"].to(_dev())
@@ -118,8 +120,27 @@ def test_fused_route_matches_reference_golden(name):
     with torch.no_grad():
         for inverse, key in ((False, "fwd"), (True, "inv")):
             y, ld = _run(m, x, inverse)
-            _compare(g, y, ld, key, name + " [fused]", name)
+            _compare(g, y, ld, key, name + (" [fused tc]" if tensor_cores else " [fused simt]"), name)
     assert N._lib.launch_count() > before
+
+
+def test_tensor_core_stack_is_taken_and_handles_ragged_batches():
+    """config-2 shape through the tcgen05 kernel explicitly, at batch sizes around the 512-row tile."""
+    g = G.load("splinestack_2_8_64_K8")
+    m = build(g).to(_dev())
+    pk = N.packing.pack_spline_stack_tc(list(m.flows), None)
+    assert pk is not None
+    gen = torch.Generator().manual_seed(3)
+    for B in (1, 127, 128, 129, 511, 512, 513, 5000):
+        x = (torch.randn(B, 2, generator=gen) * 1.5)
+        for inverse in (False, True):
+            out = N.ops.spline_stack_tc(pk[0], pk[1], x.to(_dev()), inverse)
+            assert out is not None
+            ry, rld = O.flow_model(g["sd"], "", [dict(kind="spline", num_bins=8)] * 8, x, inverse)
+            sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in g["sd"].items()}
+            y64, ld64 = O.flow_model(sd64, "", [dict(kind="spline", num_bins=8)] * 8, x.double(), inverse)
+            _within(out[0].cpu(), ry, y64, Z_ATOL, Z_RTOL, f"tc stack B={B} z")
+            _within(out[1].cpu(), rld, ld64, LD_ATOL, LD_RTOL, f"tc stack B={B} ld")
 
 
 @pytest.mark.parametrize("name", MODULE_CASES)

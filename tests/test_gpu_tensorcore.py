@@ -19,7 +19,8 @@ def test_tc_gemm128_3xtf32(n_out):
     scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T
     for passes, tol in ((3, 2e-6), (1, 2e-3)):
         d = torch.full((128, n_out), float("nan"), device="cuda")
-        N._lib.call("nf_debug_tc_gemm128", ad.data_ptr(), img.data_ptr(), d.data_ptr(), n_out, passes, N._lib.stream())
+        N._lib.call("nf_debug_tc_gemm128", ad.data_ptr(), img.data_ptr(), d.data_ptr(), n_out, passes, None, 1,
+                    N._lib.stream())
         torch.cuda.synchronize()
         err = np.abs(d.cpu().numpy().astype(np.float64) - ref) / scale
         assert np.isfinite(err).all()
