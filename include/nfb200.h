@@ -126,15 +126,16 @@ NF_API int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, int 
 /* nn.BatchNorm1d inside the coupling conditioners (coupling_layer.py:20,23), fused with the following ReLU.
  * training!=0: batch statistics normalise (biased variance), running stats are updated in place with
  * `momentum` (unbiased variance), save_mean/save_rstd [H] receive the batch statistics for backward.
- * training==0: running statistics normalise.  y = relu?(gamma*(x-mean)*rstd+beta). */
+ * training==0: running statistics normalise.  y = relu?(gamma*(x-mean)*rstd+beta).
+ * workspace: 2*H doubles (batch-statistic partial sums; may be NULL when training==0). */
 NF_API int nf_batchnorm_forward(const void* x, const void* gamma, const void* beta, void* running_mean, void* running_var,
-                         void* y, void* save_mean, void* save_rstd, int64_t B, int H, int training, double momentum,
-                         double eps, int relu, int dtype, nf_stream_t stream);
+                         void* y, void* save_mean, void* save_rstd, void* workspace, int64_t B, int H, int training,
+                         double momentum, double eps, int relu, int dtype, nf_stream_t stream);
 /* y is the forward output (post-ReLU when relu!=0).  gx [B,H], ggamma/gbeta [H] overwritten.  training
- * selects the batch-statistics Jacobian (training!=0) or the plain affine one (eval). */
+ * selects the batch-statistics Jacobian (training!=0) or the plain affine one (eval).  workspace: 2*H doubles. */
 NF_API int nf_batchnorm_backward(const void* x, const void* y, const void* gamma, const void* save_mean,
-                          const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta, int64_t B, int H,
-                          int relu, int training, int dtype, nf_stream_t stream);
+                          const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta, void* workspace,
+                          int64_t B, int H, int relu, int training, int dtype, nf_stream_t stream);
 
 /* ---- fused inference stacks (small data_dim): whole NormalizingFlowModel in one launch --------------------
  * a4-a6 + a14/a15: L SplineCouplingLayers (+ optional between-layer BatchNorm affine using running stats,

@@ -213,35 +213,68 @@ col_sum_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t rows, int64
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm1d (+ReLU).  stats: per-column mean / biased variance in double accumulators.
+// BatchNorm1d (+ReLU).  Batch statistics: every CTA owns 32 columns x one chunk of rows, accumulates in double and
+// combines with double atomics into the caller's workspace acc[2H] (sum, sum of squares); a second tiny kernel turns
+// the sums into mean / rstd and moves the running statistics.  The grid covers all SMs for any H (the first version
+// used ceil(H/32) CTAs only: 2 CTAs for H = 64).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const T* __restrict__ x, T* __restrict__ running_mean, T* __restrict__ running_var,
-                T* __restrict__ save_mean, T* __restrict__ save_rstd, int64_t B, int H, double momentum, double eps) {
+bn_partial_sums_kernel(const T* __restrict__ x, double* __restrict__ acc, int64_t B, int H, int64_t rows_per_chunk) {
     __shared__ double s1[8][33], s2[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = (B < r0 + rows_per_chunk) ? B : r0 + rows_per_chunk;
     double a = 0.0, b = 0.0;
-    if (col < H)
-        for (int64_t r = ry; r < B; r += 8) { const double v = (double)x[r * H + col]; a += v; b += v * v; }
+    if (col < H) {
+        int64_t r = r0 + ry;
+        for (; r + 24 < r1; r += 32) {             // 4 independent loads in flight per thread
+            const double v0 = (double)x[r * H + col], v1 = (double)x[(r + 8) * H + col];
+            const double v2 = (double)x[(r + 16) * H + col], v3 = (double)x[(r + 24) * H + col];
+            a += (v0 + v1) + (v2 + v3);
+            b += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+        }
+        for (; r < r1; r += 8) { const double v = (double)x[r * H + col]; a += v; b += v * v; }
+    }
     s1[ry][cx] = a; s2[ry][cx] = b;
     __syncthreads();
     if (ry == 0 && col < H) {
         double ta = 0.0, tb = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ta += s1[i][cx]; tb += s2[i][cx]; }
-        const double mean = ta / (double)B;
-        double var = tb / (double)B - mean * mean;
-        if (var < 0.0) var = 0.0;
-        save_mean[col] = (T)mean;
-        save_rstd[col] = (T)(1.0 / sqrt(var + eps));
-        if (running_mean) {
-            const double unb = (B > 1) ? var * (double)B / (double)(B - 1) : var;
-            running_mean[col] = (T)((1.0 - momentum) * (double)running_mean[col] + momentum * mean);
-            running_var[col] = (T)((1.0 - momentum) * (double)running_var[col] + momentum * unb);
-        }
+        atomicAdd(acc + col, ta);
+        atomicAdd(acc + H + col, tb);
     }
+}
+
+template <typename T>
+__global__ void bn_finish_stats_kernel(const double* __restrict__ acc, T* __restrict__ running_mean, T* __restrict__ running_var,
+                                       T* __restrict__ save_mean, T* __restrict__ save_rstd, int64_t B, int H,
+                                       double momentum, double eps) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= H) return;
+    const double mean = acc[col] / (double)B;
+    double var = acc[H + col] / (double)B - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[col] = (T)mean;
+    save_rstd[col] = (T)(1.0 / sqrt(var + eps));
+    if (running_mean) {
+        const double unb = (B > 1) ? var * (double)B / (double)(B - 1) : var;
+        running_mean[col] = (T)((1.0 - momentum) * (double)running_mean[col] + momentum * mean);
+        running_var[col] = (T)((1.0 - momentum) * (double)running_var[col] + momentum * unb);
+    }
+}
+
+static inline void bn_chunking(int64_t B, int H, int& chunks, int64_t& rpc) {
+    const int64_t col_blocks = (H + 31) / 32;
+    int64_t c = (4 * (int64_t)kNumSMs + col_blocks - 1) / col_blocks;      // ~4 CTAs per SM in total
+    const int64_t maxc = (B + 255) / 256;                                  // at least 256 rows per chunk
+    if (c > maxc) c = maxc;
+    if (c < 1) c = 1;
+    rpc = (B + c - 1) / c;
+    rpc = (rpc + 7) / 8 * 8;
+    chunks = (int)((B + rpc - 1) / rpc);
 }
 
 template <typename T>
@@ -263,19 +296,21 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ g
     }
 }
 
-// ggamma = sum gy_eff*xhat ; gbeta = sum gy_eff   (gy_eff = gy * (y>0) when relu)
+// partial sums of ggamma = sum gy_eff*xhat and gbeta = sum gy_eff (gy_eff = gy * (y>0) when relu) into acc[2H]
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ mean,
-                     const T* __restrict__ rstd, const T* __restrict__ gy, T* __restrict__ ggamma,
-                     T* __restrict__ gbeta, int64_t B, int H, int relu) {
+bn_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ mean,
+                      const T* __restrict__ rstd, const T* __restrict__ gy, double* __restrict__ acc, int64_t B, int H,
+                      int relu, int64_t rows_per_chunk) {
     __shared__ double s1[8][33], s2[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = (B < r0 + rows_per_chunk) ? B : r0 + rows_per_chunk;
     double a = 0.0, b = 0.0;
     if (col < H) {
         const double mu = (double)mean[col], rs = (double)rstd[col];
-        for (int64_t r = ry; r < B; r += 8) {
+        for (int64_t r = r0 + ry; r < r1; r += 8) {
             const int64_t o = r * H + col;
             double g = (double)gy[o];
             if (relu && !(y[o] > T(0))) g = 0.0;
@@ -289,8 +324,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* 
         double ta = 0.0, tb = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ta += s1[i][cx]; tb += s2[i][cx]; }
-        ggamma[col] = (T)ta; gbeta[col] = (T)tb;
+        atomicAdd(acc + col, ta);
+        atomicAdd(acc + H + col, tb);
     }
+}
+
+template <typename T>
+__global__ void bn_bwd_finish_kernel(const double* __restrict__ acc, T* __restrict__ ggamma, T* __restrict__ gbeta, int H) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < H) { ggamma[col] = (T)acc[col]; gbeta[col] = (T)acc[H + col]; }
 }
 
 template <typename T>
@@ -321,9 +363,18 @@ static inline int ew_grid(int64_t n) {
 
 template <typename T>
 static int bn_forward(const void* x, const void* gamma, const void* beta, void* rm, void* rv, void* y, void* sm,
-                      void* sr, int64_t B, int H, int training, double momentum, double eps, int relu, cudaStream_t st) {
+                      void* sr, void* ws, int64_t B, int H, int training, double momentum, double eps, int relu,
+                      cudaStream_t st) {
     if (training) {
-        bn_stats_kernel<T><<<(H + 31) / 32, 256, 0, st>>>((const T*)x, (T*)rm, (T*)rv, (T*)sm, (T*)sr, B, H, momentum, eps);
+        NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
+        int chunks; int64_t rpc;
+        bn_chunking(B, H, chunks, rpc);
+        dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
+        bn_partial_sums_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (double*)ws, B, H, rpc);
+        count_launch();
+        NF_LAUNCH_CHECK();
+        bn_finish_stats_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)rm, (T*)rv, (T*)sm, (T*)sr, B, H,
+                                                                  momentum, eps);
     } else {
         bn_eval_stats_kernel<T><<<(H + 255) / 256, 256, 0, st>>>((const T*)rm, (const T*)rv, (T*)sm, (T*)sr, H, eps);
     }
@@ -338,9 +389,16 @@ static int bn_forward(const void* x, const void* gamma, const void* beta, void* 
 
 template <typename T>
 static int bn_backward(const void* x, const void* y, const void* gamma, const void* sm, const void* sr, const void* gy,
-                       void* gx, void* gg, void* gb, int64_t B, int H, int relu, int training, cudaStream_t st) {
-    bn_bwd_reduce_kernel<T><<<(H + 31) / 32, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr,
-                                                           (const T*)gy, (T*)gg, (T*)gb, B, H, relu);
+                       void* gx, void* gg, void* gb, void* ws, int64_t B, int H, int relu, int training, cudaStream_t st) {
+    NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
+    int chunks; int64_t rpc;
+    bn_chunking(B, H, chunks, rpc);
+    dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
+    bn_bwd_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr, (const T*)gy,
+                                                   (double*)ws, B, H, relu, rpc);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    bn_bwd_finish_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)gg, (T*)gb, H);
     count_launch();
     NF_LAUNCH_CHECK();
     bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
@@ -423,32 +481,33 @@ extern "C" int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, 
 }
 
 extern "C" int nf_batchnorm_forward(const void* x, const void* gamma, const void* beta, void* running_mean,
-                                    void* running_var, void* y, void* save_mean, void* save_rstd, int64_t B, int H,
-                                    int training, double momentum, double eps, int relu, int dtype,
+                                    void* running_var, void* y, void* save_mean, void* save_rstd, void* workspace,
+                                    int64_t B, int H, int training, double momentum, double eps, int relu, int dtype,
                                     nf_stream_t stream) {
     if (B < 0 || H < 1) return NF_ERR_BAD_SHAPE;
     if (B == 0) return NF_OK;
     NF_REQ(x); NF_REQ(gamma); NF_REQ(beta); NF_REQ(y); NF_REQ(save_mean); NF_REQ(save_rstd);
-    if (!training) { NF_REQ(running_mean); NF_REQ(running_var); }
+    if (!training) { NF_REQ(running_mean); NF_REQ(running_var); } else { NF_REQ(workspace); }
     if ((running_mean == nullptr) != (running_var == nullptr)) return NF_ERR_NULL;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NF_F32)
-        return bn_forward<float>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, B, H, training, momentum, eps, relu, st);
+        return bn_forward<float>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, training, momentum, eps, relu, st);
     if (dtype == NF_F64)
-        return bn_forward<double>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, B, H, training, momentum, eps, relu, st);
+        return bn_forward<double>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, training, momentum, eps, relu, st);
     return NF_ERR_UNSUPPORTED;
 }
 
 extern "C" int nf_batchnorm_backward(const void* x, const void* y, const void* gamma, const void* save_mean,
                                      const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
-                                     int64_t B, int H, int relu, int training, int dtype, nf_stream_t stream) {
+                                     void* workspace, int64_t B, int H, int relu, int training, int dtype,
+                                     nf_stream_t stream) {
     if (B < 0 || H < 1) return NF_ERR_BAD_SHAPE;
     if (B == 0) return NF_OK;
-    NF_REQ(x); NF_REQ(y); NF_REQ(gamma); NF_REQ(save_mean); NF_REQ(save_rstd); NF_REQ(gy); NF_REQ(gx); NF_REQ(ggamma); NF_REQ(gbeta);
+    NF_REQ(x); NF_REQ(y); NF_REQ(gamma); NF_REQ(save_mean); NF_REQ(save_rstd); NF_REQ(gy); NF_REQ(gx); NF_REQ(ggamma); NF_REQ(gbeta); NF_REQ(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NF_F32)
-        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, B, H, relu, training, st);
+        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, training, st);
     if (dtype == NF_F64)
-        return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, B, H, relu, training, st);
+        return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, training, st);
     return NF_ERR_UNSUPPORTED;
 }

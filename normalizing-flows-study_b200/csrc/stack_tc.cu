@@ -51,10 +51,6 @@ __device__ __forceinline__ float relu_keepnan(float x) {      // torch.relu: NaN
     return r;
 }
 
-__device__ __forceinline__ void stage_block(float* dst, const float* __restrict__ src, int n_words) {
-    for (int i = threadIdx.x * 4; i < n_words; i += kTcThreads * 4) cp_async16(dst + i, src + i);
-}
-
 // between-layer BatchNorm as an invertible affine on running stats (normalizing_flow_model.py:67-128)
 template <int DM>
 __device__ __forceinline__ void bn_between_tc(const float* __restrict__ sL, int D, bool inverse, float (&xv)[DM], float& tot) {
@@ -98,20 +94,22 @@ __device__ __forceinline__ void layer1_to_tmem(const float* __restrict__ sW1k, i
     }
 }
 
-// (c): D2 + b2 -> ReLU -> split -> A operand
+// (c): D2 + b2 -> ReLU -> split -> A operand.  All four 16-column loads are issued before the single wait.
 __device__ __forceinline__ void hidden2_to_tmem(const float* __restrict__ sb2, uint32_t lane_addr) {
+    uint32_t v[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tc::tmem_ld16(lane_addr + kColD2 + c * 16, v[c]);
+    tc::wait_ld();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        uint32_t v[16], hi[16], lo[16];
-        tc::tmem_ld16(lane_addr + kColD2 + c * 16, v);
-        tc::wait_ld();
+        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(sb2 + c * 16 + j4 * 4);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
+            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
         }
         tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
         tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
@@ -146,8 +144,10 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
     const TcHdr hd = read_tc_hdr(packed);
     const int D = hd.D, K = (KS > 0) ? KS : hd.K, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, BW = hd.blk_words;
     float* sx = sbuf + (size_t)2 * BW;                         // [kTcSub][DM+1][128] row state
-    uint64_t& bar = *reinterpret_cast<uint64_t*>(sx + kTcSub * (DM + 1) * kTcThreads);
-    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(sx + kTcSub * (DM + 1) * kTcThreads + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sx + kTcSub * (DM + 1) * kTcThreads);
+    uint64_t& bar = bars[0];                                   // MMA completion
+    uint64_t* wbar = bars + 1;                                 // [2] weight-block arrival
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 3);
     const BlkOff off = blk_offsets(W1S, NO3);
 
     RqsCfg<float> cfg;
@@ -156,7 +156,7 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
-    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::fence_mbar_init(); }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -174,11 +174,13 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
     const int64_t ntiles = (B + ROWS - 1) / ROWS;
     const float* layers = packed + NF_STACK_HDR;
 
-    // prefetch the first layer of the first tile
+    // layer blocks travel through the TMA unit (cp.async.bulk, async proxy): thread 0 issues one bulk copy per block,
+    // completion is signalled on wbar[buffer]; the first layer of the first tile is requested here
     int buf = 0;
-    if ((int64_t)blockIdx.x < ntiles) {
-        stage_block(sbuf, layers + (size_t)(inverse ? L - 1 : 0) * BW, BW);
-        cp_async_commit();
+    uint32_t wphase = 0u;                       // bit b = parity to wait for on wbar[b]
+    if (tid == 0 && (int64_t)blockIdx.x < ntiles) {
+        tc::mbar_arrive_expect_tx(&wbar[0], (uint32_t)BW * 4u);
+        tc::bulk_g2s(sbuf, layers + (size_t)(inverse ? L - 1 : 0) * BW, (uint32_t)BW * 4u, &wbar[0]);
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // per-row state (x, running log-det) of the kTcSub sub-tiles: one shared-memory column per thread
@@ -190,19 +192,21 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
             sx[(s * (DM + 1) + DM) * kTcThreads + tid] = 0.f;
         }
         for (int li = 0; li < L; ++li) {
-            // this layer's block has landed; everyone is done with the other buffer -> prefetch the next layer into it
-            cp_async_wait<0>();
+            // everyone is done with the other buffer (previous layer) -> request the next layer into it, then wait
+            // for this layer's block
             tc::fence_proxy_async_smem();
             __syncthreads();
-            {
+            if (tid == 0) {
                 const bool last = (li == L - 1);
-                const bool more = !last || (tile + gridDim.x < ntiles);
-                if (more) {
+                if (!last || (tile + gridDim.x < ntiles)) {
                     const int nli = last ? 0 : li + 1;
-                    stage_block(sbuf + (size_t)(buf ^ 1) * BW, layers + (size_t)(inverse ? L - 1 - nli : nli) * BW, BW);
+                    tc::mbar_arrive_expect_tx(&wbar[buf ^ 1], (uint32_t)BW * 4u);
+                    tc::bulk_g2s(sbuf + (size_t)(buf ^ 1) * BW, layers + (size_t)(inverse ? L - 1 - nli : nli) * BW,
+                                 (uint32_t)BW * 4u, &wbar[buf ^ 1]);
                 }
-                cp_async_commit();
             }
+            tc::mbar_wait(&wbar[buf], (wphase >> buf) & 1u);
+            wphase ^= (1u << buf);
             const float* sL = sbuf + (size_t)buf * BW;
             const float* net = sL + NF_LAYER_HDR;
             const int* meta = reinterpret_cast<const int*>(sL + 16);
@@ -306,7 +310,6 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
             }
         }
     }
-    cp_async_wait<0>();
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tb, kTmemCols);
@@ -345,7 +348,7 @@ extern "C" int nf_spline_stack_tc_forward(const void* packed, const void* hdr_ho
     if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)L * BW)) return NF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
-    const size_t smem = sizeof(float) * ((size_t)2 * BW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 4);
+    const size_t smem = sizeof(float) * ((size_t)2 * BW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 8);
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
     const int rows = kTcThreads * kTcSub;
     const int64_t ntiles = cdiv(B, rows);

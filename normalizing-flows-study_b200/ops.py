@@ -121,8 +121,9 @@ class _BatchNormFn(Function):
         y = torch.empty_like(x)
         sm = torch.empty(H, dtype=x.dtype, device=x.device)
         sr = torch.empty(H, dtype=x.dtype, device=x.device)
+        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device) if training else None
         call("nf_batchnorm_forward", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
-             ptr(y), ptr(sm), ptr(sr), B, H, int(training), float(momentum), float(eps), int(relu),
+             ptr(y), ptr(sm), ptr(sr), ptr(ws), B, H, int(training), float(momentum), float(eps), int(relu),
              L.dtype_code(x), stream())
         ctx.relu, ctx.training = relu, training
         ctx.save_for_backward(x, y, gamma, sm, sr)
@@ -137,8 +138,9 @@ class _BatchNormFn(Function):
         gx = torch.empty_like(x)
         gg = torch.empty_like(sm)
         gb = torch.empty_like(sm)
+        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
         call("nf_batchnorm_backward", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(_c(gy)), ptr(gx), ptr(gg),
-             ptr(gb), B, H, int(ctx.relu), int(ctx.training), L.dtype_code(x), stream())
+             ptr(gb), ptr(ws), B, H, int(ctx.relu), int(ctx.training), L.dtype_code(x), stream())
         return gx, gg, gb, None, None, None, None, None, None
 
 

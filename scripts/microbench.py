@@ -21,7 +21,9 @@ HBM = PEAKS.get("hbm_gbs", 6650.0)
 TF = PEAKS.get("bf16_tflops", 1590.0)
 
 
-def timeit(fn, reps=10, warm=3):
+def timeit(fn, reps=5, warm=2, inner=8):
+    """median over `reps` of (CUDA-event time of `inner` back-to-back calls) / inner: the launch queue stays full, so
+    host-side call overhead (~20-50 us per op through Python) does not leak into sub-millisecond kernels"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -29,10 +31,11 @@ def timeit(fn, reps=10, warm=3):
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(inner):
+            fn()
         b.record()
         torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / inner)
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -160,12 +163,12 @@ def bench_gemm():
         if name.startswith("dW"):
             g = torch.randn(K, M, device=DEV)
             x = torch.randn(K, Nn, device=DEV)
-            ms = timeit(lambda: ops.gemm(g, x, M, Nn, K, 1, M, Nn, 1), reps=5)
+            ms = timeit(lambda: ops.gemm(g, x, M, Nn, K, 1, M, Nn, 1), reps=3, inner=2)
         else:
             a = torch.randn(M, K, device=DEV)
             w = torch.randn(Nn, K, device=DEV)
             bias = torch.randn(Nn, device=DEV)
-            ms = timeit(lambda: ops.linear_raw(a, w, bias, relu=True), reps=5)
+            ms = timeit(lambda: ops.linear_raw(a, w, bias, relu=True), reps=3, inner=2)
         report(f"nf_gemm fp32 {name} [{M}x{Nn}x{K}]", ms, None, 2.0 * M * Nn * K)
 
 
@@ -188,9 +191,9 @@ def bench_stacks():
     maf = N.MaskedAutoregressiveFlow(64, 512).to(DEV).eval()
     xm = torch.randn(262144, 64, device=DEV)
     with torch.no_grad():
-        ms = timeit(lambda: maf.inverse(xm), reps=5)
+        ms = timeit(lambda: maf.inverse(xm), reps=3, inner=2)
         report("MAF(64,512).inverse B=262144 (4 GEMMs + transform)", ms, 262144 * 516, 1245184 * 262144)
-        ms = timeit(lambda: maf.forward(xm), reps=3, warm=1)
+        ms = timeit(lambda: maf.forward(xm), reps=3, warm=1, inner=1)
         report("MAF(64,512).forward sequential B=262144", ms, 262144 * 516, 1245184 * 262144)
 
 
