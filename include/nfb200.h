@@ -77,15 +77,17 @@ NF_API int nf_rqs_unit_backward(const void* x, const void* w, const void* h, con
 NF_API int nf_spline_transform_forward(const void* x, const void* params, const void* mask, const int32_t* tidx, void* y,
                                 void* ld, int64_t B, int D, int Dt, int num_bins, int inverse, double bound,
                                 double min_bin_width, double min_bin_height, double min_derivative,
-                                const void* rescale_in, const void* rescale_lo, const void* rescale_out, int dtype,
-                                nf_stream_t stream);
-/* gx: [B,D] overwritten; gparams: [B, D*(3K-1)] -- only the transformed dims' entries are written, the
- * caller zero-fills the buffer beforehand. */
+                                const void* rescale_in, const void* rescale_lo, const void* rescale_out,
+                                int params_compact, int dtype, nf_stream_t stream);
+/* params_compact != 0: params is [B, Dt*(3K-1)], block t = parameters of dim tidx[t] (the conditioner's last layer
+ * restricted to the transformed dims: the reference computes and discards the other half).
+ * gx: [B,D] overwritten; gparams: same layout as params -- only the transformed dims' entries are written, the
+ * caller zero-fills the buffer beforehand in the non-compact layout. */
 NF_API int nf_spline_transform_backward(const void* x, const void* params, const void* mask, const int32_t* tidx,
                                  const void* gy, const void* gld, void* gx, void* gparams, int64_t B, int D, int Dt,
                                  int num_bins, int inverse, double bound, double min_bin_width, double min_bin_height,
                                  double min_derivative, const void* rescale_in, const void* rescale_lo,
-                                 const void* rescale_out, int dtype, nf_stream_t stream);
+                                 const void* rescale_out, int params_compact, int dtype, nf_stream_t stream);
 
 /* ---- a1/a2: CouplingLayer.forward/.inverse minus the conditioners ---------------------------------
  * src/flows/coupling/coupling_layer.py:47-66 / :76-94.  s_raw,b_raw: [B,D] un-clamped s_net/b_net outputs. */

@@ -30,8 +30,8 @@ _SIGNATURES = {
     "nf_launch_count": [],
     "nf_rqs_unit_forward": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _D, _D, _D, _I, _P],
     "nf_rqs_unit_backward": [_P] * 10 + [_L, _I, _I, _D, _D, _D, _I, _P],
-    "nf_spline_transform_forward": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P],
-    "nf_spline_transform_backward": [_P] * 8 + [_L, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _I, _P],
+    "nf_spline_transform_forward": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _I, _I, _P],
+    "nf_spline_transform_backward": [_P] * 8 + [_L, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _I, _I, _P],
     "nf_affine_coupling_forward": [_P] * 6 + [_L, _I, _I, _I, _P],
     "nf_affine_coupling_backward": [_P] * 9 + [_L, _I, _I, _I, _P],
     "nf_affine_ar_forward": [_P] * 4 + [_L, _I, _I, _I, _P],

@@ -32,13 +32,14 @@ template <typename T, bool BWD>
 static int spline_tf_any(const void* x, const void* params, const void* mask, const int32_t* tidx, void* y, void* ld,
                          const void* gy, const void* gld, void* gx, void* gparams, int64_t B, int D, int Dt, int K,
                          int inverse, double bound, double mw, double mh, double md, const void* r_in,
-                         const void* r_lo, const void* r_out, cudaStream_t st) {
+                         const void* r_lo, const void* r_out, int compact, cudaStream_t st) {
     SplineTfArgs<T> a;
     a.x = (const T*)x; a.params = (const T*)params; a.mask = (const T*)mask; a.tidx = tidx;
     a.y = (T*)y; a.ld = (T*)ld; a.gy = (const T*)gy; a.gld = (const T*)gld; a.gx = (T*)gx; a.gparams = (T*)gparams;
     a.B = B; a.D = D; a.Dt = Dt; a.K = K; a.inverse = inverse;
     a.c = make_rqs_cfg<T>(true, K, bound, mw, mh, md);
     a.r_in = (const T*)r_in; a.r_lo = (const T*)r_lo; a.r_out = (const T*)r_out;
+    a.compact = compact;
     return K <= 16 ? spline_transform_launch<T, BWD, false>(a, st) : spline_transform_launch<T, BWD, true>(a, st);
 }
 }  // namespace nf
@@ -78,8 +79,8 @@ extern "C" int nf_rqs_unit_backward(const void* x, const void* w, const void* h,
 extern "C" int nf_spline_transform_forward(const void* x, const void* params, const void* mask, const int32_t* tidx,
                                            void* y, void* ld, int64_t B, int D, int Dt, int num_bins, int inverse,
                                            double bound, double min_w, double min_h, double min_d,
-                                           const void* r_in, const void* r_lo, const void* r_out, int dtype,
-                                           nf_stream_t stream) {
+                                           const void* r_in, const void* r_lo, const void* r_out, int params_compact,
+                                           int dtype, nf_stream_t stream) {
     if (B < 0 || D < 1 || Dt < 0 || Dt > D || num_bins < 1 || num_bins > 32) return NF_ERR_BAD_SHAPE;
     if (B == 0) return NF_OK;
     NF_REQ(x); NF_REQ(mask); NF_REQ(y); NF_REQ(ld);
@@ -88,10 +89,10 @@ extern "C" int nf_spline_transform_forward(const void* x, const void* params, co
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NF_F32)
         return spline_tf_any<float, false>(x, params, mask, tidx, y, ld, nullptr, nullptr, nullptr, nullptr, B, D, Dt,
-                                           num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, st);
+                                           num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, params_compact, st);
     if (dtype == NF_F64)
         return spline_tf_any<double, false>(x, params, mask, tidx, y, ld, nullptr, nullptr, nullptr, nullptr, B, D, Dt,
-                                            num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, st);
+                                            num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, params_compact, st);
     return NF_ERR_UNSUPPORTED;
 }
 
@@ -99,7 +100,7 @@ extern "C" int nf_spline_transform_backward(const void* x, const void* params, c
                                             const void* gy, const void* gld, void* gx, void* gparams, int64_t B, int D,
                                             int Dt, int num_bins, int inverse, double bound, double min_w,
                                             double min_h, double min_d, const void* r_in, const void* r_lo,
-                                            const void* r_out, int dtype, nf_stream_t stream) {
+                                            const void* r_out, int params_compact, int dtype, nf_stream_t stream) {
     if (B < 0 || D < 1 || Dt < 0 || Dt > D || num_bins < 1 || num_bins > 32) return NF_ERR_BAD_SHAPE;
     if (B == 0) return NF_OK;
     NF_REQ(x); NF_REQ(mask); NF_REQ(gy); NF_REQ(gld); NF_REQ(gx);
@@ -108,9 +109,9 @@ extern "C" int nf_spline_transform_backward(const void* x, const void* params, c
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NF_F32)
         return spline_tf_any<float, true>(x, params, mask, tidx, nullptr, nullptr, gy, gld, gx, gparams, B, D, Dt,
-                                          num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, st);
+                                          num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, params_compact, st);
     if (dtype == NF_F64)
         return spline_tf_any<double, true>(x, params, mask, tidx, nullptr, nullptr, gy, gld, gx, gparams, B, D, Dt,
-                                           num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, st);
+                                           num_bins, inverse, bound, min_w, min_h, min_d, r_in, r_lo, r_out, params_compact, st);
     return NF_ERR_UNSUPPORTED;
 }

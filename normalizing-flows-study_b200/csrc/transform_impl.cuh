@@ -119,9 +119,10 @@ __global__ void __launch_bounds__(128)
 spline_transform_fwd_kernel(const T* __restrict__ x, const T* __restrict__ params, const T* __restrict__ mask,
                             const int32_t* __restrict__ tidx, T* __restrict__ y, T* __restrict__ ld, int64_t B, int D,
                             int Dt, int Krt, int inverse, RqsCfg<T> c, const T* __restrict__ r_in,
-                            const T* __restrict__ r_lo, const T* __restrict__ r_out) {
+                            const T* __restrict__ r_lo, const T* __restrict__ r_out, int compact) {
     const int K = SK ? KMAX : Krt;
     const int P = 3 * K - 1;
+    const int PD = compact ? Dt : D;                   // parameter blocks per row
     constexpr int RPW = 32 / G;                        // rows per warp
     const int lane = threadIdx.x & 31, g = lane % G;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -140,7 +141,7 @@ spline_transform_fwd_kernel(const T* __restrict__ x, const T* __restrict__ param
                 const int dim = __ldg(tidx + t);
                 T v = xr[dim];
                 if (r_in) v = r_in[dim] * (v - r_lo[dim]) - c.hi;
-                const T* pp = params + (row * D + dim) * P;
+                const T* pp = params + (row * PD + (compact ? t : dim)) * P;
                 T uw[KMAX], uh[KMAX], ud[KMAX];
                 load_row_rt<T, KMAX>(pp, K, uw);
                 load_row_rt<T, KMAX>(pp + K, K, uh);
@@ -157,15 +158,83 @@ spline_transform_fwd_kernel(const T* __restrict__ x, const T* __restrict__ param
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// a5/a6 forward, compact parameter layout [B, Dt*(3K-1)]: the parameter blocks of consecutive (row, t) elements are
+// contiguous, so a warp fetches the blocks of its 32 elements with fully coalesced loads (one 128-byte line per
+// instruction) into a per-warp shared-memory slab and every lane then reads its own block at stride 3K-1 (odd:
+// bank-conflict free).  The register-path kernel above issues one strided LDG per parameter instead (3K-1 LDGs
+// touching ~24 lines each), which makes it L1-wavefront bound at ~1/3 of this kernel's rate.
+// G lanes per row (G = pow2 >= min(Dt,32)); Dt > 32 walks the row in chunks of 32 elements.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int KMAX, bool SK, int G>
+__global__ void __launch_bounds__(256)
+spline_transform_compact_fwd_kernel(const T* __restrict__ x, const T* __restrict__ params, const T* __restrict__ mask,
+                                    const int32_t* __restrict__ tidx, T* __restrict__ y, T* __restrict__ ld, int64_t B,
+                                    int D, int Dt, int Krt, int inverse, RqsCfg<T> c, const T* __restrict__ r_in,
+                                    const T* __restrict__ r_lo, const T* __restrict__ r_out) {
+    extern __shared__ __align__(16) unsigned char slab_raw[];
+    const int K = SK ? KMAX : Krt;
+    const int P = 3 * K - 1;
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane % G, rsub = lane / G;
+    T* slab = reinterpret_cast<T*>(slab_raw) + (size_t)wib * 32 * P;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nblk = (B + RPW - 1) / RPW;
+    for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+        const int64_t row0 = blk * RPW;
+        const int64_t row = row0 + rsub;
+        const bool valid = row < B;
+        const int nrows = (int)((B - row0) < RPW ? (B - row0) : RPW);
+        if (valid)
+            for (int dd = g; dd < D; dd += G)
+                if (__ldg(mask + dd) != T(0)) y[row * D + dd] = scrub0(x[row * D + dd]);
+        T acc = T(0);
+        for (int t0 = 0; t0 < Dt; t0 += G) {
+            // blocks of this chunk: rows row0..row0+nrows-1, dims t0..min(t0+G,Dt)-1 -- contiguous when G >= Dt
+            // (several whole rows) or RPW == 1 (a slice of one row)
+            const int tn = (Dt - t0) < G ? (Dt - t0) : G;
+            const int nblocks = (G >= Dt) ? nrows * Dt : tn;
+            const T* src = params + ((G >= Dt) ? row0 * Dt : row0 * Dt + t0) * (int64_t)P;
+            const int nfl = nblocks * P;
+            __syncwarp();
+            for (int i = lane; i < nfl; i += 32) slab[i] = __ldcs(src + i);
+            __syncwarp();
+            const int t = t0 + g;
+            if (valid && t < Dt) {
+                const int dim = __ldg(tidx + t);
+                T v = x[row * D + dim];
+                if (r_in) v = r_in[dim] * (v - r_lo[dim]) - c.hi;
+                const T* pp = slab + (size_t)((G >= Dt) ? rsub * Dt + t : g) * P;
+                T uw[KMAX], uh[KMAX], ud[KMAX];
+NF_UNROLL
+                for (int j = 0; j < KMAX; ++j) {
+                    uw[j] = (j < K) ? pp[j] : T(0);
+                    uh[j] = (j < K) ? pp[K + j] : T(0);
+                    ud[j] = (j < K - 1) ? pp[2 * K + j] : T(0);
+                }
+                T out, lad;
+                rqs_eval<T, KMAX, true>(v, uw, uh, ud, K, inverse != 0, c, out, lad);
+                if (r_in) out = (out + c.hi) * r_out[dim] + r_lo[dim];
+                y[row * D + dim] = scrub0(out);
+                acc += lad;
+            }
+        }
+        acc = group_sum<T, G>(acc);
+        if (valid && g == 0) ld[row] = scrub0(acc);
+    }
+}
+
 template <typename T, int KMAX, bool SK, int G>
 __global__ void __launch_bounds__(128)
 spline_transform_bwd_kernel(const T* __restrict__ x, const T* __restrict__ params, const T* __restrict__ mask,
                             const int32_t* __restrict__ tidx, const T* __restrict__ gy, const T* __restrict__ gld,
                             T* __restrict__ gx, T* __restrict__ gparams, int64_t B, int D, int Dt, int Krt,
                             int inverse, RqsCfg<T> c, const T* __restrict__ r_in, const T* __restrict__ r_lo,
-                            const T* __restrict__ r_out) {
+                            const T* __restrict__ r_out, int compact) {
     const int K = SK ? KMAX : Krt;
     const int P = 3 * K - 1;
+    const int PD = compact ? Dt : D;
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31, g = lane % G;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -183,7 +252,8 @@ spline_transform_bwd_kernel(const T* __restrict__ x, const T* __restrict__ param
             const T xin = xr[dim];
             T v = xin;
             if (r_in) v = r_in[dim] * (v - r_lo[dim]) - c.hi;
-            const T* pp = params + (row * D + dim) * P;
+            const int64_t pblk = row * PD + (compact ? t : dim);
+            const T* pp = params + pblk * P;
             T uw[KMAX], uh[KMAX], ud[KMAX];
             load_row_rt<T, KMAX>(pp, K, uw);
             load_row_rt<T, KMAX>(pp + K, K, uh);
@@ -203,7 +273,7 @@ NF_UNROLL
             rqs_eval_bwd<T, KMAX, true>(v, uw, uh, ud, K, inverse != 0, c, go, gl, gv, guw, guh, gud);
             if (r_in) gv *= r_in[dim];
             gx[row * D + dim] = gv;
-            T* gp = gparams + (row * D + dim) * P;
+            T* gp = gparams + pblk * P;
 NF_UNROLL
             for (int j = 0; j < KMAX; ++j) if (j < K) { gp[j] = guw[j]; gp[K + j] = guh[j]; }
 NF_UNROLL
@@ -273,20 +343,58 @@ struct SplineTfArgs {
     int64_t B; int D, Dt, K, inverse;
     RqsCfg<T> c;
     const T* r_in; const T* r_lo; const T* r_out;
+    int compact;                       // params / gparams rows hold only the Dt transformed dims' blocks
 };
+
+static inline int pick_group_pow2(int n) { int g = 1; while (g < n && g < 32) g <<= 1; return g; }
+
+template <typename T, bool GENERIC>
+int spline_transform_compact_fwd_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
+    const int G = pick_group_pow2(a.Dt);
+    const int P = 3 * a.K - 1;
+    const size_t smem = (size_t)8 * 32 * P * sizeof(T);
+    const int grid = grid_for(cdiv(a.B, 32 / G), 8, 8);
+#define NF_SC(KM, SKF, GG)                                                                                            \
+    do {                                                                                                              \
+        auto kern = spline_transform_compact_fwd_kernel<T, KM, SKF, GG>;                                              \
+        if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 256, smem, st>>>(a.x, a.params, a.mask, a.tidx, a.y, a.ld, a.B, a.D, a.Dt, a.K, a.inverse, a.c,  \
+                                      a.r_in, a.r_lo, a.r_out);                                                       \
+    } while (0)
+#define NF_SC_G(KM, SKF)                                                                                              \
+    do {                                                                                                              \
+        switch (G) { case 1: NF_SC(KM, SKF, 1); break; case 2: NF_SC(KM, SKF, 2); break; case 4: NF_SC(KM, SKF, 4); break; \
+                     case 8: NF_SC(KM, SKF, 8); break; case 16: NF_SC(KM, SKF, 16); break; default: NF_SC(KM, SKF, 32); break; } \
+    } while (0)
+    if constexpr (GENERIC) { NF_SC_G(32, false); }
+    else {
+        if (a.K == 8) NF_SC_G(8, true);
+        else if (a.K == 10) NF_SC_G(10, true);
+        else if (a.K < 8) NF_SC_G(8, false);
+        else NF_SC_G(16, false);
+    }
+#undef NF_SC_G
+#undef NF_SC
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
 
 template <typename T, bool BWD, bool GENERIC>
 int spline_transform_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
+    if constexpr (!BWD) {
+        if (a.compact && a.Dt > 0) return spline_transform_compact_fwd_launch<T, GENERIC>(a, st);
+    }
     const int G = pick_group3(a.Dt);
     const int grid = grid_for(cdiv(a.B, 32 / G), 4, 64);
 #define NF_ST(KM, GG)                                                                                              \
     do {                                                                                                           \
         if constexpr (BWD)                                                                                         \
             spline_transform_bwd_kernel<T, KM, false, GG><<<grid, 128, 0, st>>>(a.x, a.params, a.mask, a.tidx, a.gy, \
-                a.gld, a.gx, a.gparams, a.B, a.D, a.Dt, a.K, a.inverse, a.c, a.r_in, a.r_lo, a.r_out);               \
+                a.gld, a.gx, a.gparams, a.B, a.D, a.Dt, a.K, a.inverse, a.c, a.r_in, a.r_lo, a.r_out, a.compact);    \
         else                                                                                                       \
             spline_transform_fwd_kernel<T, KM, false, GG><<<grid, 128, 0, st>>>(a.x, a.params, a.mask, a.tidx, a.y,  \
-                a.ld, a.B, a.D, a.Dt, a.K, a.inverse, a.c, a.r_in, a.r_lo, a.r_out);                                 \
+                a.ld, a.B, a.D, a.Dt, a.K, a.inverse, a.c, a.r_in, a.r_lo, a.r_out, a.compact);                      \
     } while (0)
 #define NF_ST_G(KM)                                        \
     do {                                                   \

@@ -221,11 +221,11 @@ class SplineCouplingLayer(Flow):
         return (self.min_bin_width, self.min_bin_height, self.min_derivative)
 
     def _aux_tensors(self, v):
-        """(tidx int32 [Dt], rescale (a, lo, c) or None) on v's device/dtype."""
+        """(tidx int32 [Dt] on device, rescale (a, lo, c) or None, transformed dims as a host list)."""
         def build():
-            m = self.mask.detach().to("cpu")
-            tidx = torch.nonzero(m == 0).flatten().to(torch.int32).to(v.device)
-            return tidx, packing.rescale_tensors(self, self.data_dim, v.dtype, v.device)
+            tlist = torch.nonzero(self.mask.detach().to("cpu") == 0).flatten().tolist()
+            tidx = torch.tensor(tlist, dtype=torch.int32, device=v.device)
+            return tidx, packing.rescale_tensors(self, self.data_dim, v.dtype, v.device), tlist
         return self._aux.get([self.mask, torch.empty(0, dtype=v.dtype, device=v.device)], build)
 
     def fusable(self, v):
@@ -238,16 +238,30 @@ class SplineCouplingLayer(Flow):
             out = run_spline_stack(self._pack, _module_tensors(self), [self], None, v, inverse)
             if out is not None:
                 return out
-        tidx, rescale = self._aux_tensors(v)
+        tidx, rescale, tlist = self._aux_tensors(v)
         net = self.param_net
         vin = v
         if rescale is not None:                       # conditioner sees the rescaled input (:101-102)
             vin = ops.feature_affine(v, rescale[1], None, rescale[0], -float(self.bound))
         h = ops.linear(vin, net[0].weight, net[0].bias, mask=self.mask, relu=True)
         h = ops.linear(h, net[2].weight, net[2].bias, relu=True)
-        params = ops.linear(h, net[4].weight, net[4].bias)
+        # head restricted to the transformed dims: the reference evaluates all D*(3K-1) outputs and discards the rows
+        # of the conditioning dims; no used value changes
+        w4, b4 = self._head_rows(net[4], tlist)
+        params = ops.linear(h, w4, b4)
         return ops.spline_transform(v, params, self.mask, tidx, self.num_bins, inverse, self.bound, self._mins,
-                                    rescale)
+                                    rescale, compact=True)
+
+    def _head_rows(self, lin, t):
+        """Rows d*(3K-1)+j of the last Linear for the transformed dims d in `t`: a contiguous slice (a view) for the
+        half-split masks of RealNVPSpline, an index_select otherwise."""
+        P = 3 * self.num_bins - 1
+        if not t:
+            return lin.weight[:0], lin.bias[:0]
+        if t == list(range(t[0], t[0] + len(t))):
+            return lin.weight[t[0] * P:(t[-1] + 1) * P], lin.bias[t[0] * P:(t[-1] + 1) * P]
+        rows = torch.cat([torch.arange(d * P, (d + 1) * P, device=lin.weight.device) for d in t])
+        return lin.weight.index_select(0, rows), lin.bias.index_select(0, rows)
 
     def forward(self, z):
         return self._run(z, False)

@@ -196,7 +196,7 @@ def affine_coupling(x, s_raw, b_raw, mask, inverse):
 
 class _SplineTransformFn(Function):
     @staticmethod
-    def forward(ctx, x, params, mask, tidx, K, inverse, bound, mins, rescale):
+    def forward(ctx, x, params, mask, tidx, K, inverse, bound, mins, rescale, compact):
         x, params = _c(x), _c(params)
         B, D = x.shape
         y = torch.empty_like(x)
@@ -204,8 +204,8 @@ class _SplineTransformFn(Function):
         r = rescale if rescale is not None else (None, None, None)
         call("nf_spline_transform_forward", ptr(x), ptr(params), ptr(mask), ptr(tidx), ptr(y), ptr(ld), B, D,
              tidx.numel(), K, int(inverse), bound, mins[0], mins[1], mins[2], ptr(r[0]), ptr(r[1]), ptr(r[2]),
-             L.dtype_code(x), stream())
-        ctx.cfg = (K, inverse, bound, mins)
+             int(compact), L.dtype_code(x), stream())
+        ctx.cfg = (K, inverse, bound, mins, compact)
         ctx.rescale = rescale
         ctx.save_for_backward(x, params, mask, tidx)
         return y, ld
@@ -214,20 +214,21 @@ class _SplineTransformFn(Function):
     @once_differentiable
     def backward(ctx, gy, gld):
         x, params, mask, tidx = ctx.saved_tensors
-        K, inverse, bound, mins = ctx.cfg
+        K, inverse, bound, mins, compact = ctx.cfg
         B, D = x.shape
         r = ctx.rescale if ctx.rescale is not None else (None, None, None)
         gx = torch.empty_like(x)
-        gp = torch.zeros_like(params)
+        gp = torch.empty_like(params) if compact else torch.zeros_like(params)
         call("nf_spline_transform_backward", ptr(x), ptr(params), ptr(mask), ptr(tidx), ptr(_c(gy)), ptr(_c(gld)),
              ptr(gx), ptr(gp), B, D, tidx.numel(), K, int(inverse), bound, mins[0], mins[1], mins[2], ptr(r[0]),
-             ptr(r[1]), ptr(r[2]), L.dtype_code(x), stream())
-        return gx, gp, None, None, None, None, None, None, None
+             ptr(r[1]), ptr(r[2]), int(compact), L.dtype_code(x), stream())
+        return gx, gp, None, None, None, None, None, None, None, None
 
 
-def spline_transform(x, params, mask, tidx, K, inverse, bound, mins, rescale=None):
+def spline_transform(x, params, mask, tidx, K, inverse, bound, mins, rescale=None, compact=False):
+    """params: [B, D*(3K-1)] (reference layout) or, with compact=True, [B, Dt*(3K-1)] (transformed dims only)."""
     return _SplineTransformFn.apply(x, params, _c(mask.to(x.dtype)), tidx, K, inverse, float(bound),
-                                    tuple(float(m) for m in mins), rescale)
+                                    tuple(float(m) for m in mins), rescale, bool(compact))
 
 
 class _AffineARFn(Function):

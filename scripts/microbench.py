@@ -88,23 +88,28 @@ def bench_spline_tf():
         Dt = int((mask == 0).sum())
         tidx = torch.nonzero(mask == 0).flatten().to(torch.int32).to(DEV)
         x = torch.randn(B, D, device=DEV) * 2
-        params = torch.randn(B, D * P, device=DEV)
         maskd = mask.to(DEV)
-        nbytes = B * 4 * (2 * D + 1 + Dt * P)
-        for inv in (False, True):
-            with torch.no_grad():
-                ms = timeit(lambda: ops.spline_transform(x, params, maskd, tidx, K, inv, 5.0, (1e-3, 1e-3, 1e-3)))
-            report(f"spline_transform B={B} D={D} K={K} {'inv' if inv else 'fwd'}", ms, nbytes,
-                   note="bytes count only the transformed dims' parameters")
-        gy, gl = torch.randn(B, D, device=DEV), torch.randn(B, device=DEV)
-        gx, gp = torch.empty_like(x), torch.zeros_like(params)
+        for compact in (True, False):
+            params = torch.randn(B, (Dt if compact else D) * P, device=DEV)
+            tag = "compact" if compact else "full  "
+            nbytes = B * 4 * (2 * D + 1 + (Dt if compact else D) * P)
+            for inv in (False, True):
+                with torch.no_grad():
+                    ms = timeit(lambda: ops.spline_transform(x, params, maskd, tidx, K, inv, 5.0, (1e-3, 1e-3, 1e-3),
+                                                            None, compact))
+                report(f"spline_transform {tag} B={B} D={D} K={K} {'inv' if inv else 'fwd'}", ms, nbytes,
+                       note="bytes = x + y + ld + the params tensor as laid out")
+            gy, gl = torch.randn(B, D, device=DEV), torch.randn(B, device=DEV)
+            gx, gp = torch.empty_like(x), torch.zeros_like(params)
 
-        def bwd():
-            N._lib.call("nf_spline_transform_backward", x.data_ptr(), params.data_ptr(), maskd.data_ptr(),
-                        tidx.data_ptr(), gy.data_ptr(), gl.data_ptr(), gx.data_ptr(), gp.data_ptr(), B, D, Dt, K, 0, 5.0,
-                        1e-3, 1e-3, 1e-3, None, None, None, 0, N._lib.stream())
-        report(f"spline_transform B={B} D={D} K={K} backward", timeit(bwd), B * 4 * (3 * D + 1 + 2 * Dt * P))
-        del x, params, gy, gl, gx, gp
+            def bwd():
+                N._lib.call("nf_spline_transform_backward", x.data_ptr(), params.data_ptr(), maskd.data_ptr(),
+                            tidx.data_ptr(), gy.data_ptr(), gl.data_ptr(), gx.data_ptr(), gp.data_ptr(), B, D, Dt, K, 0,
+                            5.0, 1e-3, 1e-3, 1e-3, None, None, None, int(compact), 0, N._lib.stream())
+            report(f"spline_transform {tag} B={B} D={D} K={K} backward", timeit(bwd, reps=3, inner=2),
+                   B * 4 * (3 * D + 1 + 2 * (Dt if compact else D) * P))
+            del params, gy, gl, gx, gp
+        del x
 
 
 def bench_affine():

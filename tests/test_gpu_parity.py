@@ -251,3 +251,40 @@ def test_bounded_spline_transform_kernel(name):
                 lambda: noise()[0])
         _within(ld.cpu().reshape(-1), g[key + "_ld"].reshape(-1), l64.reshape(-1), LD_ATOL, LD_RTOL,
                 f"{name} {key} ld", lambda: noise()[1])
+
+
+@pytest.mark.parametrize("D,K,B", [(2, 8, 200003), (16, 10, 40001), (5, 4, 150001)])
+@pytest.mark.parametrize("compact", [True, False])
+def test_spline_transform_large_batch(D, K, B, compact):
+    """Forward transform kernels at large, ragged batch sizes (warp-transposed compact-layout kernel and the
+    register-path kernel for the reference layout) against the oracle's bounded spline, alternating mask."""
+    gen = torch.Generator().manual_seed(D * 100 + K)
+    P = 3 * K - 1
+    mask = torch.zeros(D)
+    mask[::2] = 1
+    tl = torch.nonzero(mask == 0).flatten()
+    Dt = tl.numel()
+    x = torch.randn(B, D, generator=gen) * 3
+    full = torch.randn(B, D, P, generator=gen)
+    par = (full[:, tl, :] if compact else full).reshape(B, -1).contiguous()
+    d = _dev()
+    tidx = tl.to(torch.int32).to(d)
+    for inverse in (False, True):
+        y, ld = N.ops.spline_transform(x.to(d), par.to(d), mask.to(d), tidx, K, inverse, 5.0, (1e-3, 1e-3, 1e-3), None,
+                                       compact)
+        uw, uh, ud = full[:, tl, :K], full[:, tl, K:2 * K], full[:, tl, 2 * K:]
+        yt, lt = O.rqs_bounded(x[:, tl], uw, uh, ud, inverse, bound=5.0)
+        y64, l64 = O.rqs_bounded(x[:, tl].double(), uw.double(), uh.double(), ud.double(), inverse, bound=5.0)
+        ref = x.clone()
+        ref[:, tl] = yt
+        ref64 = x.double().clone()
+        ref64[:, tl] = y64
+        noise = lambda: tuple(2 * t for t in _param_noise(lambda a, b, c: O.rqs_bounded(x[:, tl], a, b, c, inverse, bound=5.0),
+                                                          [uw, uh, ud], 8))   # 10^5..10^6 wild elements: widen the draw
+        def ynoise():
+            n = torch.zeros(B, D, dtype=torch.float64)
+            n[:, tl] = noise()[0].reshape(B, Dt)
+            return n
+        _within(y.cpu(), ref, ref64, Z_ATOL, Z_RTOL, f"staged z inv={inverse}", ynoise)
+        _within(ld.cpu(), lt.sum(1), l64.sum(1), LD_ATOL, LD_RTOL, f"staged ld inv={inverse}",
+                lambda: noise()[1].reshape(B, Dt).sum(1))
