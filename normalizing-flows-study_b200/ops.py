@@ -48,6 +48,26 @@ def linear_raw(x, w, bias=None, relu=False, k_extent=None):
     return gemm(x, w, M, N, K, K, 1, 1, K, bias=bias, relu=relu, k_extent=k_extent)
 
 
+def split_tf32(w):
+    """(hi, lo) operands of the 3xTF32 tensor-core GEMM for a contiguous fp32 weight."""
+    w = _c(w)
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    call("nf_split_tf32", ptr(w), ptr(hi), ptr(lo), w.numel(), stream())
+    return hi, lo
+
+
+def linear_tc(x, w_hi, w_lo, bias=None, relu=False, k_extent=None, out=None):
+    """y = relu?(x @ W.T + bias) on tcgen05 (3xTF32, fp32-accurate); returns None when the shape / alignment is not
+    taken by the tensor-core kernel (caller uses linear_raw)."""
+    M, K = x.shape
+    N = w_hi.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    ok = L.try_call("nf_linear_tc", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, N, int(relu),
+                    ptr(k_extent), stream())
+    return out if ok else None
+
+
 def mul_rows(a, b):
     """a * b where b has a's shape or is a single row broadcast over a's rows."""
     a2 = a.view(-1, a.shape[-1])
