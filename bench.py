@@ -343,16 +343,27 @@ def run_product(args):
     ms_dom = 0.5 * (ms_inv + ms_fwd) if wl == "c2" else ms_inv
     flops_launch = FLOPS_DENSE[wl] * rows
     achieved = flops_launch / (ms_dom * 1e-3) / 1e12
+    if wl == "c2":
+        kernel = ("spline_stack_tc_kernel: one launch = all 8 layers of one direction; layer-2 and head GEMMs on tcgen05 "
+                  "(3xTF32, A operand in TMEM), layer 1 + spline on the FP32 pipe")
+        note = ("GEMM FLOPs on the dense accounting of SURVEY 8d (what the reference's F.linear calls execute); the kernel "
+                "skips the unused half of the head (D9) and runs the remaining GEMM FLOPs 3x on the tensor pipe for fp32 "
+                "parity (tensor_flops_per_row_executed); the kernel is bound by the per-row spline / split work on the "
+                "FP32 pipe, not by the tensor pipe or HBM (20 B per row)")
+        tensor_exec = 8 * 3 * 2 * (64 * 64 + 64 * 32)
+    else:
+        kernel = "gemm_tc_kernel x4 (tcgen05 3xTF32, TMA-fed, masked-out K tiles skipped) + affine_ar_fwd_kernel"
+        note = ("dense GEMM FLOPs of one MADE evaluation (SURVEY 8d) over the time of the whole MAF.inverse chain; the "
+                "tensor pipe executes 3x the unskipped FLOPs (3xTF32 keeps fp32 parity)")
+        tensor_exec = None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "traffic": None,
-        "kernel": "spline_stack_kernel (one launch = all 8 layers of one direction)" if wl == "c2"
-                  else "gemm_kernel chain of MAF.inverse (4 launches + affine_ar)",
-        "flops_per_row": FLOPS_DENSE[wl], "flops_per_row_executed": FLOPS_EXEC[wl], "peak_source": which,
+        "traffic": None, "kernel": kernel,
+        "flops_per_row": FLOPS_DENSE[wl], "flops_per_row_executed": FLOPS_EXEC[wl],
+        "tensor_flops_per_row_executed": tensor_exec, "peak_source": which,
         "ms_per_launch": {"inverse": ms_inv, "forward": ms_fwd, "log_prob_head": ms_head},
         "hbm_gbs_algorithmic": (rows * (2 * D + 1) * 4) / (ms_dom * 1e-3) / 1e9,
-        "note": "GEMM FLOPs on the dense accounting of SURVEY 8d; the kernel runs them on the FP32 FFMA pipe "
-                "(fp32 parity), so the tensor-peak fraction is the headroom a tcgen05 3xTF32 path would address",
+        "note": note,
     }
 
     out = {

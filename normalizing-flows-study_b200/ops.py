@@ -20,6 +20,8 @@ from . import _lib as L
 
 ptr, call, stream = L.ptr, L.call, L.stream
 
+USE_TENSOR_CORE_GEMM = True      # tcgen05 3xTF32 GEMMs for float32 layers; False forces the FP32-pipe GEMM
+
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
@@ -92,12 +94,26 @@ def relu_backward(y, gy):
 # --------------------------------------------------------------------------------------------
 # Linear (+ optional weight mask, + optional fused ReLU)
 # --------------------------------------------------------------------------------------------
+def _tc_ok(x, K):
+    return USE_TENSOR_CORE_GEMM and x.dtype == torch.float32 and x.shape[0] >= 256 and K % 4 == 0
+
+
 class _LinearFn(Function):
+    """F.linear(x, W*mask, b) (+ReLU).  float32 with >= 256 rows: forward and the input gradient run on tcgen05
+    (3xTF32, fp32-accurate; the weight is split hi/lo per call -- weights are small next to the activations);
+    the weight gradient (reduction over the batch) and float64 use the FP32/FP64-pipe GEMM."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, mask, relu):
         x = _c(x)
         w_eff = _c(weight) if mask is None else mul_rows(_c(weight), mask)
-        y = linear_raw(x, w_eff, None if bias is None else _c(bias), relu)
+        b = None if bias is None else _c(bias)
+        y = None
+        if _tc_ok(x, x.shape[1]):
+            hi, lo = split_tf32(w_eff)
+            y = linear_tc(x, hi, lo, b, relu)
+        if y is None:
+            y = linear_raw(x, w_eff, b, relu)
         ctx.relu = relu
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, w_eff, mask, y if relu else None)
@@ -114,7 +130,11 @@ class _LinearFn(Function):
         N = w_eff.shape[0]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm(g, w_eff, M, K, N, N, 1, K, 1)                 # dX = dY W
+            if _tc_ok(g, N):
+                hi, lo = split_tf32(w_eff.t().contiguous())             # [K, N]: dX = dY (W^T)^T
+                gx = linear_tc(g, hi, lo)
+            if gx is None:
+                gx = gemm(g, w_eff, M, K, N, N, 1, K, 1)                 # dX = dY W
         if ctx.needs_input_grad[1]:
             gw = gemm(g, x, N, K, M, 1, N, K, 1)                     # dW = dY^T X
             if mask is not None:
@@ -479,10 +499,24 @@ def coupling_stack(packed, hdr_host, x, inverse):
 
 
 def made_affine(v, folded, mode):
-    """MADE chain + MAF.inverse / IAF.forward.  folded: packing.FoldedMade."""
+    """MADE chain + MAF.inverse / IAF.forward.  folded: packing.FoldedMade.  float32: four tcgen05 GEMMs (3xTF32,
+    bias/ReLU epilogues, masked-out K tiles skipped) + the transform kernel; float64 or tiny shapes: FP32/FP64-pipe chain."""
     v = _c(v)
     B, D = v.shape
     H = folded.H
+    if USE_TENSOR_CORE_GEMM and folded.w_split is not None and v.dtype == torch.float32 and B >= 128:
+        h, ok = v, True
+        for i in range(4):
+            hi, lo = folded.w_split[i]
+            h = linear_tc(h, hi, lo, folded.b[i], relu=(i < 3), k_extent=(folded.kext[i - 1] if i > 0 else None))
+            if h is None:
+                ok = False
+                break
+        if ok:
+            out = torch.empty_like(v)
+            ld = torch.empty(B, dtype=v.dtype, device=v.device)
+            call("nf_affine_ar_forward", ptr(v), ptr(h), ptr(out), ptr(ld), B, D, mode, L.dtype_code(v), stream())
+            return out, ld
     ws = torch.empty(2 * B * max(H, 2 * D), dtype=v.dtype, device=v.device)
     out = torch.empty_like(v)
     ld = torch.empty(B, dtype=v.dtype, device=v.device)

@@ -207,6 +207,7 @@ class FoldedMade:
     b: list
     kext: list          # per-layer int32 k-extent arrays for layers 1..3 (None entries allowed)
     gstart: torch.Tensor
+    w_split: Optional[list] = None      # [(hi, lo)] x 4: 3xTF32 operands of the tensor-core GEMM (float32 only)
 
 
 def fold_made(made) -> Optional[FoldedMade]:
@@ -242,7 +243,11 @@ def fold_made(made) -> Optional[FoldedMade]:
         return torch.tensor(out, dtype=torch.int32, device=dev)
 
     kext = [hh_ext(), hh_ext(), out_ext()]
-    return FoldedMade(D, H, w, b, kext, torch.as_tensor(gstart, device=dev))
+    folded = FoldedMade(D, H, w, b, kext, torch.as_tensor(gstart, device=dev))
+    if w[0].dtype == torch.float32 and w[0].is_cuda:
+        from . import ops
+        folded.w_split = [ops.split_tf32(t) for t in w]
+    return folded
 
 
 # ------------------------------------------------------------------------------------------------

@@ -175,6 +175,12 @@ def bench_gemm():
             bias = torch.randn(Nn, device=DEV)
             ms = timeit(lambda: ops.linear_raw(a, w, bias, relu=True), reps=3, inner=2)
         report(f"nf_gemm fp32 {name} [{M}x{Nn}x{K}]", ms, None, 2.0 * M * Nn * K)
+        if not name.startswith("dW"):
+            hi, lo = ops.split_tf32(w)
+            if ops.linear_tc(a, hi, lo, bias, relu=True) is not None:
+                ms = timeit(lambda: ops.linear_tc(a, hi, lo, bias, relu=True), reps=3, inner=4)
+                report(f"nf_linear_tc 3xTF32 {name} [{M}x{Nn}x{K}]", ms, None, 2.0 * M * Nn * K,
+                       note="tensor pipe executes 3x these FLOPs")
 
 
 def bench_stacks():
