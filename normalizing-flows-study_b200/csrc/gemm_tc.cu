@@ -255,6 +255,7 @@ extern "C" int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, c
         return NF_ERR_UNSUPPORTED;
     const size_t smem = (size_t)kGemmStages * kStageBytes + 256;
     NF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t nblocks = cdiv(N, kGemmBN) * cdiv(M, kGemmBM);
     if (nblocks > 2147483647LL) return NF_ERR_BAD_SHAPE;
     gemm_tc_kernel<<<(unsigned)nblocks, kGemmThreads, smem, (cudaStream_t)stream>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N,

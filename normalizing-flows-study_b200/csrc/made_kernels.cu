@@ -158,6 +158,7 @@ extern "C" int nf_ar_sequential_forward(const void* v, const void* w0, const voi
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;   // caller falls back to D dense passes (reference algorithm)
     cudaStream_t st = (cudaStream_t)stream;
     NF_CUDA(cudaFuncSetAttribute(ar_sequential_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NF_CUDA(cudaFuncSetAttribute(ar_sequential_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int64_t ntiles = cdiv(B, kSeqRows);
     int per_sm = 1;
     NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ar_sequential_kernel, kSeqRows * kSeqWarps, smem));

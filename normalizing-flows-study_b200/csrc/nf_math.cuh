@@ -62,6 +62,25 @@ NF_HD float sm_exp(float x) {
 // reciprocal used to normalise the softmax (one division per row of bins instead of one per bin)
 NF_HD float t_rcp(float x) { return 1.0f / x; }
 NF_HD double t_rcp(double x) { return 1.0 / x; }
+// division / logarithm inside the spline bin evaluation.  Device float: a * rcp.approx(b) (2 ulp) and lg2.approx
+// (absolute error < 4e-7 on the log-det terms, tolerance 1e-4); both cut the dependent-instruction chain of the
+// per-row spline from ~40 to ~10 cycles per operation.  Host and double: exact.
+NF_HD double t_div(double a, double b) { return a / b; }
+NF_HD float t_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+NF_HD double t_logf(double x) { return log(x); }
+NF_HD float t_logf(float x) {
+#if defined(__CUDA_ARCH__)
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
 
 template <typename T> NF_HD bool is_finite(T x) { return (x - x) == T(0); }       // false for NaN and +-Inf
 template <typename T> NF_HD T clamp_min(T x, T lo) { return x < lo ? lo : x; }    // NaN stays NaN (torch.clamp)
@@ -71,7 +90,7 @@ template <typename T> NF_HD bool pass_min(T x, T lo) { return x >= lo; }        
 template <typename T> NF_HD bool pass_mm(T x, T lo, T hi) { return x >= lo && x <= hi; }
 template <typename T> NF_HD T scrub0(T x) { return is_finite(x) ? x : T(0); }
 // F.softplus, beta=1, threshold=20
-template <typename T> NF_HD T softplus(T x) { return x > T(20) ? x : t_log1p(t_exp(x)); }
+template <typename T> NF_HD T softplus(T x) { return x > T(20) ? x : t_log1p(sm_exp(x)); }
 template <typename T> NF_HD T softplus_grad(T x) {
     if (x > T(20)) return T(1);
     T z = t_exp(x);
@@ -189,29 +208,73 @@ struct RqsCfg {
     T eps;
 };
 
+// compile-time unrolled pairwise reductions / inclusive scan over register arrays (depth log2 instead of K)
+template <typename T, int N> NF_HD T tree_max(const T* a) {
+    if constexpr (N == 1) return a[0];
+    else { const T l = tree_max<T, N / 2>(a), r = tree_max<T, N - N / 2>(a + N / 2); return (r > l) ? r : l; }
+}
+template <typename T, int N> NF_HD T tree_sum(const T* a) {
+    if constexpr (N == 1) return a[0];
+    else return tree_sum<T, N / 2>(a) + tree_sum<T, N - N / 2>(a + N / 2);
+}
+template <typename T, int N> NF_HD void inclusive_scan(T* a) {      // Hillis-Steele
+#pragma unroll
+    for (int off = 1; off < N; off <<= 1) {
+        T t[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) t[j] = (j >= off) ? a[j] + a[j - off] : a[j];
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[j] = t[j];
+    }
+}
+
 // softmax -> floor -> clamp -> cumulative knots.  wn: normalised widths (post clamp); kn: K+1 knots.
+// KMAX <= 16: max / sum / cumulative sum as trees (the per-row dependent chain is what bounds the fused stack
+// kernels; summation order differs from torch.cumsum by a few ulp).  KMAX > 16 (generic path): sequential loops.
 template <typename T, int KMAX, bool BOUNDED>
 NF_HD void rqs_knots(const T* u, int K, T floor_, T scale, const RqsCfg<T>& c, T* wn, T* kn) {
-    T mx = u[0];
+    if constexpr (KMAX <= 16) {
+        T m[KMAX];
 NF_UNROLL
-    for (int j = 1; j < KMAX; ++j) if (j < K) mx = (u[j] > mx) ? u[j] : mx;
-    T sum = T(0);
+        for (int j = 0; j < KMAX; ++j) m[j] = (j < K) ? u[j] : u[0];
+        const T mx = tree_max<T, KMAX>(m);
 NF_UNROLL
-    for (int j = 0; j < KMAX; ++j) if (j < K) { wn[j] = sm_exp(u[j] - mx); sum += wn[j]; }
-    const T inv = t_rcp(sum);
-    T run = T(0);
-    kn[0] = BOUNDED ? c.lo : T(0);
+        for (int j = 0; j < KMAX; ++j) wn[j] = (j < K) ? sm_exp(u[j] - mx) : T(0);
+        const T inv = t_rcp(tree_sum<T, KMAX>(wn));
+        T run[KMAX];
 NF_UNROLL
-    for (int j = 0; j < KMAX; ++j) if (j < K) {
-        T w = floor_ + scale * (wn[j] * inv);
-        w = clamp_min(w, c.eps);
-        wn[j] = w;
-        run += w;
-        kn[j + 1] = BOUNDED ? (c.span * run + c.lo) : run;
-    }
-    if (BOUNDED) {
+        for (int j = 0; j < KMAX; ++j) {
+            T w = floor_ + scale * (wn[j] * inv);
+            w = clamp_min(w, c.eps);
+            wn[j] = w;
+            run[j] = (j < K) ? w : T(0);
+        }
+        inclusive_scan<T, KMAX>(run);
+        kn[0] = BOUNDED ? c.lo : T(0);
 NF_UNROLL
-        for (int j = 0; j < KMAX; ++j) if (j + 1 == K) kn[j + 1] = c.hi;
+        for (int j = 0; j < KMAX; ++j) kn[j + 1] = BOUNDED ? ((j + 1 == K) ? c.hi : (c.span * run[j] + c.lo)) : run[j];
+    } else {
+        T mx = u[0];
+NF_UNROLL
+        for (int j = 1; j < KMAX; ++j) if (j < K) mx = (u[j] > mx) ? u[j] : mx;
+        T sum = T(0);
+NF_UNROLL
+        for (int j = 0; j < KMAX; ++j) if (j < K) { wn[j] = sm_exp(u[j] - mx); sum += wn[j]; }
+        const T inv = t_rcp(sum);
+        T run = T(0);
+        kn[0] = BOUNDED ? c.lo : T(0);
+NF_UNROLL
+        for (int j = 0; j < KMAX; ++j) if (j < K) {
+            T w = floor_ + scale * (wn[j] * inv);
+            w = clamp_min(w, c.eps);
+            wn[j] = w;
+            run += w;
+            kn[j + 1] = BOUNDED ? (c.span * run + c.lo) : run;
+        }
+        if (BOUNDED) {
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) if (j + 1 == K) kn[j + 1] = c.hi;
+        }
     }
 }
 
@@ -225,18 +288,45 @@ struct RqsBin {
     bool lo_edge, hi_edge;// derivative pinned to 1 at k==0 / k==K-1
 };
 
-// searchsorted(right=True)-1, clamped to [0,K-1]: the last j<K with knot_j <= v (j=0 always taken).
+// value of a[k] for a register array through a binary multiplexer tree (depth log2 N, no local memory)
+template <typename T, int N> NF_HD T mux(const T* a, int k) {
+    if constexpr (N == 1) return a[0];
+    else {
+        constexpr int H = (N + 1) / 2;
+        const T lo = mux<T, H>(a, k), hi = mux<T, N - H>(a + H, k - H);
+        return (k >= H) ? hi : lo;
+    }
+}
+
+// searchsorted(right=True)-1, clamped to [0,K-1]: the last j<K with knot_j <= v (j=0 always taken).  The knots are
+// non-decreasing (cumulative sums of positive bin sizes), so that index equals the number of knots 1..K-1 that are
+// <= v; NaN knots compare false and give bin 0, as the sequential scan did.
 template <typename T, int KMAX>
 NF_HD void rqs_select(T v, const T* sk /*search knots*/, const T* cw, const T* ch, const T* wn, const T* hn,
                       const T* ud, int K, RqsBin<T>& b) {
-    b.k = 0; b.xk = cw[0]; b.xk1 = cw[1]; b.yk = ch[0]; b.yk1 = ch[1]; b.wn = wn[0]; b.hn = hn[0];
-    b.udk = T(0); b.udk1 = ud[0];
+    if constexpr (KMAX <= 16) {
+        int cnt[KMAX];
+        cnt[0] = 0;
 NF_UNROLL
-    for (int j = 1; j < KMAX; ++j) if (j < K) {
-        if (sk[j] <= v) {
-            b.k = j; b.xk = cw[j]; b.xk1 = cw[j + 1]; b.yk = ch[j]; b.yk1 = ch[j + 1];
-            b.wn = wn[j]; b.hn = hn[j]; b.udk = ud[j - 1];
-            b.udk1 = (j < KMAX - 1) ? ud[j] : T(0);     // unused when j==K-1 (hi_edge)
+        for (int j = 1; j < KMAX; ++j) cnt[j] = (j < K && sk[j] <= v) ? 1 : 0;
+        const int k = tree_sum<int, KMAX>(cnt);
+        b.k = k;
+        b.xk = mux<T, KMAX>(cw, k); b.xk1 = mux<T, KMAX>(cw + 1, k);
+        b.yk = mux<T, KMAX>(ch, k); b.yk1 = mux<T, KMAX>(ch + 1, k);
+        b.wn = mux<T, KMAX>(wn, k); b.hn = mux<T, KMAX>(hn, k);
+        // ud[j] = raw derivative parameter of knot j+1: knot k -> ud[k-1] (k >= 1), knot k+1 -> ud[k] (k <= K-2)
+        b.udk1 = mux<T, KMAX>(ud, (k < KMAX - 1) ? k : KMAX - 1);
+        b.udk = (k >= 1) ? mux<T, KMAX>(ud, k - 1) : T(0);
+    } else {
+        b.k = 0; b.xk = cw[0]; b.xk1 = cw[1]; b.yk = ch[0]; b.yk1 = ch[1]; b.wn = wn[0]; b.hn = hn[0];
+        b.udk = T(0); b.udk1 = ud[0];
+NF_UNROLL
+        for (int j = 1; j < KMAX; ++j) if (j < K) {
+            if (sk[j] <= v) {
+                b.k = j; b.xk = cw[j]; b.xk1 = cw[j + 1]; b.yk = ch[j]; b.yk1 = ch[j + 1];
+                b.wn = wn[j]; b.hn = hn[j]; b.udk = ud[j - 1];
+                b.udk1 = (j < KMAX - 1) ? ud[j] : T(0);     // unused when j==K-1 (hi_edge)
+            }
         }
     }
     b.lo_edge = (b.k == 0);
@@ -247,19 +337,19 @@ NF_UNROLL
 template <typename T, bool BOUNDED>
 NF_HD void rqs_bin_eval(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, T eps, T& out, T& lad) {
     const T wkc = clamp_min(wk, eps);
-    const T s = hk / wkc;
+    const T s = t_div(hk, wkc);
     if (!inverse) {
-        const T xi = clamp_mm((v - xk) / wkc, T(0), T(1));
+        const T xi = clamp_mm(t_div(v - xk, wkc), T(0), T(1));
         const T om = T(1) - xi;
         const T A = dk1 + dk - T(2) * s;
         const T den0 = s + A * xi * om;
         const T denc = clamp_min(den0, eps);
         const T N1 = s * (xi * xi) + dk * xi * om;
-        out = yk + hk * N1 / denc;
+        out = yk + t_div(hk * N1, denc);
         const T num = (s * s) * (dk1 * (xi * xi) + T(2) * s * xi * om + dk * (om * om));
         const T den2 = BOUNDED ? denc * denc : den0 * den0;
-        const T der = num / clamp_min(den2, eps);
-        lad = t_log(clamp_min(der, eps));
+        const T der = t_div(num, clamp_min(den2, eps));
+        lad = t_logf(clamp_min(der, eps));
     } else {
         const T t0 = v - yk;
         const T A = dk + dk1 - T(2) * s;
@@ -270,18 +360,18 @@ NF_HD void rqs_bin_eval(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, 
         const T disc = clamp_min(b * b - T(4) * a * c, T(0));
         T q = -b - t_sqrt(disc);
         if (BOUNDED) { if (t_abs(q) < eps) q = eps; }
-        const T xi = clamp_mm((T(2) * c) / q, T(0), T(1));
+        const T xi = clamp_mm(t_div(T(2) * c, q), T(0), T(1));
         out = xi * wk + xk;
         const T om = T(1) - xi;
         const T Q = dk1 * (xi * xi) + (BOUNDED ? T(2) * s * xi * om : T(2) * s * (xi * om)) + dk * (om * om);
         const T num = (s * s) * Q;
         if (BOUNDED) {
             const T den0 = s + (dk1 + dk - T(2) * s) * xi * om;
-            lad = -t_log(clamp_min(num, eps)) + T(2) * t_log(clamp_min(den0, eps));
+            lad = -t_logf(clamp_min(num, eps)) + T(2) * t_logf(clamp_min(den0, eps));
         } else {
             const T den0 = s + A * (xi * om);
-            const T der = num / clamp_min(den0 * den0, eps);
-            lad = -t_log(clamp_min(der, eps));
+            const T der = t_div(num, clamp_min(den0 * den0, eps));
+            lad = -t_logf(clamp_min(der, eps));
         }
     }
 }

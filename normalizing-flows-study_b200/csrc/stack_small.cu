@@ -346,6 +346,7 @@ static int launch_stack(Kern kern, size_t smem_bytes, int rows_per_cta, const vo
                         void* ld, int64_t B, int inverse, int extra, bool has_extra, cudaStream_t st) {
     if (smem_bytes > 227 * 1024) return NF_ERR_UNSUPPORTED;
     NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStackThreads, smem_bytes));
     if (per_sm < 1) return NF_ERR_UNSUPPORTED;

@@ -356,8 +356,10 @@ extern "C" int nf_spline_stack_tc_forward(const void* packed, const void* hdr_ho
     do {                                                                                                             \
         auto kern = spline_stack_tc_kernel<DMv, KMv, KSv>;                                                           \
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        int per_sm = 0;                                                                                              \
-        NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTcThreads, smem));                     \
+        /* ask for the largest shared-memory carveout: with the default preference the driver sizes the SM for ONE   \
+           CTA of this kernel and the second co-resident CTA (the latency hiding of this design) never arrives */    \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        int per_sm = (int)((227 * 1024) / (smem + 1024));                                                            \
         if (per_sm < 1) return NF_ERR_UNSUPPORTED;                                                                   \
         if (per_sm > 512 / kTmemCols) per_sm = 512 / kTmemCols;   /* TMEM: 512 columns per SM */                     \
         const int64_t cap = (int64_t)kNumSMs * per_sm;                                                               \

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Training-step throughput of the layered (autograd) route, optionally data-parallel over NCCL.
+
+    python scripts/train_step_bench.py --model realnvp256 --batch 65536 --steps 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        scripts/train_step_bench.py --model realnvp256 --batch 65536 --steps 5
+
+One step = inverse -> NLL (standard-normal head kernel) -> backward -> gradient allreduce (N > 1) -> Adam.
+--batch is per GPU (weak scaling).  Prints one JSON line on rank 0; with N > 1 it also checks that every rank holds
+identical parameters after the run (the allreduce really synchronised them).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import nfb200 as N  # noqa: E402
+
+MODELS = {
+    "realnvp2": lambda: (N.RealNVP(2, 8, 64), 2),                                   # C1
+    "realnvp256": lambda: (N.RealNVP(256, 8, 512), 256),                            # C5a
+    "maf256": lambda: (N.NormalizingFlowModel([N.MaskedAutoregressiveFlow(256, 1024) for _ in range(4)]), 256),   # C5b
+    "maf64": lambda: (N.MaskedAutoregressiveFlow(64, 512), 64),                     # C3 (training direction)
+    "spline784": lambda: (N.RealNVPSpline(784, 16, 1024), 784),                     # C4
+    "spline2": lambda: (N.NormalizingFlowModel([N.SplineCouplingLayer(2, 64, m, num_bins=8) for m in
+                                                [torch.tensor([1., 0.]) if i % 2 == 0 else torch.tensor([0., 1.]) for i in range(8)]]), 2),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="realnvp256", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)            # different init per rank: the wrapper must broadcast rank 0's weights
+    model, D = MODELS[a.model]()
+    model.to(dev).train()
+    dp = N.parallel.DataParallelFlow(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn(a.batch, D, device=dev, generator=gen)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        z, ld = dp.inverse(x)
+        loss = -N.ops.std_normal_log_prob(z, ld).mean()
+        loss.backward()
+        dp.sync_gradients()
+        opt.step()
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = N._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    in_sync = True
+    if world > 1:
+        for p in model.parameters():
+            ref = p.detach().clone()
+            dist.broadcast(ref, src=0)
+            in_sync &= bool(torch.equal(ref, p.detach()))
+        flag = torch.tensor([int(in_sync)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        in_sync = bool(flag.item())
+    if rank == 0:
+        nparam = sum(p.numel() for p in model.parameters())
+        print(json.dumps({"model": a.model, "n_gpus": world, "batch_per_gpu": a.batch, "ms_per_step": ms.item(),
+                          "samples_per_s": a.batch * world / (ms.item() * 1e-3), "loss": float(loss),
+                          "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
+                          "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
+                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
