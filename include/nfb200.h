@@ -219,13 +219,24 @@ NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
 
 /* ---- a8/a10 and the conditioner MLPs on the tensor cores: y[M,N] = relu?(x[M,K] * W[N,K]^T + bias) ---------
  * fp32 in / fp32 out, 3xTF32 on tcgen05 (fp32-accurate), TMA-fed, accumulators in TMEM (csrc/gemm_tc.cu).
- * w_hi / w_lo: the split of W produced by nf_split_tf32 ([N,K] each, K contiguous).  ldx / ldy: row pitches in
- * elements.  k_extent as in nf_gemm.  Requires 16-byte aligned x / w_hi / w_lo and K % 4 == 0, ldx % 4 == 0
- * (NF_ERR_UNSUPPORTED otherwise: use nf_gemm). */
+ * w_hi / w_lo: the split of W produced by nf_split_tf32 (K contiguous).  ldx / ldw / ldy: row pitches in elements
+ * (sub-matrices of larger arrays are addressed by pointer offset + pitch).  k_extent as in nf_gemm.  Requires
+ * 16-byte aligned x / w_hi / w_lo and ldx % 4 == 0, ldw % 4 == 0 (NF_ERR_UNSUPPORTED otherwise: use nf_gemm). */
 NF_API int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N,
-                 int64_t K, int64_t ldx, int64_t ldy, int relu, const int32_t* k_extent, nf_stream_t stream);
+                 int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_extent,
+                 nf_stream_t stream);
 /* hi = w with the 13 low mantissa bits cleared (exactly representable in TF32), lo = w - hi; n elements, fp32 */
 NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_stream_t stream);
+
+/* ---- a12/a13 sequential directions, blocked: dense contributions of previous degree blocks on tcgen05
+ * (nf_linear_tc on column slices), in-block dependent steps in a small-footprint kernel (csrc/ar_blocked.cu).
+ * w / w_hi / w_lo / b: arrays of 4 device pointers (mask-folded, degree-sorted weights of the 4 MADE layers, their
+ * TF32 splits, biases); gstart: int32[D+1] (device and host copies); workspace: nf_ar_blocked_workspace_floats()
+ * floats; block_degrees: consecutive degrees per block (8).  float32; D % 4 == 0 and H % 4 == 0. */
+NF_API int nf_ar_blocked_forward(const void* v, const void* const* w, const void* const* w_hi, const void* const* w_lo,
+                          const void* const* b, const int32_t* gstart_dev, const int32_t* gstart_host, void* workspace,
+                          void* out, void* ld, int64_t B, int D, int H, int mode, int block_degrees, nf_stream_t stream);
+NF_API int64_t nf_ar_blocked_workspace_floats(int64_t B, int D, int H);
 
 /* ---- unit-test hook of the tcgen05 tile primitive (csrc/tc_common.cuh): D[128,N] = A[128,64] * W[N,64]^T.
  * w_images: the hi then the lo K-major SWIZZLE_128B image of W (packing.umma_sw128_images); N % 16 == 0, <= 128;

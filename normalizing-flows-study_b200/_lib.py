@@ -58,8 +58,10 @@ _SIGNATURES = {
     "nf_std_normal_log_prob_forward": [_P] * 3 + [_L, _I, _I, _P],
     "nf_std_normal_log_prob_backward": [_P] * 3 + [_L, _I, _I, _P],
     "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P, _I, _P],
-    "nf_linear_tc": [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _P, _P],
+    "nf_linear_tc": [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P, _P],
     "nf_split_tf32": [_P, _P, _P, _L, _P],
+    "nf_ar_blocked_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "nf_ar_blocked_workspace_floats": [_L, _I, _I],
     "nf_spline_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
     "nf_spline_stack_tc_block_words": [_I, _I, _I],
 }
@@ -70,6 +72,7 @@ _RESTYPES = {
     "nf_spline_stack_packed_floats": _L,
     "nf_coupling_stack_packed_floats": _L,
     "nf_spline_stack_tc_block_words": _L,
+    "nf_ar_blocked_workspace_floats": _L,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

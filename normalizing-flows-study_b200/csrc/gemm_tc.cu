@@ -20,8 +20,14 @@
 
 namespace nf {
 
-constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32;
-constexpr int kGemmStages = 2;                 // shared-memory stages per CTA (x2 CTAs per SM)
+#ifndef NF_GEMM_BN
+#define NF_GEMM_BN 128
+#endif
+#ifndef NF_GEMM_STAGES
+#define NF_GEMM_STAGES 2
+#endif
+constexpr int kGemmBM = 128, kGemmBN = NF_GEMM_BN, kGemmBK = 32;
+constexpr int kGemmStages = NF_GEMM_STAGES;                 // shared-memory stages per CTA (x2 CTAs per SM)
 constexpr int kGemmAStages = 2;                // TMEM A-operand stages
 constexpr int kGemmThreads = 192;              // 6 warps
 constexpr int kGemmTmemCols = 256;             // D: 128 | A stage 0: hi 32 + lo 32 | A stage 1: hi 32 + lo 32
@@ -242,16 +248,16 @@ extern "C" int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, n
 }
 
 extern "C" int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M,
-                            int64_t N, int64_t K, int64_t ldx, int64_t ldy, int relu, const int32_t* k_extent,
-                            nf_stream_t stream) {
-    if (M < 0 || N < 1 || K < 1 || ldx < K || ldy < N) return NF_ERR_BAD_SHAPE;
+                            int64_t N, int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu,
+                            const int32_t* k_extent, nf_stream_t stream) {
+    if (M < 0 || N < 1 || K < 1 || ldx < K || ldw < K || ldy < N) return NF_ERR_BAD_SHAPE;
     if (M == 0) return NF_OK;
     NF_REQ(x); NF_REQ(w_hi); NF_REQ(w_lo); NF_REQ(y);
     // TMA: 16-byte aligned bases and row pitches
-    if (!aligned16(x) || !aligned16(w_hi) || !aligned16(w_lo) || (ldx % 4) != 0 || (K % 4) != 0) return NF_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w_hi) || !aligned16(w_lo) || (ldx % 4) != 0 || (ldw % 4) != 0) return NF_ERR_UNSUPPORTED;
     if (M > 2147483647LL - 128 || N > 2147483647LL - 128 || K > 2147483647LL - 64) return NF_ERR_BAD_SHAPE;
     alignas(64) CUtensorMap tx, twh, twl;
-    if (!make_map(&tx, x, M, K, ldx, kGemmBM) || !make_map(&twh, w_hi, N, K, K, kGemmBN) || !make_map(&twl, w_lo, N, K, K, kGemmBN))
+    if (!make_map(&tx, x, M, K, ldx, kGemmBM) || !make_map(&twh, w_hi, N, K, ldw, kGemmBN) || !make_map(&twl, w_lo, N, K, ldw, kGemmBN))
         return NF_ERR_UNSUPPORTED;
     const size_t smem = (size_t)kGemmStages * kStageBytes + 256;
     NF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

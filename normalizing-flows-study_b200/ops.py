@@ -65,7 +65,9 @@ def linear_tc(x, w_hi, w_lo, bias=None, relu=False, k_extent=None, out=None):
     N = w_hi.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
-    ok = L.try_call("nf_linear_tc", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, N, int(relu),
+    if K % 4 != 0:
+        return None
+    ok = L.try_call("nf_linear_tc", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, K, N, int(relu),
                     ptr(k_extent), stream())
     return out if ok else None
 
@@ -527,10 +529,44 @@ def made_affine(v, folded, mode):
     return out, ld
 
 
+AR_BLOCK_DEGREES = 8
+
+
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def ar_sequential_blocked(v, folded, mode):
+    """MAF.forward / IAF.inverse, blocked: previous-block contributions on tcgen05, in-block steps in ar_block_kernel.
+    Returns None when the configuration is not taken (no TF32 splits, D or H not a multiple of 4)."""
+    if folded.w_split is None or v.dtype != torch.float32 or folded.D % 4 or folded.H % 4:
+        return None
+    v = _c(v)
+    B, D = v.shape
+    H = folded.H
+    nws = L.lib().nf_ar_blocked_workspace_floats(B, D, H)
+    ws = torch.empty(nws, dtype=torch.float32, device=v.device)
+    out = torch.empty_like(v)
+    ld = torch.empty(B, dtype=v.dtype, device=v.device)
+    w = _ptr_array(folded.w)
+    whi = _ptr_array([s[0] for s in folded.w_split])
+    wlo = _ptr_array([s[1] for s in folded.w_split])
+    bb = _ptr_array(folded.b)
+    ok = L.try_call("nf_ar_blocked_forward", ptr(v), w, whi, wlo, bb, ptr(folded.gstart), folded.gstart_host.ctypes.data,
+                    ptr(ws), ptr(out), ptr(ld), B, D, H, mode, AR_BLOCK_DEGREES, stream())
+    return (out, ld) if ok else None
+
+
 def ar_sequential(v, folded, mode):
-    """MAF.forward / IAF.inverse incremental kernel; returns None when unsupported (H too large, fp64)."""
+    """MAF.forward / IAF.inverse: blocked tensor-core evaluation for wide conditioners, otherwise the one-launch
+    incremental kernel; returns None when unsupported (H too large for it, fp64)."""
     if v.dtype != torch.float32:
         return None
+    if USE_TENSOR_CORE_GEMM and folded.H >= 128 and folded.D >= 2 * AR_BLOCK_DEGREES and v.shape[0] >= 1024:
+        res = ar_sequential_blocked(v, folded, mode)
+        if res is not None:
+            return res
     v = _c(v)
     B, D = v.shape
     out = torch.empty_like(v)

@@ -208,6 +208,7 @@ class FoldedMade:
     kext: list          # per-layer int32 k-extent arrays for layers 1..3 (None entries allowed)
     gstart: torch.Tensor
     w_split: Optional[list] = None      # [(hi, lo)] x 4: 3xTF32 operands of the tensor-core GEMM (float32 only)
+    gstart_host: Optional[np.ndarray] = None
 
 
 def fold_made(made) -> Optional[FoldedMade]:
@@ -244,6 +245,7 @@ def fold_made(made) -> Optional[FoldedMade]:
 
     kext = [hh_ext(), hh_ext(), out_ext()]
     folded = FoldedMade(D, H, w, b, kext, torch.as_tensor(gstart, device=dev))
+    folded.gstart_host = np.ascontiguousarray(gstart, dtype=np.int32)
     if w[0].dtype == torch.float32 and w[0].is_cuda:
         from . import ops
         folded.w_split = [ops.split_tf32(t) for t in w]
