@@ -35,6 +35,15 @@ def wants_grad(module: nn.Module, *tensors) -> bool:
     return any(p.requires_grad for p in module.parameters())
 
 
+def compute_input(v):
+    """Inputs arriving in half precision (a caller running under torch.autocast, e.g. the reference's
+    MixedPrecisionFlow wrapper, optimization/mixed_precision.py:89-105) are widened: the kernels compute in the
+    parameters' float32 / float64, which is what autocast leaves these ops in anyway."""
+    if v.dtype in (torch.float16, torch.bfloat16):
+        return v.float()
+    return v
+
+
 def _module_tensors(module: nn.Module):
     return list(module.parameters()) + list(module.buffers())
 
@@ -164,6 +173,7 @@ class CouplingLayer(Flow):
                 and self.data_dim <= packing.DMAX and self.s_net[0].out_features <= 128)
 
     def _run(self, v, inverse):
+        v = compute_input(v)
         if not wants_grad(self, v) and self.fusable(v):
             pk = self._pack.get(_module_tensors(self), lambda: packing.pack_coupling_stack([self], None))
             if pk is not None:
@@ -234,6 +244,7 @@ class SplineCouplingLayer(Flow):
                 and 2 <= self.num_bins <= 16)
 
     def _run(self, v, inverse):
+        v = compute_input(v)
         if not wants_grad(self, v) and self.fusable(v):
             out = run_spline_stack(self._pack, _module_tensors(self), [self], None, v, inverse)
             if out is not None:
@@ -274,6 +285,7 @@ def rational_quadratic_spline(inputs, widths, heights, derivatives, inverse=Fals
                               min_bin_height=1e-3, min_derivative=1e-3, epsilon=1e-6):
     """Public spline on [0,1] (rational_quadratic_spline.py:4-104): per-element outputs and log|dy/dx|.
     `epsilon` is accepted and ignored, as in the reference (it is overwritten with 1e-6, :19)."""
+    inputs, widths, heights, derivatives = (compute_input(t) for t in (inputs, widths, heights, derivatives))
     K = widths.shape[-1]
     x = inputs.reshape(-1)
     y, ld = ops.rqs_unit(x, widths.reshape(-1, K), heights.reshape(-1, K), derivatives.reshape(-1, K - 1), inverse,
@@ -387,6 +399,7 @@ class _AffineAutoregressive(Flow):
         self.conditioner = MADE(dim, hidden_dim, 2, use_batch_norm=use_batch_norm)
 
     def _parallel(self, v):
+        v = compute_input(v)
         if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
             f = self.conditioner.folded()
             if f is not None and f.w[0].dtype == v.dtype:
@@ -394,6 +407,7 @@ class _AffineAutoregressive(Flow):
         return ops.affine_ar(v, self.conditioner(v), self._mode_parallel)
 
     def _sequential(self, v):
+        v = compute_input(v)
         if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
             f = self.conditioner.folded()
             if f is not None and f.w[0].dtype == v.dtype:
@@ -476,6 +490,7 @@ class ChainPlan:
     def run(self, flows, bns, training, v, inverse):
         """(y, log_det) from one fused launch, or None when the chain must be walked layer by layer."""
         flows = list(flows)
+        v = compute_input(v)
         if not flows or not v.is_cuda or v.dim() != 2:
             return None
         if bns is not None and training:          # train mode moves the running statistics layer by layer

@@ -1,0 +1,128 @@
+"""GPU: the reference's optimisation wrappers keep working around the CUDA modules: autocast
+regions (MixedPrecisionFlow, optimization/mixed_precision.py:89-105), activation checkpointing (CheckpointedFlow,
+optimization/gradient_checkpointing.py:36-64), Flow.log_prob / Flow.sample, clip_grad_norm_, deepcopy / state_dict
+round trips, and the samples_per_sec harness recipe (plots/_common.py:264-274)."""
+import copy
+import time
+
+import pytest
+import torch
+from torch.utils.checkpoint import checkpoint
+
+import nfb200 as N
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _models():
+    torch.manual_seed(0)
+    alt = torch.tensor([1., 0., 1., 0.])
+    ms = {
+        "realnvp": N.RealNVP(4, 4, 16),
+        "spline": N.RealNVPSpline(4, 2, 16),
+        "maf": N.SequentialFlow([N.MaskedAutoregressiveFlow(4, 16), N.MaskedAutoregressiveFlow(4, 16)]),
+        "iaf": N.InverseAutoregressiveFlow(4, 16),
+        "coupling": N.CouplingLayer(4, 16, alt),
+    }
+    gen = torch.Generator().manual_seed(1)
+    for m in ms.values():
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.1 * torch.randn(p.shape, generator=gen))
+        m.to(DEV)
+    return ms
+
+
+@pytest.mark.parametrize("amp_dtype", [torch.bfloat16, torch.float16])
+def test_autocast_regions(amp_dtype):
+    for name, m in _models().items():
+        m.eval()
+        x = torch.randn(64, 4, device=DEV)
+        with torch.no_grad():
+            ref = m.inverse(x)
+            with torch.autocast("cuda", dtype=amp_dtype):
+                got = m.inverse(x)
+                got_half = m.inverse(x.to(amp_dtype))          # half inputs are widened, not rejected
+        assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]), name
+        assert got_half[0].dtype == torch.float32 and torch.isfinite(got_half[0]).all()
+        # training under autocast with a GradScaler-free bf16 recipe
+        m.train()
+        xt = torch.randn(64, 4, device=DEV)
+        with torch.autocast("cuda", dtype=amp_dtype):
+            z, ld = m.inverse(xt)
+            loss = -(N.ops.std_normal_log_prob(z, ld)).mean()
+        loss.backward()
+        assert all(p.grad is None or torch.isfinite(p.grad).all() for p in m.parameters()), name
+
+
+def test_activation_checkpointing_matches_plain_backward():
+    for name, m in _models().items():
+        m.eval()
+        x = torch.randn(32, 4, device=DEV, requires_grad=True)
+        z, ld = m.inverse(x)
+        (z.sum() + ld.sum()).backward()
+        g_plain = [p.grad.clone() for p in m.parameters() if p.grad is not None]
+        gx_plain = x.grad.clone()
+        m.zero_grad()
+        x.grad = None
+        z2, ld2 = checkpoint(m.inverse, x, use_reentrant=False)
+        (z2.sum() + ld2.sum()).backward()
+        g_ckpt = [p.grad for p in m.parameters() if p.grad is not None]
+        assert torch.allclose(gx_plain, x.grad, rtol=1e-6, atol=1e-7), name
+        assert len(g_plain) == len(g_ckpt) and all(torch.allclose(a, b, rtol=1e-6, atol=1e-7) for a, b in zip(g_plain, g_ckpt)), name
+
+
+def test_flow_log_prob_and_sample_api():
+    base = torch.distributions.Normal(torch.zeros(4, device=DEV), torch.ones(4, device=DEV))
+    mv = torch.distributions.MultivariateNormal(torch.zeros(4, device=DEV), torch.eye(4, device=DEV))
+    for name in ("maf", "iaf", "coupling"):
+        m = _models()[name].eval()
+        x = torch.randn(16, 4, device=DEV)
+        with torch.no_grad():
+            lp = m.log_prob(x, base)
+            lp2 = m.log_prob(x, mv)
+            z, ld = m.inverse(x)
+            fused = N.ops.std_normal_log_prob(z, ld)
+            s = m.sample(8, base, device=DEV)
+        assert lp.shape == (16,) and torch.allclose(lp, lp2, atol=1e-5) and torch.allclose(lp, fused, atol=1e-5), name
+        assert s.shape == (8, 4) and torch.isfinite(s).all()
+
+
+def test_clip_grad_deepcopy_state_dict_roundtrip():
+    m = _models()["realnvp"]
+    m.train()
+    x = torch.randn(128, 4, device=DEV)
+    z, ld = m.inverse(x)
+    (-(N.ops.std_normal_log_prob(z, ld)).mean()).backward()
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    assert torch.isfinite(total)
+    m.eval()
+    m2 = copy.deepcopy(m)
+    m3 = N.RealNVP(4, 4, 16).to(DEV).eval()
+    m3.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        a, b, c = m.forward(x), m2.forward(x), m3.forward(x)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    # packed-weight caches follow in-place parameter updates
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.01)
+        d = m.forward(x)
+    assert not torch.equal(a[0], d[0])
+
+
+def test_reference_samples_per_sec_recipe():
+    """plots/_common.py:264-274: model.forward(z), n=4000, dim=2, eval, 1 warm-up + 3 reps."""
+    torch.manual_seed(0)
+    m = N.RealNVPSpline(2, 8, 64).to(DEV).eval()
+    z = torch.randn(4000, 2, device=DEV)
+    with torch.no_grad():
+        m.forward(z)
+        torch.cuda.synchronize()
+        t = time.time()
+        for _ in range(3):
+            x, _ = m.forward(z)
+        torch.cuda.synchronize()
+        dt = (time.time() - t) / 3
+    assert x.shape == (4000, 2) and 4000 / dt > 1e5
