@@ -214,6 +214,11 @@ NF_API int nf_std_normal_log_prob_backward(const void* z, const void* glp, void*
  * follows the tensor-core layout (csrc/stack_tc.cu; magic 'NFS2').  NF_ERR_UNSUPPORTED otherwise. */
 NF_API int nf_spline_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
                                void* ld, int64_t B, int inverse, nf_stream_t stream);
+/* affine coupling stack (eval mode) on the tensor cores: same contract as nf_coupling_stack_forward for hidden_dim <= 64;
+ * `packed` in the tensor-core layout (magic 'NFA2': two net blocks per layer, csrc/stack_tc.cu). */
+NF_API int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
+                                 void* y, void* ld, int64_t B, int inverse, nf_stream_t stream);
+NF_API int64_t nf_coupling_stack_tc_block_words(int D);
 /* words per layer block of that layout (-1 if the configuration is not supported) */
 NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
 
@@ -225,7 +230,7 @@ NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
 NF_API int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N,
                  int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_extent,
                  nf_stream_t stream);
-/* hi = w with the 13 low mantissa bits cleared (exactly representable in TF32), lo = w - hi; n elements, fp32 */
+/* hi = w rounded to the nearest TF32, lo = (w - hi) rounded to the nearest TF32; n elements, fp32 */
 NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_stream_t stream);
 
 /* ---- a12/a13 sequential directions, blocked: dense contributions of previous degree blocks on tcgen05

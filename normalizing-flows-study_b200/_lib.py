@@ -64,6 +64,8 @@ _SIGNATURES = {
     "nf_ar_blocked_workspace_floats": [_L, _I, _I],
     "nf_spline_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
     "nf_spline_stack_tc_block_words": [_I, _I, _I],
+    "nf_coupling_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
+    "nf_coupling_stack_tc_block_words": [_I],
 }
 _RESTYPES = {
     "nf_status_string": _c.c_char_p,
@@ -73,6 +75,7 @@ _RESTYPES = {
     "nf_coupling_stack_packed_floats": _L,
     "nf_spline_stack_tc_block_words": _L,
     "nf_ar_blocked_workspace_floats": _L,
+    "nf_coupling_stack_tc_block_words": _L,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -189,12 +189,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     if (warp == 1) tc::tmem_dealloc(tb, kGemmTmemCols);
 }
 
-// W = hi + lo, hi = W with the low 13 mantissa bits cleared (exact TF32), lo = W - hi (exact)
+// W ~= hi + lo: hi = W rounded to the nearest TF32, lo = (W - hi) rounded to the nearest TF32 (|W - hi - lo| <= 2^-24 |W|)
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         uint32_t h, l;
-        tc::split_tf32(w[i], h, l);
+        tc::split_tf32_weight(w[i], h, l);
         hi[i] = __uint_as_float(h);
         lo[i] = __uint_as_float(l);
     }

@@ -321,6 +321,152 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------
+// affine coupling stack (eval mode; conditioner BatchNorm folded into the Linears at pack time)
+//   per layer two conditioner nets (s_net, b_net: coupling_layer.py:18-35) run one after the other through the same
+//   TMEM regions; the staging unit is one NET block (header lead + W1k | b2 | b3 | W2 hi/lo | W3 hi/lo, ~43 KB), double
+//   buffered: while net b computes, the next layer's net s arrives.  Head: D outputs padded to 16 columns.
+// ------------------------------------------------------------------------------------------------
+template <int DM>
+__global__ void __launch_bounds__(kTcThreads, 2)
+coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
+                         float* __restrict__ ld, int64_t B, int inverse) {
+    extern __shared__ __align__(1024) float sbuf[];
+    const TcHdr hd = read_tc_hdr(packed);
+    const int D = hd.D, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, NBW = hd.blk_words;       // NBW: words per net block
+    float* sx = sbuf + (size_t)2 * NBW;                          // [kTcSub][DM+1][128] row state
+    float* sraw = sx + kTcSub * (DM + 1) * kTcThreads;           // [kTcSub][DM][128] raw s_net outputs
+    float* shdr = sraw + kTcSub * DM * kTcThreads;               // [80] layer header (outlives the net-s buffer)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(shdr + NF_LAYER_HDR);
+    uint64_t& bar = bars[0];
+    uint64_t* wbar = bars + 1;
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 3);
+    const BlkOff off = blk_offsets(W1S, NO3);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1); tc::fence_mbar_init(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0, wphase = 0u;
+
+    constexpr int ROWS = kTcThreads * kTcSub;
+    const int64_t ntiles = (B + ROWS - 1) / ROWS;
+    const float* blocks = packed + NF_STACK_HDR;
+    const int NQ = 2 * L;                                         // net blocks per pass, order: layer (direction-aware), net
+    auto block_of = [&](int q) { const int li = q >> 1; return (size_t)(2 * (inverse ? L - 1 - li : li) + (q & 1)) * NBW; };
+
+    int buf = 0;
+    if (tid == 0 && (int64_t)blockIdx.x < ntiles) {
+        tc::mbar_arrive_expect_tx(&wbar[0], (uint32_t)NBW * 4u);
+        tc::bulk_g2s(sbuf, blocks + block_of(0), (uint32_t)NBW * 4u, &wbar[0]);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+        for (int s = 0; s < kTcSub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+#pragma unroll
+            for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = (d < D && r < B) ? ld_stream(x + r * D + d) : 0.f;
+            sx[(s * (DM + 1) + DM) * kTcThreads + tid] = 0.f;
+        }
+        for (int q = 0; q < NQ; ++q) {
+            const int net = q & 1;
+            tc::fence_proxy_async_smem();
+            __syncthreads();                                      // everyone is done with the other buffer
+            if (tid == 0) {
+                const bool last = (q == NQ - 1);
+                if (!last || (tile + gridDim.x < ntiles)) {
+                    tc::mbar_arrive_expect_tx(&wbar[buf ^ 1], (uint32_t)NBW * 4u);
+                    tc::bulk_g2s(sbuf + (size_t)(buf ^ 1) * NBW, blocks + block_of(last ? 0 : q + 1), (uint32_t)NBW * 4u, &wbar[buf ^ 1]);
+                }
+            }
+            tc::mbar_wait(&wbar[buf], (wphase >> buf) & 1u);
+            wphase ^= (1u << buf);
+            const float* sN = sbuf + (size_t)buf * NBW;
+            if (net == 0) {
+                if (tid < NF_LAYER_HDR) shdr[tid] = sN[tid];
+                __syncthreads();
+            }
+            const float* nb = sN + NF_LAYER_HDR;
+            const int* meta = reinterpret_cast<const int*>(shdr + 16);
+            const bool bn_on = meta[2] != 0;
+            const float* mask = shdr;
+            const uint32_t w2hi = tc::smem_u32(nb + off.w2hi), w2lo = tc::smem_u32(nb + off.w2lo);
+            const uint32_t w3hi = tc::smem_u32(nb + off.w3hi), w3lo = tc::smem_u32(nb + off.w3lo);
+#pragma unroll 1
+            for (int s = 0; s < kTcSub; ++s) {
+                float xv[DM], tot;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                if (net == 0 && inverse && bn_on) {
+                    bn_between_tc<DM>(shdr, D, true, xv, tot);
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = xv[d];
+                    sx[(s * (DM + 1) + DM) * kTcThreads + tid] = tot;
+                }
+                float xa[DM];
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xa[d] = (d < D) ? xv[d] * mask[d] : 0.f;
+                layer1_to_tmem<DM>(nb + off.w1k, W1S, xa, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, 64u, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                hidden2_to_tmem(nb + off.b2, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD3, kColAhi, kColAlo, w3hi, w3lo, (uint32_t)NO3, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                uint32_t p[8];
+                tc::tmem_ld8(lane_addr + kColD3, p);
+                tc::wait_ld();
+                float raw[DM];
+#pragma unroll
+                for (int d = 0; d < DM; ++d) raw[d] = __uint_as_float(p[d]) + nb[off.b3 + d];
+                if (net == 0) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) sraw[(s * DM + d) * kTcThreads + tid] = raw[d];
+                } else {
+                    float lsum = 0.f;
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) {
+                        float out, t;
+                        affine_coupling_elem<float>(xv[d], mask[d], sraw[(s * DM + d) * kTcThreads + tid], raw[d], inverse != 0, out, t);
+                        xv[d] = scrub0(out);
+                        lsum += t;
+                    }
+                    tot += scrub0(lsum);
+                    if (!inverse && bn_on) bn_between_tc<DM>(shdr, D, false, xv, tot);
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = xv[d];
+                    sx[(s * (DM + 1) + DM) * kTcThreads + tid] = tot;
+                }
+            }
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int s = 0; s < kTcSub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+            if (r < B) {
+#pragma unroll
+                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + tid]);
+                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + tid]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, kTmemCols);
+}
+
 }  // namespace nf
 
 using namespace nf;
@@ -389,3 +535,45 @@ extern "C" __attribute__((visibility("default"))) int nf_debug_tc_profile(long l
     return cudaMemcpyFromSymbol(out, nf::g_tc_prof, sizeof(long long) * 8) == cudaSuccess ? 0 : -4;
 }
 #endif
+
+extern "C" int64_t nf_coupling_stack_tc_block_words(int D) {
+    if (D < 1 || D > NF_STACK_DMAX) return -1;
+    return NF_LAYER_HDR + blk_offsets(nf_stack_w1s(D), 16).net_words;      // words per NET block (2 per layer)
+}
+
+extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
+                                            void* y, void* ld, int64_t B, int inverse, nf_stream_t stream) {
+    if (B < 0) return NF_ERR_BAD_SHAPE;
+    NF_REQ(hdr_host);
+    if (B == 0) return NF_OK;
+    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    if (!aligned16(packed)) return NF_ERR_MISALIGNED;
+    const int32_t* h = (const int32_t*)hdr_host;
+    if (h[0] != NF_STACK_MAGIC_AFFINE_TC) return NF_ERR_BAD_SHAPE;
+    const int D = h[1], H = h[2], L = h[5], W1S = h[6], NO3 = h[7], NBW = h[8];
+    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 64 || L < 1 || NO3 != 16) return NF_ERR_UNSUPPORTED;
+    if (W1S != nf_stack_w1s(D) || NBW != NF_LAYER_HDR + blk_offsets(W1S, NO3).net_words) return NF_ERR_BAD_SHAPE;
+    if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)2 * L * NBW)) return NF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
+    const size_t smem = sizeof(float) * ((size_t)2 * NBW + (size_t)kTcSub * (2 * DMh + 1) * kTcThreads + NF_LAYER_HDR + 8);
+    if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
+    const int64_t ntiles = cdiv(B, kTcThreads * kTcSub);
+#define NF_CTC(DMv)                                                                                                  \
+    do {                                                                                                             \
+        auto kern = coupling_stack_tc_kernel<DMv>;                                                                   \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        int per_sm = (int)((227 * 1024) / (smem + 1024));                                                            \
+        if (per_sm < 1) return NF_ERR_UNSUPPORTED;                                                                   \
+        if (per_sm > 512 / kTmemCols) per_sm = 512 / kTmemCols;                                                      \
+        const int64_t cap = (int64_t)kNumSMs * per_sm;                                                               \
+        const int grid = (int)(ntiles < cap ? ntiles : cap);                                                         \
+        kern<<<grid, kTcThreads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, inverse); \
+    } while (0)
+    if (D <= 2) NF_CTC(2); else if (D <= 3) NF_CTC(4); else NF_CTC(8);
+#undef NF_CTC
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}

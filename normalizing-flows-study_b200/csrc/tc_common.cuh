@@ -3,8 +3,8 @@
 //
 // Conventions used by every kernel here:
 //   * operands are fp32 containers read as TF32 by the tensor core; fp32 accuracy comes from the 3xTF32 split
-//       a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   x_hi = x & 0xffffe000 (exact TF32), x_lo = x - x_hi (exact fp32)
-//     (the dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22) relative);
+//       a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,   x_hi = x rounded to TF32, x_lo = x - x_hi (exact in fp32)
+//     (the dropped a_lo*b_lo term and the truncation of a_lo are O(2^-23) relative);
 //   * B (weights, [N][K] row-major = K-major) lives in shared memory in the canonical UMMA K-major SWIZZLE_128B
 //     layout: K is cut into atoms of 32 floats (128 B); inside an atom block row n occupies 128 B at
 //     (n/8)*1024 + (n%8)*128 and its eight 16-byte chunks are XOR-swizzled with (n%8); the host packs that image;
@@ -145,9 +145,17 @@ __device__ __forceinline__ void warp_issue_gemm_k64_3xtf32(uint32_t tmem_base, u
 }
 
 // ---- 3xTF32 split -----------------------------------------------------------------------------------
+// hi = a rounded to the nearest TF32 (add half an ulp of the 13 dropped bits, then clear them; the carry walks into
+// the exponent correctly, Inf stays Inf), lo = a - hi exactly, |lo| <= 2^-12 |a|.  The tensor core truncates lo to
+// TF32 (error <= 2^-23 |a|); with the dropped lo*lo term the 3-pass product is within ~2.4e-7 of sum |a||b|.
 __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(a) & 0xffffe000u;
+    hi = (__float_as_uint(a) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(a - __uint_as_float(hi));
+}
+// weights (split once per weight version): lo is additionally rounded to TF32 so that the hardware truncation is exact
+__device__ __forceinline__ void split_tf32_weight(float a, uint32_t& hi, uint32_t& lo) {
+    split_tf32(a, hi, lo);
+    lo = (lo + 0x1000u) & 0xffffe000u;
 }
 
 // byte offset of element (n, k) inside a K-major SWIZZLE_128B image of an [rows][K] fp32 matrix (K % 32 == 0, rows % 8 == 0)

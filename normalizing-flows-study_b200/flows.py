@@ -175,11 +175,9 @@ class CouplingLayer(Flow):
     def _run(self, v, inverse):
         v = compute_input(v)
         if not wants_grad(self, v) and self.fusable(v):
-            pk = self._pack.get(_module_tensors(self), lambda: packing.pack_coupling_stack([self], None))
-            if pk is not None:
-                out = ops.coupling_stack(pk[0], pk[1], v, inverse)
-                if out is not None:
-                    return out
+            out = run_coupling_stack(self._pack, _module_tensors(self), [self], None, v, inverse)
+            if out is not None:
+                return out
         s_raw = self._conditioner(self.s_net, v)
         b_raw = self._conditioner(self.b_net, v)
         return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
@@ -473,6 +471,23 @@ def run_spline_stack(cache: _PackCache, tensors, flows, bns, v, inverse):
     return ops.spline_stack(pk[0], pk[1], v, inverse)
 
 
+def run_coupling_stack(cache: _PackCache, tensors, flows, bns, v, inverse):
+    """Eval-mode affine coupling stack in one launch: tcgen05 kernel when hidden_dim <= 64, FP32-pipe kernel otherwise."""
+    def build():
+        tcp = packing.pack_coupling_stack_tc(flows, bns) if USE_TENSOR_CORES else None
+        return ("tc", tcp) if tcp is not None else ("simt", packing.pack_coupling_stack(flows, bns))
+    kind, pk = cache.get(tensors + [_TC_FLAG[USE_TENSOR_CORES]], build)
+    if pk is None:
+        return None
+    if kind == "tc":
+        out = ops.coupling_stack_tc(pk[0], pk[1], v, inverse)
+        if out is not None:
+            return out
+        pk = packing.pack_coupling_stack(flows, bns)
+        return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse)
+    return ops.coupling_stack(pk[0], pk[1], v, inverse)
+
+
 _TC_FLAG = {True: torch.zeros(1), False: torch.zeros(2)}     # distinct cache-key tensors for the two settings
 
 
@@ -505,6 +520,5 @@ class ChainPlan:
             return None
         tensors = [t for m in mods for t in _module_tensors(m)]
         if kind is CouplingLayer:
-            pk = self._pack.get(tensors, lambda: packing.pack_coupling_stack(flows, bns))
-            return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse)
+            return run_coupling_stack(self._pack, tensors, flows, bns, v, inverse)
         return run_spline_stack(self._pack, tensors, flows, bns, v, inverse)

@@ -490,6 +490,17 @@ def spline_stack_tc(packed, hdr_host, x, inverse):
     return (y, ld) if ok else None
 
 
+def coupling_stack_tc(packed, hdr_host, x, inverse):
+    """Tensor-core (tcgen05) variant of coupling_stack; returns None if the configuration is unsupported."""
+    x = _c(x)
+    B, D = x.shape
+    y = torch.empty_like(x)
+    ld = torch.empty(B, dtype=x.dtype, device=x.device)
+    ok = L.try_call("nf_coupling_stack_tc_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
+                    ptr(ld), B, int(inverse), stream())
+    return (y, ld) if ok else None
+
+
 def coupling_stack(packed, hdr_host, x, inverse):
     x = _c(x)
     B, D = x.shape

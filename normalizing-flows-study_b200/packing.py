@@ -255,11 +255,17 @@ def fold_made(made) -> Optional[FoldedMade]:
 # ------------------------------------------------------------------------------------------------
 # tensor-core operand images (csrc/tc_common.cuh)
 # ------------------------------------------------------------------------------------------------
+def _round_tf32(w: np.ndarray) -> np.ndarray:
+    bits = np.ascontiguousarray(w, dtype=np.float32).view(np.uint32)
+    return ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def split_tf32(w: np.ndarray):
-    """w = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = w - hi (exact)."""
+    """w ~= hi + lo: hi = w rounded to the nearest TF32, lo = (w - hi) rounded to the nearest TF32 (mirrors
+    tc::split_tf32_weight; |w - hi - lo| <= 2^-24 |w|)."""
     w = np.ascontiguousarray(w, dtype=np.float32)
-    hi = (w.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-    return hi, (w - hi).astype(np.float32)
+    hi = _round_tf32(w)
+    return hi, _round_tf32((w - hi).astype(np.float32))
 
 
 def umma_sw128_image(w: np.ndarray) -> np.ndarray:
@@ -353,4 +359,43 @@ def pack_spline_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
     flat = np.concatenate(words).astype(np.float32)
     assert flat.size == HDR + len(layers) * bw, (flat.size, bw)
     dev = l0.param_net[0].weight.device
+    return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)
+
+
+def pack_coupling_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
+    """Tensor-core layout of an eval-mode affine coupling stack (hidden_dim <= 64, data_dim <= 8): per layer two
+    net blocks (s_net then b_net), each `lead (80 words: the layer header for s_net, zeros for b_net) | W1k | b2 | b3 |
+    pad | W2 hi/lo images | W3 hi/lo images`, conditioner BatchNorm folded into the Linears."""
+    l0 = layers[0]
+    D = l0.data_dim
+    H = l0.s_net[0].out_features
+    for l in layers:
+        if l.data_dim != D or l.s_net[0].out_features != H:
+            return None
+    if D > DMAX or H > 64 or l0.s_net[0].weight.dtype != torch.float32:
+        return None
+    nbw = L.lib().nf_coupling_stack_tc_block_words(D)
+    if nbw < 0:
+        return None
+    W1S, NO3 = _w1s(D), 16
+    hdr = np.zeros(HDR, dtype=np.float32)
+    hdr.view(np.int32)[0:10] = [MAGIC_AFFINE_TC, D, H, 2, 0, len(layers), W1S, NO3, nbw, int(bns is not None)]
+    words = [hdr]
+    for i, l in enumerate(layers):
+        m = _np(l.mask)
+        bn = _bn_between_consts(bns[i]) if (bns is not None and i < len(layers) - 1) else None
+        lead = [_layer_header(m.astype(np.float32), [d for d in range(D) if m[d] == 0], None, bn),
+                np.zeros(LAYER_HDR, dtype=np.float32)]
+        for net, ld in zip((l.s_net, l.b_net), lead):
+            W1, b1 = _fold_bn(_np(net[0].weight), _np(net[0].bias), net[1])
+            W2, b2 = _fold_bn(_np(net[3].weight), _np(net[3].bias), net[4])
+            W3rows = np.zeros((NO3, H))
+            b3rows = np.zeros(NO3)
+            W3rows[:D] = _np(net[6].weight)
+            b3rows[:D] = _np(net[6].bias)
+            blk = _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, LAYER_HDR)
+            words += [ld, blk]
+    flat = np.concatenate(words).astype(np.float32)
+    assert flat.size == HDR + 2 * len(layers) * nbw, (flat.size, nbw)
+    dev = l0.s_net[0].weight.device
     return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)

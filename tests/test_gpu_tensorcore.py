@@ -18,7 +18,7 @@ def test_tc_gemm128_3xtf32(n_out):
     ad = torch.from_numpy(a).cuda()
     ref = a.astype(np.float64) @ w.astype(np.float64).T
     scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T
-    for passes, tol in ((3, 2e-6), (1, 2e-3)):
+    for passes, tol in ((3, 1e-6), (1, 2e-3)):
         d = torch.full((128, n_out), float("nan"), device="cuda")
         N._lib.call("nf_debug_tc_gemm128", ad.data_ptr(), img.data_ptr(), d.data_ptr(), n_out, passes, None, 1,
                     N._lib.stream())
@@ -40,7 +40,11 @@ def test_linear_tc_matches_float64(M, N, K, relu):
     b = torch.randn(N, generator=gen)
     xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
     hi, lo = N_.ops.split_tf32(wd)
-    assert torch.equal((hi + lo).cpu(), w) and torch.equal(hi.cpu().view(torch.int32) & 0x1FFF, torch.zeros(N, K, dtype=torch.int32))
+    assert torch.equal(hi.cpu().view(torch.int32) & 0x1FFF, torch.zeros(N, K, dtype=torch.int32))
+    assert torch.equal(lo.cpu().view(torch.int32) & 0x1FFF, torch.zeros(N, K, dtype=torch.int32))
+    assert bool((((hi + lo).cpu().double() - w.double()).abs() <= 2.0 ** -23 * w.double().abs()).all())
+    hn, ln = N_.packing.split_tf32(w.numpy())
+    assert torch.equal(hi.cpu(), torch.from_numpy(hn)) and torch.equal(lo.cpu(), torch.from_numpy(ln))
     y = N_.ops.linear_tc(xd, hi, lo, bd, relu)
     assert y is not None
     ref = x.double() @ w.double().T + b.double()
@@ -48,7 +52,7 @@ def test_linear_tc_matches_float64(M, N, K, relu):
     if relu:
         ref = ref.clamp_min(0)
     err = ((y.cpu().double() - ref).abs() / scale).max().item()
-    assert err < 2e-6, f"scaled error {err:.3e}"
+    assert err < 2e-6, f"scaled error {err:.3e}"      # K up to 1024: fp32 accumulation in TMEM adds ~sqrt(K) ulp
     # and against the FP32-pipe GEMM (same inputs): both are fp32-accurate
     y2 = N_.ops.linear_raw(xd, wd, bd, relu)
     assert ((y - y2).abs() / scale.cuda().float()).max().item() < 2e-6
