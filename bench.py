@@ -273,20 +273,42 @@ def run_product(args):
             ev[3].record()
         return lp, xs
 
-    lp_host = torch.empty(rows, dtype=torch.float32).pin_memory()
-    xs_host = torch.empty(rows, D, dtype=torch.float32).pin_memory()
-    x_in = torch.empty(rows, D, dtype=torch.float32, device=dev)
-    z_in = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    # end-to-end arm: the same step through the public modules from pinned HOST buffers.  Two input/output buffer
+    # sets and three streams (H2D, compute, D2H) let the copy engines run under the kernels, as a serving loop would;
+    # every byte still crosses PCIe inside the timed region.
+    NB = 2
+    lp_host = [torch.empty(rows, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    xs_host = [torch.empty(rows, D, dtype=torch.float32).pin_memory() for _ in range(NB)]
+    x_in = [torch.empty(rows, D, dtype=torch.float32, device=dev) for _ in range(NB)]
+    z_in = [torch.empty(rows, D, dtype=torch.float32, device=dev) for _ in range(NB)]
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    ev_in = [torch.cuda.Event() for _ in range(NB)]
+    ev_done = [torch.cuda.Event() for _ in range(NB)]
+    ev_free = [torch.cuda.Event() for _ in range(NB)]
+    keep = [None] * NB
 
     def step_e2e(i):
+        b = i % NB
         xh, zh = host_sets[i % ring]
-        x_in.copy_(xh, non_blocking=True)
-        zz, ld = model.inverse(x_in)
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_free[b])                 # the previous user of this buffer set has read it
+            x_in[b].copy_(xh, non_blocking=True)
+            z_in[b].copy_(zh, non_blocking=True)
+            ev_in[b].record(s_in)
+        cur.wait_event(ev_in[b])
+        zz, ld = model.inverse(x_in[b])
         lp = ops.std_normal_log_prob(zz, ld)
-        lp_host.copy_(lp, non_blocking=True)
-        z_in.copy_(zh, non_blocking=True)
-        xs, _ = model.forward(z_in)
-        xs_host.copy_(xs, non_blocking=True)
+        xs, _ = model.forward(z_in[b])
+        ev_done[b].record(cur)
+        lp.record_stream(s_out)
+        xs.record_stream(s_out)
+        keep[b] = (lp, xs)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[b])
+            lp_host[b].copy_(lp, non_blocking=True)
+            xs_host[b].copy_(xs, non_blocking=True)
+            ev_free[b].record(s_out)
 
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
@@ -318,6 +340,7 @@ def run_product(args):
         s2.record()
         for i in range(args.steps):
             step_e2e(i)
+        torch.cuda.current_stream().wait_stream(s_out)      # the last device->host copies close the timed region
         e2.record()
         barrier()
         ms_e2e = s2.elapsed_time(e2)
