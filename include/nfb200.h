@@ -56,6 +56,8 @@ NF_API const char* nf_status_string(int status);
 NF_API const char* nf_last_cuda_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 NF_API int64_t nf_launch_count(void);
+/* library options for A/B measurements: key 1 = fused spline stack variant (0: one warpgroup per CTA, 1: two, default) */
+NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------
  * src/flows/spline/rational_quadratic_spline.py:4-104.  x,y,ld: [n]; w,h: [n,K]; d: [n,K-1].

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "nf_status_string": [_I],
     "nf_last_cuda_error": [],
     "nf_launch_count": [],
+    "nf_set_option": [_I, _I],
     "nf_rqs_unit_forward": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _D, _D, _D, _I, _P],
     "nf_rqs_unit_backward": [_P] * 10 + [_L, _I, _I, _D, _D, _D, _I, _P],
     "nf_spline_transform_forward": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _D, _P, _P, _P, _I, _I, _P],

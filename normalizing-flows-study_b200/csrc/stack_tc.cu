@@ -25,6 +25,7 @@ namespace nf {
 #ifdef NF_TC_PROFILE
 __device__ long long g_tc_prof[8];
 #endif
+static int g_tc_two_warpgroups = 1;      // nf_set_option(1, v): spline stack kernel variant (1 = two warpgroups per CTA)
 constexpr int kTcThreads = 128;
 constexpr int kTcSub = 4;            // sub-tiles (of 128 rows) per weight staging
 constexpr int kColAhi = 0, kColAlo = 64, kColD2 = 128, kColD3 = 192;
@@ -113,6 +114,37 @@ __device__ __forceinline__ void hidden2_to_tmem(const float* __restrict__ sb2, u
         }
         tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
         tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
+    }
+}
+
+
+// named barriers (ids 1..15; id 0 is __syncthreads): sub-block synchronisation of the two-warpgroup kernel
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// (c) with two 16-column loads in flight per wait (register budget of the 256-thread kernel: 128 per thread)
+__device__ __forceinline__ void hidden2_to_tmem_2x(const float* __restrict__ sb2, uint32_t lane_addr) {
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[2][16];
+        tc::tmem_ld16(lane_addr + kColD2 + (2 * cc) * 16, v[0]);
+        tc::tmem_ld16(lane_addr + kColD2 + (2 * cc + 1) * 16, v[1]);
+        tc::wait_ld();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * cc + h;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = *reinterpret_cast<const float4*>(sb2 + c * 16 + j4 * 4);
+                tc::split_tf32(relu_keepnan(__uint_as_float(v[h][j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
+                tc::split_tf32(relu_keepnan(__uint_as_float(v[h][j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
+                tc::split_tf32(relu_keepnan(__uint_as_float(v[h][j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
+                tc::split_tf32(relu_keepnan(__uint_as_float(v[h][j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+            }
+            tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
+            tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
+        }
     }
 }
 
@@ -322,6 +354,255 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// spline stack, two independent warpgroups per CTA (256 threads), half-K staging.
+// Each warpgroup owns 128 TMEM columns: A_hi 32 | A_lo 32 | D 64.  A K=64 contraction is fed in two halves of 32
+// (st half 1 -> 12 MMAs -> st half 2 -> 12 accumulating MMAs), the second half being computed on the FP32 pipe while
+// the first half's MMAs run; the head accumulator aliases D2 (read out to registers first).  Halving the A footprint
+// doubles the number of concurrent tensor windows per SM: 2 CTAs x 2 warpgroups = 4 windows, 16 resident warps.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTc2Threads = 256;
+constexpr int kWgCols = 128, kWgAhi = 0, kWgAlo = 32, kWgD = 64;
+
+// 16 hidden-layer-1 outputs (units u0..u0+15) of this thread's row: relu, split
+template <int DM>
+__device__ __forceinline__ void layer1_chunk(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], int u0,
+                                             uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float* w1 = sW1k + (u0 + j) * W1S;
+        float t;
+        if constexpr (DM <= 4) {
+            const float4 v = *reinterpret_cast<const float4*>(w1);
+            t = v.w;
+            t = fmaf(v.x, xa[0], t);
+            if constexpr (DM > 1) t = fmaf(v.y, xa[1], t);
+            if constexpr (DM > 2) t = fmaf(v.z, xa[2], t);
+        } else {
+            const float4 v0 = *reinterpret_cast<const float4*>(w1);
+            const float4 v1 = *reinterpret_cast<const float4*>(w1 + 4);
+            t = w1[W1S - 1];
+            t = fmaf(v0.x, xa[0], t); t = fmaf(v0.y, xa[1], t); t = fmaf(v0.z, xa[2], t); t = fmaf(v0.w, xa[3], t);
+            t = fmaf(v1.x, xa[4], t); t = fmaf(v1.y, xa[5], t); t = fmaf(v1.z, xa[6], t); t = fmaf(v1.w, xa[7], t);
+        }
+        tc::split_tf32(relu_keepnan(t), hi[j], lo[j]);
+    }
+}
+
+// 16 raw layer-2 accumulators + bias -> relu -> split
+__device__ __forceinline__ void hidden2_chunk(const uint32_t (&v)[16], const float* __restrict__ sb2, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b = *reinterpret_cast<const float4*>(sb2 + j4 * 4);
+        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
+        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
+        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
+        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+    }
+}
+
+template <int DM, int KMAX, int KS>
+__global__ void __launch_bounds__(kTc2Threads, 2)
+spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
+                        float* __restrict__ ld, int64_t B, int inverse) {
+    extern __shared__ __align__(1024) float sbuf[];
+    const TcHdr hd = read_tc_hdr(packed);
+    const int D = hd.D, K = (KS > 0) ? KS : hd.K, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, BW = hd.blk_words;
+    float* sx = sbuf + (size_t)2 * BW;                         // [kTcSub][DM+1][128] row state
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sx + kTcSub * (DM + 1) * kTcThreads);
+    uint64_t* mbar = bars;                                     // [2] MMA completion, one per warpgroup
+    uint64_t* wbar = bars + 2;                                 // [2] weight-block arrival
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 4);
+    const BlkOff off = blk_offsets(W1S, NO3);
+
+    RqsCfg<float> cfg;
+    cfg.lo = -hd.bound; cfg.hi = hd.bound; cfg.span = 2.0f * hd.bound; cfg.eps = 1e-8f;
+    cfg.min_w = hd.min_w; cfg.min_h = hd.min_h; cfg.min_d = hd.min_d; cfg.scale_w = hd.scale_w; cfg.scale_h = hd.scale_h;
+
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, wtid = tid & 127, wwarp = warp & 3;
+    const int bar_local = 1 + wg;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 0) {
+        tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::mbar_init(&wbar[0], 1); tc::mbar_init(&wbar[1], 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = tmem_base_s + (uint32_t)(wg * kWgCols);           // this warpgroup's 128 columns
+    const uint32_t lane_addr = tb + ((uint32_t)(wwarp * 32) << 16);
+    uint64_t* mb = &mbar[wg];
+    uint32_t phase = 0, wphase = 0u;
+
+    constexpr int ROWS = kTcThreads * kTcSub;
+    const int64_t ntiles = (B + ROWS - 1) / ROWS;
+    const float* layers = packed + NF_STACK_HDR;
+    int buf = 0;
+    if (tid == 0 && (int64_t)blockIdx.x < ntiles) {
+        tc::mbar_arrive_expect_tx(&wbar[0], (uint32_t)BW * 4u);
+        tc::bulk_g2s(sbuf, layers + (size_t)(inverse ? L - 1 : 0) * BW, (uint32_t)BW * 4u, &wbar[0]);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = wg; s < kTcSub; s += 2) {
+            const int64_t r = tile * ROWS + s * kTcThreads + wtid;
+#pragma unroll
+            for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + wtid] = (d < D && r < B) ? ld_stream(x + r * D + d) : 0.f;
+            sx[(s * (DM + 1) + DM) * kTcThreads + wtid] = 0.f;
+        }
+        for (int li = 0; li < L; ++li) {
+            tc::fence_proxy_async_smem();
+            __syncthreads();                                    // both warpgroups are done with the other buffer
+            if (tid == 0) {
+                const bool last = (li == L - 1);
+                if (!last || (tile + gridDim.x < ntiles)) {
+                    const int nli = last ? 0 : li + 1;
+                    tc::mbar_arrive_expect_tx(&wbar[buf ^ 1], (uint32_t)BW * 4u);
+                    tc::bulk_g2s(sbuf + (size_t)(buf ^ 1) * BW, layers + (size_t)(inverse ? L - 1 - nli : nli) * BW,
+                                 (uint32_t)BW * 4u, &wbar[buf ^ 1]);
+                }
+            }
+            tc::mbar_wait(&wbar[buf], (wphase >> buf) & 1u);
+            wphase ^= (1u << buf);
+            const float* sL = sbuf + (size_t)buf * BW;
+            const float* net = sL + NF_LAYER_HDR;
+            const int* meta = reinterpret_cast<const int*>(sL + 16);
+            const bool rescale = meta[1] != 0, bn_on = meta[2] != 0;
+            const float* mask = sL;
+            const uint32_t w2hi = tc::smem_u32(net + off.w2hi), w2lo = tc::smem_u32(net + off.w2lo);
+            const uint32_t w3hi = tc::smem_u32(net + off.w3hi), w3lo = tc::smem_u32(net + off.w3lo);
+            const float* sW1k = net + off.w1k;
+            const float* sb2 = net + off.b2;
+
+#pragma unroll 1
+            for (int s = wg; s < kTcSub; s += 2) {
+                float xv[DM], tot;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = sx[(s * (DM + 1) + d) * kTcThreads + wtid];
+                tot = sx[(s * (DM + 1) + DM) * kTcThreads + wtid];
+                if (inverse && bn_on) bn_between_tc<DM>(sL, D, true, xv, tot);
+                float xs[DM], xa[DM];
+#pragma unroll
+                for (int d = 0; d < DM; ++d) {
+                    float v = xv[d];
+                    if (rescale && d < D) v = sL[24 + d] * (v - sL[32 + d]) - hd.bound;
+                    xs[d] = v;
+                    xa[d] = (d < D) ? v * mask[d] : 0.f;
+                }
+                uint32_t hi[16], lo[16];
+                // ---- layer 2, K half 1: hidden units 0..31 ----
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    layer1_chunk<DM>(sW1k, W1S, xa, c * 16, hi, lo);
+                    tc::tmem_st16(lane_addr + kWgAhi + c * 16, hi);
+                    tc::tmem_st16(lane_addr + kWgAlo + c * 16, lo);
+                }
+                tc::wait_st();
+                tc::fence_before_sync();
+                named_sync(bar_local, kTcThreads);
+                if (wwarp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_krange_3xtf32(tb, kWgD, kWgAhi, kWgAlo, w2hi, w2lo, 64u, 0, 4, 0u, mb); }
+                // ---- K half 2: hidden units 32..63, computed while half 1 multiplies ----
+                uint32_t hi2[16], lo2[16];
+                layer1_chunk<DM>(sW1k, W1S, xa, 32, hi, lo);
+                layer1_chunk<DM>(sW1k, W1S, xa, 48, hi2, lo2);
+                tc::mbar_wait(mb, phase); phase ^= 1;           // half-1 MMAs done: the A columns are free
+                tc::fence_after_sync();
+                tc::tmem_st16(lane_addr + kWgAhi, hi);   tc::tmem_st16(lane_addr + kWgAlo, lo);
+                tc::tmem_st16(lane_addr + kWgAhi + 16, hi2); tc::tmem_st16(lane_addr + kWgAlo + 16, lo2);
+                tc::wait_st();
+                tc::fence_before_sync();
+                named_sync(bar_local, kTcThreads);
+                if (wwarp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_krange_3xtf32(tb, kWgD, kWgAhi, kWgAlo, w2hi, w2lo, 64u, 4, 4, 1u, mb); }
+                tc::mbar_wait(mb, phase); phase ^= 1;
+                tc::fence_after_sync();
+                // ---- head: D2 -> registers (the head accumulator aliases it), two K halves again ----
+                uint32_t v0[16], v1[16], v2[16], v3[16];
+                tc::tmem_ld16(lane_addr + kWgD, v0);      tc::tmem_ld16(lane_addr + kWgD + 16, v1);
+                tc::tmem_ld16(lane_addr + kWgD + 32, v2); tc::tmem_ld16(lane_addr + kWgD + 48, v3);
+                tc::wait_ld();
+                hidden2_chunk(v0, sb2, hi, lo);
+                tc::tmem_st16(lane_addr + kWgAhi, hi); tc::tmem_st16(lane_addr + kWgAlo, lo);
+                hidden2_chunk(v1, sb2 + 16, hi, lo);
+                tc::tmem_st16(lane_addr + kWgAhi + 16, hi); tc::tmem_st16(lane_addr + kWgAlo + 16, lo);
+                tc::wait_st();
+                tc::fence_before_sync();
+                named_sync(bar_local, kTcThreads);
+                if (wwarp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_krange_3xtf32(tb, kWgD, kWgAhi, kWgAlo, w3hi, w3lo, (uint32_t)NO3, 0, 4, 0u, mb); }
+                hidden2_chunk(v2, sb2 + 32, hi, lo);
+                hidden2_chunk(v3, sb2 + 48, hi2, lo2);
+                tc::mbar_wait(mb, phase); phase ^= 1;
+                tc::fence_after_sync();
+                tc::tmem_st16(lane_addr + kWgAhi, hi);   tc::tmem_st16(lane_addr + kWgAlo, lo);
+                tc::tmem_st16(lane_addr + kWgAhi + 16, hi2); tc::tmem_st16(lane_addr + kWgAlo + 16, lo2);
+                tc::wait_st();
+                tc::fence_before_sync();
+                named_sync(bar_local, kTcThreads);
+                if (wwarp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_krange_3xtf32(tb, kWgD, kWgAhi, kWgAlo, w3hi, w3lo, (uint32_t)NO3, 4, 4, 1u, mb); }
+                tc::mbar_wait(mb, phase); phase ^= 1;
+                tc::fence_after_sync();
+
+                // ---- spline parameters of this row: 32 columns per transformed dim ----
+                float lsum = 0.f;
+                int t = 0;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) {
+                    if (d < D && mask[d] == 0.f) {
+                        uint32_t p0[16], p1[16];
+                        tc::tmem_ld16(lane_addr + kWgD + t * 32, p0);
+                        if constexpr (3 * KMAX - 1 <= 24) {
+                            uint32_t q[8];
+                            tc::tmem_ld8(lane_addr + kWgD + t * 32 + 16, q);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) p1[j] = q[j];
+#pragma unroll
+                            for (int j = 8; j < 16; ++j) p1[j] = 0u;
+                        } else {
+                            tc::tmem_ld16(lane_addr + kWgD + t * 32 + 16, p1);
+                        }
+                        tc::wait_ld();
+                        const float* b3 = net + off.b3 + t * 32;
+                        float prm[32];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { prm[j] = __uint_as_float(p0[j]) + b3[j]; prm[16 + j] = __uint_as_float(p1[j]) + b3[16 + j]; }
+                        float uw[KMAX], uh[KMAX], ud[KMAX];
+#pragma unroll
+                        for (int j = 0; j < KMAX; ++j) {
+                            uw[j] = prm[j];
+                            uh[j] = prm[KMAX + j];
+                            ud[j] = (j < KMAX - 1) ? prm[2 * KMAX + j] : 0.f;
+                        }
+                        float out, lad;
+                        rqs_eval<float, KMAX, true>(xs[d], uw, uh, ud, K, inverse != 0, cfg, out, lad);
+                        if (rescale) out = (out + hd.bound) * sL[40 + d] + sL[32 + d];
+                        xv[d] = out;
+                        lsum += lad;
+                        ++t;
+                    }
+                }
+                tc::fence_before_sync();                        // D3 reads precede the next sub-tile's MMA writes
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = scrub0(xv[d]);
+                tot += scrub0(lsum);
+                if (!inverse && bn_on) bn_between_tc<DM>(sL, D, false, xv, tot);
+#pragma unroll
+                for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + wtid] = xv[d];
+                sx[(s * (DM + 1) + DM) * kTcThreads + wtid] = tot;
+            }
+            buf ^= 1;
+        }
+        for (int s = wg; s < kTcSub; s += 2) {
+            const int64_t r = tile * ROWS + s * kTcThreads + wtid;
+            if (r < B) {
+#pragma unroll
+                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + wtid]);
+                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + wtid]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // affine coupling stack (eval mode; conditioner BatchNorm folded into the Linears at pack time)
 //   per layer two conditioner nets (s_net, b_net: coupling_layer.py:18-35) run one after the other through the same
 //   TMEM regions; the staging unit is one NET block (header lead + W1k | b2 | b3 | W2 hi/lo | W3 hi/lo, ~43 KB), double
@@ -494,12 +775,25 @@ extern "C" int nf_spline_stack_tc_forward(const void* packed, const void* hdr_ho
     if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)L * BW)) return NF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
-    const size_t smem = sizeof(float) * ((size_t)2 * BW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 8);
+    const size_t smem = sizeof(float) * ((size_t)2 * BW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 12);
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
     const int rows = kTcThreads * kTcSub;
     const int64_t ntiles = cdiv(B, rows);
+    const bool two_wg = g_tc_two_warpgroups && NO3 <= 64;
 #define NF_TC(DMv, KMv, KSv)                                                                                         \
     do {                                                                                                             \
+        if (two_wg) {                                                                                                \
+            auto kern2 = spline_stack_tc2_kernel<DMv, KMv, KSv>;                                                     \
+            NF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            NF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+            int per_sm2 = (int)((227 * 1024) / (smem + 1024));                                                       \
+            if (per_sm2 < 1) return NF_ERR_UNSUPPORTED;                                                              \
+            if (per_sm2 > 512 / kTmemCols) per_sm2 = 512 / kTmemCols;                                                \
+            const int64_t cap2 = (int64_t)kNumSMs * per_sm2;                                                         \
+            const int grid2 = (int)(ntiles < cap2 ? ntiles : cap2);                                                  \
+            kern2<<<grid2, kTc2Threads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, inverse); \
+            break;                                                                                                   \
+        }                                                                                                            \
         auto kern = spline_stack_tc_kernel<DMv, KMv, KSv>;                                                           \
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         /* ask for the largest shared-memory carveout: with the default preference the driver sizes the SM for ONE   \
@@ -576,4 +870,10 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;
+}
+
+// library options (debugging / A-B measurements): key 1 = spline stack kernel variant (0: one warpgroup, 1: two)
+extern "C" int nf_set_option(int key, int value) {
+    if (key == 1) { nf::g_tc_two_warpgroups = value != 0; return NF_OK; }
+    return NF_ERR_UNSUPPORTED;
 }

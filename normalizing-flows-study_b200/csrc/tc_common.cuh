@@ -144,6 +144,30 @@ __device__ __forceinline__ void warp_issue_gemm_k64_3xtf32(uint32_t tmem_base, u
     __syncwarp();
 }
 
+// Same for a K range: k-steps [k0, k0+nk) of the weight images against nk*8 A columns starting at a_hi_col / a_lo_col
+// (the A operand of those k-steps only); acc_first = 0 overwrites the accumulator with the first MMA.
+__device__ __forceinline__ void warp_issue_gemm_krange_3xtf32(uint32_t tmem_base, uint32_t d_col, uint32_t a_hi_col, uint32_t a_lo_col,
+                                                              uint32_t w_hi, uint32_t w_lo, uint32_t N, int k0, int nk,
+                                                              uint32_t acc_first, uint64_t* bar) {
+    const uint32_t idesc = idesc_tf32_m128(N);
+    const uint32_t atom16 = (N * 128u) >> 4;
+    const uint64_t d_hi = smem_desc_k_sw128(w_hi), d_lo = smem_desc_k_sw128(w_lo);
+    const bool leader = elect_one();
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a_col = (pass == 1) ? a_lo_col : a_hi_col;
+        const uint64_t wd = (pass == 2) ? d_lo : d_hi;
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+            const int k = k0 + kk;
+            const uint64_t bd = wd + (uint64_t)((uint32_t)(k >> 2) * atom16 + (uint32_t)(k & 3) * 2u);
+            if (leader) mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + kk * 8, bd, idesc, (pass | kk) != 0 ? 1u : acc_first);
+        }
+    }
+    if (leader) mma_commit(bar);
+    __syncwarp();
+}
+
 // ---- 3xTF32 split -----------------------------------------------------------------------------------
 // hi = a rounded to the nearest TF32 (add half an ulp of the 13 dropped bits, then clear them; the carry walks into
 // the exponent correctly, Inf stays Inf), lo = a - hi exactly, |lo| <= 2^-12 |a|.  The tensor core truncates lo to
