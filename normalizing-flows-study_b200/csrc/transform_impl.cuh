@@ -198,7 +198,17 @@ spline_transform_compact_fwd_kernel(const T* __restrict__ x, const T* __restrict
             const T* src = params + ((G >= Dt) ? row0 * Dt : row0 * Dt + t0) * (int64_t)P;
             const int nfl = nblocks * P;
             __syncwarp();
-            for (int i = lane; i < nfl; i += 32) slab[i] = __ldcs(src + i);
+            if constexpr (sizeof(T) == 4) {
+                // 4-byte cp.async: all 3K-1 coalesced line fetches of the warp are in flight at once, no register staging
+                for (int i = lane; i < nfl; i += 32) {
+                    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i));
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            } else {
+                for (int i = lane; i < nfl; i += 32) slab[i] = __ldcs(src + i);
+            }
             __syncwarp();
             const int t = t0 + g;
             if (valid && t < Dt) {
