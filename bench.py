@@ -333,7 +333,9 @@ def run_product(args):
         ms_total = e_start.elapsed_time(e_end)
         clk = clocks.stop(t0, t1)
         # ---- end-to-end through the public API from pinned host buffers ----------------------
-        for i in range(2):
+        # warm the copy path as well: a PCIe link that idled trains back up over the first transfers (the first
+        # bench run on a fresh box measured 2-12 GB/s copies with a 2-step warm-up)
+        for i in range(max(args.warmup, 3) + 12):
             step_e2e(i)
         barrier()
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -199,6 +199,18 @@ def bench_stacks():
             p.add_(0.05 * torch.randn_like(p))
         ms = timeit(lambda: m.inverse(x))
     report("spline_stack RealNVPSpline(2,8,64) K=10 inverse B=2^20", ms, B * 20, 8 * 2 * (2 * 64 + 64 * 64 + 64 * 58) * B)
+    import time
+    xs = torch.randn(128, 2, device=DEV)
+    with torch.no_grad():
+        for _ in range(20):
+            m.inverse(xs)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(200):
+            m.inverse(xs)
+        host_us = (time.perf_counter() - t) / 200 * 1e6
+        torch.cuda.synchronize()
+    print(f"host-side cost of one fused model.inverse call (B=128, launch queue not full): {host_us:.1f} us")
     maf = N.MaskedAutoregressiveFlow(64, 512).to(DEV).eval()
     xm = torch.randn(262144, 64, device=DEV)
     with torch.no_grad():
