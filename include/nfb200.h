@@ -56,7 +56,8 @@ NF_API const char* nf_status_string(int status);
 NF_API const char* nf_last_cuda_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 NF_API int64_t nf_launch_count(void);
-/* library options for A/B measurements: key 1 = fused spline stack variant (0: one warpgroup per CTA, 1: two, default) */
+/* library options for A/B measurements: key 1 = fused spline stack variant (0: one warpgroup per CTA, 1: two, default);
+ * key 2 = nf_linear_wgrad_tc: longest TMEM accumulation chain in 32-row blocks (default 64) */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------
@@ -234,6 +235,17 @@ NF_API int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const
                  nf_stream_t stream);
 /* hi = w rounded to the nearest TF32, lo = (w - hi) rounded to the nearest TF32; n elements, fp32 */
 NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_stream_t stream);
+
+/* ---- weight gradient of those layers on the tensor cores: dw[N,K] = sum_b dy[b,N] * x[b,K] -----------------
+ * (autograd of F.linear, masked_linear.py:18; fp32, 3xTF32 on tcgen05, both operands consumed in their row-major
+ * layout: dy through TMEM as the A operand, x as an MN-major shared-memory B operand; csrc/wgrad_tc.cu).
+ * The reduction over the batch is split across CTAs; partial tiles go to `workspace`
+ * (nf_linear_wgrad_tc_workspace(B,N,K) bytes, 0 when no split is needed) and are summed in a fixed order
+ * (deterministic).  Requires 16-byte aligned dy / x and ld_dy % 4 == 0, ld_x % 4 == 0 (NF_ERR_UNSUPPORTED
+ * otherwise: use nf_gemm).  B == 0 writes zeros. */
+NF_API int64_t nf_linear_wgrad_tc_workspace(int64_t B, int64_t N, int64_t K);
+NF_API int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
+                       int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, nf_stream_t stream);
 
 /* ---- a12/a13 sequential directions, blocked: dense contributions of previous degree blocks on tcgen05
  * (nf_linear_tc on column slices), in-block dependent steps in a small-footprint kernel (csrc/ar_blocked.cu).

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P, _I, _P],
     "nf_linear_tc": [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P, _P],
     "nf_split_tf32": [_P, _P, _P, _L, _P],
+    "nf_linear_wgrad_tc_workspace": [_L, _L, _L],
+    "nf_linear_wgrad_tc": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _P, _L, _P],
     "nf_ar_blocked_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "nf_ar_blocked_workspace_floats": [_L, _I, _I],
     "nf_spline_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
@@ -77,6 +79,7 @@ _RESTYPES = {
     "nf_spline_stack_tc_block_words": _L,
     "nf_ar_blocked_workspace_floats": _L,
     "nf_coupling_stack_tc_block_words": _L,
+    "nf_linear_wgrad_tc_workspace": _L,
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -872,8 +872,11 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
     return NF_OK;
 }
 
-// library options (debugging / A-B measurements): key 1 = spline stack kernel variant (0: one warpgroup, 1: two)
+// library options (debugging / A-B measurements): key 1 = spline stack kernel variant (0: one warpgroup, 1: two);
+// key 2 = weight-gradient kernel: maximum number of 32-row K blocks accumulated in TMEM per split (wgrad_tc.cu)
+namespace nf { int g_wgrad_max_kb = 64; }
 extern "C" int nf_set_option(int key, int value) {
     if (key == 1) { nf::g_tc_two_warpgroups = value != 0; return NF_OK; }
+    if (key == 2) { if (value < 1) return NF_ERR_BAD_SHAPE; nf::g_wgrad_max_kb = value; return NF_OK; }
     return NF_ERR_UNSUPPORTED;
 }

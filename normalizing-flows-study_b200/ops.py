@@ -72,6 +72,21 @@ def linear_tc(x, w_hi, w_lo, bias=None, relu=False, k_extent=None, out=None):
     return out if ok else None
 
 
+def linear_wgrad_tc(gy, x, out=None):
+    """dW[N,K] = gy[B,N]^T x[B,K] on tcgen05 (3xTF32, deterministic split over the batch); None when the shape /
+    alignment is not taken by the tensor-core kernel (caller uses gemm)."""
+    B, N = gy.shape
+    K = x.shape[1]
+    if N % 4 != 0 or K % 4 != 0:
+        return None
+    if out is None:
+        out = torch.empty((N, K), dtype=gy.dtype, device=gy.device)
+    ws_bytes = int(L.lib().nf_linear_wgrad_tc_workspace(B, N, K))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=gy.device) if ws_bytes else None
+    ok = L.try_call("nf_linear_wgrad_tc", ptr(gy), ptr(x), ptr(out), B, N, K, N, K, K, ptr(ws), ws_bytes, stream())
+    return out if ok else None
+
+
 def mul_rows(a, b):
     """a * b where b has a's shape or is a single row broadcast over a's rows."""
     a2 = a.view(-1, a.shape[-1])
@@ -103,7 +118,8 @@ def _tc_ok(x, K):
 class _LinearFn(Function):
     """F.linear(x, W*mask, b) (+ReLU).  float32 with >= 256 rows: forward and the input gradient run on tcgen05
     (3xTF32, fp32-accurate; the weight is split hi/lo per call -- weights are small next to the activations);
-    the weight gradient (reduction over the batch) and float64 use the FP32/FP64-pipe GEMM."""
+    so does the weight gradient (reduction over the batch, both operands in their row-major layout, wgrad_tc.cu);
+    float64 and tiny / unaligned shapes use the FP32/FP64-pipe GEMM."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, mask, relu):
@@ -138,7 +154,9 @@ class _LinearFn(Function):
             if gx is None:
                 gx = gemm(g, w_eff, M, K, N, N, 1, K, 1)                 # dX = dY W
         if ctx.needs_input_grad[1]:
-            gw = gemm(g, x, N, K, M, 1, N, K, 1)                     # dW = dY^T X
+            gw = linear_wgrad_tc(g, x) if _tc_ok(g, K) else None      # dW = dY^T X
+            if gw is None:
+                gw = gemm(g, x, N, K, M, 1, N, K, 1)
             if mask is not None:
                 gw = mul_rows(gw, mask)
         if ctx.has_bias and ctx.needs_input_grad[2]:

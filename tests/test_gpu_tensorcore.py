@@ -72,3 +72,48 @@ def test_linear_tc_k_extent_matches_masked_dense():
     scale = x.double().abs() @ w.double().abs().T + 1e-30
     err = ((y.cpu().double() - ref).abs() / scale).max().item()
     assert err < 2e-6, f"scaled error {err:.3e}"
+
+
+@pytest.mark.parametrize("B,N,K", [(32, 128, 128), (256, 128, 128), (4096, 512, 512), (5000, 512, 64), (777, 132, 100),
+                                   (100000, 128, 256), (3000, 2844, 1024), (1, 64, 64), (0, 64, 32)])
+def test_linear_wgrad_tc_matches_float64(B, N, K):
+    """dW = dY^T X on tcgen05 (MN-major operands, split over the batch) against a float64 product."""
+    gen = torch.Generator().manual_seed(B + N + K)
+    g = torch.randn(B, N, generator=gen) * 1.5
+    x = torch.randn(B, K, generator=gen)
+    gd, xd = g.cuda(), x.cuda()
+    dw = N_.ops.linear_wgrad_tc(gd, xd, out=torch.full((N, K), float("nan"), device="cuda"))
+    assert dw is not None
+    torch.cuda.synchronize()
+    ref = g.double().T @ x.double()
+    scale = g.double().abs().T @ x.double().abs() + 1e-30
+    err = ((dw.cpu().double() - ref).abs() / scale).max().item()
+    # the tensor core's fp32 accumulation truncates: measured bias 2^-25 of the running sum per MMA (scripts/
+    # wgrad_accuracy.py); a TMEM chain is at most 64 K blocks x 12 MMAs long => <= 2.3e-5 of sum|a||b| in the worst
+    # (same-sign) case, ~1e-6 for random signs; the split partials are then added with round-to-nearest
+    assert err < 1e-5, f"scaled error {err:.3e}"
+    if B:
+        dw2 = N_.ops.gemm(gd, xd, N, K, B, 1, N, K, 1)
+        assert ((dw - dw2).abs() / scale.cuda().float()).max().item() < 1e-5
+        rms = (dw.cpu().double() - ref).pow(2).mean().sqrt().item() / max(ref.pow(2).mean().sqrt().item(), 1e-30)
+        assert rms < 3e-5, f"rms error / rms(dW) {rms:.3e}"
+        # deterministic: the split partials are summed in a fixed order
+        assert torch.equal(dw, N_.ops.linear_wgrad_tc(gd, xd))
+
+
+def test_linear_autograd_uses_tc_wgrad_and_matches_float64():
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2048, 256, generator=gen)
+    w = torch.randn(512, 256, generator=gen) / 16
+    b = torch.randn(512, generator=gen)
+    xd = x.cuda().requires_grad_(True)
+    wd = w.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True)
+    y = N_.ops.linear(xd, wd, bd, relu=True)
+    (y * y).sum().backward()
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    y64 = torch.relu(x64 @ w64.T + b64)
+    (y64 * y64).sum().backward()
+    for got, ref in ((xd.grad, x64.grad), (wd.grad, w64.grad), (bd.grad, b64.grad)):
+        rel = (got.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+        assert rel < 2e-5, rel
