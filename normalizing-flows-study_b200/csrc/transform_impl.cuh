@@ -109,6 +109,71 @@ NF_UNROLL
     }
 }
 
+// a7 backward with shared-memory staging: a warp handles 32 consecutive elements; their width / height / derivative
+// rows are three contiguous runs of 32K, 32K and 32(K-1) values, fetched with coalesced cp.async into the warp's
+// slab, and the three gradient runs leave through the same slab with coalesced stores (the register-path kernel
+// above issues 3K-1 strided 4-byte loads and stores per element: 12 % of HBM).
+template <typename T, int KMAX, bool SK>
+__global__ void __launch_bounds__(128)
+rqs_unit_bwd_slab_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ h,
+                         const T* __restrict__ d, const T* __restrict__ gy, const T* __restrict__ gld,
+                         T* __restrict__ gx, T* __restrict__ gw, T* __restrict__ gh, T* __restrict__ gd, int64_t n,
+                         int Krt, int inverse, RqsCfg<T> c) {
+    extern __shared__ __align__(16) unsigned char slab_raw[];
+    const int K = SK ? KMAX : Krt;
+    const int P = 3 * K - 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    T* sw = reinterpret_cast<T*>(slab_raw) + (size_t)wib * 32 * P;
+    T* sh = sw + 32 * K;
+    T* sd = sh + 32 * K;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nblk = (n + 31) / 32;
+    for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+        const int64_t i0 = blk * 32;
+        const int cnt = (int)((n - i0) < 32 ? (n - i0) : 32);
+        const int nk = cnt * K, nd = cnt * (K - 1);
+        __syncwarp();
+        if constexpr (sizeof(T) == 4) {
+            for (int i = lane; i < nk; i += 32) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sw + i))), "l"(w + i0 * K + i));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sh + i))), "l"(h + i0 * K + i));
+            }
+            for (int i = lane; i < nd; i += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(sd + i))), "l"(d + i0 * (K - 1) + i));
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        } else {
+            for (int i = lane; i < nk; i += 32) { sw[i] = __ldcs(w + i0 * K + i); sh[i] = __ldcs(h + i0 * K + i); }
+            for (int i = lane; i < nd; i += 32) sd[i] = __ldcs(d + i0 * (K - 1) + i);
+        }
+        __syncwarp();
+        if (lane < cnt) {
+            const int64_t i = i0 + lane;
+            T uw[KMAX], uh[KMAX], ud[KMAX];
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) {
+                uw[j] = (j < K) ? sw[lane * K + j] : T(0);
+                uh[j] = (j < K) ? sh[lane * K + j] : T(0);
+                ud[j] = (j < K - 1) ? sd[lane * (K - 1) + j] : T(0);
+            }
+            T guw[KMAX], guh[KMAX], gud[KMAX];
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) { guw[j] = T(0); guh[j] = T(0); gud[j] = T(0); }
+            T gv = T(0);
+            rqs_eval_bwd<T, KMAX, false>(ld_stream(x + i), uw, uh, ud, K, inverse != 0, c, ld_stream(gy + i), ld_stream(gld + i), gv, guw, guh, gud);
+            st_stream(gx + i, gv);
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) if (j < K) { sw[lane * K + j] = guw[j]; sh[lane * K + j] = guh[j]; }
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) if (j < K - 1) sd[lane * (K - 1) + j] = gud[j];
+        }
+        __syncwarp();
+        for (int i = lane; i < nk; i += 32) { st_stream(gw + i0 * K + i, sw[i]); st_stream(gh + i0 * K + i, sh[i]); }
+        for (int i = lane; i < nd; i += 32) st_stream(gd + i0 * (K - 1) + i, sd[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // a5/a6: spline coupling transform from interleaved params [B, D*P].  G lanes cooperate on one row
 // (G = pow2 >= min(Dt,32)); each lane walks transformed dims t = g, g+G, ...; row log-det via
@@ -199,10 +264,18 @@ spline_transform_compact_fwd_kernel(const T* __restrict__ x, const T* __restrict
             const int nfl = nblocks * P;
             __syncwarp();
             if constexpr (sizeof(T) == 4) {
-                // 4-byte cp.async: all 3K-1 coalesced line fetches of the warp are in flight at once, no register staging
-                for (int i = lane; i < nfl; i += 32) {
-                    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i));
+                // cp.async: all coalesced line fetches of the warp are in flight at once, no register staging; 16-byte
+                // copies when the run is 16-byte aligned (32 blocks are a multiple of 128 bytes), 4-byte otherwise
+                if ((((uintptr_t)src | (uintptr_t)(nfl * 4)) & 15) == 0) {
+                    for (int i = lane * 4; i < nfl; i += 128) {
+                        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i));
+                    }
+                } else {
+                    for (int i = lane; i < nfl; i += 32) {
+                        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i));
+                    }
                 }
                 asm volatile("cp.async.commit_group;\n" ::);
                 asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -292,6 +365,115 @@ NF_UNROLL
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// a5/a6 backward, compact parameter layout: same staging as spline_transform_compact_fwd_kernel.  A warp fetches the
+// parameter blocks of its 32 elements with coalesced cp.async into its shared-memory slab, every lane recomputes its
+// element and overwrites its own block with the parameter gradients, and the slab goes back to gparams with
+// coalesced 128-byte stores (the register-path kernel above issues 3K-1 strided loads and 3K-1 strided stores per
+// element and is L1-wavefront bound at 8-15 % of HBM).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int KMAX, bool SK, int G>
+__global__ void __launch_bounds__(128)
+spline_transform_compact_bwd_kernel(const T* __restrict__ x, const T* __restrict__ params, const T* __restrict__ mask,
+                                    const int32_t* __restrict__ tidx, const T* __restrict__ gy,
+                                    const T* __restrict__ gld, T* __restrict__ gx, T* __restrict__ gparams, int64_t B,
+                                    int D, int Dt, int Krt, int inverse, RqsCfg<T> c, const T* __restrict__ r_in,
+                                    const T* __restrict__ r_lo, const T* __restrict__ r_out) {
+    extern __shared__ __align__(16) unsigned char slab_raw[];
+    const int K = SK ? KMAX : Krt;
+    const int P = 3 * K - 1;
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane % G, rsub = lane / G;
+    T* slab = reinterpret_cast<T*>(slab_raw) + (size_t)wib * 32 * P;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nblk = (B + RPW - 1) / RPW;
+    for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+        const int64_t row0 = blk * RPW;
+        const int64_t row = row0 + rsub;
+        const bool valid = row < B;
+        const int nrows = (int)((B - row0) < RPW ? (B - row0) : RPW);
+        T gl = T(0);
+        if (valid) {
+            gl = gld[row];
+            for (int dd = g; dd < D; dd += G)
+                if (__ldg(mask + dd) != T(0)) gx[row * D + dd] = is_finite(x[row * D + dd]) ? gy[row * D + dd] : T(0);
+        }
+        for (int t0 = 0; t0 < Dt; t0 += G) {
+            const int tn = (Dt - t0) < G ? (Dt - t0) : G;
+            const int nblocks = (G >= Dt) ? nrows * Dt : tn;
+            const int64_t off = ((G >= Dt) ? row0 * Dt : row0 * Dt + t0) * (int64_t)P;
+            const T* src = params + off;
+            const int nfl = nblocks * P;
+            T* dst = gparams + off;
+            const bool vec16 = sizeof(T) == 4 && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)(nfl * 4)) & 15) == 0;
+            __syncwarp();
+            if constexpr (sizeof(T) == 4) {
+                if (vec16) {
+                    for (int i = lane * 4; i < nfl; i += 128) {
+                        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src + i));
+                    }
+                } else {
+                    for (int i = lane; i < nfl; i += 32) {
+                        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(slab + i));
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(src + i));
+                    }
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            } else {
+                for (int i = lane; i < nfl; i += 32) slab[i] = __ldcs(src + i);
+            }
+            __syncwarp();
+            const int t = t0 + g;
+            if (valid && t < Dt) {
+                const int dim = __ldg(tidx + t);
+                T v = x[row * D + dim];
+                if (r_in) v = r_in[dim] * (v - r_lo[dim]) - c.hi;
+                T* pp = slab + (size_t)((G >= Dt) ? rsub * Dt + t : g) * P;
+                T uw[KMAX], uh[KMAX], ud[KMAX];
+NF_UNROLL
+                for (int j = 0; j < KMAX; ++j) {
+                    uw[j] = (j < K) ? pp[j] : T(0);
+                    uh[j] = (j < K) ? pp[K + j] : T(0);
+                    ud[j] = (j < K - 1) ? pp[2 * K + j] : T(0);
+                }
+                T go = gy[row * D + dim];
+                {   // layer-level scrub of y (:130): recompute the output to see whether it was replaced by 0
+                    T out, lad;
+                    rqs_eval<T, KMAX, true>(v, uw, uh, ud, K, inverse != 0, c, out, lad);
+                    if (r_in) out = (out + c.hi) * r_out[dim] + r_lo[dim];
+                    if (!is_finite(out)) go = T(0);
+                }
+                if (r_in) go *= r_out[dim];
+                T guw[KMAX], guh[KMAX], gud[KMAX];
+NF_UNROLL
+                for (int j = 0; j < KMAX; ++j) { guw[j] = T(0); guh[j] = T(0); gud[j] = T(0); }
+                T gv = T(0);
+                rqs_eval_bwd<T, KMAX, true>(v, uw, uh, ud, K, inverse != 0, c, go, gl, gv, guw, guh, gud);
+                if (r_in) gv *= r_in[dim];
+                gx[row * D + dim] = gv;
+NF_UNROLL
+                for (int j = 0; j < KMAX; ++j) if (j < K) { pp[j] = guw[j]; pp[K + j] = guh[j]; }
+NF_UNROLL
+                for (int j = 0; j < KMAX; ++j) if (j < K - 1) pp[2 * K + j] = gud[j];
+            }
+            __syncwarp();
+            if constexpr (sizeof(T) == 4) {
+                if (vec16) {
+                    for (int i = lane * 4; i < nfl; i += 128)
+                        __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(slab + i));
+                } else {
+                    for (int i = lane; i < nfl; i += 32) st_stream(dst + i, slab[i]);
+                }
+            } else {
+                for (int i = lane; i < nfl; i += 32) st_stream(dst + i, slab[i]);
+            }
+        }
+    }
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // host-side launchers (explicitly instantiated per translation unit)
@@ -329,13 +511,22 @@ template <typename T, bool GENERIC>
 int rqs_unit_bwd_launch(const void* x, const void* w, const void* h, const void* d, const void* gy, const void* gld,
                         void* gx, void* gw, void* gh, void* gd, int64_t n, int K, int inverse, RqsCfg<T> c,
                         cudaStream_t st) {
-    const int grid = grid_for(n, 128, 32);
-#define NF_RQS_BWD(KM)                                                                                          \
-    rqs_unit_bwd_kernel<T, KM, false><<<grid, 128, 0, st>>>((const T*)x, (const T*)w, (const T*)h, (const T*)d, \
-                                                            (const T*)gy, (const T*)gld, (T*)gx, (T*)gw, (T*)gh, \
-                                                            (T*)gd, n, K, inverse, c)
-    if constexpr (GENERIC) { NF_RQS_BWD(32); }
-    else { if (K <= 8) NF_RQS_BWD(8); else NF_RQS_BWD(16); }
+    const int grid = grid_for(n, 128, 8);
+    const size_t smem = (size_t)4 * 32 * (3 * K - 1) * sizeof(T);
+#define NF_RQS_BWD(KM, SKF)                                                                                     \
+    do {                                                                                                        \
+        auto kern = rqs_unit_bwd_slab_kernel<T, KM, SKF>;                                                       \
+        if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 128, smem, st>>>((const T*)x, (const T*)w, (const T*)h, (const T*)d, (const T*)gy, (const T*)gld, \
+                                      (T*)gx, (T*)gw, (T*)gh, (T*)gd, n, K, inverse, c);                        \
+    } while (0)
+    if constexpr (GENERIC) { NF_RQS_BWD(32, false); }
+    else {
+        if (K == 8) NF_RQS_BWD(8, true);
+        else if (K == 10) NF_RQS_BWD(10, true);
+        else if (K < 8) NF_RQS_BWD(8, false);
+        else NF_RQS_BWD(16, false);
+    }
 #undef NF_RQS_BWD
     count_launch();
     NF_LAUNCH_CHECK();
@@ -390,10 +581,44 @@ int spline_transform_compact_fwd_launch(const SplineTfArgs<T>& a, cudaStream_t s
     return NF_OK;
 }
 
+template <typename T, bool GENERIC>
+int spline_transform_compact_bwd_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
+    const int G = pick_group_pow2(a.Dt);
+    const int P = 3 * a.K - 1;
+    const size_t smem = (size_t)4 * 32 * P * sizeof(T);
+    const int grid = grid_for(cdiv(a.B, 32 / G), 4, 8);
+#define NF_SB(KM, SKF, GG)                                                                                            \
+    do {                                                                                                              \
+        auto kern = spline_transform_compact_bwd_kernel<T, KM, SKF, GG>;                                              \
+        if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 128, smem, st>>>(a.x, a.params, a.mask, a.tidx, a.gy, a.gld, a.gx, a.gparams, a.B, a.D, a.Dt, a.K, \
+                                      a.inverse, a.c, a.r_in, a.r_lo, a.r_out);                                       \
+    } while (0)
+#define NF_SB_G(KM, SKF)                                                                                              \
+    do {                                                                                                              \
+        switch (G) { case 1: NF_SB(KM, SKF, 1); break; case 2: NF_SB(KM, SKF, 2); break; case 4: NF_SB(KM, SKF, 4); break; \
+                     case 8: NF_SB(KM, SKF, 8); break; case 16: NF_SB(KM, SKF, 16); break; default: NF_SB(KM, SKF, 32); break; } \
+    } while (0)
+    if constexpr (GENERIC) { NF_SB_G(32, false); }
+    else {
+        if (a.K == 8) NF_SB_G(8, true);
+        else if (a.K == 10) NF_SB_G(10, true);
+        else if (a.K < 8) NF_SB_G(8, false);
+        else NF_SB_G(16, false);
+    }
+#undef NF_SB_G
+#undef NF_SB
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
 template <typename T, bool BWD, bool GENERIC>
 int spline_transform_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
     if constexpr (!BWD) {
         if (a.compact && a.Dt > 0) return spline_transform_compact_fwd_launch<T, GENERIC>(a, st);
+    } else {
+        if (a.compact && a.Dt > 0) return spline_transform_compact_bwd_launch<T, GENERIC>(a, st);
     }
     const int G = pick_group3(a.Dt);
     const int grid = grid_for(cdiv(a.B, 32 / G), 4, 64);

@@ -141,6 +141,8 @@ def bench_affine():
         report(f"feature_affine fwd B={B} D={D}", ms, B * 4 * 2 * D)
         ms = timeit(lambda: ops.col_stats(x))
         report(f"col_stats B={B} D={D}", ms, B * 4 * D)
+        ms = timeit(lambda: ops.col_sum(x))
+        report(f"col_sum (bias gradient) B={B} D={D}", ms, B * 4 * D)
         del x, s, b, gy, gl, gx, gs, gb, params
 
 
@@ -163,12 +165,16 @@ def bench_gemm():
     shapes = [("MADE(64,512) in->H", 262144, 512, 64), ("MADE(64,512) H->H", 262144, 512, 512),
               ("MADE(64,512) H->2D", 262144, 128, 512), ("coupling(256,512) H->H", 262144, 512, 512),
               ("spline(784,1024) H->H", 4096, 1024, 1024), ("spline(784,1024) H->D*P", 4096, 22736, 1024),
-              ("dW = dY^T X (512x512, B=262144)", 512, 512, 262144)]
+              ("dW = dY^T X (512x512, B=262144)", 512, 512, 262144), ("dW = dY^T X (1024x1024, B=65536)", 1024, 1024, 65536),
+              ("dW = dY^T X (11368x1024, B=4096)", 11368, 1024, 4096)]
     for name, M, Nn, K in shapes:
         if name.startswith("dW"):
             g = torch.randn(K, M, device=DEV)
             x = torch.randn(K, Nn, device=DEV)
             ms = timeit(lambda: ops.gemm(g, x, M, Nn, K, 1, M, Nn, 1), reps=3, inner=2)
+            ms_tc = timeit(lambda: ops.linear_wgrad_tc(g, x), reps=3, inner=4)
+            report(f"nf_linear_wgrad_tc 3xTF32 {name} [{M}x{Nn}x{K}]", ms_tc, None, 2.0 * M * Nn * K,
+                   note="tensor pipe executes 3x these FLOPs")
         else:
             a = torch.randn(M, K, device=DEV)
             w = torch.randn(Nn, K, device=DEV)

@@ -117,3 +117,14 @@ def test_linear_autograd_uses_tc_wgrad_and_matches_float64():
     for got, ref in ((xd.grad, x64.grad), (wd.grad, w64.grad), (bd.grad, b64.grad)):
         rel = (got.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
         assert rel < 2e-5, rel
+
+
+@pytest.mark.parametrize("rows,cols", [(5, 8), (1024, 4), (1500, 132), (65536, 512), (4096, 11368), (3000, 7), (0, 16)])
+def test_col_sum_matches_float64(rows, cols):
+    """bias gradient reduction (autograd of F.linear's bias): vectorised and scalar kernels."""
+    gen = torch.Generator().manual_seed(rows + cols)
+    a = torch.randn(rows, cols, generator=gen) + 0.25
+    got = N_.ops.col_sum(a.cuda()).cpu().double()
+    ref = a.double().sum(0)
+    scale = a.double().abs().sum(0) + 1e-30
+    assert ((got - ref).abs() / scale).max().item() < 1e-6
