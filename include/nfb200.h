@@ -247,6 +247,21 @@ NF_API int64_t nf_linear_wgrad_tc_workspace(int64_t B, int64_t N, int64_t K);
 NF_API int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
                        int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, nf_stream_t stream);
 
+/* ---- (f2) ARQS, one step of either sequential loop (src/flows/spline/arqs.py:53-76 / :93-116) ------------------
+ * out[B,D] = cur with column `col` replaced by rational_quadratic_spline(v[:, col]; params[row]) on [0,1]
+ * (rational_quadratic_spline.py:4-104), ld_out = ld_in + log|dy/dx| (ld_in NULL = zeros).  params: the [B, 3K-1]
+ * conditioner outputs of dimension `col` (row pitch ldp elements).  ld_in / ld_out / gld are float32 for every
+ * dtype (the reference accumulates into torch.zeros(B), arqs.py:52).  out may alias cur.  num_bins <= 16. */
+NF_API int nf_arqs_step_forward(const void* cur, const void* v, const void* params, int64_t ldp, const void* ld_in,
+                         void* out, void* ld_out, int64_t B, int D, int col, int num_bins, int inverse,
+                         double min_bin_width, double min_bin_height, double min_derivative, int dtype,
+                         nf_stream_t stream);
+/* gcur = gout with column col zeroed; gv [B,D] zero outside col; gparams [B, 3K-1] dense; gld may be NULL */
+NF_API int nf_arqs_step_backward(const void* v, const void* params, int64_t ldp, const void* gout, const void* gld,
+                          void* gcur, void* gv, void* gparams, int64_t B, int D, int col, int num_bins, int inverse,
+                          double min_bin_width, double min_bin_height, double min_derivative, int dtype,
+                          nf_stream_t stream);
+
 /* ---- a12/a13 sequential directions, blocked: dense contributions of previous degree blocks on tcgen05
  * (nf_linear_tc on column slices), in-block dependent steps in a small-footprint kernel (csrc/ar_blocked.cu).
  * w / w_hi / w_lo / b: arrays of 4 device pointers (mask-folded, degree-sorted weights of the 4 MADE layers, their

@@ -6,9 +6,9 @@ The directory name is not a Python identifier; import it through the `nfb200` al
 """
 from . import _lib, ops, packing, parallel  # noqa: F401
 from .flows import (Flow, SequentialFlow, CouplingLayer, SplineCouplingLayer, rational_quadratic_spline,  # noqa: F401
-                    MaskedLinear, MADE, MaskedAutoregressiveFlow, InverseAutoregressiveFlow)
+                    MaskedLinear, MADE, MaskedAutoregressiveFlow, InverseAutoregressiveFlow, ARQS)
 from .models import NormalizingFlowModel, RealNVP, RealNVPSpline  # noqa: F401
 
 __all__ = ["Flow", "SequentialFlow", "CouplingLayer", "SplineCouplingLayer", "rational_quadratic_spline",
-           "MaskedLinear", "MADE", "MaskedAutoregressiveFlow", "InverseAutoregressiveFlow",
+           "MaskedLinear", "MADE", "MaskedAutoregressiveFlow", "InverseAutoregressiveFlow", "ARQS",
            "NormalizingFlowModel", "RealNVP", "RealNVPSpline"]

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "nf_split_tf32": [_P, _P, _P, _L, _P],
     "nf_linear_wgrad_tc_workspace": [_L, _L, _L],
     "nf_linear_wgrad_tc": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _P, _L, _P],
+    "nf_arqs_step_forward": [_P, _P, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _I, _P],
+    "nf_arqs_step_backward": [_P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _I, _P],
     "nf_ar_blocked_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "nf_ar_blocked_workspace_floats": [_L, _I, _I],
     "nf_spline_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],

@@ -368,15 +368,21 @@ class MADE(nn.Module):
         nn.init.zeros_(linears[-1].bias)
         return nn.Sequential(*layers)
 
-    def forward(self, x):
-        """Layered route: masked linears with the ReLU (or BatchNorm+ReLU) fused into the producing kernel."""
+    def forward(self, x, out_rows=None):
+        """Layered route: masked linears with the ReLU (or BatchNorm+ReLU) fused into the producing kernel.
+        out_rows=(r0, r1) evaluates only output features [r0, r1) of the last masked linear (ARQS needs the 3K-1
+        outputs of one dimension per step; the reference computes all of them and slices, arqs.py:56-64)."""
         mods = list(self.net)
         i, h = 0, x
         while i < len(mods):
             m = mods[i]
             if isinstance(m, MaskedLinear):
                 nxt = mods[i + 1] if i + 1 < len(mods) else None
-                if isinstance(nxt, nn.ReLU):
+                if out_rows is not None and i == len(mods) - 1:
+                    r0, r1 = out_rows
+                    h = ops.linear(h, m.weight[r0:r1], None if m.bias is None else m.bias[r0:r1], mask=m.mask[r0:r1])
+                    i += 1
+                elif isinstance(nxt, nn.ReLU):
                     h = ops.linear(h, m.weight, m.bias, mask=m.mask, relu=True)
                     i += 2
                 elif isinstance(nxt, nn.BatchNorm1d) and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU):
@@ -460,6 +466,53 @@ class InverseAutoregressiveFlow(_AffineAutoregressive):
 
     def inverse(self, x):
         return self._sequential(x)
+
+
+class ARQS(Flow):
+    """Autoregressive rational-quadratic-spline flow (src/flows/spline/arqs.py:7-114): a MADE conditioner with 3K-1
+    outputs per dimension and the public [0,1] spline.  As in the reference, BOTH directions are D-step sequential
+    loops that re-evaluate the conditioner on the partially filled output; here every step runs the three hidden
+    masked linears, only the 3K-1 head rows of the current dimension, and one fused spline-step kernel."""
+
+    def __init__(self, dim, hidden_dim=128, num_bins=8, layers=2, data_min=None, data_max=None, use_batch_norm=False):
+        super().__init__()
+        self.dim = dim
+        self.data_dim = dim
+        self.num_bins = num_bins
+        self.data_min = data_min
+        self.data_max = data_max
+        self.conditioner = MADE(input_dim=dim, hidden_dim=hidden_dim, output_dim_multiplier=3 * num_bins - 1,
+                                use_batch_norm=use_batch_norm)
+
+    def _rescale(self, v, to_unit):
+        """(x - data_min) / (data_max - data_min) and its inverse (arqs.py:28-42); identity when either bound is None."""
+        if self.data_min is None or self.data_max is None:
+            return v
+        span = self.data_max - self.data_min            # python scalars subtract in double, as in the reference
+        lo = torch.as_tensor(self.data_min, dtype=v.dtype, device=v.device).expand(v.shape[1]).contiguous()
+        span = torch.as_tensor(span, dtype=v.dtype, device=v.device).expand(v.shape[1]).contiguous()
+        if to_unit:
+            return ops.feature_affine(v, lo, span, None, None)
+        return ops.feature_affine(v, None, None, span, lo)
+
+    def _run(self, v, inverse):
+        v = compute_input(v)
+        vr = self._rescale(v, True)
+        P = 3 * self.num_bins - 1
+        cur = torch.zeros_like(vr)
+        ld = None
+        for i in range(self.dim):
+            params = self.conditioner(cur, out_rows=(i * P, (i + 1) * P))
+            cur, ld = ops.arqs_step(cur, vr, params, ld, i, self.num_bins, inverse)
+        if ld is None:
+            ld = torch.zeros(v.shape[0], dtype=torch.float32, device=v.device)
+        return self._rescale(cur, False), ld
+
+    def forward(self, z):
+        return self._run(z, False)
+
+    def inverse(self, x):
+        return self._run(x, True)
 
 
 USE_TENSOR_CORES = True      # tcgen05 stack kernels (3xTF32, fp32-accurate); False forces the FP32-pipe kernels

@@ -425,6 +425,39 @@ def ar_step(cur, v, params, ld_in, col, mode):
     return _ArStepFn.apply(cur, v, params, ld_in, col, mode)
 
 
+class _ArqsStepFn(Function):
+    """One step of ARQS's sequential loops (arqs.py:53-76 / :93-116): column `col` of `cur` is replaced by the public
+    [0,1] spline of v[:, col] under the [B, 3K-1] parameter block `params`; the float32 log-det vector accumulates."""
+
+    @staticmethod
+    def forward(ctx, cur, v, params, ld_in, col, K, inverse, mins):
+        cur, v, params = _c(cur), _c(v), _c(params)
+        B, D = v.shape
+        out = torch.empty_like(v)
+        ld = torch.empty(B, dtype=torch.float32, device=v.device)
+        call("nf_arqs_step_forward", ptr(cur), ptr(v), ptr(params), params.shape[1], ptr(None if ld_in is None else _c(ld_in)),
+             ptr(out), ptr(ld), B, D, col, K, int(inverse), mins[0], mins[1], mins[2], L.dtype_code(v), stream())
+        ctx.cfg = (col, K, inverse, mins, ld_in is not None)
+        ctx.save_for_backward(v, params)
+        return out, ld
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gld):
+        v, params = ctx.saved_tensors
+        col, K, inverse, mins, has_ld = ctx.cfg
+        B, D = v.shape
+        gcur, gv, gp = torch.empty_like(v), torch.empty_like(v), torch.empty_like(params)
+        gld = _c(gld.to(torch.float32))
+        call("nf_arqs_step_backward", ptr(v), ptr(params), params.shape[1], ptr(_c(gout)), ptr(gld), ptr(gcur), ptr(gv),
+             ptr(gp), B, D, col, K, int(inverse), mins[0], mins[1], mins[2], L.dtype_code(v), stream())
+        return gcur, gv, gp, (gld if has_ld else None), None, None, None, None
+
+
+def arqs_step(cur, v, params, ld_in, col, K, inverse, mins=(1e-3, 1e-3, 1e-3)):
+    return _ArqsStepFn.apply(cur, v, params, ld_in, col, K, bool(inverse), tuple(float(m) for m in mins))
+
+
 class _ArFinishFn(Function):
     @staticmethod
     def forward(ctx, cur, v, ld_sum, mode):

@@ -344,6 +344,31 @@ def iaf_inverse(sd: SD, p: str, x: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 # --------------------------------------------------------------------------- #
+# (f2)  ARQS  (src/flows/spline/arqs.py:7-114): MADE conditioner with 3K-1 outputs per dim, viewed [B, D, 3K-1];
+#       BOTH directions are D-step sequential loops that re-evaluate the conditioner on the partially filled OUTPUT
+#       and apply the public [0,1] spline (rqs_unit) to one column; log-dets accumulate in a float32 vector.
+# --------------------------------------------------------------------------- #
+def arqs(sd: SD, p: str, v: Tensor, inverse: bool, num_bins=8, data_min=None, data_max=None) -> Tuple[Tensor, Tensor]:
+    K = num_bins
+    P = 3 * K - 1
+    rescale = data_min is not None and data_max is not None
+    vr = (v - data_min) / (data_max - data_min) if rescale else v          # :28-34
+    cur = torch.zeros_like(vr)                                               # :51 / :91
+    ld = torch.zeros(v.size(0))                                              # :52 / :92 (float32 whatever v's dtype)
+    B, D = v.shape
+    for i in range(D):
+        params = made(sd, p + "conditioner.", cur).view(B, D, P)            # :56-59
+        out_i, ld_i = rqs_unit(vr[:, i], params[:, i, :K], params[:, i, K:2 * K], params[:, i, 2 * K:],
+                               inverse=inverse)                              # :61-70 / :101-110
+        new = cur.clone()
+        new[:, i] = out_i
+        cur = new
+        ld += ld_i
+    out = cur * (data_max - data_min) + data_min if rescale else cur         # :36-42
+    return out, ld
+
+
+# --------------------------------------------------------------------------- #
 # a14-a16  stacks (normalizing_flow_model.py:25-128, sequential_flow.py:15-34)
 # --------------------------------------------------------------------------- #
 def layer_apply(sd: SD, p: str, spec: dict, x: Tensor, inverse: bool,

@@ -37,6 +37,8 @@ def build(g, sd=None):
         m = N.MaskedAutoregressiveFlow(g["D"], g["H"])
     elif k == "iaf":
         m = N.InverseAutoregressiveFlow(g["D"], g["H"])
+    elif k == "arqs":
+        m = N.ARQS(g["D"], hidden_dim=g["H"], num_bins=g["K"], **g["extra"])
     elif k in ("realnvp", "realnvp_train"):
         m = N.RealNVP(g["D"], g["L"], g["H"], batch_norm_between_layers=g["bn"])
     elif k == "realnvpspline":
@@ -57,7 +59,8 @@ def build(g, sd=None):
     return m
 
 
-MODULE_KINDS = ("coupling", "spline", "maf", "iaf", "realnvp", "realnvpspline", "splinestack", "mixed", "sequential")
+MODULE_KINDS = ("coupling", "spline", "maf", "iaf", "realnvp", "realnvpspline", "splinestack", "mixed", "sequential",
+                "arqs")
 
 
 def assert_close(a, b, atol, rtol, what=""):

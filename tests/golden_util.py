@@ -48,6 +48,8 @@ def oracle_eval(g, inverse):
             return O.maf_inverse(g["sd"], "", x) if inverse else O.maf_forward(g["sd"], "", x)
         if k == "iaf":
             return O.iaf_inverse(g["sd"], "", x) if inverse else O.iaf_forward(g["sd"], "", x)
+        if k == "arqs":
+            return O.arqs(g["sd"], "", x, inverse, num_bins=g["K"], **g["extra"])
         if k == "sequential":
             p, specs = stack_specs(g)
             return O.sequential_flow(g["sd"], p, specs, x, inverse)

@@ -169,7 +169,10 @@ def test_float64_route_matches_float64_oracle(name):
             y, ld = _run(m, x.to(_dev()), inverse)
             assert y.dtype == torch.float64
             assert_close(y, ry, 1e-9, 1e-9, f"{name} f64 z inv={inverse}")
-            assert_close(ld, torch.as_tensor(rld).expand(ld.shape), 1e-8, 1e-9, f"{name} f64 ld inv={inverse}")
+            # ARQS keeps its log-det in a float32 vector whatever the data dtype (arqs.py:52): one float32 ulp
+            ld_atol, ld_rtol = (1e-6, 2e-7) if g["kind"] == "arqs" else (1e-8, 1e-9)
+            assert ld.dtype == torch.as_tensor(rld).dtype
+            assert_close(ld, torch.as_tensor(rld).expand(ld.shape), ld_atol, ld_rtol, f"{name} f64 ld inv={inverse}")
 
 
 @pytest.mark.parametrize("name", G.golden_names("coupling_train"))

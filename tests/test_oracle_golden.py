@@ -8,7 +8,7 @@ from oracle import flows_oracle as O
 from tests import golden_util as G
 
 EVAL_KINDS = ("coupling", "spline", "rqs_bounded", "rqs_unit", "maf", "iaf", "realnvp", "realnvpspline",
-              "splinestack", "mixed", "sequential")
+              "splinestack", "mixed", "sequential", "arqs")
 
 
 def _same(a, b):
