@@ -143,11 +143,24 @@ gemm_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C
     }
 }
 
+// skinny_kernels.cu: products with one dimension <= 8 (data_dim of the low-dimensional flows)
+template <typename T>
+int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K, int64_t sam,
+                    int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate, const int32_t* k_extent,
+                    cudaStream_t st);
+template <typename T>
+int col_sum_small_launch(const void* a, void* out, int64_t rows, int cols, cudaStream_t st);
+
 template <typename T>
 static int gemm_launch(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K,
                        int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate,
                        const int32_t* k_extent, cudaStream_t st) {
     using Cfg = GemmCfg<T>;
+    {
+        const int rc = skinny_gemm_try<T>(A, Bm, C, bias, M, N, K, sam, sak, sbk, sbn, ldc, relu, accumulate, k_extent, st);
+        if (rc < 0) return rc;
+        if (rc == 1) { count_launch(); NF_LAUNCH_CHECK(); return NF_OK; }
+    }
     const int64_t tm = cdiv(M, Cfg::BM), tn = cdiv(N, Cfg::BN);
     if (tn > 65535 || tm > 2147483647LL) return NF_ERR_BAD_SHAPE;
     int splits = 1;
@@ -517,6 +530,14 @@ extern "C" int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, 
         if (ch > 65535) return NF_ERR_BAD_SHAPE;
         if (ch > 1) NF_CUDA(cudaMemsetAsync(out, 0, es * cols, st));
         col_sum_vec4_kernel<<<dim3((unsigned)cblocks, (unsigned)ch), 256, 0, st>>>((const float*)a, (float*)out, rows, cols, rpc4);
+        count_launch();
+        NF_LAUNCH_CHECK();
+        return NF_OK;
+    }
+    if (cols <= 8 && rows >= 1 && a) {
+        int rc = dtype == NF_F32 ? col_sum_small_launch<float>(a, out, rows, (int)cols, st)
+               : dtype == NF_F64 ? col_sum_small_launch<double>(a, out, rows, (int)cols, st) : NF_ERR_UNSUPPORTED;
+        if (rc) return rc;
         count_launch();
         NF_LAUNCH_CHECK();
         return NF_OK;

@@ -1,0 +1,229 @@
+// skinny_kernels.cu -- dense products with one very small dimension (data_dim = 2..8 next to hidden_dim 64+):
+// the first and last Linear of the conditioners of low-dimensional flows (coupling_layer.py:18-35,
+// spline_coupling_layer.py:55-62, made.py:81-134) and their gradients.  A 128x128-tile GEMM wastes > 90 % of its
+// work on them and, for the weight gradients, leaves a handful of CTAs walking the whole batch (measured: 201 us per
+// launch at 5 000 rows, 55 % of a RealNVP(2,8,64) training step).  These kernels are streaming, HBM-bound:
+//   skinny_reduce   C = sum_b Wd[b,:]^T (x) Sk[b,:]      one operand <= 8 columns wide, reduction over the batch
+//                   (dW of the first / last Linear; bias gradients go through col_sum_small in dense_kernels.cu)
+//   skinny_k        C[m,:] = sum_{k<=8} A[m,k] B[k,:]    (first Linear forward, input gradient of the last Linear)
+//   skinny_n        C[m,n<=8] = A[m,:] . B[:,n]          (last Linear forward)
+// Called from nf_gemm's dispatcher (dense_kernels.cu); same semantics as gemm_kernel (bias, ReLU, strides).
+#include "nf_common.cuh"
+
+namespace nf {
+
+// ---- C[w,s] (or C[s,w]) = sum_b Wd[b*ldw + w] * Sk[b*lds + s];  S <= 8 -------------------------------------------------
+// block = 8 warps sharing 128 columns of Wd (lane + 32 j), rows strided over the warps and over blockIdx.y chunks;
+// per-thread accumulators [4][S]; block reduction in shared memory; chunks combine with atomics (C zeroed by the host)
+template <typename T, int S>
+__global__ void __launch_bounds__(256)
+skinny_reduce_kernel(const T* __restrict__ Wd, const T* __restrict__ Sk, T* __restrict__ C, int64_t B, int W, int64_t ldw,
+                     int64_t lds, int64_t so_w, int64_t so_s, int s_live, int64_t rows_per_chunk) {
+    __shared__ T red[4][128 * S + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    const int64_t r1 = (B < r0 + rows_per_chunk) ? B : r0 + rows_per_chunk;
+    T acc[4][S];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[j][s] = T(0);
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        T sk[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) sk[s] = (s < s_live) ? Sk[r * lds + s] : T(0);
+        T v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int c = c0 + lane + 32 * j; v[j] = (c < W) ? Wd[r * ldw + c] : T(0); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[j][s] += v[j] * sk[s];
+    }
+    if (warp >= 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int s = 0; s < S; ++s) red[warp - 4][(lane + 32 * j) * S + s] = acc[j][s];
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int s = 0; s < S; ++s) red[warp][(lane + 32 * j) * S + s] += acc[j][s];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * S; i += 256) {
+        const int cl = i / S, s = i - cl * S, c = c0 + cl;
+        if (c >= W || s >= s_live) continue;
+        T t = T(0);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t += red[w][i];
+        T* dst = C + (int64_t)c * so_w + (int64_t)s * so_s;
+        if (gridDim.y == 1) *dst = t; else atomicAdd(dst, t);
+    }
+}
+
+// ---- C[m, n] = act(sum_{k<K<=8} A[m*sam + k*sak] * Bm[k*sbk + n*sbn] + bias[n]) -----------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+skinny_k_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C, const T* __restrict__ bias, int64_t M,
+                int N, int K, int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate) {
+    const int64_t total = M * N, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < K) acc += A[m * sam + k * sak] * __ldg(Bm + k * sbk + n * sbn);
+        if (bias) acc += __ldg(bias + n);
+        T* cp = C + m * ldc + n;
+        if (accumulate) acc += *cp;
+        if (relu) acc = relu_nan(acc);
+        *cp = acc;
+    }
+}
+
+// ---- C[m, n<N<=8] = act(sum_k A[m*sam + k] * Bm[k*sbk + n*sbn] + bias[n]);  8 lanes per row, coalesced row reads ----------
+template <typename T, int NS>
+__global__ void __launch_bounds__(256)
+skinny_n_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C, const T* __restrict__ bias, int64_t M,
+                int N, int K, int64_t sam, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate) {
+    const int sub = threadIdx.x & 7;
+    const int64_t rows_per_pass = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    // every lane of a warp runs the same number of iterations (shuffles below): loop on the warp's first row
+    for (int64_t m0 = (((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 3); m0 < M; m0 += rows_per_pass) {
+        const int64_t m = m0 + ((threadIdx.x & 31) >> 3);
+        T acc[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) acc[n] = T(0);
+        if (m < M) {
+            const T* ar = A + m * sam;
+            for (int k = sub; k < K; k += 8) {
+                const T a = ar[k];
+#pragma unroll
+                for (int n = 0; n < NS; ++n) if (n < N) acc[n] += a * __ldg(Bm + k * sbk + n * sbn);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) acc[n] = group_sum<T, 8>(acc[n]);
+        if (m < M && sub == 0) {
+#pragma unroll
+            for (int n = 0; n < NS; ++n) if (n < N) {
+                T v = acc[n] + (bias ? __ldg(bias + n) : T(0));
+                T* cp = C + m * ldc + n;
+                if (accumulate) v += *cp;
+                if (relu) v = relu_nan(v);
+                *cp = v;
+            }
+        }
+    }
+}
+
+// column sums of a[rows, cols], cols <= 8: the array is walked flat, every thread keeps `cols` phase-aligned
+// accumulators; block reduction, then atomics across blocks (out zeroed by the host)
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_sum_small_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t rows, int cols, int64_t rows_per_block) {
+    __shared__ double red[8][8];
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (rows < r0 + rows_per_block) ? rows : r0 + rows_per_block;
+    double acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) if (c < cols) acc[c] += (double)a[r * cols + c];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double t = warp_sum<double>(acc[c]);
+        if (lane == 0) red[warp][c] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        if (gridDim.x == 1) out[threadIdx.x] = (T)t; else atomicAdd(out + threadIdx.x, (T)t);
+    }
+}
+
+// ---- dispatcher used by nf_gemm ------------------------------------------------------------------------------------------
+// returns 1 when the product was handled here (launch issued), 0 when the shape is not skinny, < 0 on error
+template <typename T>
+int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, int64_t M, int64_t N, int64_t K, int64_t sam,
+                    int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate, const int32_t* k_extent,
+                    cudaStream_t st) {
+    if (k_extent) return 0;
+    // (1) reduction over a long batch with one narrow operand: C[M,N] = sum_k A[m + k*sak] * Bm[k*sbk + n]
+    if (!bias && !relu && !accumulate && sam == 1 && sbn == 1 && K >= 256 && (M <= 8 || N <= 8) && M * N <= (1 << 20)) {
+        const bool narrow_b = N <= 8 && !(M <= 8 && M < N);      // Sk = Bm (S = N), Wd = A (W = M); else the transpose
+        const T* Wd = (const T*)(narrow_b ? A : Bm);
+        const T* Sk = (const T*)(narrow_b ? Bm : A);
+        const int W = (int)(narrow_b ? M : N), S = (int)(narrow_b ? N : M);
+        const int64_t ldw = narrow_b ? sak : sbk, lds = narrow_b ? sbk : sak;
+        const int64_t so_w = narrow_b ? ldc : 1, so_s = narrow_b ? 1 : ldc;
+        const int64_t cblocks = cdiv(W, 128);
+        int64_t ch = cdiv((int64_t)kNumSMs * 4, cblocks);
+        const int64_t chmax = K / 64 > 1 ? K / 64 : 1;           // at least 64 rows (8 per warp) per chunk
+        if (ch > chmax) ch = chmax;
+        const int64_t rpc = cdiv(K, ch);
+        ch = cdiv(K, rpc);
+        if (ch > 65535) return 0;
+        if (ch > 1) {
+            if (ldc == N) NF_CUDA(cudaMemsetAsync(C, 0, sizeof(T) * M * N, st));
+            else NF_CUDA(cudaMemset2DAsync(C, sizeof(T) * ldc, 0, sizeof(T) * N, M, st));
+        }
+        dim3 grid((unsigned)cblocks, (unsigned)ch);
+#define NF_SR(SS) skinny_reduce_kernel<T, SS><<<grid, 256, 0, st>>>(Wd, Sk, (T*)C, K, W, ldw, lds, so_w, so_s, S, rpc)
+        if (S <= 2) NF_SR(2); else if (S <= 4) NF_SR(4); else NF_SR(8);
+#undef NF_SR
+        return 1;
+    }
+    // (2) tiny reduction dimension: one output element per thread
+    if (K >= 1 && K <= 8 && M >= 64) {
+        const int64_t total = M * N;
+        int64_t g = cdiv(total, 256), cap = (int64_t)kNumSMs * 16;
+        skinny_k_kernel<T><<<(int)(g < cap ? g : cap), 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, (int)N,
+                                                                      (int)K, sam, sak, sbk, sbn, ldc, relu, accumulate);
+        return 1;
+    }
+    // (3) narrow output: per-row dot products, contiguous A rows
+    if (N <= 8 && sak == 1 && M >= 64 && K >= 16) {
+        int64_t g = cdiv(M * 8, 256), cap = (int64_t)kNumSMs * 16;
+        const int grid = (int)(g < cap ? g : cap);
+#define NF_SN(NS) skinny_n_kernel<T, NS><<<grid, 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, (int)N, (int)K, \
+                                                             sam, sbk, sbn, ldc, relu, accumulate)
+        if (N <= 2) NF_SN(2); else if (N <= 4) NF_SN(4); else NF_SN(8);
+#undef NF_SN
+        return 1;
+    }
+    return 0;
+}
+
+template int skinny_gemm_try<float>(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                                    int64_t, int64_t, int64_t, int, int, const int32_t*, cudaStream_t);
+template int skinny_gemm_try<double>(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                                     int64_t, int64_t, int64_t, int, int, const int32_t*, cudaStream_t);
+
+template <typename T>
+int col_sum_small_launch(const void* a, void* out, int64_t rows, int cols, cudaStream_t st) {
+    int64_t blocks = cdiv(rows, 2048);
+    const int64_t cap = (int64_t)kNumSMs * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const int64_t rpb = cdiv(rows, blocks);
+    blocks = cdiv(rows, rpb);
+    if (blocks > 1) NF_CUDA(cudaMemsetAsync(out, 0, sizeof(T) * cols, st));
+    col_sum_small_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)out, rows, cols, rpb);
+    return NF_OK;
+}
+template int col_sum_small_launch<float>(const void*, void*, int64_t, int, cudaStream_t);
+template int col_sum_small_launch<double>(const void*, void*, int64_t, int, cudaStream_t);
+
+}  // namespace nf

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--graph", action="store_true", help="capture the whole step (fwd, bwd, Adam) in one CUDA graph (1 GPU)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -49,7 +50,7 @@ def main():
     model, D = MODELS[a.model]()
     model.to(dev).train()
     dp = N.parallel.DataParallelFlow(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=a.graph)
     gen = torch.Generator(device=dev).manual_seed(rank)
     x = torch.randn(a.batch, D, device=dev, generator=gen)
 
@@ -62,6 +63,18 @@ def main():
         opt.step()
         return loss
 
+    if a.graph:
+        # launch-bound small batches (C1: 5000 rows, ~500 launches per step): replay the step as one CUDA graph.
+        # Every kernel of the step goes through the C ABI on torch's current stream, so stream capture records them.
+        assert world == 1
+
+        def loss_fn(mdl, xin):
+            z, ld = mdl.inverse(xin)
+            return -N.ops.std_normal_log_prob(z, ld).mean()
+        graphed = N.graphs.GraphedTrainStep(model, opt, loss_fn, x)
+
+        def step():        # noqa: F811
+            return graphed()
     for _ in range(a.warmup):
         step()
     if world > 1:
@@ -93,7 +106,7 @@ def main():
         print(json.dumps({"model": a.model, "n_gpus": world, "batch_per_gpu": a.batch, "ms_per_step": ms.item(),
                           "samples_per_s": a.batch * world / (ms.item() * 1e-3), "loss": float(loss),
                           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
-                          "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
+                          "cuda_graph": bool(a.graph), "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
     if world > 1:
         dist.destroy_process_group()

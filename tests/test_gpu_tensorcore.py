@@ -128,3 +128,38 @@ def test_col_sum_matches_float64(rows, cols):
     ref = a.double().sum(0)
     scale = a.double().abs().sum(0) + 1e-30
     assert ((got - ref).abs() / scale).max().item() < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,H,D", [(5000, 64, 2), (300, 64, 2), (70000, 128, 3), (4096, 40, 8), (1000, 16, 1)])
+def test_skinny_products_match_float64(B, H, D, dtype):
+    """nf_gemm's skinny routes (one dimension <= 8): first / last Linear of a low-dimensional conditioner, forward,
+    input gradient and weight gradient, against float64 products."""
+    gen = torch.Generator().manual_seed(B + H + D)
+    x = torch.randn(B, D, generator=gen, dtype=torch.float64)
+    h = torch.randn(B, H, generator=gen, dtype=torch.float64)
+    w1 = torch.randn(H, D, generator=gen, dtype=torch.float64)          # first Linear  [H, D]
+    w3 = torch.randn(D, H, generator=gen, dtype=torch.float64)          # last Linear   [D, H]
+    b1 = torch.randn(H, generator=gen, dtype=torch.float64)
+    b3 = torch.randn(D, generator=gen, dtype=torch.float64)
+    gy1 = torch.randn(B, H, generator=gen, dtype=torch.float64)         # grad of the first Linear's output
+    gy3 = torch.randn(B, D, generator=gen, dtype=torch.float64)
+    c = lambda t: t.to(dtype).cuda().contiguous()
+    tol = 2e-6 if dtype == torch.float32 else 1e-12
+
+    def check(got, ref, scale, what):
+        err = ((got.cpu().double() - ref).abs() / (scale + 1e-30)).max().item()
+        assert err < tol, f"{what}: scaled error {err:.3e}"
+
+    # forward, K = D small (bias + ReLU) and N = D small (bias)
+    check(N_.ops.linear_raw(c(x), c(w1), c(b1), relu=True), torch.relu(x @ w1.T + b1), x.abs() @ w1.abs().T + b1.abs(), "fwd K small")
+    check(N_.ops.linear_raw(c(h), c(w3), c(b3)), h @ w3.T + b3, h.abs() @ w3.abs().T + b3.abs(), "fwd N small")
+    # input gradient of the last Linear: dX[B,H] = dY[B,D] W3[D,H]
+    check(N_.ops.gemm(c(gy3), c(w3), B, H, D, D, 1, H, 1), gy3 @ w3, gy3.abs() @ w3.abs(), "dX K small")
+    # input gradient of the first Linear: dX[B,D] = dY[B,H] W1[H,D]
+    check(N_.ops.gemm(c(gy1), c(w1), B, D, H, H, 1, D, 1), gy1 @ w1, gy1.abs() @ w1.abs(), "dX N small")
+    # weight gradients: dW1[H,D] = dY1^T x, dW3[D,H] = dY3^T h
+    check(N_.ops.gemm(c(gy1), c(x), H, D, B, 1, H, D, 1), gy1.T @ x, gy1.abs().T @ x.abs(), "dW narrow K")
+    check(N_.ops.gemm(c(gy3), c(h), D, H, B, 1, D, H, 1), gy3.T @ h, gy3.abs().T @ h.abs(), "dW narrow N")
+    # bias gradient of the last Linear
+    check(N_.ops.col_sum(c(gy3)), gy3.sum(0), gy3.abs().sum(0), "col_sum small")

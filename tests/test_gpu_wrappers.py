@@ -126,3 +126,38 @@ def test_reference_samples_per_sec_recipe():
         torch.cuda.synchronize()
         dt = (time.time() - t) / 3
     assert x.shape == (4000, 2) and 4000 / dt > 1e5
+
+
+def test_graphed_train_step_matches_eager_steps():
+    """CUDA-graph replay of forward + backward + optimizer (graphs.GraphedTrainStep) follows the eager trajectory."""
+    import copy
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    base = N.RealNVP(2, 4, 32).to(dev).train()
+    x = torch.randn(3, 2000, 2, device=dev)
+
+    def loss_fn(m, xin):
+        z, ld = m.inverse(xin)
+        return -N.ops.std_normal_log_prob(z, ld).mean()
+
+    eager_m = copy.deepcopy(base)
+    opt_e = torch.optim.SGD(eager_m.parameters(), lr=1e-2, momentum=0.9)       # SGD: no sign(g)-style sensitivity
+    graph_m = copy.deepcopy(base)
+    opt_g = torch.optim.SGD(graph_m.parameters(), lr=1e-2, momentum=0.9)
+    # the constructor's warm-up steps are real optimizer steps on example_input: give the eager twin the same ones
+    step = N.graphs.GraphedTrainStep(graph_m, opt_g, loss_fn, x[0], warmup=2)
+    for _ in range(3):                      # 2 warm-up + the captured step itself
+        opt_e.zero_grad(set_to_none=True)
+        loss_fn(eager_m, x[0]).backward()
+        opt_e.step()
+    losses_g, losses_e = [], []
+    for i in range(3):
+        losses_g.append(float(step(x[i])))
+        opt_e.zero_grad(set_to_none=True)
+        le = loss_fn(eager_m, x[i])
+        le.backward()
+        opt_e.step()
+        losses_e.append(float(le))
+    assert all(abs(a - b) <= 1e-4 * (1 + abs(b)) for a, b in zip(losses_g, losses_e)), (losses_g, losses_e)
+    for (k, p), (_, q) in zip(graph_m.named_parameters(), eager_m.named_parameters()):
+        assert torch.allclose(p, q, atol=1e-5, rtol=1e-4), k
