@@ -146,7 +146,7 @@ def test_graphed_train_step_matches_eager_steps():
     opt_g = torch.optim.SGD(graph_m.parameters(), lr=1e-2, momentum=0.9)
     # the constructor's warm-up steps are real optimizer steps on example_input: give the eager twin the same ones
     step = N.graphs.GraphedTrainStep(graph_m, opt_g, loss_fn, x[0], warmup=2)
-    for _ in range(3):                      # 2 warm-up + the captured step itself
+    for _ in range(2):                      # the 2 warm-up steps (capture records the step, it does not run it)
         opt_e.zero_grad(set_to_none=True)
         loss_fn(eager_m, x[0]).backward()
         opt_e.step()
