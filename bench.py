@@ -376,14 +376,19 @@ def run_product(args):
                 "parity (tensor_flops_per_row_executed); the kernel is bound by the per-row spline / split work on the "
                 "FP32 pipe, not by the tensor pipe or HBM (20 B per row)")
         tensor_exec = 8 * 3 * 2 * (64 * 64 + 64 * 32)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch in the ncu --set full capture
+        # profiles/r01c_c2_spline_stack_tc2_ncu.txt (8.85 MB read, 0 written: the 12 MB of outputs of a single replayed
+        # launch stay in the 126 MB L2; algorithmic traffic is 20 B x 2^20 rows = 21 MB)
+        traffic = 8.854528e6 if rows == 1 << 20 else None
     else:
         kernel = "gemm_tc_kernel x4 (tcgen05 3xTF32, TMA-fed, masked-out K tiles skipped) + affine_ar_fwd_kernel"
         note = ("dense GEMM FLOPs of one MADE evaluation (SURVEY 8d) over the time of the whole MAF.inverse chain; the "
                 "tensor pipe executes 3x the unskipped FLOPs (3xTF32 keeps fp32 parity)")
         tensor_exec = None
+        traffic = None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "traffic": None, "kernel": kernel,
+        "traffic": traffic, "kernel": kernel,
         "flops_per_row": FLOPS_DENSE[wl], "flops_per_row_executed": FLOPS_EXEC[wl],
         "tensor_flops_per_row_executed": tensor_exec, "peak_source": which,
         "ms_per_launch": {"inverse": ms_inv, "forward": ms_fwd, "log_prob_head": ms_head},
