@@ -57,7 +57,8 @@ NF_API const char* nf_last_cuda_error(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 NF_API int64_t nf_launch_count(void);
 /* library options for A/B measurements: key 1 = fused spline stack variant (0: one warpgroup per CTA, 1: two, default);
- * key 2 = nf_linear_wgrad_tc: longest TMEM accumulation chain in 32-row blocks (default 64) */
+ * key 2 = nf_linear_wgrad_tc: longest TMEM accumulation chain in 32-row blocks (default 64);
+ * key 3 = nf_ar_blocked_forward in-block kernel (0: CTA-barrier version, 1: warp-private tiles, default) */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------

@@ -128,6 +128,236 @@ ar_block_kernel(const float* __restrict__ vin, float* __restrict__ xcur, const f
     if (threadIdx.x < nrow) { ldacc[r0 + threadIdx.x] = sld[threadIdx.x]; bad[r0 + threadIdx.x] = sbad[threadIdx.x]; }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second version of the in-block kernel.  Every tile access above is [unit][lane]: a lane only ever touches its own
+// row, so nothing in the step loop needs a CTA barrier -- the first version still split the units of a degree across
+// four warps and paid four __syncthreads per degree (plus two loads per FMA in dot_tile): 0.83 ms per block at
+// 262 144 rows.  Here a warp owns 32 rows for the whole block (no barrier after the weight staging), the in-block
+// weights sit in shared memory TRANSPOSED ([v][unit]) so that the weights of four consecutive units are one
+// broadcast LDS.128, and up to three 4-unit chunks share every activation load: 1 LDS.32 + 3 LDS.128 per 12 FMAs.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kWarpChunks = 3;       // 4-unit chunks evaluated together (12 independent FMA chains per lane)
+
+// [32 rows x n] slice of a row-major [B, ld] array -> transposed tile [n][kBlkPad] of the calling warp.  4-byte cp.async:
+// every element of the slice is in flight at once (the warp is alone on its scheduler: a register-staged loop would
+// expose the full global-memory latency per element); rows are walked in the outer loop, so no integer division.
+__device__ __forceinline__ void warp_fill_tile(float* tile, const float* __restrict__ src, int64_t r0, int nrow, int ld, int c0,
+                                               int n, int lane) {
+    if (!src) {
+        for (int c = 0; c < n; ++c) tile[c * kBlkPad + lane] = 0.f;
+        return;
+    }
+    // lanes along the columns (coalesced 128-byte row segments), rows in the unrolled inner loop: one LDGSTS and one
+    // pointer bump per element (the first version recomputed both addresses per element: 25 instructions per copy)
+    for (int c = lane; c < n; c += 32) {
+        const float* gp = src + r0 * (int64_t)ld + c0 + c;
+        const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(tile + c * kBlkPad));
+        if (nrow == kBlkRows) {
+#pragma unroll 8
+            for (int r = 0; r < kBlkRows; ++r, gp += ld)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa + 4u * r), "l"(gp));
+        } else {
+            for (int r = 0; r < kBlkRows; ++r, gp += ld) {
+                if (r < nrow) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa + 4u * r), "l"(gp));
+                else tile[c * kBlkPad + r] = 0.f;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void warp_drain_tile(const float* tile, float* __restrict__ dst, int64_t r0, int nrow, int ld, int c0,
+                                                int n, int lane) {
+    for (int c = lane; c < n; c += 32) {
+        float* gp = dst + r0 * (int64_t)ld + c0 + c;
+        const float* sp = tile + c * kBlkPad;
+        if (nrow == kBlkRows) {
+#pragma unroll 8
+            for (int r = 0; r < kBlkRows; ++r, gp += ld) *gp = sp[r];
+        } else {
+            for (int r = 0; r < nrow; ++r, gp += ld) *gp = sp[r];
+        }
+    }
+}
+
+template <int NCH, int NUP>
+__device__ __forceinline__ void warp_units_chunk(const float* __restrict__ wt, const float* __restrict__ bias,
+                                                 const float* __restrict__ in, int nv, float* __restrict__ out, int cu, int ub0,
+                                                 int ub1, int lane) {
+    float acc[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+    // compile-time row pitches (NUP, kBlkPad): the unrolled body addresses everything with immediate offsets
+    const float* ap = in + lane;
+    const float* wp = wt + cu;
+    int v = 0;
+    for (; v + 4 <= nv; v += 4, ap += 4 * kBlkPad, wp += 4 * NUP) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = ap[k * kBlkPad];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const float4 w = *reinterpret_cast<const float4*>(wp + k * NUP + 4 * c);    // rows padded by 4*kWarpChunks floats
+                acc[c][0] = fmaf(w.x, a, acc[c][0]); acc[c][1] = fmaf(w.y, a, acc[c][1]);
+                acc[c][2] = fmaf(w.z, a, acc[c][2]); acc[c][3] = fmaf(w.w, a, acc[c][3]);
+            }
+        }
+    }
+    for (; v < nv; ++v, ap += kBlkPad, wp += NUP) {
+        const float a = *ap;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + 4 * c);
+            acc[c][0] = fmaf(w.x, a, acc[c][0]); acc[c][1] = fmaf(w.y, a, acc[c][1]);
+            acc[c][2] = fmaf(w.z, a, acc[c][2]); acc[c][3] = fmaf(w.w, a, acc[c][3]);
+        }
+    }
+    float* op = out + cu * kBlkPad + lane;
+    const float* bp = bias + cu;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = cu + 4 * c + j;
+            if (u >= ub0 && u < ub1) op[(4 * c + j) * kBlkPad] = relu_nan(op[(4 * c + j) * kBlkPad] + bp[4 * c + j] + acc[c][j]);
+        }
+}
+
+template <int NUP>
+__device__ __forceinline__ void warp_units(const float* __restrict__ wt, const float* __restrict__ bias,
+                                           const float* __restrict__ in, int nv, float* __restrict__ out, int ub0, int ub1,
+                                           int lane) {
+    int cu = ub0 & ~3;
+    while (cu < ub1) {
+        const int left = (ub1 - cu + 3) >> 2;          // 4-unit chunks still to do (warp-uniform)
+        if (left >= 3) { warp_units_chunk<3, NUP>(wt, bias, in, nv, out, cu, ub0, ub1, lane); cu += 12; }
+        else if (left == 2) { warp_units_chunk<2, NUP>(wt, bias, in, nv, out, cu, ub0, ub1, lane); cu += 8; }
+        else { warp_units_chunk<1, NUP>(wt, bias, in, nv, out, cu, ub0, ub1, lane); cu += 4; }
+    }
+}
+
+template <int NUP>
+__global__ void __launch_bounds__(256)
+ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, const float* __restrict__ pre1,
+                     const float* __restrict__ pre2, const float* __restrict__ pre3, const float* __restrict__ preo,
+                     float* __restrict__ act1, float* __restrict__ act2, float* __restrict__ act3,
+                     const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                     const float* __restrict__ w3, const float* __restrict__ b3, const int32_t* __restrict__ gstart,
+                     float* __restrict__ ldacc, int* __restrict__ bad, int64_t B, int D, int H, int g0, int g1, int u0, int u1,
+                     int mode) {
+    extern __shared__ __align__(16) float sm[];
+    const int nd = g1 - g0, nu = u1 - u0;
+    constexpr int nup = NUP;                                     // padded row length of the transposed weight tiles
+    const int nwarps = blockDim.x >> 5;
+    // shared weights: W0t [nd][nup], W1t / W2t [nu][nup], W3t [nu][2*nd] (mu, alpha interleaved per dim), biases [3][nu]
+    float* W0t = sm;
+    float* W1t = W0t + nd * nup;
+    float* W2t = W1t + nu * nup;
+    float* W3t = W2t + nu * nup;
+    float* bs = W3t + nu * 2 * nd;
+    float* tiles = bs + ((3 * nu + 3) & ~3);
+    const int tile_floats = (nd + 3 * nu) * kBlkPad;
+    for (int i = threadIdx.x; i < (nd + 2 * nu) * nup; i += blockDim.x) W0t[i] = 0.f;      // padding columns must be finite
+    __syncthreads();
+    {
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nw_ = blockDim.x >> 5;
+#define NF_CPA4(dst, srcp) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(srcp))
+        for (int u = warp_; u < nu; u += nw_) {                   // one unit (weight row) per warp, lanes along v; all copies in flight
+            const float* r0p = w0 + (size_t)(u0 + u) * D + g0;
+            for (int d = lane_; d < nd; d += 32) NF_CPA4(W0t + d * nup + u, r0p + d);
+            const float* r1p = w1 + (size_t)(u0 + u) * H + u0;
+            const float* r2p = w2 + (size_t)(u0 + u) * H + u0;
+            for (int v = lane_; v < nu; v += 32) { NF_CPA4(W1t + v * nup + u, r1p + v); NF_CPA4(W2t + v * nup + u, r2p + v); }
+        }
+        for (int d = warp_; d < nd; d += nw_) {
+            const float* rm = w3 + (size_t)(g0 + d) * H + u0;
+            const float* ra = w3 + (size_t)(D + g0 + d) * H + u0;
+            for (int v = lane_; v < nu; v += 32) { NF_CPA4(W3t + v * 2 * nd + 2 * d, rm + v); NF_CPA4(W3t + v * 2 * nd + 2 * d + 1, ra + v); }
+        }
+#undef NF_CPA4
+    }
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) { bs[i] = b0[u0 + i]; bs[nu + i] = b1[u0 + i]; bs[2 * nu + i] = b2[u0 + i]; }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t r0 = ((int64_t)blockIdx.x * nwarps + warp) * kBlkRows;
+    const bool idle = r0 >= B;                       // keeps going to the barrier below, touches nothing
+    if (idle) r0 = 0;
+    const int nrow = idle ? 0 : (int)((B - r0) < kBlkRows ? (B - r0) : kBlkRows);
+    const bool first = (g0 == 0);
+    float* sx = tiles + (size_t)warp * tile_floats;
+    float* a1 = sx + nd * kBlkPad;
+    float* a2 = a1 + nu * kBlkPad;
+    float* a3 = a2 + nu * kBlkPad;
+    warp_fill_tile(sx, vin, r0, nrow, D, g0, nd, lane);
+    warp_fill_tile(a1, pre1, r0, nrow, H, u0, nu, lane);
+    warp_fill_tile(a2, pre2, r0, nrow, H, u0, nu, lane);
+    warp_fill_tile(a3, pre3, r0, nrow, H, u0, nu, lane);
+    asm volatile("cp.async.commit_group;\n" ::);
+    const bool ok = lane < nrow;
+    float ld = (!first && ok) ? ldacc[r0 + lane] : 0.f;
+    int poisoned = (!first && ok) ? bad[r0 + lane] : 0;
+    // previous blocks' contributions to the parameters of this block's dims, and the degree boundaries, up front:
+    // inside the step loop every global load would sit on the critical path of a warp that is alone on its scheduler
+    const float* prow = (preo && ok) ? preo + (r0 + lane) * 2 * D : nullptr;
+    float cmu = prow ? prow[g0] : 0.f, cal = prow ? prow[D + g0] : 0.f;      // consumed by the first step
+    int ub_lo = gstart[g0] - u0, ub_hi = gstart[g0 + 1] - u0;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();                                 // weights (all warps' copies) and this warp's tiles have landed
+    if (idle) return;
+
+    for (int g = g0; g < g1; ++g) {
+        const int ub0 = ub_lo, ub1 = ub_hi;                           // in-block units of degree g
+        // next step's global operands are requested now and consumed one iteration later
+        const bool more = g + 1 < g1;
+        const float nmu = (more && prow) ? prow[g + 1] : 0.f, nal = (more && prow) ? prow[D + g + 1] : 0.f;
+        const int nub = more ? gstart[g + 2] - u0 : ub_hi;
+        // (A) parameters of dim g: previous blocks (preo) + in-block layer-3 units of degree < g
+        {
+            float mu0 = __ldg(b3 + g), al0 = __ldg(b3 + D + g), mu1 = 0.f, al1 = 0.f;
+            const float* wq = W3t + 2 * (g - g0);
+            int v = 0;
+            for (; v + 2 <= ub0; v += 2) {
+                const float2 wa = *reinterpret_cast<const float2*>(wq + v * 2 * nd);
+                const float2 wb = *reinterpret_cast<const float2*>(wq + (v + 1) * 2 * nd);
+                const float xa = a3[v * kBlkPad + lane], xb = a3[(v + 1) * kBlkPad + lane];
+                mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
+                mu1 = fmaf(wb.x, xb, mu1); al1 = fmaf(wb.y, xb, al1);
+            }
+            if (v < ub0) {
+                const float2 wa = *reinterpret_cast<const float2*>(wq + v * 2 * nd);
+                const float xa = a3[v * kBlkPad + lane];
+                mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
+            }
+            float mu = mu0 + mu1, al = al0 + al1;
+            mu += cmu; al += cal;
+            float o, t;
+            affine_ar_elem<float>(mode, sx[(g - g0) * kBlkPad + lane], mu, al, o, t);
+            if (poisoned) { o = __int_as_float(0x7fc00000); t = o; }
+            if (!is_finite(o)) poisoned = 1;        // 0*NaN of the dense reference poisons every later dim
+            sx[(g - g0) * kBlkPad + lane] = o;
+            ld += t;
+        }
+        if (g == D - 1) break;
+        // (B) hidden units of degree g, layer by layer (all lane-private: no synchronisation)
+        warp_units<NUP>(W0t, bs, sx, g - g0 + 1, a1, ub0, ub1, lane);
+        warp_units<NUP>(W1t, bs + nu, a1, ub1, a2, ub0, ub1, lane);
+        warp_units<NUP>(W2t, bs + 2 * nu, a2, ub1, a3, ub0, ub1, lane);
+        cmu = nmu; cal = nal; ub_lo = ub_hi; ub_hi = nub;
+    }
+    __syncwarp();
+    warp_drain_tile(sx, xcur, r0, nrow, D, g0, nd, lane);
+    if (g1 < D) {
+        warp_drain_tile(a1, act1, r0, nrow, H, u0, nu, lane);
+        warp_drain_tile(a2, act2, r0, nrow, H, u0, nu, lane);
+        warp_drain_tile(a3, act3, r0, nrow, H, u0, nu, lane);
+    }
+    if (ok) { ldacc[r0 + lane] = ld; bad[r0 + lane] = poisoned; }
+}
+
+int g_ar_block_variant = 1;          // nf_set_option(3, v): 0 = first in-block kernel (CTA barriers), 1 = warp-private tiles
+
 }  // namespace nf
 
 using namespace nf;
@@ -191,6 +421,32 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
             }
         }
         const bool hp = prev && u0 > 0;
+        {
+            // warp-private variant: shared transposed weights + one tile per warp; as many warps as fit in 220 KB
+            const int need = ((nu + 3) & ~3) + 4 * kWarpChunks;
+            const int nup = need <= 48 ? 48 : (need <= 96 ? 96 : 160);       // compile-time pitches of ar_block_warp_kernel
+            const size_t wfl = (size_t)(nd + 2 * nu) * nup + (size_t)nu * 2 * nd + ((3 * nu + 3) & ~3);
+            const size_t tfl = (size_t)(nd + 3 * nu) * kBlkPad;
+            int nw = wfl * sizeof(float) < 200 * 1024 ? (int)((220 * 1024 / sizeof(float) - wfl) / tfl) : 0;
+            if (nw > 8) nw = 8;
+            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= 8) {
+                const size_t smem2 = sizeof(float) * (wfl + (size_t)nw * tfl);
+                const int grid2 = (int)cdiv(B, (int64_t)kBlkRows * nw);
+#define NF_ABW(NUPV)                                                                                                          \
+                do {                                                                                                          \
+                    NF_CUDA(cudaFuncSetAttribute(ar_block_warp_kernel<NUPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+                    ar_block_warp_kernel<NUPV><<<grid2, 32 * nw, smem2, st>>>(                                                 \
+                        (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr, hp ? preo : nullptr, \
+                        act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2, (const float*)b[2], w3,           \
+                        (const float*)b[3], gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, u1, mode);                            \
+                } while (0)
+                if (nup == 48) NF_ABW(48); else if (nup == 96) NF_ABW(96); else NF_ABW(160);
+#undef NF_ABW
+                count_launch();
+                NF_LAUNCH_CHECK();
+                continue;
+            }
+        }
         if (smem > 48 * 1024)
             NF_CUDA(cudaFuncSetAttribute(ar_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ar_block_kernel<<<grid, kBlkRows * kBlkWarps, smem, st>>>(
