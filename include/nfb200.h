@@ -234,6 +234,11 @@ NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
 NF_API int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N,
                  int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_extent,
                  nf_stream_t stream);
+/* same, with a per-64-output-columns lower bound of the K loop: columns k < k_begin[n/64] of those outputs' weights
+ * are exact zeros (the transposed, block-lower-triangular MADE weights of the input-gradient product) */
+NF_API int nf_linear_tc_range(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M,
+                       int64_t N, int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin,
+                       const int32_t* k_extent, nf_stream_t stream);
 /* hi = w rounded to the nearest TF32, lo = (w - hi) rounded to the nearest TF32; n elements, fp32 */
 NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_stream_t stream);
 
@@ -247,6 +252,11 @@ NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_st
 NF_API int64_t nf_linear_wgrad_tc_workspace(int64_t B, int64_t N, int64_t K);
 NF_API int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
                        int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, nf_stream_t stream);
+/* tile_live: NULL, or uint8[ceil(N/128) * ceil(K/128)] (K tiles fastest): 0 marks a 128 x 128 tile of dw on which the
+ * layer's weight mask is entirely zero (MaskedLinear, masked_linear.py:17) -- it is written as zeros without being computed */
+NF_API int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
+                              int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, const uint8_t* tile_live,
+                              nf_stream_t stream);
 
 /* ---- (f2) ARQS, one step of either sequential loop (src/flows/spline/arqs.py:53-76 / :93-116) ------------------
  * out[B,D] = cur with column `col` replaced by rational_quadratic_spline(v[:, col]; params[row]) on [0,1]

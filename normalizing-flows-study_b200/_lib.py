@@ -60,9 +60,11 @@ _SIGNATURES = {
     "nf_std_normal_log_prob_backward": [_P] * 3 + [_L, _I, _I, _P],
     "nf_debug_tc_gemm128": [_P, _P, _P, _I, _I, _P, _I, _P],
     "nf_linear_tc": [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P, _P],
+    "nf_linear_tc_range": [_P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _I, _P, _P, _P],
     "nf_split_tf32": [_P, _P, _P, _L, _P],
     "nf_linear_wgrad_tc_workspace": [_L, _L, _L],
     "nf_linear_wgrad_tc": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _P, _L, _P],
+    "nf_linear_wgrad_tc_masked": [_P, _P, _P, _L, _L, _L, _L, _L, _L, _P, _L, _P, _P],
     "nf_arqs_step_forward": [_P, _P, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _I, _P],
     "nf_arqs_step_backward": [_P, _P, _L, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _D, _D, _D, _I, _P],
     "nf_ar_blocked_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
@@ -141,7 +143,16 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device.  torch.cuda.current_stream() builds a Python
+    Stream object through several layers (measured: a quarter of the host time of a 510-launch training step); the
+    raw-handle accessor is ~30x cheaper."""
+    if _raw_stream is not None and _get_device is not None:
+        return _raw_stream(_get_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -43,7 +43,8 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
-               int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent) {
+               int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
+               const int32_t* __restrict__ k_begin) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // [stage: X | W_hi | W_lo] x kGemmStages, then barriers
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kStageBytes);
@@ -64,7 +65,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int c = n0 / 64; c <= (n0 + kGemmBN - 1) / 64 && c * 64 < N; ++c) e = max(e, k_extent[c]);
         k_end = min(K, e);
     }
-    const int nkb = (k_end + kGemmBK - 1) / kGemmBK;
+    // k_begin[n/64]: columns k < k_begin contribute exact zeros to these outputs (upper-triangular blocks of a
+    // transposed MADE weight in the input-gradient product): the K loop starts at that block
+    int kb_first = 0;
+    if (k_begin) {
+        int b = K;
+        for (int c = n0 / 64; c <= (n0 + kGemmBN - 1) / 64 && c * 64 < N; ++c) b = min(b, k_begin[c]);
+        kb_first = max(0, min(b, k_end)) / kGemmBK;
+    }
+    const int nkb = max(0, (k_end + kGemmBK - 1) / kGemmBK - kb_first);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kGemmStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
@@ -86,9 +95,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 if (kb >= kGemmStages) tc::mbar_wait(&empty[s], ((kb / kGemmStages) - 1) & 1);
                 uint8_t* st = smem + s * kStageBytes;
                 tc::mbar_arrive_expect_tx(&full[s], kStageBytes);
-                tma_load_2d(st, &tm_x, kb * kGemmBK, m0, &full[s]);
-                tma_load_2d(st + kXBytes, &tm_wh, kb * kGemmBK, n0, &full[s]);
-                tma_load_2d(st + kXBytes + kWBytes, &tm_wl, kb * kGemmBK, n0, &full[s]);
+                tma_load_2d(st, &tm_x, (kb_first + kb) * kGemmBK, m0, &full[s]);
+                tma_load_2d(st + kXBytes, &tm_wh, (kb_first + kb) * kGemmBK, n0, &full[s]);
+                tma_load_2d(st + kXBytes + kWBytes, &tm_wl, (kb_first + kb) * kGemmBK, n0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -247,9 +256,19 @@ extern "C" int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, n
     return NF_OK;
 }
 
+extern "C" int nf_linear_tc_range(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M,
+                                  int64_t N, int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu,
+                                  const int32_t* k_begin, const int32_t* k_extent, nf_stream_t stream);
+
 extern "C" int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M,
                             int64_t N, int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu,
                             const int32_t* k_extent, nf_stream_t stream) {
+    return nf_linear_tc_range(x, w_hi, w_lo, bias, y, M, N, K, ldx, ldw, ldy, relu, nullptr, k_extent, stream);
+}
+
+extern "C" int nf_linear_tc_range(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M,
+                                  int64_t N, int64_t K, int64_t ldx, int64_t ldw, int64_t ldy, int relu,
+                                  const int32_t* k_begin, const int32_t* k_extent, nf_stream_t stream) {
     if (M < 0 || N < 1 || K < 1 || ldx < K || ldw < K || ldy < N) return NF_ERR_BAD_SHAPE;
     if (M == 0) return NF_OK;
     NF_REQ(x); NF_REQ(w_hi); NF_REQ(w_lo); NF_REQ(y);
@@ -265,7 +284,7 @@ extern "C" int nf_linear_tc(const void* x, const void* w_hi, const void* w_lo, c
     const int64_t nblocks = cdiv(N, kGemmBN) * cdiv(M, kGemmBM);
     if (nblocks > 2147483647LL) return NF_ERR_BAD_SHAPE;
     gemm_tc_kernel<<<(unsigned)nblocks, kGemmThreads, smem, (cudaStream_t)stream>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N,
-                                                                       (int)K, ldy, relu, k_extent);
+                                                                       (int)K, ldy, relu, k_extent, k_begin);
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;

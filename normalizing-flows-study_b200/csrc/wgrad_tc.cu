@@ -52,7 +52,8 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_byte_ad
 
 __global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, float* __restrict__ out,
-                int N, int K, int nkb, int kb_per_split, int64_t ld_out, int64_t split_stride) {
+                int N, int K, int nkb, int kb_per_split, int64_t ld_out, int64_t split_stride,
+                const uint8_t* __restrict__ tile_live) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
     uint64_t* full = bars;                       // [S] TMA landed
@@ -67,7 +68,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
     const int k0 = (int)(blockIdx.x % k_tiles) * kWgBN;          // dW column block = X column block
     const int kb0 = (int)blockIdx.y * kb_per_split;
     const int kb1 = min(nkb, kb0 + kb_per_split);
-    const int nloc = max(0, kb1 - kb0);
+    // tile_live[tile] == 0: the weight mask is zero on this whole 128 x 128 tile (MADE): nothing to accumulate, zeros out
+    const int nloc = (tile_live && !tile_live[blockIdx.x]) ? 0 : max(0, kb1 - kb0);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kWgStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); tc::mbar_init(&ready[i], 128); }
@@ -279,8 +281,18 @@ extern "C" int64_t nf_linear_wgrad_tc_workspace(int64_t B, int64_t N, int64_t K)
     return splits > 1 ? (int64_t)splits * N * K * 4 : 0;
 }
 
+extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
+                                         int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes,
+                                         const uint8_t* tile_live, nf_stream_t stream);
+
 extern "C" int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
                                   int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, nf_stream_t stream) {
+    return nf_linear_wgrad_tc_masked(dy, x, dw, B, N, K, ld_dy, ld_x, ld_dw, workspace, ws_bytes, nullptr, stream);
+}
+
+extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
+                                         int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes,
+                                         const uint8_t* tile_live, nf_stream_t stream) {
     if (B < 0 || N < 1 || K < 1 || ld_dy < N || ld_x < K || ld_dw < K) return NF_ERR_BAD_SHAPE;
     if (B > 2147483647LL - 64 || N > 2147483647LL - 128 || K > 2147483647LL - 128) return NF_ERR_BAD_SHAPE;
     NF_REQ(dw);
@@ -313,7 +325,7 @@ extern "C" int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64
     float* out = splits > 1 ? (float*)workspace : (float*)dw;
     const int64_t ld_out = splits > 1 ? K : ld_dw;
     wgrad_tc_kernel<<<dim3((unsigned)tiles, (unsigned)splits), kWgThreads, smem, st>>>(tg, tx, out, (int)N, (int)K, nkb, per, ld_out,
-                                                                                         (int64_t)N * K);
+                                                                                         (int64_t)N * K, tile_live);
     count_launch();
     NF_LAUNCH_CHECK();
     if (splits > 1) {

@@ -21,6 +21,7 @@ from . import _lib as L
 ptr, call, stream = L.ptr, L.call, L.stream
 
 USE_TENSOR_CORE_GEMM = True      # tcgen05 3xTF32 GEMMs for float32 layers; False forces the FP32-pipe GEMM
+USE_MASK_PLANS = True            # skip the exactly-zero K ranges / tiles of 2-D weight masks (MADE) in the training GEMMs
 
 
 def _c(t):
@@ -58,23 +59,71 @@ def split_tf32(w):
     return hi, lo
 
 
-def linear_tc(x, w_hi, w_lo, bias=None, relu=False, k_extent=None, out=None):
+def linear_tc(x, w_hi, w_lo, bias=None, relu=False, k_extent=None, out=None, k_begin=None):
     """y = relu?(x @ W.T + bias) on tcgen05 (3xTF32, fp32-accurate); returns None when the shape / alignment is not
-    taken by the tensor-core kernel (caller uses linear_raw)."""
+    taken by the tensor-core kernel (caller uses linear_raw).  k_extent / k_begin: int32 per 64 output columns, the
+    K range outside of which W is exactly zero for those outputs (mask-folded MADE weights)."""
     M, K = x.shape
     N = w_hi.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=x.dtype, device=x.device)
     if K % 4 != 0:
         return None
-    ok = L.try_call("nf_linear_tc", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, K, N, int(relu),
-                    ptr(k_extent), stream())
+    if k_begin is None:
+        ok = L.try_call("nf_linear_tc", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, K, N, int(relu),
+                        ptr(k_extent), stream())
+    else:
+        ok = L.try_call("nf_linear_tc_range", ptr(x), ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), M, N, K, K, K, N,
+                        int(relu), ptr(k_begin), ptr(k_extent), stream())
     return out if ok else None
 
 
-def linear_wgrad_tc(gy, x, out=None):
+class MaskPlan:
+    """Zero structure of a 2-D weight mask [N, K] (MaskedLinear.mask, masked_linear.py:10): the K ranges / tiles the
+    tensor-core GEMMs of the layer may skip.  MADE masks are block lower-triangular once the hidden units are sorted
+    by degree (they are for data_dim > 2, made.py:36), so ~44 % of the 128 x 128 tiles are exactly zero."""
+    __slots__ = ("k_extent", "k_begin_t", "tile_live", "live_fraction")
+
+
+_MASK_PLANS = {}
+
+
+def mask_plan(mask):
+    if mask is None or mask.dim() != 2 or mask.shape[0] < 256 or mask.shape[1] < 256:
+        return None
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
+    plan = _MASK_PLANS.get(key)
+    if plan is None:
+        if len(_MASK_PLANS) > 256:
+            _MASK_PLANS.clear()
+        nz = mask != 0
+        N, K = nz.shape
+        dev = mask.device
+        last = torch.where(nz, torch.arange(1, K + 1, device=dev)[None, :], 0).amax(dim=1)        # per output row n
+        first = torch.where(nz, torch.arange(N, device=dev)[:, None], N).amin(dim=0)              # per input column k
+
+        def grouped(v, g, fill, red):
+            pad = (-v.numel()) % g
+            if pad:
+                v = torch.cat([v, torch.full((pad,), fill, dtype=v.dtype, device=dev)])
+            return red(v.view(-1, g), dim=1).to(torch.int32).contiguous()
+        plan = MaskPlan()
+        plan.k_extent = grouped(last, 64, 0, torch.amax)
+        plan.k_begin_t = grouped(first, 64, N, torch.amin)
+        tn, tk = (N + 127) // 128, (K + 127) // 128
+        padded = torch.zeros(tn * 128, tk * 128, dtype=torch.bool, device=dev)
+        padded[:N, :K] = nz
+        live = padded.view(tn, 128, tk, 128).any(dim=3).any(dim=1)
+        plan.tile_live = live.to(torch.uint8).contiguous().view(-1)
+        plan.live_fraction = float(live.float().mean())
+        _MASK_PLANS[key] = plan
+    return plan if plan.live_fraction < 0.95 else None
+
+
+def linear_wgrad_tc(gy, x, out=None, tile_live=None):
     """dW[N,K] = gy[B,N]^T x[B,K] on tcgen05 (3xTF32, deterministic split over the batch); None when the shape /
-    alignment is not taken by the tensor-core kernel (caller uses gemm)."""
+    alignment is not taken by the tensor-core kernel (caller uses gemm).  tile_live: MaskPlan.tile_live (128 x 128
+    tiles on which the weight mask is all zero are written as zeros without being computed)."""
     B, N = gy.shape
     K = x.shape[1]
     if N % 4 != 0 or K % 4 != 0:
@@ -83,7 +132,11 @@ def linear_wgrad_tc(gy, x, out=None):
         out = torch.empty((N, K), dtype=gy.dtype, device=gy.device)
     ws_bytes = int(L.lib().nf_linear_wgrad_tc_workspace(B, N, K))
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=gy.device) if ws_bytes else None
-    ok = L.try_call("nf_linear_wgrad_tc", ptr(gy), ptr(x), ptr(out), B, N, K, N, K, K, ptr(ws), ws_bytes, stream())
+    if tile_live is None:
+        ok = L.try_call("nf_linear_wgrad_tc", ptr(gy), ptr(x), ptr(out), B, N, K, N, K, K, ptr(ws), ws_bytes, stream())
+    else:
+        ok = L.try_call("nf_linear_wgrad_tc_masked", ptr(gy), ptr(x), ptr(out), B, N, K, N, K, K, ptr(ws), ws_bytes,
+                        ptr(tile_live), stream())
     return out if ok else None
 
 
@@ -127,9 +180,10 @@ class _LinearFn(Function):
         w_eff = _c(weight) if mask is None else mul_rows(_c(weight), mask)
         b = None if bias is None else _c(bias)
         y = None
+        plan = mask_plan(mask) if USE_MASK_PLANS else None
         if _tc_ok(x, x.shape[1]):
             hi, lo = split_tf32(w_eff)
-            y = linear_tc(x, hi, lo, b, relu)
+            y = linear_tc(x, hi, lo, b, relu, k_extent=None if plan is None else plan.k_extent)
         if y is None:
             y = linear_raw(x, w_eff, b, relu)
         ctx.relu = relu
@@ -147,14 +201,15 @@ class _LinearFn(Function):
         M, K = x.shape
         N = w_eff.shape[0]
         gx = gw = gb = None
+        plan = mask_plan(mask) if USE_MASK_PLANS else None
         if ctx.needs_input_grad[0]:
             if _tc_ok(g, N):
                 hi, lo = split_tf32(w_eff.t().contiguous())             # [K, N]: dX = dY (W^T)^T
-                gx = linear_tc(g, hi, lo)
+                gx = linear_tc(g, hi, lo, k_begin=None if plan is None else plan.k_begin_t)
             if gx is None:
                 gx = gemm(g, w_eff, M, K, N, N, 1, K, 1)                 # dX = dY W
         if ctx.needs_input_grad[1]:
-            gw = linear_wgrad_tc(g, x) if _tc_ok(g, K) else None      # dW = dY^T X
+            gw = linear_wgrad_tc(g, x, tile_live=None if plan is None else plan.tile_live) if _tc_ok(g, K) else None   # dW = dY^T X
             if gw is None:
                 gw = gemm(g, x, N, K, M, 1, N, K, 1)
             if mask is not None:

@@ -163,3 +163,43 @@ def test_skinny_products_match_float64(B, H, D, dtype):
     check(N_.ops.gemm(c(gy3), c(h), D, H, B, 1, D, H, 1), gy3.T @ h, gy3.abs().T @ h.abs(), "dW narrow N")
     # bias gradient of the last Linear
     check(N_.ops.col_sum(c(gy3)), gy3.sum(0), gy3.abs().sum(0), "col_sum small")
+
+
+@pytest.mark.parametrize("D,H,B", [(64, 512, 1024), (256, 1024, 512), (20, 256, 700)])
+def test_mask_plans_skip_only_exact_zeros(D, H, B):
+    """MADE-masked linear layers (masked_linear.py:14-18) through the autograd op with and without the zero-structure
+    plans (K-range / tile skipping in the forward, input-gradient and weight-gradient GEMMs): same results, and both
+    match a float64 masked product."""
+    made = N_.MADE(D, H)
+    gen = torch.Generator().manual_seed(D + H)
+    for idx in (2, 6):                                   # hidden->hidden [H,H] and hidden->out [2D,H]
+        lin = made.net[idx]
+        w = (torch.randn(lin.weight.shape, generator=gen) / lin.weight.shape[1] ** 0.5)
+        b = torch.randn(lin.weight.shape[0], generator=gen)
+        mask = lin.mask.clone()
+        x = torch.randn(B, lin.weight.shape[1], generator=gen)
+        gy = torch.randn(B, lin.weight.shape[0], generator=gen)
+        res = {}
+        for use in (True, False):
+            N_.ops.USE_MASK_PLANS = use
+            try:
+                xd = x.cuda().requires_grad_(True)
+                wd = w.cuda().requires_grad_(True)
+                bd = b.cuda().requires_grad_(True)
+                y = N_.ops.linear(xd, wd, bd, mask=mask.cuda(), relu=True)
+                y.backward(gy.cuda())
+                res[use] = (y.detach().cpu(), xd.grad.cpu(), wd.grad.cpu(), bd.grad.cpu())
+            finally:
+                N_.ops.USE_MASK_PLANS = True
+        plan = N_.ops.mask_plan(mask.cuda())
+        if min(mask.shape) >= 256:
+            assert plan is not None and plan.live_fraction < 0.9
+        x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+        y64 = torch.relu(x64 @ (w64 * mask.double()).T + b64)
+        y64.backward(gy.double())
+        refs = (y64.detach(), x64.grad, w64.grad, b64.grad)
+        for got_a, got_b, ref, what in zip(res[True], res[False], refs, ("y", "dx", "dw", "db")):
+            scale = ref.abs().max().item() + 1e-30
+            assert (got_a.double() - ref).abs().max().item() / scale < 2e-5, what
+            assert (got_a - got_b).abs().max().item() / scale < 2e-5, what
+        assert torch.equal(res[True][2] == 0, res[False][2] == 0) or bool((res[True][2][mask == 0] == 0).all())
