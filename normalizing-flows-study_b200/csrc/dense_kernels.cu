@@ -534,7 +534,7 @@ extern "C" int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, 
         NF_LAUNCH_CHECK();
         return NF_OK;
     }
-    if (cols <= 8 && rows >= 1 && a) {
+    if ((cols <= 8 || (cols <= 32 && cols % 4 != 0)) && rows >= 1 && a) {
         int rc = dtype == NF_F32 ? col_sum_small_launch<float>(a, out, rows, (int)cols, st)
                : dtype == NF_F64 ? col_sum_small_launch<double>(a, out, rows, (int)cols, st) : NF_ERR_UNSUPPORTED;
         if (rc) return rc;

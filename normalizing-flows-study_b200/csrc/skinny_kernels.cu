@@ -3,9 +3,9 @@
 // spline_coupling_layer.py:55-62, made.py:81-134) and their gradients.  A 128x128-tile GEMM wastes > 90 % of its
 // work on them and, for the weight gradients, leaves a handful of CTAs walking the whole batch (measured: 201 us per
 // launch at 5 000 rows, 55 % of a RealNVP(2,8,64) training step).  These kernels are streaming, HBM-bound:
-//   skinny_reduce   C = sum_b Wd[b,:]^T (x) Sk[b,:]      one operand <= 8 columns wide, reduction over the batch
+//   skinny_reduce   C = sum_b Wd[b,:]^T (x) Sk[b,:]      one operand <= 32 columns wide, reduction over the batch
 //                   (dW of the first / last Linear; bias gradients go through col_sum_small in dense_kernels.cu)
-//   skinny_k        C[m,:] = sum_{k<=8} A[m,k] B[k,:]    (first Linear forward, input gradient of the last Linear)
+//   skinny_k        C[m,:] = sum_{k<=32} A[m,k] B[k,:]   (first Linear forward, input gradient of the last Linear / spline head)
 //   skinny_n        C[m,n<=8] = A[m,:] . B[:,n]          (last Linear forward)
 // Called from nf_gemm's dispatcher (dense_kernels.cu); same semantics as gemm_kernel (bias, ReLU, strides).
 #include "nf_common.cuh"
@@ -15,47 +15,47 @@ namespace nf {
 // ---- C[w,s] (or C[s,w]) = sum_b Wd[b*ldw + w] * Sk[b*lds + s];  S <= 8 -------------------------------------------------
 // block = 8 warps sharing 128 columns of Wd (lane + 32 j), rows strided over the warps and over blockIdx.y chunks;
 // per-thread accumulators [4][S]; block reduction in shared memory; chunks combine with atomics (C zeroed by the host)
-template <typename T, int S>
+template <typename T, int S, int JW>
 __global__ void __launch_bounds__(256)
 skinny_reduce_kernel(const T* __restrict__ Wd, const T* __restrict__ Sk, T* __restrict__ C, int64_t B, int W, int64_t ldw,
                      int64_t lds, int64_t so_w, int64_t so_s, int s_live, int64_t rows_per_chunk) {
-    __shared__ T red[4][128 * S + 8];
+    __shared__ T red[4][32 * JW * S + 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 128;
+    const int c0 = blockIdx.x * 32 * JW;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     const int64_t r1 = (B < r0 + rows_per_chunk) ? B : r0 + rows_per_chunk;
-    T acc[4][S];
+    T acc[JW][S];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < JW; ++j)
 #pragma unroll
         for (int s = 0; s < S; ++s) acc[j][s] = T(0);
     for (int64_t r = r0 + warp; r < r1; r += 8) {
         T sk[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) sk[s] = (s < s_live) ? Sk[r * lds + s] : T(0);
-        T v[4];
+        T v[JW];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const int c = c0 + lane + 32 * j; v[j] = (c < W) ? Wd[r * ldw + c] : T(0); }
+        for (int j = 0; j < JW; ++j) { const int c = c0 + lane + 32 * j; v[j] = (c < W) ? Wd[r * ldw + c] : T(0); }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int s = 0; s < S; ++s) acc[j][s] += v[j] * sk[s];
     }
     if (warp >= 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int s = 0; s < S; ++s) red[warp - 4][(lane + 32 * j) * S + s] = acc[j][s];
     }
     __syncthreads();
     if (warp < 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < JW; ++j)
 #pragma unroll
             for (int s = 0; s < S; ++s) red[warp][(lane + 32 * j) * S + s] += acc[j][s];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 128 * S; i += 256) {
+    for (int i = threadIdx.x; i < 32 * JW * S; i += 256) {
         const int cl = i / S, s = i - cl * S, c = c0 + cl;
         if (c >= W || s >= s_live) continue;
         T t = T(0);
@@ -66,24 +66,35 @@ skinny_reduce_kernel(const T* __restrict__ Wd, const T* __restrict__ Sk, T* __re
     }
 }
 
-// ---- C[m, n] = act(sum_{k<K<=8} A[m*sam + k*sak] * Bm[k*sbk + n*sbn] + bias[n]) -----------------------------------------
-template <typename T>
+// ---- C[m, n] = act(sum_{k<K<=32} A[m*sam + k*sak] * Bm[k*sbk + n*sbn] + bias[n]) ----------------------------------------
+// a block walks rows; a thread keeps its column (no per-element division: the first version divided a 64-bit index by N
+// for every output and ran at 0.55 TB/s); the K values of a row are broadcast loads shared by the row's threads
+template <typename T, int KM>
 __global__ void __launch_bounds__(256)
 skinny_k_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C, const T* __restrict__ bias, int64_t M,
                 int N, int K, int64_t sam, int64_t sak, int64_t sbk, int64_t sbn, int64_t ldc, int relu, int accumulate) {
-    const int64_t total = M * N, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t m = i / N;
-        const int n = (int)(i - m * N);
-        T acc = T(0);
+    // thread layout: tx columns x ty rows per pass, tx = smallest power of two >= min(N, 256)
+    int tx = 1;
+    while (tx < N && tx < 256) tx <<= 1;
+    const int ty = 256 / tx;
+    const int cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;           // tx is a power of two: shift
+    for (int n = cx; n < N; n += tx) {
+        T w[KM];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < K) acc += A[m * sam + k * sak] * __ldg(Bm + k * sbk + n * sbn);
-        if (bias) acc += __ldg(bias + n);
-        T* cp = C + m * ldc + n;
-        if (accumulate) acc += *cp;
-        if (relu) acc = relu_nan(acc);
-        *cp = acc;
+        for (int k = 0; k < KM; ++k) w[k] = (k < K) ? __ldg(Bm + k * sbk + n * sbn) : T(0);
+        const T bv = bias ? __ldg(bias + n) : T(0);
+        for (int64_t m = (int64_t)blockIdx.x * ty + ry; m < M; m += (int64_t)gridDim.x * ty) {
+            const T* ar = A + m * sam;
+            T acc = T(0);
+#pragma unroll
+            for (int k = 0; k < KM; ++k)
+                if (k < K) acc += ar[k * sak] * w[k];
+            acc += bv;
+            T* cp = C + m * ldc + n;
+            if (accumulate) acc += *cp;
+            if (relu) acc = relu_nan(acc);
+            *cp = acc;
+        }
     }
 }
 
@@ -123,24 +134,24 @@ skinny_n_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict
     }
 }
 
-// column sums of a[rows, cols], cols <= 8: the array is walked flat, every thread keeps `cols` phase-aligned
-// accumulators; block reduction, then atomics across blocks (out zeroed by the host)
-template <typename T>
+// column sums of a[rows, cols], cols <= CM: every thread walks whole rows with `cols` accumulators (a warp reads 32
+// consecutive rows = one contiguous run); block reduction, then atomics across blocks (out zeroed by the host)
+template <typename T, int CM>
 __global__ void __launch_bounds__(256)
 col_sum_small_kernel(const T* __restrict__ a, T* __restrict__ out, int64_t rows, int cols, int64_t rows_per_block) {
-    __shared__ double red[8][8];
+    __shared__ double red[8][CM];
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (rows < r0 + rows_per_block) ? rows : r0 + rows_per_block;
-    double acc[8];
+    double acc[CM];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.0;
+    for (int c = 0; c < CM; ++c) acc[c] = 0.0;
     for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) if (c < cols) acc[c] += (double)a[r * cols + c];
+        for (int c = 0; c < CM; ++c) if (c < cols) acc[c] += (double)a[r * cols + c];
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < CM; ++c) {
         const double t = warp_sum<double>(acc[c]);
         if (lane == 0) red[warp][c] = t;
     }
@@ -161,14 +172,15 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
                     cudaStream_t st) {
     if (k_extent) return 0;
     // (1) reduction over a long batch with one narrow operand: C[M,N] = sum_k A[m + k*sak] * Bm[k*sbk + n]
-    if (!bias && !relu && !accumulate && sam == 1 && sbn == 1 && K >= 256 && (M <= 8 || N <= 8) && M * N <= (1 << 20)) {
-        const bool narrow_b = N <= 8 && !(M <= 8 && M < N);      // Sk = Bm (S = N), Wd = A (W = M); else the transpose
+    if (!bias && !relu && !accumulate && sam == 1 && sbn == 1 && K >= 256 && (M <= 32 || N <= 32) && M * N <= (1 << 20)) {
+        const bool narrow_b = N <= M;                             // Sk = Bm (S = N), Wd = A (W = M); else the transpose
         const T* Wd = (const T*)(narrow_b ? A : Bm);
         const T* Sk = (const T*)(narrow_b ? Bm : A);
         const int W = (int)(narrow_b ? M : N), S = (int)(narrow_b ? N : M);
         const int64_t ldw = narrow_b ? sak : sbk, lds = narrow_b ? sbk : sak;
         const int64_t so_w = narrow_b ? ldc : 1, so_s = narrow_b ? 1 : ldc;
-        const int64_t cblocks = cdiv(W, 128);
+        const int JW = S <= 8 ? 4 : 1;                            // columns of Wd per lane (accumulators: JW x S)
+        const int64_t cblocks = cdiv(W, 32 * JW);
         int64_t ch = cdiv((int64_t)kNumSMs * 4, cblocks);
         const int64_t chmax = K / 64 > 1 ? K / 64 : 1;           // at least 64 rows (8 per warp) per chunk
         if (ch > chmax) ch = chmax;
@@ -180,17 +192,24 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
             else NF_CUDA(cudaMemset2DAsync(C, sizeof(T) * ldc, 0, sizeof(T) * N, M, st));
         }
         dim3 grid((unsigned)cblocks, (unsigned)ch);
-#define NF_SR(SS) skinny_reduce_kernel<T, SS><<<grid, 256, 0, st>>>(Wd, Sk, (T*)C, K, W, ldw, lds, so_w, so_s, S, rpc)
-        if (S <= 2) NF_SR(2); else if (S <= 4) NF_SR(4); else NF_SR(8);
+#define NF_SR(SS, JJ) skinny_reduce_kernel<T, SS, JJ><<<grid, 256, 0, st>>>(Wd, Sk, (T*)C, K, W, ldw, lds, so_w, so_s, S, rpc)
+        if (S <= 2) NF_SR(2, 4); else if (S <= 4) NF_SR(4, 4); else if (S <= 8) NF_SR(8, 4);
+        else if (S <= 16) NF_SR(16, 1); else NF_SR(32, 1);
 #undef NF_SR
         return 1;
     }
-    // (2) tiny reduction dimension: one output element per thread
-    if (K >= 1 && K <= 8 && M >= 64) {
-        const int64_t total = M * N;
-        int64_t g = cdiv(total, 256), cap = (int64_t)kNumSMs * 16;
-        skinny_k_kernel<T><<<(int)(g < cap ? g : cap), 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, (int)N,
-                                                                      (int)K, sam, sak, sbk, sbn, ldc, relu, accumulate);
+    // (2) small reduction dimension: a thread per output column, rows walked by the block
+    if (K >= 1 && K <= 32 && M >= 64 && (K <= 8 || (K % 4) != 0)) {
+        int tx = 1;
+        while (tx < N && tx < 256) tx <<= 1;
+        const int ty = 256 / tx;
+        int64_t g = cdiv(M, (int64_t)ty * 4), cap = (int64_t)kNumSMs * 16;
+        if (g < 1) g = 1;
+        const int grid = (int)(g < cap ? g : cap);
+#define NF_SK(KMV) skinny_k_kernel<T, KMV><<<grid, 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, (int)N, (int)K, \
+                                                               sam, sak, sbk, sbn, ldc, relu, accumulate)
+        if (K <= 2) NF_SK(2); else if (K <= 4) NF_SK(4); else if (K <= 8) NF_SK(8); else NF_SK(32);
+#undef NF_SK
         return 1;
     }
     // (3) narrow output: per-row dot products, contiguous A rows
@@ -220,7 +239,8 @@ int col_sum_small_launch(const void* a, void* out, int64_t rows, int cols, cudaS
     const int64_t rpb = cdiv(rows, blocks);
     blocks = cdiv(rows, rpb);
     if (blocks > 1) NF_CUDA(cudaMemsetAsync(out, 0, sizeof(T) * cols, st));
-    col_sum_small_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)out, rows, cols, rpb);
+    if (cols <= 8) col_sum_small_kernel<T, 8><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)out, rows, cols, rpb);
+    else col_sum_small_kernel<T, 32><<<(int)blocks, 256, 0, st>>>((const T*)a, (T*)out, rows, cols, rpb);
     return NF_OK;
 }
 template int col_sum_small_launch<float>(const void*, void*, int64_t, int, cudaStream_t);

@@ -131,7 +131,8 @@ def test_col_sum_matches_float64(rows, cols):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("B,H,D", [(5000, 64, 2), (300, 64, 2), (70000, 128, 3), (4096, 40, 8), (1000, 16, 1)])
+@pytest.mark.parametrize("B,H,D", [(5000, 64, 2), (300, 64, 2), (70000, 128, 3), (4096, 40, 8), (1000, 16, 1), (30000, 64, 23),
+                                   (9000, 300, 29), (2000, 64, 17)])
 def test_skinny_products_match_float64(B, H, D, dtype):
     """nf_gemm's skinny routes (one dimension <= 8): first / last Linear of a low-dimensional conditioner, forward,
     input gradient and weight gradient, against float64 products."""
@@ -192,7 +193,7 @@ def test_mask_plans_skip_only_exact_zeros(D, H, B):
             finally:
                 N_.ops.USE_MASK_PLANS = True
         plan = N_.ops.mask_plan(mask.cuda())
-        if min(mask.shape) >= 256:
+        if min(mask.shape) >= 512:                      # 4 x 4 tiles or more: the upper triangle is skippable
             assert plan is not None and plan.live_fraction < 0.9
         x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
         y64 = torch.relu(x64 @ (w64 * mask.double()).T + b64)
