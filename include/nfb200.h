@@ -247,8 +247,8 @@ NF_API int nf_split_tf32(const void* w, void* w_hi, void* w_lo, int64_t n, nf_st
  * layout: dy through TMEM as the A operand, x as an MN-major shared-memory B operand; csrc/wgrad_tc.cu).
  * The reduction over the batch is split across CTAs; partial tiles go to `workspace`
  * (nf_linear_wgrad_tc_workspace(B,N,K) bytes, 0 when no split is needed) and are summed in a fixed order
- * (deterministic).  Requires 16-byte aligned dy / x and ld_dy % 4 == 0, ld_x % 4 == 0 (NF_ERR_UNSUPPORTED
- * otherwise: use nf_gemm).  B == 0 writes zeros. */
+ * (deterministic).  Requires 16-byte aligned x and ld_x % 4 == 0 (NF_ERR_UNSUPPORTED otherwise: use nf_gemm); a dy
+ * whose pitch TMA cannot take (ld_dy % 4 != 0: the 3K-1 wide spline heads) is read with plain loads.  B == 0 writes zeros. */
 NF_API int64_t nf_linear_wgrad_tc_workspace(int64_t B, int64_t N, int64_t K);
 NF_API int nf_linear_wgrad_tc(const void* dy, const void* x, void* dw, int64_t B, int64_t N, int64_t K, int64_t ld_dy,
                        int64_t ld_x, int64_t ld_dw, void* workspace, int64_t ws_bytes, nf_stream_t stream);

@@ -53,7 +53,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_byte_ad
 __global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, float* __restrict__ out,
                 int N, int K, int nkb, int kb_per_split, int64_t ld_out, int64_t split_stride,
-                const uint8_t* __restrict__ tile_live) {
+                const uint8_t* __restrict__ tile_live, const float* __restrict__ dy_direct, int64_t ld_dy, int64_t B) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
     uint64_t* full = bars;                       // [S] TMA landed
@@ -90,10 +90,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
                 if (i >= kWgStages) tc::mbar_wait(&empty[s], ((i / kWgStages) - 1) & 1);
                 uint8_t* st = smem + s * kWgStageBytes;
                 const int b0 = (kb0 + i) * kWgBK;
-                tc::mbar_arrive_expect_tx(&full[s], 2 * kWgTileBytes);
+                tc::mbar_arrive_expect_tx(&full[s], dy_direct ? kWgTileBytes : 2 * kWgTileBytes);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    wg_tma_load_2d(st + j * kWgChunkBytes, &tm_g, n0 + 32 * j, b0, &full[s]);
+                    if (!dy_direct) wg_tma_load_2d(st + j * kWgChunkBytes, &tm_g, n0 + 32 * j, b0, &full[s]);
                     wg_tma_load_2d(st + kWgTileBytes + j * kWgChunkBytes, &tm_x, k0 + 32 * j, b0, &full[s]);
                 }
             }
@@ -138,10 +138,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
             // dY column n = 32q + lane: element (b, n) sits at chunk q, row b, 16-byte slot ((lane/4) ^ (b%8))
             const uint8_t* gcol = st + q * kWgChunkBytes + (lane & 3) * 4;
             uint32_t hi[32], lo[32];
+            if (dy_direct) {
+                // dY rows whose pitch TMA cannot take (N % 4 != 0, e.g. the 3K-1 = 23 / 29 wide spline heads): the converter
+                // thread fetches its column straight from global memory (a warp reads 32 consecutive floats per row)
+                const int n = n0 + q * 32 + lane;
+                const int64_t b0 = (int64_t)(kb0 + i) * kWgBK;
+                const float* gp = dy_direct + b0 * ld_dy + (n < N ? n : 0);
+                float v[32];
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const float v = *reinterpret_cast<const float*>(gcol + b * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(b & 7)) << 4));
-                tc::split_tf32(v, hi[b], lo[b]);
+                for (int b = 0; b < 32; ++b) v[b] = (n < N && b0 + b < B) ? __ldg(gp + b * ld_dy) : 0.f;
+#pragma unroll
+                for (int b = 0; b < 32; ++b) tc::split_tf32(v[b], hi[b], lo[b]);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    const float v = *reinterpret_cast<const float*>(gcol + b * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(b & 7)) << 4));
+                    tc::split_tf32(v, hi[b], lo[b]);
+                }
             }
             const uint32_t a_hi = lane_addr + kWgColA + s * 64, a_lo = a_hi + 32;
             {
@@ -306,7 +319,8 @@ extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw
         return NF_OK;
     }
     NF_REQ(dy); NF_REQ(x);
-    if (!aligned16(dy) || !aligned16(x) || (ld_dy % 4) != 0 || (ld_x % 4) != 0) return NF_ERR_UNSUPPORTED;
+    if (!aligned16(x) || (ld_x % 4) != 0) return NF_ERR_UNSUPPORTED;
+    const bool direct = !aligned16(dy) || (ld_dy % 4) != 0;          // dY through plain loads instead of TMA
     int splits, per, nkb;
     wg_plan(B, N, K, &splits, &per, &nkb);
     if (splits > 1) {
@@ -314,9 +328,9 @@ extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw
         if (ws_bytes < (int64_t)splits * N * K * 4) return NF_ERR_WORKSPACE;
     }
     alignas(64) CUtensorMap tg, tx;
-    if (!wg_make_map(&tg, dy, B, N, ld_dy, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        !wg_make_map(&tx, x, B, K, ld_x, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-        return NF_ERR_UNSUPPORTED;
+    if (!wg_make_map(&tx, x, B, K, ld_x, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return NF_ERR_UNSUPPORTED;
+    if (direct) tg = tx;                                              // unused by the kernel in direct mode
+    else if (!wg_make_map(&tg, dy, B, N, ld_dy, CU_TENSOR_MAP_SWIZZLE_128B)) return NF_ERR_UNSUPPORTED;
     const size_t smem = (size_t)kWgStages * kWgStageBytes + 256;
     NF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -325,7 +339,7 @@ extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw
     float* out = splits > 1 ? (float*)workspace : (float*)dw;
     const int64_t ld_out = splits > 1 ? K : ld_dw;
     wgrad_tc_kernel<<<dim3((unsigned)tiles, (unsigned)splits), kWgThreads, smem, st>>>(tg, tx, out, (int)N, (int)K, nkb, per, ld_out,
-                                                                                         (int64_t)N * K, tile_live);
+                                                                                         (int64_t)N * K, tile_live, direct ? (const float*)dy : nullptr, ld_dy, B);
     count_launch();
     NF_LAUNCH_CHECK();
     if (splits > 1) {

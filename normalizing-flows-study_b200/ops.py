@@ -126,7 +126,7 @@ def linear_wgrad_tc(gy, x, out=None, tile_live=None):
     tiles on which the weight mask is all zero are written as zeros without being computed)."""
     B, N = gy.shape
     K = x.shape[1]
-    if N % 4 != 0 or K % 4 != 0:
+    if K % 4 != 0:
         return None
     if out is None:
         out = torch.empty((N, K), dtype=gy.dtype, device=gy.device)

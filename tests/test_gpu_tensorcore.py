@@ -75,7 +75,8 @@ def test_linear_tc_k_extent_matches_masked_dense():
 
 
 @pytest.mark.parametrize("B,N,K", [(32, 128, 128), (256, 128, 128), (4096, 512, 512), (5000, 512, 64), (777, 132, 100),
-                                   (100000, 128, 256), (3000, 2844, 1024), (1, 64, 64), (0, 64, 32)])
+                                   (100000, 128, 256), (3000, 2844, 1024), (1, 64, 64), (0, 64, 32), (30000, 23, 64),
+                                   (5000, 29, 1024), (1000, 11369, 128)])
 def test_linear_wgrad_tc_matches_float64(B, N, K):
     """dW = dY^T X on tcgen05 (MN-major operands, split over the batch) against a float64 product."""
     gen = torch.Generator().manual_seed(B + N + K)
