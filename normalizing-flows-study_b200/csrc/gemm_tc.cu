@@ -164,6 +164,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         tc::mbar_wait(d_full, 0);
         tc::fence_after_sync();
         float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;
+        // NOTE on accuracy: the tensor core truncates its fp32 accumulator on every MMA (measured, scripts/gemm_accuracy.py:
+        // rms error 3e-6 / 7e-6 of rms(y) at K = 512 / 1024 against 4e-7 / 6e-7 for an FFMA GEMM; a bias of -T * 2^-25 for
+        // same-sign sums).  Scaling the result by the expected loss was tried and dropped: it over-corrects mixed-sign sums
+        // (C4 log-det bias +4.4e-4 -> -3.3e-4).  Shorter chains (rotating accumulators) are the fix; see DESIGN.md.
         for (int c = 0; c < kGemmBN / 32; ++c) {
             uint32_t v0[16], v1[16];
             if (nkb > 0) {

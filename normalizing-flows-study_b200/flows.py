@@ -74,6 +74,30 @@ class _PackCache:
         return self._tensors
 
 
+def _fold_bn_eval(W, b, bn):
+    """Linear followed by eval-mode BatchNorm1d == Linear with scaled rows (coupling_layer.py:19-24); device tensors."""
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return W * s[:, None], (b - bn.running_mean) * s + bn.bias
+
+
+def _tc_layer(W, b, relu):
+    hi, lo = ops.split_tf32(W.detach().float().contiguous())
+    return hi, lo, b.detach().float().contiguous(), relu
+
+
+def _tc_mlp(v, layers):
+    """relu?(... relu?(v W0^T + b0) ...) through the tcgen05 GEMM with cached TF32 splits; None if a layer is refused."""
+    h = v
+    for hi, lo, b, relu in layers:
+        h = ops.linear_tc(h, hi, lo, b, relu)
+        if h is None:
+            return None
+    return h
+
+
+WIDE_TC_MIN_ROWS = 256
+
+
 # ------------------------------------------------------------------------------------------------
 # base classes
 # ------------------------------------------------------------------------------------------------
@@ -158,6 +182,7 @@ class CouplingLayer(Flow):
         self.b_net = _coupling_net(data_dim, hidden_dim)
         self._initialize_weights()
         self._pack = _PackCache()
+        self._wide = _PackCache()
 
     def _initialize_weights(self):
         """xavier-normal hidden layers with zero bias, zero final layer => identity at init (:98-111)."""
@@ -189,9 +214,27 @@ class CouplingLayer(Flow):
             out = run_coupling_stack(self._pack, self._pack.tensors_of([self]), [self], None, v, inverse)
             if out is not None:
                 return out
+        if (not wants_grad(self, v) and not self.training and USE_TENSOR_CORES and v.dtype == torch.float32
+                and self.s_net[0].weight.dtype == torch.float32 and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0):
+            # wide eval route: mask and eval-mode BatchNorm folded into the Linears once per weight version, TF32 splits
+            # cached, three tensor-core GEMMs per net (the layered route re-folds and re-splits on every call)
+            nets = self._wide.get(self._wide.tensors_of([self]), self._fold_wide)
+            s_raw = _tc_mlp(v, nets[0])
+            b_raw = _tc_mlp(v, nets[1]) if s_raw is not None else None
+            if b_raw is not None:
+                return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
         s_raw = self._conditioner(self.s_net, v)
         b_raw = self._conditioner(self.b_net, v)
         return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
+
+    def _fold_wide(self):
+        with torch.no_grad():
+            out = []
+            for net in (self.s_net, self.b_net):
+                W0, b0 = _fold_bn_eval(net[0].weight * self.mask[None, :], net[0].bias, net[1])
+                W1, b1 = _fold_bn_eval(net[3].weight, net[3].bias, net[4])
+                out.append([_tc_layer(W0, b0, True), _tc_layer(W1, b1, True), _tc_layer(net[6].weight, net[6].bias, False)])
+            return out
 
     def forward(self, z):
         return self._run(z, False)
@@ -225,6 +268,7 @@ class SplineCouplingLayer(Flow):
         self._initialize_weights()
         self._pack = _PackCache()
         self._aux = _PackCache()
+        self._wide = _PackCache()
 
     def _initialize_weights(self):
         """:311-323."""
@@ -263,6 +307,13 @@ class SplineCouplingLayer(Flow):
         vin = v
         if rescale is not None:                       # conditioner sees the rescaled input (:101-102)
             vin = ops.feature_affine(v, rescale[1], None, rescale[0], -float(self.bound))
+        if (not wants_grad(self, v) and USE_TENSOR_CORES and v.dtype == torch.float32 and net[0].weight.dtype == torch.float32
+                and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0 and tlist):
+            layers = self._wide.get(self._wide.tensors_of([self]), lambda: self._fold_wide(tlist))
+            params = _tc_mlp(vin, layers)
+            if params is not None:
+                return ops.spline_transform(v, params, self.mask, tidx, self.num_bins, inverse, self.bound, self._mins,
+                                            rescale, compact=True)
         h = ops.linear(vin, net[0].weight, net[0].bias, mask=self.mask, relu=True)
         h = ops.linear(h, net[2].weight, net[2].bias, relu=True)
         # head restricted to the transformed dims: the reference evaluates all D*(3K-1) outputs and discards the rows
@@ -271,6 +322,14 @@ class SplineCouplingLayer(Flow):
         params = ops.linear(h, w4, b4)
         return ops.spline_transform(v, params, self.mask, tidx, self.num_bins, inverse, self.bound, self._mins,
                                     rescale, compact=True)
+
+    def _fold_wide(self, tlist):
+        """Mask-folded first Linear, compact head, TF32 splits: cached per weight version for the no-grad route."""
+        with torch.no_grad():
+            net = self.param_net
+            w4, b4 = self._head_rows(net[4], tlist)
+            return [_tc_layer(net[0].weight * self.mask[None, :], net[0].bias, True),
+                    _tc_layer(net[2].weight, net[2].bias, True), _tc_layer(w4, b4, False)]
 
     def _head_rows(self, lin, t):
         """Rows d*(3K-1)+j of the last Linear for the transformed dims d in `t`: a contiguous slice (a view) for the

