@@ -214,7 +214,7 @@ class CouplingLayer(Flow):
             out = run_coupling_stack(self._pack, self._pack.tensors_of([self]), [self], None, v, inverse)
             if out is not None:
                 return out
-        if (not wants_grad(self, v) and not self.training and USE_TENSOR_CORES and v.dtype == torch.float32
+        if (not wants_grad(self, v) and not self.training and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM and v.dtype == torch.float32
                 and self.s_net[0].weight.dtype == torch.float32 and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0):
             # wide eval route: mask and eval-mode BatchNorm folded into the Linears once per weight version, TF32 splits
             # cached, three tensor-core GEMMs per net (the layered route re-folds and re-splits on every call)
@@ -307,7 +307,7 @@ class SplineCouplingLayer(Flow):
         vin = v
         if rescale is not None:                       # conditioner sees the rescaled input (:101-102)
             vin = ops.feature_affine(v, rescale[1], None, rescale[0], -float(self.bound))
-        if (not wants_grad(self, v) and USE_TENSOR_CORES and v.dtype == torch.float32 and net[0].weight.dtype == torch.float32
+        if (not wants_grad(self, v) and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM and v.dtype == torch.float32 and net[0].weight.dtype == torch.float32
                 and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0 and tlist):
             layers = self._wide.get(self._wide.tensors_of([self]), lambda: self._fold_wide(tlist))
             params = _tc_mlp(vin, layers)

@@ -376,12 +376,12 @@ def test_wide_eval_route_matches_oracle(kind, D, H, B):
             assert (ez > 1e-5).double().mean().item() < 0.02 and ez.max().item() < 1e-4, (ez.max().item(), (ez > 1e-5).double().mean().item())
             assert (ld.cpu().double() - ld64).abs().max().item() <= 2e-3
             e_ref = (rld.double() - ld64).abs().max().item()
-            N.ops.USE_TENSOR_CORE_GEMM, N.flows.USE_TENSOR_CORES = False, False
+            N.set_strict_fp32(True)
             try:
                 with torch.no_grad():
                     ys, lds = _run(m, x.to(_dev()), inverse)
             finally:
-                N.ops.USE_TENSOR_CORE_GEMM, N.flows.USE_TENSOR_CORES = True, True
+                N.set_strict_fp32(False)
             assert (lds.cpu().double() - ld64).abs().max().item() <= 2 * e_ref + 1e-4
             _within(ys.cpu(), ry, y64, Z_ATOL, Z_RTOL, f"strict {kind} z inv={inverse}")
         else:
