@@ -1,0 +1,312 @@
+// gemm_tc2.cu -- second tensor-core dense layer:  Y[M,N] = act(X[M,K] * W[N,K]^T + bias), 3xTF32 on tcgen05 with
+// SHORT accumulation chains.  (F.linear of MaskedLinear / MADE and of the coupling / spline conditioners; same contract
+// as gemm_tc.cu's nf_linear_tc_range.)
+//
+// Why: the tensor core truncates its fp32 accumulator on every MMA, so the error of a TMEM accumulation chain grows
+// linearly with its length (K = 1024 -> 384 MMAs -> rms 7e-6 of rms(y), 12x an FFMA GEMM, and a coherent
+// log-det bias of 4e-4 over a 784-dim spline layer).  Here a chain is at most kChainKB = 2 K-blocks (24 MMAs, the
+// K = 64 error class) whatever K is: the MMA warp rotates over three TMEM accumulators, and four *drainer* warps
+// fold every finished chain into fp32 registers with round-to-nearest adds -- thread r keeps row r's 128 running sums
+// in registers for the whole tile, so the epilogue (bias, ReLU, store) comes straight from registers.
+//
+// One persistent CTA per SM (the 512 TMEM columns hold three 128-column chain accumulators and two A stages), 10 warps:
+//   warp 0      TMA producer: X tile [128x32] and W_hi / W_lo tiles [128x32] per stage, 4 stages, running across tiles
+//   warp 1      MMA issuer: 12 tcgen05.mma per K block (A from TMEM, B from shared memory), commits stage / A-stage /
+//               chain barriers
+//   warps 2-5   converters: split the X tile into hi / lo and store it into the TMEM A stage (lane = row)
+//   warps 6-9   drainers: tcgen05.ld the finished chain accumulator, add into registers, release it; after the tile's
+//               last chain: bias + ReLU + coalesced stores (through a per-warp transpose buffer), overlapping the next
+//               tile's main loop
+#include <cuda.h>
+#include "nf_common.cuh"
+#include "tc_common.cuh"
+
+namespace nf {
+
+constexpr int k2BM = 128, k2BN = 128, k2BK = 32;
+constexpr int k2Stages = 4;
+constexpr int k2Threads = 320;
+constexpr int k2ChainKB = 2;                  // K blocks per TMEM accumulation chain
+constexpr int k2NAcc = 3;                     // chain accumulators in flight (drain latency hides behind two chains)
+constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A stage 0: 384 (hi 32 + lo 32) | A stage 1: 448
+constexpr int k2ColA = 384;
+constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
+constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
+constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;
+
+int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
+
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+// tile t -> (column block, row block).  Column blocks rotate with the row block: with k_extent (block-triangular MADE
+// weights) the K length depends on the column block, and a CTA's tiles t, t + gridDim.x, ... would otherwise all fall on
+// the same column block whenever gridDim.x is a multiple of n_tiles (148 = 4 * 37: measured +23 % on the C3 chain).
+// Consecutive tiles still share their X row block (L2 reuse).
+__device__ __forceinline__ void tile_decode(int t, int n_tiles, int& n0, int& m0) {
+    const int mt = t / n_tiles;
+    const int nt = (t - mt * n_tiles + mt) % n_tiles;
+    n0 = nt * k2BN; m0 = mt * k2BM;
+}
+
+// K-block range [kb_first, kb_first + nkb) of the output tile starting at column n0
+__device__ __forceinline__ void tile_k_range(int n0, int N, int K, const int32_t* __restrict__ k_extent,
+                                             const int32_t* __restrict__ k_begin, int& kb_first, int& nkb) {
+    int k_end = K;
+    if (k_extent) {
+        int e = 0;
+        for (int c = n0 / 64; c <= (n0 + k2BN - 1) / 64 && c * 64 < N; ++c) e = max(e, k_extent[c]);
+        k_end = min(K, e);
+    }
+    kb_first = 0;
+    if (k_begin) {
+        int b = K;
+        for (int c = n0 / 64; c <= (n0 + k2BN - 1) / 64 && c * 64 < N; ++c) b = min(b, k_begin[c]);
+        kb_first = max(0, min(b, k_end)) / k2BK;
+    }
+    nkb = max(0, (k_end + k2BK - 1) / k2BK - kb_first);
+}
+
+__global__ void __launch_bounds__(k2Threads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
+                const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
+                int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
+                const int32_t* __restrict__ k_begin, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* tbuf_base = smem + k2Stages * k2StageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + k2TbufBytes);
+    uint64_t* full = bars;                         // [S] TMA landed
+    uint64_t* empty = full + k2Stages;             // [S] stage consumed (MMA commit)
+    uint64_t* a_full = empty + k2Stages;           // [2] converters wrote the TMEM A stage
+    uint64_t* a_empty = a_full + 2;                // [2] MMAs consumed the TMEM A stage
+    uint64_t* d_full = a_empty + 2;                // [NAcc] chain accumulator complete
+    uint64_t* d_empty = d_full + k2NAcc;           // [NAcc] drainers read the chain accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + k2NAcc);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (N + k2BN - 1) / k2BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < k2Stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < k2NAcc; ++i) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_empty[i], 128); }
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, k2TmemCols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int n0, m0;
+                tile_decode(t, n_tiles, n0, m0);
+                int kb_first, nkb;
+                tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % k2Stages;
+                    if (it >= k2Stages) tc::mbar_wait(&empty[s], ((it / k2Stages) - 1) & 1);
+                    uint8_t* st = smem + s * k2StageBytes;
+                    tc::mbar_arrive_expect_tx(&full[s], k2StageBytes);
+                    tma2_load_2d(st, &tm_x, (kb_first + kb) * k2BK, m0, &full[s]);
+                    tma2_load_2d(st + k2XBytes, &tm_wh, (kb_first + kb) * k2BK, n0, &full[s]);
+                    tma2_load_2d(st + k2XBytes + k2WBytes, &tm_wl, (kb_first + kb) * k2BK, n0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (whole warp, convergent; one elected lane issues) ----------------
+        const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)k2BN);
+        const bool leader = tc::elect_one();
+        int it = 0, cc = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int n0, m0;
+            tile_decode(t, n_tiles, n0, m0);
+            (void)m0;
+            int kb_first, nkb;
+            tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % k2Stages, a = it & 1;
+                const int in_chain = kb % k2ChainKB;
+                const int cb = cc % k2NAcc;
+                if (in_chain == 0 && cc >= k2NAcc) tc::mbar_wait(&d_empty[cb], ((cc / k2NAcc) - 1) & 1);
+                tc::mbar_wait(&full[s], (it / k2Stages) & 1);
+                tc::mbar_wait(&a_full[a], (it >> 1) & 1);
+                tc::fence_after_sync();
+                const uint32_t st = tc::smem_u32(smem + s * k2StageBytes);
+                const uint64_t d_hi = tc::smem_desc_k_sw128(st + k2XBytes), d_lo = tc::smem_desc_k_sw128(st + k2XBytes + k2WBytes);
+                const uint32_t a_hi = tb + k2ColA + a * 64, a_lo = a_hi + 32;
+                const uint32_t dcol = tb + cb * 128;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ac = (pass == 1) ? a_lo : a_hi;
+                    const uint64_t wd = (pass == 2) ? d_lo : d_hi;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (in_chain | pass | k) != 0 ? 1u : 0u);
+                    }
+                }
+                const bool chain_end = (in_chain == k2ChainKB - 1) || (kb == nkb - 1);
+                if (leader) {
+                    tc::mma_commit(&empty[s]);
+                    tc::mma_commit(&a_empty[a]);
+                    if (chain_end) tc::mma_commit(&d_full[cb]);
+                }
+                __syncwarp();
+                if (chain_end) ++cc;
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- converters (warps 2..5; TMEM lane quadrant = warp % 4) ----------------
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int n0, m0;
+            tile_decode(t, n_tiles, n0, m0);
+            (void)m0;
+            int kb_first, nkb;
+            tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % k2Stages, a = it & 1;
+                tc::mbar_wait(&full[s], (it / k2Stages) & 1);
+                if (it >= 2) tc::mbar_wait(&a_empty[a], ((it >> 1) - 1) & 1);
+                tc::fence_after_sync();
+                const uint8_t* xrow = smem + s * k2StageBytes + (r >> 3) * 1024 + (r & 7) * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(xrow + ((c ^ (r & 7)) << 4));
+                    tc::split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]);
+                    tc::split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+                    tc::split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]);
+                    tc::split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
+                }
+                const uint32_t a_hi = lane_addr + k2ColA + a * 64, a_lo = a_hi + 32;
+                {
+                    uint32_t t0[16], t1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { t0[j] = hi[j]; t1[j] = hi[16 + j]; }
+                    tc::tmem_st16(a_hi, t0); tc::tmem_st16(a_hi + 16, t1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
+                    tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                }
+                tc::wait_st();
+                tc::fence_before_sync();
+                tc::mbar_arrive(&a_full[a]);
+            }
+        }
+    } else {
+        // ---------------- drainers (warps 6..9; TMEM lane quadrant = warp % 4), then the tile epilogue ----------------
+        const int q = warp & 3;
+        const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
+        float* tbuf = reinterpret_cast<float*>(tbuf_base) + (size_t)(warp - 6) * 32 * 33;
+        int cc = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int n0, m0;
+            tile_decode(t, n_tiles, n0, m0);
+            int kb_first, nkb;
+            tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+            const int nchains = (nkb + k2ChainKB - 1) / k2ChainKB;
+            float acc[128];
+#pragma unroll
+            for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+            for (int c = 0; c < nchains; ++c, ++cc) {
+                const int cb = cc % k2NAcc;
+                tc::mbar_wait(&d_full[cb], (cc / k2NAcc) & 1);
+                tc::fence_after_sync();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint32_t v[16];
+                    tc::tmem_ld16(lane_addr + cb * 128 + ch * 16, v);
+                    tc::wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[ch * 16 + j] += __uint_as_float(v[j]);      // round-to-nearest fp32 adds
+                }
+                tc::fence_before_sync();
+                tc::mbar_arrive(&d_empty[cb]);
+            }
+            // epilogue from registers: bias + ReLU, transposed through the warp's buffer, 128-byte row stores
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = acc[c * 32 + j];
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                const float bv = (bias && col < N) ? __ldg(bias + col) : 0.f;
+                if (col < N) {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = m0 + q * 32 + rr;
+                        if (row < M) {
+                            float o = tbuf[rr * 33 + lane] + bv;
+                            if (relu) o = (o < 0.f) ? 0.f : o;          // NaN stays NaN (torch.relu)
+                            Y[(int64_t)row * ldc + col] = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tb, k2TmemCols);
+}
+
+typedef CUresult (*Encode2Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static Encode2Fn encode2_fn() {
+    static Encode2Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<Encode2Fn>(p);
+    }
+    return fn;
+}
+
+static bool make_map2(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    Encode2Fn fn = encode2_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)k2BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns NF_OK when launched; NF_ERR_UNSUPPORTED when the caller should use gemm_tc.cu
+int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                    int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
+                    cudaStream_t st) {
+    alignas(64) CUtensorMap tx, twh, twl;
+    if (!make_map2(&tx, x, M, K, ldx, k2BM) || !make_map2(&twh, w_hi, N, K, ldw, k2BN) || !make_map2(&twl, w_lo, N, K, ldw, k2BN))
+        return NF_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
+    NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
+    if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    gemm_tc2_kernel<<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy, relu,
+                                                   k_extent, k_begin, (int)tiles);
+    return NF_OK;
+}
+
+}  // namespace nf

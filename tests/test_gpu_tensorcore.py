@@ -205,3 +205,30 @@ def test_mask_plans_skip_only_exact_zeros(D, H, B):
             assert (got_a.double() - ref).abs().max().item() / scale < 2e-5, what
             assert (got_a - got_b).abs().max().item() / scale < 2e-5, what
         assert torch.equal(res[True][2] == 0, res[False][2] == 0) or bool((res[True][2][mask == 0] == 0).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 512), (2048, 1024, 1024), (1000, 300, 2048), (512, 128, 4096)])
+def test_long_contractions_are_fp32_grade(M, N, K):
+    """Short-chain kernel (gemm_tc2.cu): the rms error of a K-long product stays at the FFMA-GEMM level whatever K is
+    (the single-chain kernel grows linearly: 4e-6 at K = 1024, 3e-5 at K = 4096), also for same-sign data (no bias)."""
+    gen = torch.Generator().manual_seed(K)
+    for positive in (False, True):
+        x = torch.randn(M, K, generator=gen)
+        w = torch.randn(N, K, generator=gen) / K ** 0.5
+        if positive:
+            x, w = x.abs(), w.abs()
+        hi, lo = N_.ops.split_tf32(w.cuda())
+        y = N_.ops.linear_tc(x.cuda(), hi, lo)
+        ref = x.double() @ w.double().T
+        rms = ref.pow(2).mean().sqrt().item()
+        e = y.cpu().double() - ref
+        assert e.pow(2).mean().sqrt().item() / rms < 1.5e-6, (positive, e.pow(2).mean().sqrt().item() / rms)
+        # same-sign data: a 48-MMA chain still loses ~48 * 2^-25 = 1.4e-6 of the running sum (384 MMAs: 1.2e-5)
+        assert abs(e.mean().item()) / rms < (2e-6 if positive else 5e-7), (positive, e.mean().item() / rms)
+        N_._lib.call("nf_set_option", 5, 0)
+        try:
+            y0 = N_.ops.linear_tc(x.cuda(), hi, lo)
+        finally:
+            N_._lib.call("nf_set_option", 5, 1)
+        e0 = y0.cpu().double() - ref
+        assert e.pow(2).mean().sqrt().item() <= e0.pow(2).mean().sqrt().item() * 1.05
