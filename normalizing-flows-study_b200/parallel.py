@@ -33,15 +33,33 @@ def shard_rows(x: torch.Tensor, rank: int = None, world: int = None):
 
 class DataParallelFlow(nn.Module):
     """Wraps a flow module for data-parallel training.  forward / inverse / log_prob delegate to the wrapped
-    module on the local shard; call `sync_gradients()` between `backward()` and `optimizer.step()`."""
+    module on the local shard; call `sync_gradients()` between `backward()` and `optimizer.step()`.
 
-    def __init__(self, module: nn.Module, process_group=None, bucket_bytes: int = 64 << 20, broadcast: bool = True):
+    With `overlap=True` (default) the gradient buckets are all-reduced *during* backward: a post-accumulate hook per
+    parameter counts its bucket down, and a complete bucket is flattened and handed to an asynchronous all-reduce on
+    the communication stream while autograd keeps producing the earlier layers' gradients.  Buckets are always
+    launched in the same (reverse-parameter) order on every rank; `sync_gradients()` launches what backward did not
+    reach (parameters without a gradient contribute zeros), waits, averages and scatters the results back.
+    Gradient accumulation over micro-batches: wrap all but the last backward in `no_sync()`."""
+
+    def __init__(self, module: nn.Module, process_group=None, bucket_bytes: int = 64 << 20, broadcast: bool = True,
+                 overlap: bool = True):
         super().__init__()
         self.module = module
         self.process_group = process_group
         self.bucket_bytes = int(bucket_bytes)
+        self.overlap = bool(overlap)
+        self._bucket_list = None
+        self._pending = []            # (bucket index, flat tensor, work handle) in launch order
+        self._ready = None            # per bucket: number of parameters whose gradient has arrived this round
+        self._next = 0                # next bucket to launch
+        self._dirty = False           # a bucket fired twice without sync_gradients(): fall back to the plain path
+        self._hooks_on = True
+        self._hook_handles = []
         if broadcast and dist.is_initialized():
             self.broadcast_parameters()
+        if self.overlap and dist.is_initialized() and self._world() > 1:
+            self._install_hooks()
 
     # -- delegation ---------------------------------------------------------------------------------------
     def forward(self, z):
@@ -78,6 +96,62 @@ class DataParallelFlow(nn.Module):
         if bucket:
             yield bucket
 
+    # -- overlap with backward ------------------------------------------------------------------------------
+    def _install_hooks(self):
+        self._bucket_list = list(self._buckets())
+        self._ready = [0] * len(self._bucket_list)
+        for bi, bucket in enumerate(self._bucket_list):
+            for p in bucket:
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+
+    def _make_hook(self, bi):
+        def hook(param):
+            if not self._hooks_on:
+                return
+            if bi < self._next or self._ready[bi] >= len(self._bucket_list[bi]):
+                self._dirty = True                      # second backward without sync_gradients() / no_sync()
+                return
+            self._ready[bi] += 1
+            while self._next < len(self._bucket_list) and self._ready[self._next] == len(self._bucket_list[self._next]):
+                self._launch(self._next)
+                self._next += 1
+        return hook
+
+    @torch.no_grad()
+    def _launch(self, bi):
+        bucket = self._bucket_list[bi]
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+        self._pending.append((bi, flat, work))
+
+    class _NoSync:
+        def __init__(self, owner):
+            self.owner = owner
+
+        def __enter__(self):
+            self.prev = self.owner._hooks_on
+            self.owner._hooks_on = False
+
+        def __exit__(self, *exc):
+            self.owner._hooks_on = self.prev
+
+    def no_sync(self):
+        """Context manager: backward passes inside do not start gradient all-reduces (micro-batch accumulation)."""
+        return DataParallelFlow._NoSync(self)
+
+    @torch.no_grad()
+    def _scatter_back(self, bucket, flat, world):
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+
     @torch.no_grad()
     def sync_gradients(self):
         """Average gradients over ranks.  Parameters without a gradient on this rank contribute zeros, so the
@@ -85,19 +159,25 @@ class DataParallelFlow(nn.Module):
         world = self._world()
         if world == 1:
             return
-        for bucket in self._buckets():
-            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)
-            flat.div_(world)
-            off = 0
-            for p in bucket:
-                n = p.numel()
-                g = flat[off:off + n].view_as(p)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-                off += n
+        if self._bucket_list is not None and not self._dirty:
+            while self._next < len(self._bucket_list):          # buckets backward did not complete on this rank
+                self._launch(self._next)
+                self._next += 1
+            for bi, flat, work in self._pending:
+                work.wait()
+                self._scatter_back(self._bucket_list[bi], flat, world)
+        else:
+            for _, _, work in self._pending:                    # drain what was started, then the plain path
+                work.wait()
+            for bucket in (self._bucket_list if self._bucket_list is not None else self._buckets()):
+                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)
+                self._scatter_back(bucket, flat, world)
+        self._pending = []
+        self._next = 0
+        self._dirty = False
+        if self._ready is not None:
+            self._ready = [0] * len(self._bucket_list)
 
     @torch.no_grad()
     def sync_running_stats(self):

@@ -85,3 +85,85 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
             sizes = [hi - lo for lo, hi in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _overlap_worker(rank, world, port, bucket_bytes, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(7)                                 # same weights everywhere
+        net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                  torch.nn.Linear(16, 3))
+        twin = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                   torch.nn.Linear(16, 3))
+        twin.load_state_dict(net.state_dict())
+        dp = P.DataParallelFlow(net, bucket_bytes=bucket_bytes)
+        assert dp._bucket_list is not None                   # hooks installed (world 2)
+        g = torch.Generator().manual_seed(50 + rank)
+        x1, x2 = torch.randn(9, 5, generator=g), torch.randn(4, 5, generator=g)
+
+        def expected(batches):
+            twin.zero_grad(set_to_none=True)
+            for xb in batches:
+                twin(xb).pow(2).sum().backward()
+            outs = []
+            for p in twin.parameters():
+                t = p.grad.clone()
+                dist.all_reduce(t)
+                outs.append(t / world)
+            return outs
+
+        results = []
+        # (1) one backward: buckets are reduced from the hooks, sync_gradients only waits and scatters
+        net.zero_grad(set_to_none=True)
+        net(x1).pow(2).sum().backward()
+        launched_in_backward = len(dp._pending)
+        dp.sync_gradients()
+        results.append(all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), expected([x1]))))
+        # (2) accumulation over two micro-batches with no_sync on the first
+        net.zero_grad(set_to_none=True)
+        with dp.no_sync():
+            net(x1).pow(2).sum().backward()
+        net(x2).pow(2).sum().backward()
+        dp.sync_gradients()
+        results.append(all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), expected([x1, x2]))))
+        # (3) two backwards without no_sync: detected, plain path gives the right average of the accumulated gradients
+        net.zero_grad(set_to_none=True)
+        net(x1).pow(2).sum().backward()
+        net(x2).pow(2).sum().backward()
+        dp.sync_gradients()
+        results.append(all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), expected([x1, x2]))))
+        # (4) a rank whose backward skips the last layers' parameters (unused branch): zeros contributed, same order
+        net.zero_grad(set_to_none=True)
+        if rank == 0:
+            net(x1).pow(2).sum().backward()
+        else:
+            net[:3](x1).pow(2).sum().backward()              # only the first two Linears get gradients on rank 1
+        dp.sync_gradients()
+        exp4 = []
+        twin.zero_grad(set_to_none=True)
+        (twin(x1) if rank == 0 else twin[:3](x1)).pow(2).sum().backward()
+        for p in twin.parameters():
+            t = p.grad.clone() if p.grad is not None else torch.zeros_like(p)
+            dist.all_reduce(t)
+            exp4.append(t / world)
+        results.append(all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), exp4)))
+        out[rank] = (results, launched_in_backward, len(dp._bucket_list))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [64 << 20, 300])
+def test_overlapped_gradient_allreduce_world2(bucket_bytes):
+    """Gradient buckets all-reduced from post-accumulate hooks during backward (parallel.DataParallelFlow, overlap=True):
+    same averages as the plain path, fixed bucket order on every rank, no_sync accumulation, double-backward fallback."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, _free_port(), bucket_bytes, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        results, launched, nb = out[rank]
+        assert all(results), (rank, results)
+        assert launched == nb                                # every bucket was started before sync_gradients()
+    assert out[0][2] == (1 if bucket_bytes > 1000 else out[0][2]) and out[0][2] >= 1
