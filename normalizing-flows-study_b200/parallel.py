@@ -98,16 +98,51 @@ class DataParallelFlow(nn.Module):
 
     # -- overlap with backward ------------------------------------------------------------------------------
     def _install_hooks(self):
-        self._bucket_list = list(self._buckets())
-        self._ready = [0] * len(self._bucket_list)
-        for bi, bucket in enumerate(self._bucket_list):
-            for p in bucket:
-                self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+        """First round: the hooks only record the order in which gradients arrive (it depends on the direction the model
+        is trained in: `inverse` walks the layers backwards, so its gradients arrive in *forward* parameter order).
+        sync_gradients() then adopts rank 0's order on every rank and cuts the buckets along it."""
+        self._params = [p for p in self.module.parameters() if p.requires_grad]
+        self._arrival = []
+        self._learning = True
+        self._bucket_of = {}
+        for i, p in enumerate(self._params):
+            self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
 
-    def _make_hook(self, bi):
+    def _adopt_arrival_order(self):
+        n = len(self._params)
+        seen = set()
+        order = [i for i in self._arrival if not (i in seen or seen.add(i))]
+        order += [i for i in reversed(range(n)) if i not in seen]           # never fired: reverse parameter order
+        dev = self._params[0].device if n else torch.device("cpu")
+        t = torch.tensor(order, dtype=torch.int64, device=dev)
+        dist.broadcast(t, src=0, group=self.process_group)                  # every rank cuts the same buckets
+        order = t.tolist()
+        buckets, bucket, size, key = [], [], 0, None
+        for i in order:
+            p = self._params[i]
+            k = (p.dtype, p.device)
+            nbytes = p.numel() * p.element_size()
+            if bucket and (k != key or size + nbytes > self.bucket_bytes):
+                buckets.append(bucket)
+                bucket, size = [], 0
+            bucket.append(p)
+            size += nbytes
+            key = k
+        if bucket:
+            buckets.append(bucket)
+        self._bucket_list = buckets
+        self._bucket_of = {id(p): bi for bi, b in enumerate(buckets) for p in b}
+        self._ready = [0] * len(buckets)
+        self._learning = False
+
+    def _make_hook(self, pi):
         def hook(param):
             if not self._hooks_on:
                 return
+            if self._learning:
+                self._arrival.append(pi)
+                return
+            bi = self._bucket_of[id(param)]
             if bi < self._next or self._ready[bi] >= len(self._bucket_list[bi]):
                 self._dirty = True                      # second backward without sync_gradients() / no_sync()
                 return
@@ -158,6 +193,13 @@ class DataParallelFlow(nn.Module):
         collective sequence is identical on every rank (ragged / empty shards included)."""
         world = self._world()
         if world == 1:
+            return
+        if getattr(self, "_learning", False):
+            for bucket in self._buckets():                      # first round: plain path, then fix the bucket order
+                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)
+                self._scatter_back(bucket, flat, world)
+            self._adopt_arrival_order()
             return
         if self._bucket_list is not None and not self._dirty:
             while self._next < len(self._bucket_list):          # buckets backward did not complete on this rank

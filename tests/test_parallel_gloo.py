@@ -98,9 +98,16 @@ def _overlap_worker(rank, world, port, bucket_bytes, out):
                                    torch.nn.Linear(16, 3))
         twin.load_state_dict(net.state_dict())
         dp = P.DataParallelFlow(net, bucket_bytes=bucket_bytes)
-        assert dp._bucket_list is not None                   # hooks installed (world 2)
+        assert dp._hook_handles                              # hooks installed (world 2)
         g = torch.Generator().manual_seed(50 + rank)
         x1, x2 = torch.randn(9, 5, generator=g), torch.randn(4, 5, generator=g)
+        # round 0 learns the gradient arrival order (plain all-reduce), later rounds overlap
+        net.zero_grad(set_to_none=True)
+        net(x2).pow(2).sum().backward()
+        dp.sync_gradients()
+        assert dp._bucket_list is not None and not dp._learning
+        first_bucket_param = dp._bucket_list[0][0]
+        arrival_ok = any(first_bucket_param is q for q in net[-1].parameters())   # the last layer's gradients arrive first
 
         def expected(batches):
             twin.zero_grad(set_to_none=True)
@@ -148,6 +155,7 @@ def _overlap_worker(rank, world, port, bucket_bytes, out):
             dist.all_reduce(t)
             exp4.append(t / world)
         results.append(all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(net.parameters(), exp4)))
+        results.append(arrival_ok)
         out[rank] = (results, launched_in_backward, len(dp._bucket_list))
     finally:
         dist.destroy_process_group()
