@@ -161,3 +161,36 @@ def test_graphed_train_step_matches_eager_steps():
     assert all(abs(a - b) <= 1e-4 * (1 + abs(b)) for a, b in zip(losses_g, losses_e)), (losses_g, losses_e)
     for (k, p), (_, q) in zip(graph_m.named_parameters(), eager_m.named_parameters()):
         assert torch.allclose(p, q, atol=1e-5, rtol=1e-4), k
+
+
+@pytest.mark.parametrize("make,shape", [(lambda: N.RealNVP(2, 8, 64), (2,)), (lambda: N.RealNVPSpline(2, 8, 64), (2,)),
+                                        (lambda: N.MaskedAutoregressiveFlow(8, 64), (8,)),
+                                        (lambda: N.InverseAutoregressiveFlow(8, 64), (8,))])
+def test_reference_flow_profiler_recipe(make, shape):
+    """FlowProfiler.profile_flow / _profile_single_batch_size (src/flows/utils/profiling.py:63-200) restated: .to(device),
+    .eval(), warm-up forward + inverse under no_grad, CUDA-event timing per call at batch sizes 1, 8, 32, 64, peak-memory
+    and parameter-count queries."""
+    flow = make().to(DEV)
+    flow.eval()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for batch_size in (1, 8, 32, 64):
+        full = (batch_size,) + shape
+        for _ in range(2):
+            x = torch.randn(full, device=DEV)
+            with torch.no_grad():
+                flow.forward(x)
+                flow.inverse(x)
+        torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        for fn in (flow.forward, flow.inverse):
+            x = torch.randn(full, device=DEV)
+            start.record()
+            with torch.no_grad():
+                out, log_det = fn(x)
+            end.record()
+            torch.cuda.synchronize()
+            assert out.shape == full and log_det.shape == (batch_size,) and start.elapsed_time(end) > 0
+            assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(log_det).all())
+        assert torch.cuda.max_memory_allocated() > 0
+    assert sum(p.numel() for p in flow.parameters()) > 0
