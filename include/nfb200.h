@@ -60,7 +60,8 @@ NF_API int64_t nf_launch_count(void);
  * key 2 = nf_linear_wgrad_tc: longest TMEM accumulation chain in 32-row blocks (default 64);
  * key 3 = nf_ar_blocked_forward in-block kernel (0: CTA-barrier version, 1: warp-private tiles, default);
  * key 5 = nf_linear_tc*: 0 = one TMEM accumulation chain per output tile (gemm_tc.cu), 1 = chains of 2 K blocks folded into
- *         registers with round-to-nearest adds (gemm_tc2.cu, default for K > 128) */
+ *         registers with round-to-nearest adds (gemm_tc2.cu, default);
+ * key 6 = nf_linear_tc*: K <= 128 through gemm_tc2.cu's persistent direct variant (1, default) or gemm_tc.cu (0) */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------

@@ -26,15 +26,17 @@ namespace nf {
 constexpr int k2BM = 128, k2BN = 128, k2BK = 32;
 constexpr int k2Stages = 4;
 constexpr int k2Threads = 320;
+constexpr int k2ThreadsDirect = 448;          // two drainer groups
 constexpr int k2ChainKB = 2;                  // K blocks per TMEM accumulation chain
 constexpr int k2NAcc = 3;                     // chain accumulators in flight (drain latency hides behind two chains)
 constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A stage 0: 384 (hi 32 + lo 32) | A stage 1: 448
 constexpr int k2ColA = 384;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
-constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;
+constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;          // per drainer group
 
 int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
+int g_gemm_tc_small_k = 1;                    // nf_set_option(6, v): K <= 128 through the persistent DIRECT variant (1) or gemm_tc.cu (0)
 
 __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -69,14 +71,20 @@ __device__ __forceinline__ void tile_k_range(int n0, int N, int K, const int32_t
     nkb = max(0, (k_end + k2BK - 1) / k2BK - kb_first);
 }
 
-__global__ void __launch_bounds__(k2Threads, 1)
+// DIRECT = true: contractions of at most 128 (<= 4 K blocks = one short chain per tile).  No register accumulation is
+// needed, so the drainers write each tile straight from TMEM and there are two drainer groups (warps 6-9 and 10-13)
+// taking alternate tiles: for small K the tile's epilogue (64 KB of output) is longer than its main loop, and the
+// non-persistent kernel in gemm_tc.cu pays launch, TMEM allocation and pipeline fill per tile (measured at
+// 2^20 x 64 x 64: 0.22 ms = 2.4 TB/s of a 0.08 ms HBM floor).
+template <bool DIRECT>
+__global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                 int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
                 const int32_t* __restrict__ k_begin, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* tbuf_base = smem + k2Stages * k2StageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + k2TbufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + (DIRECT ? 2 : 1) * k2TbufBytes);
     uint64_t* full = bars;                         // [S] TMA landed
     uint64_t* empty = full + k2Stages;             // [S] stage consumed (MMA commit)
     uint64_t* a_full = empty + k2Stages;           // [2] converters wrote the TMEM A stage
@@ -133,7 +141,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % k2Stages, a = it & 1;
-                const int in_chain = kb % k2ChainKB;
+                const int in_chain = DIRECT ? kb : kb % k2ChainKB;
                 const int cb = cc % k2NAcc;
                 if (in_chain == 0 && cc >= k2NAcc) tc::mbar_wait(&d_empty[cb], ((cc / k2NAcc) - 1) & 1);
                 tc::mbar_wait(&full[s], (it / k2Stages) & 1);
@@ -152,7 +160,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (in_chain | pass | k) != 0 ? 1u : 0u);
                     }
                 }
-                const bool chain_end = (in_chain == k2ChainKB - 1) || (kb == nkb - 1);
+                const bool chain_end = (!DIRECT && in_chain == k2ChainKB - 1) || (kb == nkb - 1);
                 if (leader) {
                     tc::mma_commit(&empty[s]);
                     tc::mma_commit(&a_empty[a]);
@@ -202,6 +210,56 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc::wait_st();
                 tc::fence_before_sync();
                 tc::mbar_arrive(&a_full[a]);
+            }
+        }
+    } else if constexpr (DIRECT) {
+        // ---------------- two drainer groups (warps 6..9, 10..13), alternate tiles, straight from TMEM ----------------
+        const int q = warp & 3, grp = (warp - 6) >> 2;
+        const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
+        float* tbuf = reinterpret_cast<float*>(tbuf_base) + (size_t)(warp - 6) * 32 * 33;
+        int cc = 0, ti = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+            int n0, m0;
+            tile_decode(t, n_tiles, n0, m0);
+            int kb_first, nkb;
+            tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+            const int my_cc = cc;
+            if (nkb > 0) ++cc;                                   // one chain per non-empty tile, counted by both groups
+            if ((ti & 1) != grp) continue;
+            const int cb = my_cc % k2NAcc;
+            if (nkb > 0) {
+                tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);
+                tc::fence_after_sync();
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v0[16], v1[16];
+                if (nkb > 0) {
+                    tc::tmem_ld16(lane_addr + cb * 128 + c * 32, v0);
+                    tc::tmem_ld16(lane_addr + cb * 128 + c * 32 + 16, v1);
+                    tc::wait_ld();
+                    if (c == 3) { tc::fence_before_sync(); tc::mbar_arrive(&d_empty[cb]); }     // accumulator free again
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { tbuf[lane * 33 + j] = __uint_as_float(v0[j]); tbuf[lane * 33 + 16 + j] = __uint_as_float(v1[j]); }
+                __syncwarp();
+                const int col = n0 + c * 32 + lane;
+                const float bv = (bias && col < N) ? __ldg(bias + col) : 0.f;
+                if (col < N) {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = m0 + q * 32 + rr;
+                        if (row < M) {
+                            float o = tbuf[rr * 33 + lane] + bv;
+                            if (relu) o = (o < 0.f) ? 0.f : o;
+                            Y[(int64_t)row * ldc + col] = o;
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -299,13 +357,20 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     alignas(64) CUtensorMap tx, twh, twl;
     if (!make_map2(&tx, x, M, K, ldx, k2BM) || !make_map2(&twh, w_hi, N, K, ldw, k2BN) || !make_map2(&twl, w_lo, N, K, ldw, k2BN))
         return NF_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
-    NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
     if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    gemm_tc2_kernel<<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy, relu,
-                                                   k_extent, k_begin, (int)tiles);
+    if (K <= 4 * k2BK) {
+        const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
+        NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc2_kernel<true><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
+                                                                   ldy, relu, k_extent, k_begin, (int)tiles);
+    } else {
+        const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
+        NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc2_kernel<false><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
+                                                              relu, k_extent, k_begin, (int)tiles);
+    }
     return NF_OK;
 }
 
