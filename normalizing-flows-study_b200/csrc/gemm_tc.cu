@@ -1,4 +1,5 @@
-// gemm_tc.cu -- fp32-accurate dense layer on the 5th-gen tensor cores:  Y[M,N] = act(X[M,K] * W[N,K]^T + bias)
+// gemm_tc.cu -- dense layer on the 5th-gen tensor cores, one TMEM accumulation chain per output tile (the first
+// kernel; nf_linear_tc* now routes through gemm_tc2.cu by default and falls back here):  Y[M,N] = act(X[M,K] * W[N,K]^T + bias)
 //   (F.linear of MaskedLinear / MADE, masked_linear.py:14-18, made.py:136-140, and of the coupling / spline
 //    conditioner MLPs, coupling_layer.py:18-35, spline_coupling_layer.py:55-62)
 //
