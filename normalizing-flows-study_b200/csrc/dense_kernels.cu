@@ -410,6 +410,182 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// float32, H % 4 == 0, 16-byte aligned: 128-bit versions of the four BatchNorm passes.  A block is TX column groups
+// (4 columns each) x TY row lanes; a thread keeps its columns' statistics in registers and streams rows with four
+// independent LDG.128 in flight.  (The scalar kernels above take `i % H` of a 64-bit index per element and move
+// 4 bytes per load: 45 % of HBM; they remain the float64 / odd-H path.)  Same operation order per element.
+// ------------------------------------------------------------------------------------------------
+struct BnVecGeom { int tx, ty, col_blocks, chunks; int64_t rpc; };
+
+static inline BnVecGeom bn_vec_geom(int64_t B, int H) {
+    BnVecGeom g;
+    const int q = H / 4;
+    g.tx = 1;
+    while (g.tx < q && g.tx < 256) g.tx <<= 1;
+    g.ty = 256 / g.tx;
+    g.col_blocks = (q + g.tx - 1) / g.tx;
+    int64_t c = ((int64_t)kNumSMs * 6 + g.col_blocks - 1) / g.col_blocks;
+    const int64_t maxc = (B + (int64_t)g.ty * 8 - 1) / ((int64_t)g.ty * 8);     // at least 8 rows per row lane
+    if (c > maxc) c = maxc;
+    if (c < 1) c = 1;
+    g.rpc = (B + c - 1) / c;
+    g.chunks = (int)((B + g.rpc - 1) / g.rpc);
+    return g;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(256)
+bn_partial_sums_vec4_kernel(const float* __restrict__ x, double* __restrict__ acc, int64_t B, int H, int64_t rpc, int tx) {
+    extern __shared__ double bn_red[];                          // [ty][tx][8]
+    const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int col = (blockIdx.x * tx + cx) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if (col < H) {
+        const float* p = x + col;
+        int64_t r = r0 + ry;
+        for (; r + 3 * ty < r1; r += 4 * ty) {
+            const float4 v0 = ld4(p + r * H), v1 = ld4(p + (r + ty) * H), v2 = ld4(p + (r + 2 * ty) * H), v3 = ld4(p + (r + 3 * ty) * H);
+            a[0] += ((double)v0.x + v1.x) + ((double)v2.x + v3.x); b[0] += ((double)v0.x * v0.x + (double)v1.x * v1.x) + ((double)v2.x * v2.x + (double)v3.x * v3.x);
+            a[1] += ((double)v0.y + v1.y) + ((double)v2.y + v3.y); b[1] += ((double)v0.y * v0.y + (double)v1.y * v1.y) + ((double)v2.y * v2.y + (double)v3.y * v3.y);
+            a[2] += ((double)v0.z + v1.z) + ((double)v2.z + v3.z); b[2] += ((double)v0.z * v0.z + (double)v1.z * v1.z) + ((double)v2.z * v2.z + (double)v3.z * v3.z);
+            a[3] += ((double)v0.w + v1.w) + ((double)v2.w + v3.w); b[3] += ((double)v0.w * v0.w + (double)v1.w * v1.w) + ((double)v2.w * v2.w + (double)v3.w * v3.w);
+        }
+        for (; r < r1; r += ty) {
+            const float4 v = ld4(p + r * H);
+            a[0] += v.x; b[0] += (double)v.x * v.x; a[1] += v.y; b[1] += (double)v.y * v.y;
+            a[2] += v.z; b[2] += (double)v.z * v.z; a[3] += v.w; b[3] += (double)v.w * v.w;
+        }
+    }
+    double* mine = bn_red + ((size_t)ry * tx + cx) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mine[j] = a[j]; mine[4 + j] = b[j]; }
+    __syncthreads();
+    if (ry == 0 && col < H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double ta = 0.0, tb = 0.0;
+            for (int i = 0; i < ty; ++i) { ta += bn_red[((size_t)i * tx + cx) * 8 + j]; tb += bn_red[((size_t)i * tx + cx) * 8 + 4 + j]; }
+            atomicAdd(acc + col + j, ta);
+            atomicAdd(acc + H + col + j, tb);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ y, int64_t B, int H,
+                     int relu, int64_t rpc, int tx) {
+    const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int col = (blockIdx.x * tx + cx) * 4;
+    if (col >= H) return;
+    const float4 mu = ld4(mean + col), rs = ld4(rstd + col), ga = ld4(gamma + col), be = ld4(beta + col);
+    const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+    const float* p = x + col;
+    float* o = y + col;
+#pragma unroll 4
+    for (int64_t r = r0 + ry; r < r1; r += ty) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p + r * H));
+        float4 w;
+        w.x = (v.x - mu.x) * rs.x * ga.x + be.x; w.y = (v.y - mu.y) * rs.y * ga.y + be.y;
+        w.z = (v.z - mu.z) * rs.z * ga.z + be.z; w.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+        if (relu) { w.x = relu_nan(w.x); w.y = relu_nan(w.y); w.z = relu_nan(w.z); w.w = relu_nan(w.w); }
+        *reinterpret_cast<float4*>(o + r * H) = w;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ gy, double* __restrict__ acc, int64_t B,
+                           int H, int relu, int64_t rpc, int tx) {
+    extern __shared__ double bn_red[];
+    const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int col = (blockIdx.x * tx + cx) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if (col < H) {
+        const float4 mu4 = ld4(mean + col), rs4 = ld4(rstd + col);
+        const double mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+#pragma unroll 2
+        for (int64_t r = r0 + ry; r < r1; r += ty) {
+            const int64_t off = r * H + col;
+            const float4 g4 = ld4(gy + off), x4 = ld4(x + off);
+            float g[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+            if (relu) {
+                const float4 y4 = ld4(y + off);
+                if (!(y4.x > 0.f)) g[0] = 0.f;
+                if (!(y4.y > 0.f)) g[1] = 0.f;
+                if (!(y4.z > 0.f)) g[2] = 0.f;
+                if (!(y4.w > 0.f)) g[3] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] += (double)g[j] * ((double)xv[j] - mu[j]) * rs[j]; b[j] += (double)g[j]; }
+        }
+    }
+    double* mine = bn_red + ((size_t)ry * tx + cx) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mine[j] = a[j]; mine[4 + j] = b[j]; }
+    __syncthreads();
+    if (ry == 0 && col < H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double ta = 0.0, tb = 0.0;
+            for (int i = 0; i < ty; ++i) { ta += bn_red[((size_t)i * tx + cx) * 8 + j]; tb += bn_red[((size_t)i * tx + cx) * 8 + 4 + j]; }
+            atomicAdd(acc + col + j, ta);
+            atomicAdd(acc + H + col + j, tb);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gy,
+                         const float* __restrict__ ggamma, const float* __restrict__ gbeta, float* __restrict__ gx, int64_t B,
+                         int H, int relu, int training, int64_t rpc, int tx) {
+    const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int col = (blockIdx.x * tx + cx) * 4;
+    if (col >= H) return;
+    const float4 mu4 = ld4(mean + col), rs4 = ld4(rstd + col), ga4 = ld4(gamma + col), gg4 = ld4(ggamma + col), gb4 = ld4(gbeta + col);
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+    const float gg[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, gb[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
+    const float invB = 1.0f / (float)B;
+    const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+#pragma unroll 2
+    for (int64_t r = r0 + ry; r < r1; r += ty) {
+        const int64_t off = r * H + col;
+        const float4 g4 = __ldcs(reinterpret_cast<const float4*>(gy + off));
+        float g[4] = {g4.x, g4.y, g4.z, g4.w};
+        if (relu) {
+            const float4 y4 = __ldcs(reinterpret_cast<const float4*>(y + off));
+            if (!(y4.x > 0.f)) g[0] = 0.f;
+            if (!(y4.y > 0.f)) g[1] = 0.f;
+            if (!(y4.z > 0.f)) g[2] = 0.f;
+            if (!(y4.w > 0.f)) g[3] = 0.f;
+        }
+        float o[4];
+        if (training) {
+            const float4 x4 = __ldcs(reinterpret_cast<const float4*>(x + off));
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xhat = (xv[j] - mu[j]) * rs[j];
+                o[j] = ga[j] * rs[j] * (g[j] - invB * (gb[j] + xhat * gg[j]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = ga[j] * rs[j] * g[j];
+        }
+        *reinterpret_cast<float4*>(gx + off) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static inline bool bn_vec_ok(int H, const void* a, const void* b, const void* c, const void* d) {
+    return H % 4 == 0 && H >= 16 && aligned16(a) && aligned16(b) && (!c || aligned16(c)) && (!d || aligned16(d));
+}
+
 static inline int ew_grid(int64_t n) {
     int64_t need = cdiv(n, 256);
     int64_t cap = (int64_t)kNumSMs * 16;
@@ -420,11 +596,17 @@ template <typename T>
 static int bn_forward(const void* x, const void* gamma, const void* beta, void* rm, void* rv, void* y, void* sm,
                       void* sr, void* ws, int64_t B, int H, int training, double momentum, double eps, int relu,
                       cudaStream_t st) {
+    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, y, gamma, beta) && aligned16(sm) && aligned16(sr);
+    const BnVecGeom vg = bn_vec_geom(B, H);
     if (training) {
         NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
         int chunks; int64_t rpc;
         bn_chunking(B, H, chunks, rpc);
         dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
+        if (vec)
+            bn_partial_sums_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
+                (const float*)x, (double*)ws, B, H, vg.rpc, vg.tx);
+        else
         bn_partial_sums_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (double*)ws, B, H, rpc);
         count_launch();
         NF_LAUNCH_CHECK();
@@ -435,6 +617,10 @@ static int bn_forward(const void* x, const void* gamma, const void* beta, void* 
     }
     count_launch();
     NF_LAUNCH_CHECK();
+    if (vec)
+        bn_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
+            (const float*)x, (const float*)gamma, (const float*)beta, (const float*)sm, (const float*)sr, (float*)y, B, H, relu, vg.rpc, vg.tx);
+    else
     bn_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)gamma, (const T*)beta, (const T*)sm,
                                                        (const T*)sr, (T*)y, B, H, relu);
     count_launch();
@@ -449,6 +635,13 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
     int chunks; int64_t rpc;
     bn_chunking(B, H, chunks, rpc);
     dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
+    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, gy, y, gx) && aligned16(sm) && aligned16(sr) && aligned16(gamma) &&
+                     aligned16(gg) && aligned16(gb);
+    const BnVecGeom vg = bn_vec_geom(B, H);
+    if (vec)
+        bn_bwd_partial_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
+            (const float*)x, (const float*)y, (const float*)sm, (const float*)sr, (const float*)gy, (double*)ws, B, H, relu, vg.rpc, vg.tx);
+    else
     bn_bwd_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr, (const T*)gy,
                                                    (double*)ws, B, H, relu, rpc);
     count_launch();
@@ -456,6 +649,11 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
     bn_bwd_finish_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)gg, (T*)gb, H);
     count_launch();
     NF_LAUNCH_CHECK();
+    if (vec)
+        bn_bwd_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
+            (const float*)x, (const float*)y, (const float*)gamma, (const float*)sm, (const float*)sr, (const float*)gy,
+            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx);
+    else
     bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
                                                            (const T*)sr, (const T*)gy, (const T*)gg, (const T*)gb,
                                                            (T*)gx, B, H, relu, training);
