@@ -61,7 +61,10 @@ NF_API int64_t nf_launch_count(void);
  * key 3 = nf_ar_blocked_forward in-block kernel (0: CTA-barrier version, 1: warp-private tiles, default);
  * key 5 = nf_linear_tc*: 0 = one TMEM accumulation chain per output tile (gemm_tc.cu), 1 = chains of 2 K blocks folded into
  *         registers with round-to-nearest adds (gemm_tc2.cu, default);
- * key 6 = nf_linear_tc*: K <= 128 through gemm_tc2.cu's persistent direct variant (1, default) or gemm_tc.cu (0) */
+ * key 6 = nf_linear_tc*: K <= 128 through gemm_tc2.cu's persistent direct variant (1, default) or gemm_tc.cu (0);
+ * key 7 = nf_linear_tc* and nf_linear_wgrad_tc*: tensor-core passes per product.  3 = 3xTF32 (fp32 parity, default);
+ *         1 = one TF32 pass, operands rounded to the nearest TF32 (the reduced-precision conditioner-GEMM mode the
+ *         reference reaches with autocast, optimization/mixed_precision.py:89-105; w_lo is not read) */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------

@@ -11,7 +11,8 @@ from .models import NormalizingFlowModel, RealNVP, RealNVPSpline  # noqa: F401
 
 __all__ = ["Flow", "SequentialFlow", "CouplingLayer", "SplineCouplingLayer", "rational_quadratic_spline",
            "MaskedLinear", "MADE", "MaskedAutoregressiveFlow", "InverseAutoregressiveFlow", "ARQS",
-           "NormalizingFlowModel", "RealNVP", "RealNVPSpline", "set_strict_fp32"]
+           "NormalizingFlowModel", "RealNVP", "RealNVPSpline", "set_strict_fp32", "set_gemm_precision",
+           "get_gemm_precision"]
 
 
 def set_strict_fp32(flag: bool = True) -> None:
@@ -21,3 +22,27 @@ def set_strict_fp32(flag: bool = True) -> None:
     "fp32 parity on the tensor cores").  Strict mode meets the reference's fp32 error everywhere at ~1/5 of the GEMM
     throughput; the fused D <= 8 stacks (K = 64 contractions) are unaffected and stay on the tensor cores."""
     ops.USE_TENSOR_CORE_GEMM = not flag
+
+
+_GEMM_PASSES = {"fp32": 3, "tf32": 1}
+_gemm_precision = "fp32"
+
+
+def set_gemm_precision(mode: str = "fp32") -> None:
+    """Precision of the tensor-core dense layers (conditioner MLPs, MADE masked linears, their input and weight gradients).
+
+    "fp32" (default): 3xTF32 with short accumulation chains -- the reference's fp32 tolerances hold.
+    "tf32": one TF32 pass per product, operands rounded to the nearest TF32 (10-bit mantissa, three bits more than
+    bf16) with fp32 accumulation -- the reduced-precision conditioner-GEMM mode of BASELINE config C4 (what the reference
+    reaches with `MixedPrecisionFlow` autocast, optimization/mixed_precision.py:89-105).  Spline / affine transform
+    arithmetic, BatchNorm and log-det reductions stay fp32 in both modes; the fused data_dim <= 8 stacks are unaffected.
+    Measured bounds of the mode: DESIGN.md "Reduced-precision mode", tests/test_gpu_tensorcore.py."""
+    global _gemm_precision
+    if mode not in _GEMM_PASSES:
+        raise ValueError(f"gemm precision must be one of {sorted(_GEMM_PASSES)}, got {mode!r}")
+    _lib.call("nf_set_option", 7, _GEMM_PASSES[mode])
+    _gemm_precision = mode
+
+
+def get_gemm_precision() -> str:
+    return _gemm_precision

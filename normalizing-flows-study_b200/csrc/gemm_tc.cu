@@ -13,7 +13,7 @@
 //               A operand from TMEM, B operand from shared memory; tcgen05.commit releases the stages
 //   warps 2-5   converters: thread r reads row r of the X tile from shared memory, splits it and stores the hi / lo
 //               halves into the TMEM A stage (lane = row, column = k); after the K loop the same warps run the
-//               epilogue: tcgen05.ld -> bias + ReLU -> shared-memory transpose -> coalesced 128-byte row stores.
+//               epilogue: tcgen05.ld -> bias + ReLU -> 256-bit stores into the thread's own output row.
 // Zero-tile skipping: k_extent[n/64] bounds the K loop of an output tile (block-lower-triangular MADE masks).
 #include <cuda.h>
 #include "nf_common.cuh"
@@ -45,8 +45,9 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
-               const int32_t* __restrict__ k_begin) {
+               const int32_t* __restrict__ k_begin, int passes, int vec) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    // passes: 3 = 3xTF32, 1 = one TF32 pass (reduced-precision mode, nf_set_option(7, .), see gemm_tc2.cu)
     // [stage: X | W_hi | W_lo] x kGemmStages, then barriers
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kStageBytes);
     uint64_t* full = bars;                              // [S]  TMA landed
@@ -95,10 +96,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 const int s = kb % kGemmStages;
                 if (kb >= kGemmStages) tc::mbar_wait(&empty[s], ((kb / kGemmStages) - 1) & 1);
                 uint8_t* st = smem + s * kStageBytes;
-                tc::mbar_arrive_expect_tx(&full[s], kStageBytes);
+                tc::mbar_arrive_expect_tx(&full[s], passes == 1 ? kXBytes + kWBytes : kStageBytes);
                 tma_load_2d(st, &tm_x, (kb_first + kb) * kGemmBK, m0, &full[s]);
                 tma_load_2d(st + kXBytes, &tm_wh, (kb_first + kb) * kGemmBK, n0, &full[s]);
-                tma_load_2d(st + kXBytes + kWBytes, &tm_wl, (kb_first + kb) * kGemmBK, n0, &full[s]);
+                if (passes != 1) tma_load_2d(st + kXBytes + kWBytes, &tm_wl, (kb_first + kb) * kGemmBK, n0, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -115,6 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             const uint32_t a_hi = tb + kColA + a * 64, a_lo = a_hi + 32;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
+                if (pass >= passes) break;
                 const uint32_t ac = (pass == 1) ? a_lo : a_hi;
                 const uint64_t wd = (pass == 2) ? d_lo : d_hi;
 #pragma unroll
@@ -153,9 +155,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { t0[j] = hi[j]; t1[j] = hi[16 + j]; }
                 tc::tmem_st16(a_hi, t0); tc::tmem_st16(a_hi + 16, t1);
+                if (passes != 1) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
-                tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                    for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
+                    tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                }
             }
             tc::wait_st();
             tc::fence_before_sync();
@@ -164,11 +168,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         // epilogue: all stages are free once d_full fires; stage memory doubles as the transpose buffer
         tc::mbar_wait(d_full, 0);
         tc::fence_after_sync();
-        float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;
         // NOTE on accuracy: the tensor core truncates its fp32 accumulator on every MMA (measured, scripts/gemm_accuracy.py:
         // rms error 3e-6 / 7e-6 of rms(y) at K = 512 / 1024 against 4e-7 / 6e-7 for an FFMA GEMM; a bias of -T * 2^-25 for
         // same-sign sums).  Scaling the result by the expected loss was tried and dropped: it over-corrects mixed-sign sums
         // (C4 log-det bias +4.4e-4 -> -3.3e-4).  Shorter chains (rotating accumulators) are the fix; see DESIGN.md.
+        // The thread owns row m0 + r: bias + ReLU + one 256-bit store per 8 columns (tc::epilogue_store8).
+        const int row = m0 + r;
+        float* yrow = Y + (int64_t)row * ldc;
+#pragma unroll
         for (int c = 0; c < kGemmBN / 32; ++c) {
             uint32_t v0[16], v1[16];
             if (nkb > 0) {
@@ -179,23 +186,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
+            if (row < M) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { tbuf[lane * 33 + j] = __uint_as_float(v0[j]); tbuf[lane * 33 + 16 + j] = __uint_as_float(v1[j]); }
-            __syncwarp();
-            const int col = n0 + c * 32 + lane;
-            const float bv = (bias && col < N) ? __ldg(bias + col) : 0.f;
-            if (col < N) {
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int row = m0 + q * 32 + rr;
-                    if (row < M) {
-                        float o = tbuf[rr * 33 + lane] + bv;
-                        if (relu) o = (o < 0.f) ? 0.f : o;          // NaN stays NaN (torch.relu)
-                        Y[(int64_t)row * ldc + col] = o;
-                    }
+                for (int h = 0; h < 2; ++h) {
+                    float a0[8], a1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
+                    tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias, relu, vec != 0);
+                    tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias, relu, vec != 0);
                 }
             }
-            __syncwarp();
         }
     }
     tc::fence_before_sync();
@@ -247,6 +247,7 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t col
 
 extern int g_gemm_tc_variant;
 extern int g_gemm_tc_small_k;
+extern int g_tc_passes;
 int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                     int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
                     cudaStream_t st);
@@ -302,7 +303,8 @@ extern "C" int nf_linear_tc_range(const void* x, const void* w_hi, const void* w
     const int64_t nblocks = cdiv(N, kGemmBN) * cdiv(M, kGemmBM);
     if (nblocks > 2147483647LL) return NF_ERR_BAD_SHAPE;
     gemm_tc_kernel<<<(unsigned)nblocks, kGemmThreads, smem, (cudaStream_t)stream>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N,
-                                                                       (int)K, ldy, relu, k_extent, k_begin);
+                                                                       (int)K, ldy, relu, k_extent, k_begin, g_tc_passes,
+                                                                       (aligned32(y) && (ldy % 8) == 0 && (bias == nullptr || aligned16(bias))) ? 1 : 0);
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;

@@ -37,6 +37,11 @@ constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;          // per drainer group
 
 int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
 int g_gemm_tc_small_k = 1;                    // nf_set_option(6, v): K <= 128 through the persistent DIRECT variant (1) or gemm_tc.cu (0)
+// nf_set_option(7, v): tensor-core passes per product.  3 = 3xTF32 (fp32 parity, default); 1 = one TF32 pass (operands
+// rounded to nearest TF32, 10-bit mantissa: the documented reduced-precision mode for the conditioner GEMMs -- three
+// more mantissa bits than bf16, no W_lo traffic, no lo conversions; chains of k2ChainKBFast K blocks = the same 24 MMAs)
+int g_tc_passes = 3;
+constexpr int k2ChainKBFast = 6;
 
 __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -81,8 +86,9 @@ __global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                 int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
-                const int32_t* __restrict__ k_begin, int num_tiles) {
+                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const int chain_kb = passes == 1 ? k2ChainKBFast : k2ChainKB;
     uint8_t* tbuf_base = smem + k2Stages * k2StageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + (DIRECT ? 2 : 1) * k2TbufBytes);
     uint64_t* full = bars;                         // [S] TMA landed
@@ -121,10 +127,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const int s = it % k2Stages;
                     if (it >= k2Stages) tc::mbar_wait(&empty[s], ((it / k2Stages) - 1) & 1);
                     uint8_t* st = smem + s * k2StageBytes;
-                    tc::mbar_arrive_expect_tx(&full[s], k2StageBytes);
+                    tc::mbar_arrive_expect_tx(&full[s], passes == 1 ? k2XBytes + k2WBytes : k2StageBytes);
                     tma2_load_2d(st, &tm_x, (kb_first + kb) * k2BK, m0, &full[s]);
                     tma2_load_2d(st + k2XBytes, &tm_wh, (kb_first + kb) * k2BK, n0, &full[s]);
-                    tma2_load_2d(st + k2XBytes + k2WBytes, &tm_wl, (kb_first + kb) * k2BK, n0, &full[s]);
+                    if (passes != 1) tma2_load_2d(st + k2XBytes + k2WBytes, &tm_wl, (kb_first + kb) * k2BK, n0, &full[s]);
                 }
             }
         }
@@ -141,7 +147,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % k2Stages, a = it & 1;
-                const int in_chain = DIRECT ? kb : kb % k2ChainKB;
+                const int in_chain = DIRECT ? kb : kb % chain_kb;
                 const int cb = cc % k2NAcc;
                 if (in_chain == 0 && cc >= k2NAcc) tc::mbar_wait(&d_empty[cb], ((cc / k2NAcc) - 1) & 1);
                 tc::mbar_wait(&full[s], (it / k2Stages) & 1);
@@ -153,6 +159,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const uint32_t dcol = tb + cb * 128;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
+                    if (pass >= passes) break;
                     const uint32_t ac = (pass == 1) ? a_lo : a_hi;
                     const uint64_t wd = (pass == 2) ? d_lo : d_hi;
 #pragma unroll
@@ -160,7 +167,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (in_chain | pass | k) != 0 ? 1u : 0u);
                     }
                 }
-                const bool chain_end = (!DIRECT && in_chain == k2ChainKB - 1) || (kb == nkb - 1);
+                const bool chain_end = (!DIRECT && in_chain == chain_kb - 1) || (kb == nkb - 1);
                 if (leader) {
                     tc::mma_commit(&empty[s]);
                     tc::mma_commit(&a_empty[a]);
@@ -203,9 +210,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { t0[j] = hi[j]; t1[j] = hi[16 + j]; }
                     tc::tmem_st16(a_hi, t0); tc::tmem_st16(a_hi + 16, t1);
+                    if (passes != 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
-                    tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                        for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
+                        tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                    }
                 }
                 tc::wait_st();
                 tc::fence_before_sync();
@@ -216,7 +225,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // ---------------- two drainer groups (warps 6..9, 10..13), alternate tiles, straight from TMEM ----------------
         const int q = warp & 3, grp = (warp - 6) >> 2;
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
-        float* tbuf = reinterpret_cast<float*>(tbuf_base) + (size_t)(warp - 6) * 32 * 33;
         int cc = 0, ti = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
             int n0, m0;
@@ -231,6 +239,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);
                 tc::fence_after_sync();
             }
+            const int row = m0 + q * 32 + lane;
+            float* yrow = Y + (int64_t)row * ldc;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t v0[16], v1[16];
@@ -243,37 +253,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
                 }
+                if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { tbuf[lane * 33 + j] = __uint_as_float(v0[j]); tbuf[lane * 33 + 16 + j] = __uint_as_float(v1[j]); }
-                __syncwarp();
-                const int col = n0 + c * 32 + lane;
-                const float bv = (bias && col < N) ? __ldg(bias + col) : 0.f;
-                if (col < N) {
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = m0 + q * 32 + rr;
-                        if (row < M) {
-                            float o = tbuf[rr * 33 + lane] + bv;
-                            if (relu) o = (o < 0.f) ? 0.f : o;
-                            Y[(int64_t)row * ldc + col] = o;
-                        }
+                    for (int h = 0; h < 2; ++h) {
+                        float a0[8], a1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
+                        tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias, relu, vec != 0);
+                        tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias, relu, vec != 0);
                     }
                 }
-                __syncwarp();
             }
         }
     } else {
         // ---------------- drainers (warps 6..9; TMEM lane quadrant = warp % 4), then the tile epilogue ----------------
         const int q = warp & 3;
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
-        float* tbuf = reinterpret_cast<float*>(tbuf_base) + (size_t)(warp - 6) * 32 * 33;
         int cc = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
-            const int nchains = (nkb + k2ChainKB - 1) / k2ChainKB;
+            const int nchains = (nkb + chain_kb - 1) / chain_kb;
             float acc[128];
 #pragma unroll
             for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -292,26 +294,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc::fence_before_sync();
                 tc::mbar_arrive(&d_empty[cb]);
             }
-            // epilogue from registers: bias + ReLU, transposed through the warp's buffer, 128-byte row stores
+            // epilogue from registers: the thread owns row m0 + 32q + lane; bias + ReLU + one 256-bit store per 8 columns
+            const int row = m0 + q * 32 + lane;
+            if (row < M) {
+                float* yrow = Y + (int64_t)row * ldc;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+                for (int j = 0; j < 16; ++j) {
+                    float a[8];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = acc[c * 32 + j];
-                __syncwarp();
-                const int col = n0 + c * 32 + lane;
-                const float bv = (bias && col < N) ? __ldg(bias + col) : 0.f;
-                if (col < N) {
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = m0 + q * 32 + rr;
-                        if (row < M) {
-                            float o = tbuf[rr * 33 + lane] + bv;
-                            if (relu) o = (o < 0.f) ? 0.f : o;          // NaN stays NaN (torch.relu)
-                            Y[(int64_t)row * ldc + col] = o;
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
+                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, bias, relu, vec != 0);
                 }
-                __syncwarp();
             }
         }
     }
@@ -360,16 +353,18 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
     if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    // 256-bit row stores in the epilogue: 32-byte aligned rows of Y, 16-byte aligned bias
+    const int vec = (aligned32(y) && (ldy % 8) == 0 && (bias == nullptr || aligned16(bias))) ? 1 : 0;
     if (K <= 4 * k2BK) {
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc2_kernel<true><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
-                                                                   ldy, relu, k_extent, k_begin, (int)tiles);
+                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
     } else {
         const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc2_kernel<false><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                              relu, k_extent, k_begin, (int)tiles);
+                                                              relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
     }
     return NF_OK;
 }

@@ -53,7 +53,8 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t smem_byte_ad
 __global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x, float* __restrict__ out,
                 int N, int K, int nkb, int kb_per_split, int64_t ld_out, int64_t split_stride,
-                const uint8_t* __restrict__ tile_live, const float* __restrict__ dy_direct, int64_t ld_dy, int64_t B) {
+                const uint8_t* __restrict__ tile_live, const float* __restrict__ dy_direct, int64_t ld_dy, int64_t B,
+                int passes, int vec) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
     uint64_t* full = bars;                       // [S] TMA landed
@@ -112,6 +113,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
             const uint32_t a_hi = tb + kWgColA + s * 64, a_lo = a_hi + 32;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
+                if (pass >= passes) break;                    // passes == 1: one TF32 pass (nf_set_option(7, .), gemm_tc2.cu)
                 const uint32_t ac = (pass == 1) ? a_lo : a_hi;
                 const uint64_t wd = (pass == 2) ? d_lo : d_hi;
 #pragma unroll
@@ -162,9 +164,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { t0[j] = hi[j]; t1[j] = hi[16 + j]; }
                 tc::tmem_st16(a_hi, t0); tc::tmem_st16(a_hi + 16, t1);
+                if (passes != 1) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
-                tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                    for (int j = 0; j < 16; ++j) { t0[j] = lo[j]; t1[j] = lo[16 + j]; }
+                    tc::tmem_st16(a_lo, t0); tc::tmem_st16(a_lo + 16, t1);
+                }
             }
             // X tile: elementwise hi (in place) / lo (second image, same offsets)
             uint8_t* xh = st + kWgTileBytes;
@@ -179,18 +183,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
                 tc::split_tf32_weight(v.z, h.z, l.z);
                 tc::split_tf32_weight(v.w, h.w, l.w);
                 *reinterpret_cast<uint4*>(xh + off) = h;
-                *reinterpret_cast<uint4*>(xl + off) = l;
+                if (passes != 1) *reinterpret_cast<uint4*>(xl + off) = l;
             }
             tc::fence_proxy_async_smem();
             tc::wait_st();
             tc::fence_before_sync();
             tc::mbar_arrive(&ready[s]);
         }
-        // epilogue: stage memory doubles as the transpose buffer once every MMA has completed
+        // epilogue once every MMA has completed
         tc::mbar_wait(d_full, 0);
         tc::fence_after_sync();
-        float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;
+        // the thread owns dW row n0 + 32q + lane: one 256-bit store per 8 columns (tc::epilogue_store8)
         float* dst = out + (int64_t)blockIdx.y * split_stride;
+        const int row = n0 + q * 32 + lane;
+        float* yrow = dst + (int64_t)row * ld_out;
+#pragma unroll
         for (int c = 0; c < kWgBN / 32; ++c) {
             uint32_t v0[16], v1[16];
             if (nloc > 0) {
@@ -201,18 +208,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
+            if (row < N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { tbuf[lane * 33 + j] = __uint_as_float(v0[j]); tbuf[lane * 33 + 16 + j] = __uint_as_float(v1[j]); }
-            __syncwarp();
-            const int col = k0 + c * 32 + lane;
-            if (col < K) {
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int row = n0 + q * 32 + rr;
-                    if (row < N) dst[(int64_t)row * ld_out + col] = tbuf[rr * 33 + lane];
+                for (int h = 0; h < 2; ++h) {
+                    float a0[8], a1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
+                    tc::epilogue_store8(yrow, k0 + c * 32 + h * 8, K, a0, nullptr, 0, vec != 0);
+                    tc::epilogue_store8(yrow, k0 + c * 32 + 16 + h * 8, K, a1, nullptr, 0, vec != 0);
                 }
             }
-            __syncwarp();
         }
     }
     tc::fence_before_sync();
@@ -263,6 +268,7 @@ static bool wg_make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t 
 }
 
 extern int g_wgrad_max_kb;     // nf_set_option(2, v)
+extern int g_tc_passes;        // nf_set_option(7, v)
 
 // Number of batch splits.  (1) Fill two CTAs per SM, with at least 8 K blocks (256 rows) per split.  (2) The tensor
 // core's fp32 accumulation truncates (measured: the error of a TMEM accumulation chain grows linearly, ~2^-24 of the
@@ -339,7 +345,8 @@ extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw
     float* out = splits > 1 ? (float*)workspace : (float*)dw;
     const int64_t ld_out = splits > 1 ? K : ld_dw;
     wgrad_tc_kernel<<<dim3((unsigned)tiles, (unsigned)splits), kWgThreads, smem, st>>>(tg, tx, out, (int)N, (int)K, nkb, per, ld_out,
-                                                                                         (int64_t)N * K, tile_live, direct ? (const float*)dy : nullptr, ld_dy, B);
+                                                                                         (int64_t)N * K, tile_live, direct ? (const float*)dy : nullptr, ld_dy, B, g_tc_passes,
+                                                                                         (aligned32(out) && (ld_out % 8) == 0 && (((int64_t)N * K) % 8) == 0) ? 1 : 0);
     count_launch();
     NF_LAUNCH_CHECK();
     if (splits > 1) {

@@ -175,6 +175,10 @@ def bench_gemm():
             ms_tc = timeit(lambda: ops.linear_wgrad_tc(g, x), reps=3, inner=4)
             report(f"nf_linear_wgrad_tc 3xTF32 {name} [{M}x{Nn}x{K}]", ms_tc, None, 2.0 * M * Nn * K,
                    note="tensor pipe executes 3x these FLOPs")
+            N.set_gemm_precision("tf32")
+            ms_tc = timeit(lambda: ops.linear_wgrad_tc(g, x), reps=3, inner=4)
+            N.set_gemm_precision("fp32")
+            report(f"nf_linear_wgrad_tc 1xTF32 (reduced precision) {name} [{M}x{Nn}x{K}]", ms_tc, None, 2.0 * M * Nn * K)
         else:
             a = torch.randn(M, K, device=DEV)
             w = torch.randn(Nn, K, device=DEV)
@@ -187,6 +191,10 @@ def bench_gemm():
                 ms = timeit(lambda: ops.linear_tc(a, hi, lo, bias, relu=True), reps=3, inner=4)
                 report(f"nf_linear_tc 3xTF32 {name} [{M}x{Nn}x{K}]", ms, None, 2.0 * M * Nn * K,
                        note="tensor pipe executes 3x these FLOPs")
+                N.set_gemm_precision("tf32")
+                ms = timeit(lambda: ops.linear_tc(a, hi, lo, bias, relu=True), reps=3, inner=4)
+                N.set_gemm_precision("fp32")
+                report(f"nf_linear_tc 1xTF32 (reduced precision) {name} [{M}x{Nn}x{K}]", ms, None, 2.0 * M * Nn * K)
 
 
 def bench_stacks():

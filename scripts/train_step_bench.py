@@ -38,7 +38,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="capture the whole step (fwd, bwd, Adam) in one CUDA graph (1 GPU)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="dense-layer precision: fp32 = 3xTF32 (reference tolerances), tf32 = one TF32 pass (reduced-precision mode)")
     a = ap.parse_args()
+    N.set_gemm_precision(a.precision)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -106,7 +109,7 @@ def main():
         print(json.dumps({"model": a.model, "n_gpus": world, "batch_per_gpu": a.batch, "ms_per_step": ms.item(),
                           "samples_per_s": a.batch * world / (ms.item() * 1e-3), "loss": float(loss),
                           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
-                          "cuda_graph": bool(a.graph), "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
+                          "cuda_graph": bool(a.graph), "gemm_precision": a.precision, "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
     if world > 1:
         dist.destroy_process_group()

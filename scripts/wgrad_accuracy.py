@@ -26,7 +26,7 @@ for B, Nn, K in [(262144, 512, 512), (65536, 1024, 1024), (4096, 2844, 1024)]:
         print(f"B={B} N={Nn} K={K} {kind}: rms(dW)={rms.item():.3g}")
         report("torch fp32 (cuBLAS, no tf32)", g.T @ x)
         report("FP32-pipe nf_gemm", N.ops.gemm(g, x, Nn, K, B, 1, Nn, K, 1))
-        for mk in (1 << 20, 256, 64, 16):
+        for mk in (1 << 20, 256, 64, 32, 16):
             N._lib.call("nf_set_option", 2, mk)
             ms = t(lambda: N.ops.linear_wgrad_tc(g, x))
             report(f"tcgen05 chain<={mk} blocks", N.ops.linear_wgrad_tc(g, x), ms)

@@ -232,3 +232,96 @@ def test_long_contractions_are_fp32_grade(M, N, K):
             N_._lib.call("nf_set_option", 5, 1)
         e0 = y0.cpu().double() - ref
         assert e.pow(2).mean().sqrt().item() <= e0.pow(2).mean().sqrt().item() * 1.05
+
+
+@pytest.fixture
+def tf32_mode():
+    N_.set_gemm_precision("tf32")
+    try:
+        yield
+    finally:
+        N_.set_gemm_precision("fp32")
+
+
+# Reduced-precision mode (set_gemm_precision("tf32"), BASELINE config C4's "bf16 conditioner GEMMs" slot): one TF32
+# pass, both operands rounded to the nearest TF32 (relative rounding error <= 2^-11 each) => every product is within
+# 2^-10 of |a||b|, i.e. the scaled error max|err| / sum|a||b| is bounded by 2^-10 = 9.8e-4 (+ fp32 accumulation);
+# a bf16 product would be bounded by 2^-7 = 7.8e-3.  Bounds written here are the documented ones.
+TF32_SCALED_BOUND = 1.0e-3
+TF32_RMS_BOUND = 6.0e-4          # rms error / rms(result) for random-sign data: ~2^-11 * sqrt(2/3)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 512, 64), (4096, 512, 512), (777, 130, 100), (300, 64, 1024),
+                                   (2048, 1024, 1024), (512, 128, 4096)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_linear_tc_tf32_mode_bounds(tf32_mode, M, N, K, relu):
+    gen = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=gen) * 1.5
+    w = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen)
+    hi, lo = N_.ops.split_tf32(w.cuda())
+    y = N_.ops.linear_tc(x.cuda(), hi, lo, b.cuda(), relu)
+    assert y is not None
+    ref = x.double() @ w.double().T + b.double()
+    scale = x.double().abs() @ w.double().abs().T + b.double().abs()
+    if relu:
+        ref = ref.clamp_min(0)
+    e = y.cpu().double() - ref
+    err = (e.abs() / scale).max().item()
+    assert err < TF32_SCALED_BOUND, f"scaled error {err:.3e}"
+    assert err > 1e-6                       # the mode must really be the single-pass one
+    if not relu:
+        assert e.pow(2).mean().sqrt().item() / ref.pow(2).mean().sqrt().item() < TF32_RMS_BOUND
+    # w_lo is not read in this mode
+    y_nolo = N_.ops.linear_tc(x.cuda(), hi, torch.full_like(lo, float("nan")), b.cuda(), relu)
+    assert torch.equal(y, y_nolo)
+    # and the default mode is back to fp32 grade afterwards (checked by the other tests through the fixture's finally)
+
+
+@pytest.mark.parametrize("B,N,K", [(256, 128, 128), (4096, 512, 512), (777, 132, 100), (100000, 128, 256),
+                                   (5000, 29, 1024), (3000, 2844, 1024)])
+def test_linear_wgrad_tc_tf32_mode_bounds(tf32_mode, B, N, K):
+    gen = torch.Generator().manual_seed(B + N + K)
+    g = torch.randn(B, N, generator=gen) * 1.5
+    x = torch.randn(B, K, generator=gen)
+    dw = N_.ops.linear_wgrad_tc(g.cuda(), x.cuda(), out=torch.full((N, K), float("nan"), device="cuda"))
+    assert dw is not None
+    ref = g.double().T @ x.double()
+    scale = g.double().abs().T @ x.double().abs() + 1e-30
+    e = dw.cpu().double() - ref
+    err = (e.abs() / scale).max().item()
+    assert 1e-6 < err < TF32_SCALED_BOUND, f"scaled error {err:.3e}"
+    assert e.pow(2).mean().sqrt().item() / ref.pow(2).mean().sqrt().item() < TF32_RMS_BOUND
+    assert torch.equal(dw, N_.ops.linear_wgrad_tc(g.cuda(), x.cuda()))
+
+
+def test_tf32_mode_flow_parity_bounds(tf32_mode):
+    """Whole-layer effect of the reduced-precision mode against the default mode on the same weights: MAF(64, 512)
+    density pass and a RealNVPSpline(784, 2, 1024) pass.  Documented bounds (measured values in
+    profiles/r01t_tf32_mode_accuracy.log): z within 5e-3 * max(1, |z|) and log-det within 5e-2 at D = 64; z within 2e-2
+    and log-det within 2e-1 at D = 784 (392 spline elements per row and layer, each sensitive to its 29 parameters)."""
+    torch.manual_seed(0)
+    for make, D, z_tol, ld_tol in ((lambda: N_.MaskedAutoregressiveFlow(64, 512), 64, 5e-3, 5e-2),
+                                   (lambda: N_.RealNVPSpline(784, 2, 1024), 784, 2e-2, 2e-1)):
+        m = make().cuda().eval()
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.02 * torch.randn_like(p))
+        x = torch.randn(2048, D, device="cuda")
+        with torch.no_grad():
+            z_f, ld_f = m.inverse(x)
+            N_.set_gemm_precision("fp32")
+            z_r, ld_r = m.inverse(x)
+            N_.set_gemm_precision("tf32")
+        assert torch.isfinite(z_f).all() and torch.isfinite(ld_f).all()
+        dz = ((z_f - z_r).abs() / z_r.abs().clamp_min(1)).max().item()
+        dl = (ld_f - ld_r).abs().max().item()
+        assert dz < z_tol, (D, dz)
+        assert dl < ld_tol, (D, dl)
+        assert dz > 0 or dl > 0            # the mode changed something
+
+
+def test_set_gemm_precision_rejects_unknown_modes():
+    with pytest.raises(ValueError):
+        N_.set_gemm_precision("bf16x")
+    assert N_.get_gemm_precision() == "fp32"
