@@ -175,6 +175,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         // The thread owns row m0 + r: bias + ReLU + one 256-bit store per 8 columns (tc::epilogue_store8).
         const int row = m0 + r;
         float* yrow = Y + (int64_t)row * ldc;
+        float* bias_s = reinterpret_cast<float*>(smem);       // every stage is free once d_full has fired
+        tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 2) * 32 + lane, 1);
 #pragma unroll
         for (int c = 0; c < kGemmBN / 32; ++c) {
             uint32_t v0[16], v1[16];
@@ -192,8 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     float a0[8], a1[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
-                    tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias, relu, vec != 0);
-                    tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias, relu, vec != 0);
+                    tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias_s + c * 32 + h * 8, relu, vec != 0);
+                    tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias_s + c * 32 + 16 + h * 8, relu, vec != 0);
                 }
             }
         }
@@ -304,7 +306,7 @@ extern "C" int nf_linear_tc_range(const void* x, const void* w_hi, const void* w
     if (nblocks > 2147483647LL) return NF_ERR_BAD_SHAPE;
     gemm_tc_kernel<<<(unsigned)nblocks, kGemmThreads, smem, (cudaStream_t)stream>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N,
                                                                        (int)K, ldy, relu, k_extent, k_begin, g_tc_passes,
-                                                                       (aligned32(y) && (ldy % 8) == 0 && (bias == nullptr || aligned16(bias))) ? 1 : 0);
+                                                                       (aligned32(y) && (ldy % 8) == 0) ? 1 : 0);
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;

@@ -33,7 +33,7 @@ constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A s
 constexpr int k2ColA = 384;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
-constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;          // per drainer group
+constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;          // per drainer group (now: two 128-float bias tiles per group at its start)
 
 int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
 int g_gemm_tc_small_k = 1;                    // nf_set_option(6, v): K <= 128 through the persistent DIRECT variant (1) or gemm_tc.cu (0)
@@ -235,6 +235,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (nkb > 0) ++cc;                                   // one chain per non-empty tile, counted by both groups
             if ((ti & 1) != grp) continue;
             const int cb = my_cc % k2NAcc;
+            // bias tile -> shared memory (two buffers per group, alternating with the group's tiles)
+            float* bias_s = reinterpret_cast<float*>(tbuf_base) + grp * 256 + ((ti >> 1) & 1) * 128;
+            tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6 - 4 * grp) * 32 + lane, 1 + grp);
             if (nkb > 0) {
                 tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);
                 tc::fence_after_sync();
@@ -259,8 +262,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         float a0[8], a1[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
-                        tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias, relu, vec != 0);
-                        tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias, relu, vec != 0);
+                        tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias_s + c * 32 + h * 8, relu, vec != 0);
+                        tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias_s + c * 32 + 16 + h * 8, relu, vec != 0);
                     }
                 }
             }
@@ -269,13 +272,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // ---------------- drainers (warps 6..9; TMEM lane quadrant = warp % 4), then the tile epilogue ----------------
         const int q = warp & 3;
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
-        int cc = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int cc = 0, ti = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             const int nchains = (nkb + chain_kb - 1) / chain_kb;
+            // bias tile -> shared memory while the first chain is still accumulating (two buffers, alternating tiles)
+            float* bias_s = reinterpret_cast<float*>(tbuf_base) + (ti & 1) * 128;
+            tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6) * 32 + lane, 1);
             float acc[128];
 #pragma unroll
             for (int j = 0; j < 128; ++j) acc[j] = 0.f;
@@ -303,7 +309,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     float a[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
-                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, bias, relu, vec != 0);
+                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, bias_s + j * 8, relu, vec != 0);
                 }
             }
         }
@@ -353,8 +359,8 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
     if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    // 256-bit row stores in the epilogue: 32-byte aligned rows of Y, 16-byte aligned bias
-    const int vec = (aligned32(y) && (ldy % 8) == 0 && (bias == nullptr || aligned16(bias))) ? 1 : 0;
+    // 256-bit row stores in the epilogue: 32-byte aligned rows of Y
+    const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : 0;
     if (K <= 4 * k2BK) {
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

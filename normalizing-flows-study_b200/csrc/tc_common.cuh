@@ -189,39 +189,43 @@ __device__ __forceinline__ void split_tf32_weight(float a, uint32_t& hi, uint32_
 // 128 x (LDS + STG) per thread and tile, measured at ~12 000 clk per 128 x 128 tile in gemm_tc2 -- longer than the three
 // accumulation chains the MMA warp can run ahead -- so the tensor pipe idled half of the time.)
 __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
+    // no "memory" clobber: the compiler may batch the bias loads of later stores ahead of this one
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+                 ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]));
 }
-// 8 consecutive outputs of one row starting at column col (col % 8 == 0): bias + ReLU + store.  vec: &yrow[col] is
-// 32-byte aligned and &bias[col] 16-byte aligned (checked on the host); ragged column tails take the scalar path.
+// 8 consecutive outputs of one row starting at column col (col % 8 == 0): bias + ReLU + store.  bias8 points at the 8
+// bias values of these columns in SHARED memory (16-byte aligned; staged once per tile -- a global-memory bias load in
+// front of every store serialised the epilogue on 16 load latencies per tile) or is nullptr.  vec: &yrow[col] is 32-byte
+// aligned (checked on the host); ragged column tails take the scalar path.
 __device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int col, int N, const float (&a)[8],
-                                                const float* __restrict__ bias, int relu, bool vec) {
+                                                const float* bias8, int relu, bool vec) {
     float o[8];
+    if (bias8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+        o[0] = a[0] + b0.x; o[1] = a[1] + b0.y; o[2] = a[2] + b0.z; o[3] = a[3] + b0.w;
+        o[4] = a[4] + b1.x; o[5] = a[5] + b1.y; o[6] = a[6] + b1.z; o[7] = a[7] + b1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = a[i];
+    }
+    if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (o[i] < 0.f) ? 0.f : o[i];          // NaN stays NaN (torch.relu)
+    }
     if (vec && col + 8 <= N) {
-        if (bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 1);
-            o[0] = a[0] + b0.x; o[1] = a[1] + b0.y; o[2] = a[2] + b0.z; o[3] = a[3] + b0.w;
-            o[4] = a[4] + b1.x; o[5] = a[5] + b1.y; o[6] = a[6] + b1.z; o[7] = a[7] + b1.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = a[i];
-        }
-        if (relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (o[i] < 0.f) ? 0.f : o[i];          // NaN stays NaN (torch.relu)
-        }
         st_global_v8(yrow + col, o);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (col + i < N) {
-                float v = a[i] + (bias ? __ldg(bias + col + i) : 0.f);
-                if (relu) v = (v < 0.f) ? 0.f : v;
-                yrow[col + i] = v;
-            }
-        }
+        for (int i = 0; i < 8; ++i)
+            if (col + i < N) yrow[col + i] = o[i];
     }
+}
+// 128 epilogue threads (four warps) stage the tile's 128 bias values (zeros past N or without a bias) in shared memory;
+// named barrier `bar_id` (1..15) makes them visible to the four warps
+__device__ __forceinline__ void stage_bias_tile(float* bias_s, const float* __restrict__ bias, int n0, int N, int t128, int bar_id) {
+    bias_s[t128] = (bias && n0 + t128 < N) ? __ldg(bias + n0 + t128) : 0.f;
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 }
 
 // byte offset of element (n, k) inside a K-major SWIZZLE_128B image of an [rows][K] fp32 matrix (K % 32 == 0, rows % 8 == 0)
