@@ -188,16 +188,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
-            if (row < M) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float a0[8], a1[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
-                    tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias_s + c * 32 + h * 8, relu, vec != 0);
-                    tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias_s + c * 32 + 16 + h * 8, relu, vec != 0);
-                }
-            }
+            if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, vec != 0);
         }
     }
     tc::fence_before_sync();

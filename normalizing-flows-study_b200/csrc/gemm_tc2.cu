@@ -24,7 +24,9 @@
 namespace nf {
 
 constexpr int k2BM = 128, k2BN = 128, k2BK = 32;
-constexpr int k2Stages = 4;
+constexpr int k2Stages = 4;                   // 3xTF32: 4 stages of X | W_hi | W_lo (48 KB)
+constexpr int k2StagesFast = 6;               // one pass: 6 stages of X | W_hi (32 KB) in the same 192 KB
+constexpr int k2MaxStages = 6;
 constexpr int k2Threads = 320;
 constexpr int k2ThreadsDirect = 448;          // two drainer groups
 constexpr int k2ChainKB = 2;                  // K blocks per TMEM accumulation chain
@@ -89,11 +91,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int chain_kb = passes == 1 ? k2ChainKBFast : k2ChainKB;
+    const int n_stages = passes == 1 ? k2StagesFast : k2Stages;
+    const uint32_t stage_bytes = passes == 1 ? k2XBytes + k2WBytes : k2StageBytes;
     uint8_t* tbuf_base = smem + k2Stages * k2StageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + (DIRECT ? 2 : 1) * k2TbufBytes);
     uint64_t* full = bars;                         // [S] TMA landed
-    uint64_t* empty = full + k2Stages;             // [S] stage consumed (MMA commit)
-    uint64_t* a_full = empty + k2Stages;           // [2] converters wrote the TMEM A stage
+    uint64_t* empty = full + k2MaxStages;          // [S] stage consumed (MMA commit)
+    uint64_t* a_full = empty + k2MaxStages;        // [2] converters wrote the TMEM A stage
     uint64_t* a_empty = a_full + 2;                // [2] MMAs consumed the TMEM A stage
     uint64_t* d_full = a_empty + 2;                // [NAcc] chain accumulator complete
     uint64_t* d_empty = d_full + k2NAcc;           // [NAcc] drainers read the chain accumulator
@@ -103,7 +107,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     const int n_tiles = (N + k2BN - 1) / k2BN;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < k2Stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < k2MaxStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < k2NAcc; ++i) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_empty[i], 128); }
         tc::fence_mbar_init();
@@ -117,20 +121,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            int it = 0;
+            // stage index / round parity kept incrementally (n_stages is a run-time value: no div / mod per K block)
+            int s = 0;
+            uint32_t ph = 0;
+            bool first_round = true;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int n0, m0;
                 tile_decode(t, n_tiles, n0, m0);
                 int kb_first, nkb;
                 tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % k2Stages;
-                    if (it >= k2Stages) tc::mbar_wait(&empty[s], ((it / k2Stages) - 1) & 1);
-                    uint8_t* st = smem + s * k2StageBytes;
-                    tc::mbar_arrive_expect_tx(&full[s], passes == 1 ? k2XBytes + k2WBytes : k2StageBytes);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (!first_round) tc::mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t* st = smem + s * stage_bytes;
+                    tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
                     tma2_load_2d(st, &tm_x, (kb_first + kb) * k2BK, m0, &full[s]);
                     tma2_load_2d(st + k2XBytes, &tm_wh, (kb_first + kb) * k2BK, n0, &full[s]);
                     if (passes != 1) tma2_load_2d(st + k2XBytes + k2WBytes, &tm_wl, (kb_first + kb) * k2BK, n0, &full[s]);
+                    if (++s == n_stages) { s = 0; ph ^= 1u; first_round = false; }
                 }
             }
         }
@@ -138,7 +145,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // ---------------- MMA issuer (whole warp, convergent; one elected lane issues) ----------------
         const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)k2BN);
         const bool leader = tc::elect_one();
-        int it = 0, cc = 0;
+        int it = 0, s = 0, ic = 0, cb = 0;               // K-block counter, stage, position in the chain, accumulator
+        uint32_t ph = 0, dph = 0;                        // parity of the stage round / of the accumulator round
+        bool first_acc_round = true;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
@@ -146,14 +155,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % k2Stages, a = it & 1;
-                const int in_chain = DIRECT ? kb : kb % chain_kb;
-                const int cb = cc % k2NAcc;
-                if (in_chain == 0 && cc >= k2NAcc) tc::mbar_wait(&d_empty[cb], ((cc / k2NAcc) - 1) & 1);
-                tc::mbar_wait(&full[s], (it / k2Stages) & 1);
+                const int a = it & 1;
+                if (ic == 0 && !first_acc_round) tc::mbar_wait(&d_empty[cb], dph ^ 1u);
+                tc::mbar_wait(&full[s], ph);
                 tc::mbar_wait(&a_full[a], (it >> 1) & 1);
                 tc::fence_after_sync();
-                const uint32_t st = tc::smem_u32(smem + s * k2StageBytes);
+                const uint32_t st = tc::smem_u32(smem + s * stage_bytes);
                 const uint64_t d_hi = tc::smem_desc_k_sw128(st + k2XBytes), d_lo = tc::smem_desc_k_sw128(st + k2XBytes + k2WBytes);
                 const uint32_t a_hi = tb + k2ColA + a * 64, a_lo = a_hi + 32;
                 const uint32_t dcol = tb + cb * 128;
@@ -164,17 +171,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     const uint64_t wd = (pass == 2) ? d_lo : d_hi;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (in_chain | pass | k) != 0 ? 1u : 0u);
+                        if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (ic | pass | k) != 0 ? 1u : 0u);
                     }
                 }
-                const bool chain_end = (!DIRECT && in_chain == chain_kb - 1) || (kb == nkb - 1);
+                const bool chain_end = (!DIRECT && ic == chain_kb - 1) || (kb == nkb - 1);
                 if (leader) {
                     tc::mma_commit(&empty[s]);
                     tc::mma_commit(&a_empty[a]);
                     if (chain_end) tc::mma_commit(&d_full[cb]);
                 }
                 __syncwarp();
-                if (chain_end) ++cc;
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
+                if (chain_end) {
+                    ic = 0;
+                    if (++cb == k2NAcc) { cb = 0; dph ^= 1u; first_acc_round = false; }
+                } else {
+                    ++ic;
+                }
             }
         }
     } else if (warp < 6) {
@@ -182,7 +195,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
-        int it = 0;
+        int it = 0, s = 0;
+        uint32_t ph = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
@@ -190,11 +204,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % k2Stages, a = it & 1;
-                tc::mbar_wait(&full[s], (it / k2Stages) & 1);
+                const int a = it & 1;
+                tc::mbar_wait(&full[s], ph);
                 if (it >= 2) tc::mbar_wait(&a_empty[a], ((it >> 1) - 1) & 1);
                 tc::fence_after_sync();
-                const uint8_t* xrow = smem + s * k2StageBytes + (r >> 3) * 1024 + (r & 7) * 128;
+                const uint8_t* xrow = smem + s * stage_bytes + (r >> 3) * 1024 + (r & 7) * 128;
                 uint32_t hi[32], lo[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -219,6 +233,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 tc::wait_st();
                 tc::fence_before_sync();
                 tc::mbar_arrive(&a_full[a]);
+                if (++s == n_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if constexpr (DIRECT) {
@@ -256,38 +271,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
                 }
-                if (row < M) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float a0[8], a1[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
-                        tc::epilogue_store8(yrow, n0 + c * 32 + h * 8, N, a0, bias_s + c * 32 + h * 8, relu, vec != 0);
-                        tc::epilogue_store8(yrow, n0 + c * 32 + 16 + h * 8, N, a1, bias_s + c * 32 + 16 + h * 8, relu, vec != 0);
-                    }
-                }
+                if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, vec != 0);
             }
         }
     } else {
         // ---------------- drainers (warps 6..9; TMEM lane quadrant = warp % 4), then the tile epilogue ----------------
         const int q = warp & 3;
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
-        int cc = 0, ti = 0;
+        int cb = 0, ti = 0;
+        uint32_t dph = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             const int nchains = (nkb + chain_kb - 1) / chain_kb;
-            // bias tile -> shared memory while the first chain is still accumulating (two buffers, alternating tiles)
+            // bias tile -> shared memory while the first chain is still accumulating (two buffers, alternating tiles);
+            // the running sums START from the bias, so the epilogue has no loads at all
             float* bias_s = reinterpret_cast<float*>(tbuf_base) + (ti & 1) * 128;
             tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6) * 32 + lane, 1);
             float acc[128];
 #pragma unroll
-            for (int j = 0; j < 128; ++j) acc[j] = 0.f;
-            for (int c = 0; c < nchains; ++c, ++cc) {
-                const int cb = cc % k2NAcc;
-                tc::mbar_wait(&d_full[cb], (cc / k2NAcc) & 1);
+            for (int j = 0; j < 32; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
+                acc[4 * j + 0] = b.x; acc[4 * j + 1] = b.y; acc[4 * j + 2] = b.z; acc[4 * j + 3] = b.w;
+            }
+            for (int c = 0; c < nchains; ++c) {
+                tc::mbar_wait(&d_full[cb], dph);
                 tc::fence_after_sync();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
@@ -299,8 +309,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
                 tc::fence_before_sync();
                 tc::mbar_arrive(&d_empty[cb]);
+                if (++cb == k2NAcc) { cb = 0; dph ^= 1u; }
             }
-            // epilogue from registers: the thread owns row m0 + 32q + lane; bias + ReLU + one 256-bit store per 8 columns
+            // epilogue from registers: the thread owns row m0 + 32q + lane; ReLU + one 256-bit store per 8 columns
             const int row = m0 + q * 32 + lane;
             if (row < M) {
                 float* yrow = Y + (int64_t)row * ldc;
@@ -309,7 +320,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     float a[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
-                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, bias_s + j * 8, relu, vec != 0);
+                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, relu, vec != 0);
                 }
             }
         }

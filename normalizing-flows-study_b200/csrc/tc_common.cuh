@@ -193,32 +193,40 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]));
 }
-// 8 consecutive outputs of one row starting at column col (col % 8 == 0): bias + ReLU + store.  bias8 points at the 8
-// bias values of these columns in SHARED memory (16-byte aligned; staged once per tile -- a global-memory bias load in
-// front of every store serialised the epilogue on 16 load latencies per tile) or is nullptr.  vec: &yrow[col] is 32-byte
-// aligned (checked on the host); ragged column tails take the scalar path.
-__device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int col, int N, const float (&a)[8],
-                                                const float* bias8, int relu, bool vec) {
+// 8 consecutive outputs of one row starting at column col (col % 8 == 0), bias already added: ReLU + store.  No loads
+// in here: the callers fetch the bias (from the shared-memory tile staged by stage_bias_tile) in one batch BEFORE the
+// stores -- a bias load in front of every store waited ~370 clk each behind the queued 1 KB stores (measured).
+// vec: &yrow[col] is 32-byte aligned (checked on the host); ragged column tails take the scalar path.
+__device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int col, int N, const float (&a)[8], int relu, bool vec) {
     float o[8];
-    if (bias8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(bias8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
-        o[0] = a[0] + b0.x; o[1] = a[1] + b0.y; o[2] = a[2] + b0.z; o[3] = a[3] + b0.w;
-        o[4] = a[4] + b1.x; o[5] = a[5] + b1.y; o[6] = a[6] + b1.z; o[7] = a[7] + b1.w;
-    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = a[i];
-    }
-    if (relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (o[i] < 0.f) ? 0.f : o[i];          // NaN stays NaN (torch.relu)
-    }
+    for (int i = 0; i < 8; ++i) o[i] = (relu && a[i] < 0.f) ? 0.f : a[i];          // NaN stays NaN (torch.relu)
     if (vec && col + 8 <= N) {
         st_global_v8(yrow + col, o);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if (col + i < N) yrow[col + i] = o[i];
+    }
+}
+// 32 columns [c0, c0 + 32) of one row held as the raw tcgen05.ld words v0 (first 16) / v1 (last 16); bias32 = the 32 bias
+// values of these columns in shared memory (16-byte aligned), read in one batch ahead of the stores
+__device__ __forceinline__ void epilogue_store32(float* __restrict__ yrow, int c0, int N, const uint32_t (&v0)[16],
+                                                 const uint32_t (&v1)[16], const float* __restrict__ bias32, int relu, bool vec) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = bias32 ? *reinterpret_cast<const float4*>(bias32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t* v = (j < 4) ? &v0[4 * j] : &v1[4 * (j - 4)];
+        o[4 * j + 0] = __uint_as_float(v[0]) + b.x; o[4 * j + 1] = __uint_as_float(v[1]) + b.y;
+        o[4 * j + 2] = __uint_as_float(v[2]) + b.z; o[4 * j + 3] = __uint_as_float(v[3]) + b.w;
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        float a8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a8[i] = o[8 * h + i];
+        epilogue_store8(yrow, c0 + 8 * h, N, a8, relu, vec);
     }
 }
 // 128 epilogue threads (four warps) stage the tile's 128 bias values (zeros past N or without a bias) in shared memory;

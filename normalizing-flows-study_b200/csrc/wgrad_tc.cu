@@ -208,16 +208,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
-            if (row < N) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float a0[8], a1[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { a0[j] = __uint_as_float(v0[h * 8 + j]); a1[j] = __uint_as_float(v1[h * 8 + j]); }
-                    tc::epilogue_store8(yrow, k0 + c * 32 + h * 8, K, a0, nullptr, 0, vec != 0);
-                    tc::epilogue_store8(yrow, k0 + c * 32 + 16 + h * 8, K, a1, nullptr, 0, vec != 0);
-                }
-            }
+            if (row < N) tc::epilogue_store32(yrow, k0 + c * 32, K, v0, v1, nullptr, 0, vec != 0);
         }
     }
     tc::fence_before_sync();
