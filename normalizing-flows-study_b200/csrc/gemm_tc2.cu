@@ -14,9 +14,12 @@
 //   warp 1      MMA issuer: 12 tcgen05.mma per K block (A from TMEM, B from shared memory), commits stage / A-stage /
 //               chain barriers
 //   warps 2-5   converters: split the X tile into hi / lo and store it into the TMEM A stage (lane = row)
-//   warps 6-9   drainers: tcgen05.ld the finished chain accumulator, add into registers, release it; after the tile's
-//               last chain: bias + ReLU + coalesced stores (through a per-warp transpose buffer), overlapping the next
-//               tile's main loop
+//   warps 6-9   drainers: stage the tile's bias in shared memory and start the row's 128 running sums from it;
+//               tcgen05.ld every finished chain accumulator, add it into the registers, release it; after the tile's
+//               last chain: ReLU + sixteen 256-bit stores into the thread's own output row (no transpose, no loads),
+//               overlapping the next tile's main loop
+// passes == 1 (nf_set_option(7, 1), the reduced-precision mode): one TF32 pass, no W_lo loads, 6 stages of 32 KB,
+// chains of 6 K blocks.
 #include <cuda.h>
 #include "nf_common.cuh"
 #include "tc_common.cuh"
@@ -35,7 +38,7 @@ constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A s
 constexpr int k2ColA = 384;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
-constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;          // per drainer group (now: two 128-float bias tiles per group at its start)
+constexpr uint32_t k2TbufBytes = 2 * 128 * 4;              // per drainer group: two 128-float bias tiles (alternating tiles)
 
 int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
 int g_gemm_tc_small_k = 1;                    // nf_set_option(6, v): K <= 128 through the persistent DIRECT variant (1) or gemm_tc.cu (0)
@@ -251,7 +254,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if ((ti & 1) != grp) continue;
             const int cb = my_cc % k2NAcc;
             // bias tile -> shared memory (two buffers per group, alternating with the group's tiles)
-            float* bias_s = reinterpret_cast<float*>(tbuf_base) + grp * 256 + ((ti >> 1) & 1) * 128;
+            float* bias_s = reinterpret_cast<float*>(tbuf_base) + grp * (k2TbufBytes / 4) + ((ti >> 1) & 1) * 128;
             tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6 - 4 * grp) * 32 + lane, 1 + grp);
             if (nkb > 0) {
                 tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);

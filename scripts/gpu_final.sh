@@ -12,6 +12,11 @@ for m in realnvp256:65536 maf256:65536 spline784:4096 maf64:262144 realnvp2:1048
   M=${m%%:*}; B=${m##*:}
   timeout 300 python scripts/train_step_bench.py --model $M --batch $B --steps 5 2>/dev/null | tail -1 > gpurun_out/train_${TAG}_${M}.json; echo "train $M rc=$?"; cat gpurun_out/train_${TAG}_${M}.json | cut -c1-200
 done
+for m in spline784:4096 realnvp256:65536 maf256:65536 maf64:262144; do
+  M=${m%%:*}; B=${m##*:}
+  timeout 300 python scripts/train_step_bench.py --model $M --batch $B --steps 5 --precision tf32 2>/dev/null | tail -1 > gpurun_out/train_${TAG}_${M}_tf32.json; echo "train $M tf32 rc=$?"; cat gpurun_out/train_${TAG}_${M}_tf32.json | cut -c1-200
+done
+timeout 300 python scripts/microbench.py > gpurun_out/microbench_$TAG.log 2>&1; echo "microbench rc=$?"
 for m in realnvp2 spline2 maf64; do
   for g in "" "--graph"; do
     timeout 300 python scripts/train_step_bench.py --model $m --batch 5000 --steps 50 --warmup 5 $g 2>/dev/null | tail -1 > gpurun_out/c1_${TAG}_${m}${g}.json; cat gpurun_out/c1_${TAG}_${m}${g}.json | cut -c1-200
