@@ -175,8 +175,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         // The thread owns row m0 + r: bias + ReLU + one 256-bit store per 8 columns (tc::epilogue_store8).
         const int row = m0 + r;
         float* yrow = Y + (int64_t)row * ldc;
-        float* bias_s = reinterpret_cast<float*>(smem);       // every stage is free once d_full has fired
-        tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 2) * 32 + lane, 1);
+        // every stage is free once d_full has fired: bias tile (aligned outputs) or per-warp transpose buffers (unaligned)
+        float* bias_s = reinterpret_cast<float*>(smem);
+        float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;
+        if (vec) tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 2) * 32 + lane, 1);
 #pragma unroll
         for (int c = 0; c < kGemmBN / 32; ++c) {
             uint32_t v0[16], v1[16];
@@ -188,7 +190,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
-            if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, vec != 0);
+            if (vec) {
+                if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, true);
+            } else {
+                tc::epilogue_store32_transposed(Y, ldc, m0 + q * 32, M, n0 + c * 32, N, v0, v1, bias, relu, tbuf, lane);
+            }
         }
     }
     tc::fence_before_sync();

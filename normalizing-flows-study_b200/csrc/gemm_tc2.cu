@@ -38,7 +38,8 @@ constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A s
 constexpr int k2ColA = 384;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
-constexpr uint32_t k2TbufBytes = 2 * 128 * 4;              // per drainer group: two 128-float bias tiles (alternating tiles)
+// per drainer group: two 128-float bias tiles (aligned outputs) OR four per-warp [32][33] transpose buffers (unaligned ones)
+constexpr uint32_t k2TbufBytes = 4 * 32 * 33 * 4;
 
 int g_gemm_tc_variant = 1;                    // nf_set_option(5, v): 0 = gemm_tc.cu (one chain per tile), 1 = this kernel
 int g_gemm_tc_small_k = 1;                    // nf_set_option(6, v): K <= 128 through the persistent DIRECT variant (1) or gemm_tc.cu (0)
@@ -253,9 +254,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (nkb > 0) ++cc;                                   // one chain per non-empty tile, counted by both groups
             if ((ti & 1) != grp) continue;
             const int cb = my_cc % k2NAcc;
-            // bias tile -> shared memory (two buffers per group, alternating with the group's tiles)
-            float* bias_s = reinterpret_cast<float*>(tbuf_base) + grp * (k2TbufBytes / 4) + ((ti >> 1) & 1) * 128;
-            tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6 - 4 * grp) * 32 + lane, 1 + grp);
+            // aligned outputs: bias tile -> shared memory (two buffers per group, alternating with the group's tiles);
+            // unaligned outputs: the same memory is the warps' transpose buffers
+            float* grp_mem = reinterpret_cast<float*>(tbuf_base) + grp * (k2TbufBytes / 4);
+            float* bias_s = grp_mem + ((ti >> 1) & 1) * 128;
+            float* tbuf = grp_mem + (size_t)(warp - 6 - 4 * grp) * 32 * 33;
+            if (vec) tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6 - 4 * grp) * 32 + lane, 1 + grp);
             if (nkb > 0) {
                 tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);
                 tc::fence_after_sync();
@@ -274,7 +278,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
                 }
-                if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, vec != 0);
+                if (vec) {
+                    if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, true);
+                } else {
+                    tc::epilogue_store32_transposed(Y, ldc, m0 + q * 32, M, n0 + c * 32, N, v0, v1, bias, relu, tbuf, lane);
+                }
             }
         }
     } else {
@@ -289,15 +297,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             const int nchains = (nkb + chain_kb - 1) / chain_kb;
-            // bias tile -> shared memory while the first chain is still accumulating (two buffers, alternating tiles);
-            // the running sums START from the bias, so the epilogue has no loads at all
+            // aligned outputs: bias tile -> shared memory while the first chain is still accumulating (two buffers,
+            // alternating tiles) and the running sums START from the bias, so the epilogue has no loads at all;
+            // unaligned outputs: sums start from zero and the same memory is the warps' transpose buffers
             float* bias_s = reinterpret_cast<float*>(tbuf_base) + (ti & 1) * 128;
-            tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6) * 32 + lane, 1);
+            float* tbuf = reinterpret_cast<float*>(tbuf_base) + (size_t)(warp - 6) * 32 * 33;
             float acc[128];
+            if (vec) {
+                tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6) * 32 + lane, 1);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
-                acc[4 * j + 0] = b.x; acc[4 * j + 1] = b.y; acc[4 * j + 2] = b.z; acc[4 * j + 3] = b.w;
+                for (int j = 0; j < 32; ++j) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
+                    acc[4 * j + 0] = b.x; acc[4 * j + 1] = b.y; acc[4 * j + 2] = b.z; acc[4 * j + 3] = b.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 128; ++j) acc[j] = 0.f;
             }
             for (int c = 0; c < nchains; ++c) {
                 tc::mbar_wait(&d_full[cb], dph);
@@ -316,14 +331,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             // epilogue from registers: the thread owns row m0 + 32q + lane; ReLU + one 256-bit store per 8 columns
             const int row = m0 + q * 32 + lane;
-            if (row < M) {
-                float* yrow = Y + (int64_t)row * ldc;
+            if (vec) {
+                if (row < M) {
+                    float* yrow = Y + (int64_t)row * ldc;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a[8];
+                    for (int j = 0; j < 16; ++j) {
+                        float a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
-                    tc::epilogue_store8(yrow, n0 + j * 8, N, a, relu, vec != 0);
+                        for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
+                        tc::epilogue_store8(yrow, n0 + j * 8, N, a, relu, true);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v0[16], v1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { v0[j] = __float_as_uint(acc[c * 32 + j]); v1[j] = __float_as_uint(acc[c * 32 + 16 + j]); }
+                    tc::epilogue_store32_transposed(Y, ldc, m0 + q * 32, M, n0 + c * 32, N, v0, v1, bias, relu, tbuf, lane);
                 }
             }
         }

@@ -229,6 +229,32 @@ __device__ __forceinline__ void epilogue_store32(float* __restrict__ yrow, int c
         epilogue_store8(yrow, c0 + 8 * h, N, a8, relu, vec);
     }
 }
+// Fallback for outputs the 256-bit row stores cannot take (base or pitch not 32-byte aligned: column slices starting at
+// an arbitrary unit, 23 / 29-wide heads): lane = row holds o[32] = 32 consecutive columns [c0, c0 + 32) (bias NOT yet
+// added); transposed through the warp's [32][33] shared-memory buffer so that a warp writes 128 contiguous bytes of one
+// row per store.  All 32 lanes must call it.  (Per-thread scalar stores into the own row were 2.2x slower on the
+// [262144, 64] slice products of the blocked sequential direction: 32 sectors per 128 bytes.)
+__device__ __forceinline__ void epilogue_store32_transposed(float* __restrict__ Y, int64_t ldc, int row0, int M, int c0, int N,
+                                                            const uint32_t (&v0)[16], const uint32_t (&v1)[16],
+                                                            const float* __restrict__ bias, int relu, float* tbuf, int lane) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { tbuf[lane * 33 + j] = __uint_as_float(v0[j]); tbuf[lane * 33 + 16 + j] = __uint_as_float(v1[j]); }
+    __syncwarp();
+    const int col = c0 + lane;
+    if (col < N) {
+        const float bv = bias ? __ldg(bias + col) : 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const int row = row0 + rr;
+            if (row < M) {
+                float o = tbuf[rr * 33 + lane] + bv;
+                if (relu) o = (o < 0.f) ? 0.f : o;          // NaN stays NaN (torch.relu)
+                Y[(int64_t)row * ldc + col] = o;
+            }
+        }
+    }
+    __syncwarp();
+}
 // 128 epilogue threads (four warps) stage the tile's 128 bias values (zeros past N or without a bias) in shared memory;
 // named barrier `bar_id` (1..15) makes them visible to the four warps
 __device__ __forceinline__ void stage_bias_tile(float* bias_s, const float* __restrict__ bias, int n0, int N, int t128, int bar_id) {

@@ -197,6 +197,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         float* dst = out + (int64_t)blockIdx.y * split_stride;
         const int row = n0 + q * 32 + lane;
         float* yrow = dst + (int64_t)row * ld_out;
+        float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;      // stage memory is free once d_full has fired
 #pragma unroll
         for (int c = 0; c < kWgBN / 32; ++c) {
             uint32_t v0[16], v1[16];
@@ -208,7 +209,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
             }
-            if (row < N) tc::epilogue_store32(yrow, k0 + c * 32, K, v0, v1, nullptr, 0, vec != 0);
+            if (vec) {
+                if (row < N) tc::epilogue_store32(yrow, k0 + c * 32, K, v0, v1, nullptr, 0, true);
+            } else {
+                tc::epilogue_store32_transposed(dst, ld_out, n0 + q * 32, N, k0 + c * 32, K, v0, v1, nullptr, 0, tbuf, lane);
+            }
         }
     }
     tc::fence_before_sync();
