@@ -381,8 +381,9 @@ def run_product(args):
         # launch stay in the 126 MB L2; algorithmic traffic is 20 B x 2^20 rows = 21 MB)
         traffic = 8.854528e6 if rows == 1 << 20 else None
     else:
-        kernel = ("gemm_tc2_kernel x3 + gemm_tc_kernel x1 (tcgen05 3xTF32, TMA-fed, masked-out K tiles skipped; K > 128: chains of "
-                  "24 MMAs folded into registers with round-to-nearest adds) + affine_ar_fwd_kernel")
+        kernel = ("gemm_tc2_kernel x4 (persistent, tcgen05 3xTF32, TMA-fed, masked-out K tiles skipped; K > 128: chains of "
+                  "24 MMAs folded into registers with round-to-nearest adds; K = 64 input layer: direct variant) + "
+                  "affine_ar_fwd_kernel")
         note = ("dense GEMM FLOPs of one MADE evaluation (SURVEY 8d) over the time of the whole MAF.inverse chain; the "
                 "tensor pipe executes 3x the unskipped FLOPs (3xTF32 keeps fp32 parity)")
         tensor_exec = None
