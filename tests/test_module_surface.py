@@ -107,3 +107,20 @@ def test_product_does_not_import_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("flows_oracle", "oracle") or fn == "build.py" or "import oracle" not in src
             assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_gemm_precision_switch_is_host_only_and_validated():
+    """set_gemm_precision maps onto nf_set_option(7, passes); no device is needed to flip it, unknown modes and pass
+    counts are rejected, and the default is the fp32-parity mode."""
+    assert N.get_gemm_precision() == "fp32"
+    try:
+        N.set_gemm_precision("tf32")
+        assert N.get_gemm_precision() == "tf32"
+    finally:
+        N.set_gemm_precision("fp32")
+    assert N.get_gemm_precision() == "fp32"
+    with pytest.raises(ValueError):
+        N.set_gemm_precision("bf16")
+    assert N._lib.lib().nf_set_option(7, 2) != 0          # only 1 and 3 passes exist
+    assert N._lib.lib().nf_set_option(7, 3) == 0
+    assert N._lib.lib().nf_set_option(99, 0) != 0         # unknown key
