@@ -33,9 +33,11 @@ constexpr int k2MaxStages = 6;
 constexpr int k2Threads = 320;
 constexpr int k2ThreadsDirect = 448;          // two drainer groups
 constexpr int k2ChainKB = 2;                  // K blocks per TMEM accumulation chain
-constexpr int k2NAcc = 3;                     // chain accumulators in flight (drain latency hides behind two chains)
+constexpr int k2NAcc = 3;                     // chain accumulators in flight by default (drain latency hides behind two chains)
 constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A stage 0: 384 (hi 32 + lo 32) | A stage 1: 448
-constexpr int k2ColA = 384;
+// TMEM split, template parameter NACC: 3 accumulators + 2 A stages (default) or 2 accumulators + 4 A stages
+// (nf_set_option(9, 2): the converters may run three K blocks ahead of the MMAs instead of one)
+int g_gemm_tc2_nacc = 3;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
 // per drainer group: two 128-float bias tiles (aligned outputs) OR four per-warp [32][33] transpose buffers (unaligned ones)
@@ -87,7 +89,7 @@ __device__ __forceinline__ void tile_k_range(int n0, int N, int K, const int32_t
 // taking alternate tiles: for small K the tile's epilogue (64 KB of output) is longer than its main loop, and the
 // non-persistent kernel in gemm_tc.cu pays launch, TMEM allocation and pipeline fill per tile (measured at
 // 2^20 x 64 x 64: 0.22 ms = 2.4 TB/s of a 0.08 ms HBM floor).
-template <bool DIRECT>
+template <bool DIRECT, int NACC>
 __global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
@@ -101,19 +103,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     uint64_t* bars = reinterpret_cast<uint64_t*>(tbuf_base + (DIRECT ? 2 : 1) * k2TbufBytes);
     uint64_t* full = bars;                         // [S] TMA landed
     uint64_t* empty = full + k2MaxStages;          // [S] stage consumed (MMA commit)
-    uint64_t* a_full = empty + k2MaxStages;        // [2] converters wrote the TMEM A stage
-    uint64_t* a_empty = a_full + 2;                // [2] MMAs consumed the TMEM A stage
-    uint64_t* d_full = a_empty + 2;                // [NAcc] chain accumulator complete
-    uint64_t* d_empty = d_full + k2NAcc;           // [NAcc] drainers read the chain accumulator
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + k2NAcc);
+    constexpr int kAStages = (k2TmemCols - NACC * 128) / 64;      // 64 columns (hi 32 + lo 32) per A stage: 2 or 4
+    constexpr int kAShift = kAStages == 4 ? 2 : 1;
+    constexpr int kColA = NACC * 128;
+    static_assert(kAStages == 2 || kAStages == 4, "TMEM split");
+    uint64_t* a_full = empty + k2MaxStages;        // [<= 4] converters wrote the TMEM A stage
+    uint64_t* a_empty = a_full + 4;                // [<= 4] MMAs consumed the TMEM A stage
+    uint64_t* d_full = a_empty + 4;                // [<= 3] chain accumulator complete
+    uint64_t* d_empty = d_full + 3;                // [<= 3] drainers read the chain accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (N + k2BN - 1) / k2BN;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < k2MaxStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < k2NAcc; ++i) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_empty[i], 128); }
+        for (int i = 0; i < kAStages; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NACC; ++i) { tc::mbar_init(&d_full[i], 1); tc::mbar_init(&d_empty[i], 128); }
         tc::fence_mbar_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, k2TmemCols);
@@ -159,14 +165,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int a = it & 1;
+                const int a = it & (kAStages - 1);
                 if (ic == 0 && !first_acc_round) tc::mbar_wait(&d_empty[cb], dph ^ 1u);
                 tc::mbar_wait(&full[s], ph);
-                tc::mbar_wait(&a_full[a], (it >> 1) & 1);
+                tc::mbar_wait(&a_full[a], (it >> kAShift) & 1);
                 tc::fence_after_sync();
                 const uint32_t st = tc::smem_u32(smem + s * stage_bytes);
                 const uint64_t d_hi = tc::smem_desc_k_sw128(st + k2XBytes), d_lo = tc::smem_desc_k_sw128(st + k2XBytes + k2WBytes);
-                const uint32_t a_hi = tb + k2ColA + a * 64, a_lo = a_hi + 32;
+                const uint32_t a_hi = tb + kColA + a * 64, a_lo = a_hi + 32;
                 const uint32_t dcol = tb + cb * 128;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -188,7 +194,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 if (++s == n_stages) { s = 0; ph ^= 1u; }
                 if (chain_end) {
                     ic = 0;
-                    if (++cb == k2NAcc) { cb = 0; dph ^= 1u; first_acc_round = false; }
+                    if (++cb == NACC) { cb = 0; dph ^= 1u; first_acc_round = false; }
                 } else {
                     ++ic;
                 }
@@ -208,9 +214,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int a = it & 1;
+                const int a = it & (kAStages - 1);
                 tc::mbar_wait(&full[s], ph);
-                if (it >= 2) tc::mbar_wait(&a_empty[a], ((it >> 1) - 1) & 1);
+                if (it >= kAStages) tc::mbar_wait(&a_empty[a], ((it >> kAShift) - 1) & 1);
                 tc::fence_after_sync();
                 const uint8_t* xrow = smem + s * stage_bytes + (r >> 3) * 1024 + (r & 7) * 128;
                 uint32_t hi[32], lo[32];
@@ -222,7 +228,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     tc::split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]);
                     tc::split_tf32(v.w, hi[4 * c + 3], lo[4 * c + 3]);
                 }
-                const uint32_t a_hi = lane_addr + k2ColA + a * 64, a_lo = a_hi + 32;
+                const uint32_t a_hi = lane_addr + kColA + a * 64, a_lo = a_hi + 32;
                 {
                     uint32_t t0[16], t1[16];
 #pragma unroll
@@ -253,7 +259,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             const int my_cc = cc;
             if (nkb > 0) ++cc;                                   // one chain per non-empty tile, counted by both groups
             if ((ti & 1) != grp) continue;
-            const int cb = my_cc % k2NAcc;
+            const int cb = my_cc % NACC;
             // aligned outputs: bias tile -> shared memory (two buffers per group, alternating with the group's tiles);
             // unaligned outputs: the same memory is the warps' transpose buffers
             float* grp_mem = reinterpret_cast<float*>(tbuf_base) + grp * (k2TbufBytes / 4);
@@ -261,7 +267,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             float* tbuf = grp_mem + (size_t)(warp - 6 - 4 * grp) * 32 * 33;
             if (vec) tc::stage_bias_tile(bias_s, bias, n0, N, (warp - 6 - 4 * grp) * 32 + lane, 1 + grp);
             if (nkb > 0) {
-                tc::mbar_wait(&d_full[cb], (my_cc / k2NAcc) & 1);
+                tc::mbar_wait(&d_full[cb], (my_cc / NACC) & 1);
                 tc::fence_after_sync();
             }
             const int row = m0 + q * 32 + lane;
@@ -327,7 +333,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 }
                 tc::fence_before_sync();
                 tc::mbar_arrive(&d_empty[cb]);
-                if (++cb == k2NAcc) { cb = 0; dph ^= 1u; }
+                if (++cb == NACC) { cb = 0; dph ^= 1u; }
             }
             // epilogue from registers: the thread owns row m0 + 32q + lane; ReLU + one 256-bit store per 8 columns
             const int row = m0 + q * 32 + lane;
@@ -402,14 +408,20 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : 0;
     if (K <= 4 * k2BK) {
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
-        NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tc2_kernel<true><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
+        NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc2_kernel<true, k2NAcc><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
                                                                    ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
     } else {
         const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
-        NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tc2_kernel<false><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                              relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+        if (g_gemm_tc2_nacc == 2) {
+            NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gemm_tc2_kernel<false, 2><<<grid, k2Threads, smem, st>>>((tx), twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
+                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+        } else {
+            NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gemm_tc2_kernel<false, k2NAcc><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
+                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+        }
     }
     return NF_OK;
 }

@@ -325,3 +325,27 @@ def test_set_gemm_precision_rejects_unknown_modes():
     with pytest.raises(ValueError):
         N_.set_gemm_precision("bf16x")
     assert N_.get_gemm_precision() == "fp32"
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(4096, 512, 512, True), (1000, 300, 2048, False), (257, 130, 1024, True)])
+def test_linear_tc_two_accumulator_split_matches_default(M, N, K, relu):
+    """nf_set_option(9, 2): the short-chain kernel with 2 chain accumulators + 4 TMEM A stages computes the same chains
+    in the same order as the default 3 + 2 split => bit-identical results, in both precision modes."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=gen) * 1.5).cuda()
+    w = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen).cuda()
+    hi, lo = N_.ops.split_tf32(w.cuda())
+    for mode in ("fp32", "tf32"):
+        N_.set_gemm_precision(mode)
+        try:
+            y3 = N_.ops.linear_tc(x, hi, lo, b, relu)
+            N_._lib.call("nf_set_option", 9, 2)
+            try:
+                y2 = N_.ops.linear_tc(x, hi, lo, b, relu)
+            finally:
+                N_._lib.call("nf_set_option", 9, 3)
+        finally:
+            N_.set_gemm_precision("fp32")
+        assert torch.isfinite(y2).all()
+        assert torch.equal(y2, y3), (mode, (y2 - y3).abs().max().item())
