@@ -65,7 +65,9 @@ NF_API int64_t nf_launch_count(void);
  * key 7 = nf_linear_tc* and nf_linear_wgrad_tc*: tensor-core passes per product.  3 = 3xTF32 (fp32 parity, default);
  *         1 = one TF32 pass, operands rounded to the nearest TF32 (the reduced-precision conditioner-GEMM mode the
  *         reference reaches with autocast, optimization/mixed_precision.py:89-105; w_lo is not read);
- * key 9 = nf_linear_tc* (K > 128): TMEM split of gemm_tc2.cu, 3 chain accumulators + 2 A stages (default) or 2 + 4 */
+ * key 9 = nf_linear_tc* (K > 128): TMEM split of gemm_tc2.cu, 3 chain accumulators + 2 A stages (default) or 2 + 4;
+ * key 10 = nf_linear_tc* in the one-pass mode: 1 = A operand straight from shared memory (x truncated to TF32 by the tensor
+ *         core instead of rounded by the converter warps); default 0 */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------

@@ -38,6 +38,9 @@ constexpr int k2TmemCols = 512;               // D0: 0 | D1: 128 | D2: 256 | A s
 // TMEM split, template parameter NACC: 3 accumulators + 2 A stages (default) or 2 accumulators + 4 A stages
 // (nf_set_option(9, 2): the converters may run three K blocks ahead of the MMAs instead of one)
 int g_gemm_tc2_nacc = 3;
+// nf_set_option(10, 1), one-pass mode only: feed the X tile to the MMA straight from shared memory (SS form; the tensor
+// core then TRUNCATES x to TF32 instead of the converters' round-to-nearest) -- no converter work at all.  A/B option.
+int g_gemm_tc2_ss = 0;
 constexpr uint32_t k2XBytes = k2BM * k2BK * 4, k2WBytes = k2BN * k2BK * 4;
 constexpr uint32_t k2StageBytes = k2XBytes + 2 * k2WBytes;
 // per drainer group: two 128-float bias tiles (aligned outputs) OR four per-warp [32][33] transpose buffers (unaligned ones)
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                 int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
-                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec) {
+                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec, int ss) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int chain_kb = passes == 1 ? k2ChainKBFast : k2ChainKB;
     const int n_stages = passes == 1 ? k2StagesFast : k2Stages;
@@ -168,26 +171,34 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 const int a = it & (kAStages - 1);
                 if (ic == 0 && !first_acc_round) tc::mbar_wait(&d_empty[cb], dph ^ 1u);
                 tc::mbar_wait(&full[s], ph);
-                tc::mbar_wait(&a_full[a], (it >> kAShift) & 1);
+                if (!ss) tc::mbar_wait(&a_full[a], (it >> kAShift) & 1);
                 tc::fence_after_sync();
                 const uint32_t st = tc::smem_u32(smem + s * stage_bytes);
                 const uint64_t d_hi = tc::smem_desc_k_sw128(st + k2XBytes), d_lo = tc::smem_desc_k_sw128(st + k2XBytes + k2WBytes);
                 const uint32_t a_hi = tb + kColA + a * 64, a_lo = a_hi + 32;
                 const uint32_t dcol = tb + cb * 128;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    if (pass >= passes) break;
-                    const uint32_t ac = (pass == 1) ? a_lo : a_hi;
-                    const uint64_t wd = (pass == 2) ? d_lo : d_hi;
+                if (ss) {
+                    const uint64_t d_x = tc::smem_desc_k_sw128(st);          // the X tile as landed by TMA: K-major SWIZZLE_128B
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (ic | pass | k) != 0 ? 1u : 0u);
+                        if (leader) tc::mma_tf32_ss(dcol, d_x + (uint64_t)(k * 2), d_hi + (uint64_t)(k * 2), idesc, (ic | k) != 0 ? 1u : 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        if (pass >= passes) break;
+                        const uint32_t ac = (pass == 1) ? a_lo : a_hi;
+                        const uint64_t wd = (pass == 2) ? d_lo : d_hi;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (leader) tc::mma_tf32_ts(dcol, ac + k * 8, wd + (uint64_t)(k * 2), idesc, (ic | pass | k) != 0 ? 1u : 0u);
+                        }
                     }
                 }
                 const bool chain_end = (!DIRECT && ic == chain_kb - 1) || (kb == nkb - 1);
                 if (leader) {
                     tc::mma_commit(&empty[s]);
-                    tc::mma_commit(&a_empty[a]);
+                    if (!ss) tc::mma_commit(&a_empty[a]);
                     if (chain_end) tc::mma_commit(&d_full[cb]);
                 }
                 __syncwarp();
@@ -207,7 +218,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
         int it = 0, s = 0;
         uint32_t ph = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < (ss ? 0 : num_tiles); t += gridDim.x) {       // SS form: no converter work
             int n0, m0;
             tile_decode(t, n_tiles, n0, m0);
             (void)m0;
@@ -406,21 +417,22 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
     // 256-bit row stores in the epilogue: 32-byte aligned rows of Y
     const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : 0;
+    const int ss = (g_tc_passes == 1 && g_gemm_tc2_ss) ? 1 : 0;
     if (K <= 4 * k2BK) {
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc2_kernel<true, k2NAcc><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
-                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
     } else {
         const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
         if (g_gemm_tc2_nacc == 2) {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, 2><<<grid, k2Threads, smem, st>>>((tx), twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
         } else {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, k2NAcc><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec);
+                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
         }
     }
     return NF_OK;

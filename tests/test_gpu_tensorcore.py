@@ -349,3 +349,24 @@ def test_linear_tc_two_accumulator_split_matches_default(M, N, K, relu):
             N_.set_gemm_precision("fp32")
         assert torch.isfinite(y2).all()
         assert torch.equal(y2, y3), (mode, (y2 - y3).abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 512), (777, 130, 100), (300, 64, 1024), (1000, 512, 64)])
+def test_linear_tc_one_pass_ss_option_bounds(tf32_mode, M, N, K):
+    """nf_set_option(10, 1): the one-pass mode with the A operand straight from shared memory.  The tensor core truncates
+    x to TF32 (relative error < 2^-10, toward zero) where the converters round (2^-11), w_hi is rounded:
+    max|err| / sum|a||b| <= 2^-10 + 2^-11 = 1.5e-3."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=gen) * 1.5
+    w = torch.randn(N, K, generator=gen) / K ** 0.5
+    b = torch.randn(N, generator=gen)
+    hi, lo = N_.ops.split_tf32(w.cuda())
+    N_._lib.call("nf_set_option", 10, 1)
+    try:
+        y = N_.ops.linear_tc(x.cuda(), hi, lo, b.cuda(), True)
+    finally:
+        N_._lib.call("nf_set_option", 10, 0)
+    ref = (x.double() @ w.double().T + b.double()).clamp_min(0)
+    scale = x.double().abs() @ w.double().abs().T + b.double().abs()
+    err = ((y.cpu().double() - ref).abs() / scale).max().item()
+    assert 1e-6 < err < 1.6e-3, f"scaled error {err:.3e}"
