@@ -161,6 +161,24 @@ def bench_bn():
         del x
 
 
+def bench_peaks():
+    """Library throughput of the pipes the dense layers run on (TF32 and FP32 peaks are not in
+    MEASURED_PEAKS.json): torch.matmul (cuBLAS) 8192^3 in bf16, TF32 and plain fp32."""
+    n = 8192
+    flops = 2.0 * n ** 3
+    a32, b32 = torch.randn(n, n, device=DEV), torch.randn(n, n, device=DEV)
+    a16, b16 = a32.bfloat16(), b32.bfloat16()
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        report("cuBLAS bf16 matmul 8192^3", timeit(lambda: torch.matmul(a16, b16), reps=3, inner=4), None, flops)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        report("cuBLAS TF32 matmul 8192^3 (the pipe rate of the 3xTF32 kernels)", timeit(lambda: torch.matmul(a32, b32), reps=3, inner=4), None, flops)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        report("cuBLAS fp32 matmul 8192^3 (FP32 pipe)", timeit(lambda: torch.matmul(a32, b32), reps=3, inner=2), None, flops)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def bench_gemm():
     shapes = [("MADE(64,512) in->H", 262144, 512, 64), ("MADE(64,512) H->H", 262144, 512, 512),
               ("MADE(64,512) H->2D", 262144, 128, 512), ("coupling(256,512) H->H", 262144, 512, 512),
@@ -245,7 +263,7 @@ def bench_stacks():
         report("MAF(64,512).forward sequential B=262144", ms, 262144 * 516, 1245184 * 262144)
 
 
-ALL = {"rqs": bench_rqs, "spline_tf": bench_spline_tf, "affine": bench_affine, "bn": bench_bn, "gemm": bench_gemm,
+ALL = {"peaks": bench_peaks, "rqs": bench_rqs, "spline_tf": bench_spline_tf, "affine": bench_affine, "bn": bench_bn, "gemm": bench_gemm,
        "stacks": bench_stacks}
 
 if __name__ == "__main__":
