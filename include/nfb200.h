@@ -158,7 +158,11 @@ NF_API int nf_batchnorm_backward(const void* x, const void* y, const void* gamma
  * `packed` is the float32 device buffer laid out by the host side (csrc/stack_small.cuh documents the layout);
  * `hdr_host` is a HOST copy of its first 16 words (so the library never reads device memory on the host).
  * Returns NF_ERR_UNSUPPORTED when the configuration does not fit one SM's shared memory (caller uses the
- * layer-wise path: nf_gemm + nf_spline_transform_forward). */
+ * layer-wise path: nf_gemm + nf_spline_transform_forward).
+ * `inverse` of all four fused-stack entry points is a flag word: bit 0 = direction (1: x -> z); bit 1
+ * (NF_STACK_LOG_PROB_HEAD = 2) = `ld` receives log N(z; 0, I) + log_det, the Flow.log_prob head for a standard-normal
+ * base (flow.py:56-73), evaluated on the row while it is still in registers; bit 2 (NF_STACK_SKIP_Y = 4) = the
+ * transformed rows are not stored (y may be NULL). */
 NF_API int nf_spline_stack_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
                             void* ld, int64_t B, int inverse, nf_stream_t stream);
 /* a1/a2 + a14/a15: L CouplingLayers in eval mode (conditioner BatchNorm folded into the Linears at pack time). */

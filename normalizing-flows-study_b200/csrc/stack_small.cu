@@ -139,7 +139,8 @@ __device__ __forceinline__ void bn_between(const float* __restrict__ sL, int D, 
 template <int HP, int R, int DM, int KMAX>
 __global__ void __launch_bounds__(kStackThreads)
 spline_stack_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                    float* __restrict__ ld, int64_t B, int inverse, int layer_words_pad) {
+                    float* __restrict__ ld, int64_t B, int flags, int layer_words_pad) {
+    const int inverse = flags & NF_STACK_INVERSE;
     extern __shared__ __align__(16) float smem[];
     const StackHdr hd = read_hdr(packed);
     const int D = hd.D, K = hd.K, L = hd.L, W1S = hd.W1S, NO = hd.NO, P = 3 * hd.K - 1;
@@ -241,9 +242,11 @@ spline_stack_kernel(const float* __restrict__ packed, const float* __restrict__ 
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             if (row[i] < B) {
+                if (!(flags & NF_STACK_SKIP_Y)) {
 #pragma unroll
-                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + row[i] * D + d, xv[i][d]);
-                st_stream(ld + row[i], tot[i]);
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + row[i] * D + d, xv[i][d]);
+                }
+                st_stream(ld + row[i], (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(xv[i], D, tot[i]) : tot[i]);
             }
         }
     }
@@ -255,7 +258,8 @@ spline_stack_kernel(const float* __restrict__ packed, const float* __restrict__ 
 template <int HP, int R, int DM>
 __global__ void __launch_bounds__(kStackThreads)
 coupling_stack_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                      float* __restrict__ ld, int64_t B, int inverse) {
+                      float* __restrict__ ld, int64_t B, int flags) {
+    const int inverse = flags & NF_STACK_INVERSE;
     extern __shared__ __align__(16) float smem[];
     const StackHdr hd = read_hdr(packed);
     const int D = hd.D, L = hd.L, W1S = hd.W1S;
@@ -330,9 +334,11 @@ coupling_stack_kernel(const float* __restrict__ packed, const float* __restrict_
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             if (row[i] < B) {
+                if (!(flags & NF_STACK_SKIP_Y)) {
 #pragma unroll
-                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + row[i] * D + d, xv[i][d]);
-                st_stream(ld + row[i], tot[i]);
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + row[i] * D + d, xv[i][d]);
+                }
+                st_stream(ld + row[i], (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(xv[i], D, tot[i]) : tot[i]);
             }
         }
     }
@@ -393,7 +399,8 @@ extern "C" int nf_spline_stack_forward(const void* packed, const void* hdr_host,
     if (B < 0) return NF_ERR_BAD_SHAPE;
     NF_REQ(hdr_host);
     if (B == 0) return NF_OK;
-    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    NF_REQ(packed); NF_REQ(x); NF_REQ(ld);
+    if (!(inverse & NF_STACK_SKIP_Y)) NF_REQ(y);
     if (!aligned16(packed)) return NF_ERR_MISALIGNED;
     const int32_t* h = (const int32_t*)hdr_host;
     int rc = check_hdr(h, NF_STACK_MAGIC_SPLINE);
@@ -423,7 +430,8 @@ extern "C" int nf_coupling_stack_forward(const void* packed, const void* hdr_hos
     if (B < 0) return NF_ERR_BAD_SHAPE;
     NF_REQ(hdr_host);
     if (B == 0) return NF_OK;
-    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    NF_REQ(packed); NF_REQ(x); NF_REQ(ld);
+    if (!(inverse & NF_STACK_SKIP_Y)) NF_REQ(y);
     if (!aligned16(packed)) return NF_ERR_MISALIGNED;
     const int32_t* h = (const int32_t*)hdr_host;
     int rc = check_hdr(h, NF_STACK_MAGIC_AFFINE);

@@ -29,9 +29,28 @@
 #define NF_STACK_HDR 16
 #define NF_LAYER_HDR 80
 #define NF_STACK_DMAX 8
+// `inverse` argument of the fused stack entry points is a flag word:
+//   bit 0  direction (1 = inverse, x -> z)
+//   bit 1  log-prob head: the per-row output is log N(z; 0, I) + log_det (Flow.log_prob, flow.py:56-73) instead of
+//          log_det -- the standard-normal head evaluated on the row while it is still in registers
+//   bit 2  do not store the transformed rows (y may be NULL): Flow.log_prob only returns the per-row value
+#define NF_STACK_INVERSE 1
+#define NF_STACK_LOG_PROB_HEAD 2
+#define NF_STACK_SKIP_Y 4
 
 static inline int nf_stack_hp(int H) { return H <= 64 ? 64 : 128; }
 static inline int nf_stack_w1s(int D) { return D <= 3 ? 4 : 12; }
 static inline int64_t nf_stack_net_words(int HP, int W1S, int NO) {
     return (int64_t)HP * W1S + (int64_t)HP * HP + HP + (int64_t)NO * HP + NO;
 }
+
+#ifdef __CUDACC__
+// log N(z; 0, I) + log_det for one row held in registers (same arithmetic as std_normal_log_prob_fwd_kernel)
+template <int DM>
+__device__ __forceinline__ float nf_stack_row_head(const float (&z)[DM], int D, float log_det) {
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) if (d < D) acc += -0.5f * z[d] * z[d];
+    return acc - (float)(0.5 * (double)D * 1.8378770664093453) + log_det;
+}
+#endif

@@ -169,7 +169,8 @@ __host__ __device__ inline BlkOff blk_offsets(int W1S, int NO3) {
 template <int DM, int KMAX, int KS>
 __global__ void __launch_bounds__(kTcThreads, 2)
 spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                       float* __restrict__ ld, int64_t B, int inverse) {
+                       float* __restrict__ ld, int64_t B, int flags) {
+    const int inverse = flags & NF_STACK_INVERSE;
     // dynamic shared memory only (no static __shared__), so its base is the CTA's 1024-byte aligned window start:
     // [2 x layer block | row state | mbarrier | tmem base]
     extern __shared__ __align__(1024) float sbuf[];
@@ -336,9 +337,15 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
         for (int s = 0; s < kTcSub; ++s) {
             const int64_t r = tile * ROWS + s * kTcThreads + tid;
             if (r < B) {
+                float zr[DM];
 #pragma unroll
-                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + tid]);
-                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + tid]);
+                for (int d = 0; d < DM; ++d) zr[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                if (!(flags & NF_STACK_SKIP_Y)) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, zr[d]);
+                }
+                const float tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                st_stream(ld + r, (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(zr, D, tot) : tot);
             }
         }
     }
@@ -403,7 +410,8 @@ __device__ __forceinline__ void hidden2_chunk(const uint32_t (&v)[16], const flo
 template <int DM, int KMAX, int KS>
 __global__ void __launch_bounds__(kTc2Threads, 2)
 spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                        float* __restrict__ ld, int64_t B, int inverse) {
+                        float* __restrict__ ld, int64_t B, int flags) {
+    const int inverse = flags & NF_STACK_INVERSE;
     extern __shared__ __align__(1024) float sbuf[];
     const TcHdr hd = read_tc_hdr(packed);
     const int D = hd.D, K = (KS > 0) ? KS : hd.K, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, BW = hd.blk_words;
@@ -591,9 +599,15 @@ spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restric
         for (int s = wg; s < kTcSub; s += 2) {
             const int64_t r = tile * ROWS + s * kTcThreads + wtid;
             if (r < B) {
+                float zr[DM];
 #pragma unroll
-                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + wtid]);
-                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + wtid]);
+                for (int d = 0; d < DM; ++d) zr[d] = sx[(s * (DM + 1) + d) * kTcThreads + wtid];
+                if (!(flags & NF_STACK_SKIP_Y)) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, zr[d]);
+                }
+                const float tot = sx[(s * (DM + 1) + DM) * kTcThreads + wtid];
+                st_stream(ld + r, (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(zr, D, tot) : tot);
             }
         }
     }
@@ -611,7 +625,8 @@ spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restric
 template <int DM>
 __global__ void __launch_bounds__(kTcThreads, 2)
 coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                         float* __restrict__ ld, int64_t B, int inverse) {
+                         float* __restrict__ ld, int64_t B, int flags) {
+    const int inverse = flags & NF_STACK_INVERSE;
     extern __shared__ __align__(1024) float sbuf[];
     const TcHdr hd = read_tc_hdr(packed);
     const int D = hd.D, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, NBW = hd.blk_words;       // NBW: words per net block
@@ -737,9 +752,15 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
         for (int s = 0; s < kTcSub; ++s) {
             const int64_t r = tile * ROWS + s * kTcThreads + tid;
             if (r < B) {
+                float zr[DM];
 #pragma unroll
-                for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, sx[(s * (DM + 1) + d) * kTcThreads + tid]);
-                st_stream(ld + r, sx[(s * (DM + 1) + DM) * kTcThreads + tid]);
+                for (int d = 0; d < DM; ++d) zr[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                if (!(flags & NF_STACK_SKIP_Y)) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, zr[d]);
+                }
+                const float tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                st_stream(ld + r, (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(zr, D, tot) : tot);
             }
         }
     }
@@ -764,7 +785,8 @@ extern "C" int nf_spline_stack_tc_forward(const void* packed, const void* hdr_ho
     if (B < 0) return NF_ERR_BAD_SHAPE;
     NF_REQ(hdr_host);
     if (B == 0) return NF_OK;
-    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    NF_REQ(packed); NF_REQ(x); NF_REQ(ld);
+    if (!(inverse & NF_STACK_SKIP_Y)) NF_REQ(y);
     if (!aligned16(packed)) return NF_ERR_MISALIGNED;
     const int32_t* h = (const int32_t*)hdr_host;
     if (h[0] != NF_STACK_MAGIC_SPLINE_TC) return NF_ERR_BAD_SHAPE;
@@ -840,7 +862,8 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
     if (B < 0) return NF_ERR_BAD_SHAPE;
     NF_REQ(hdr_host);
     if (B == 0) return NF_OK;
-    NF_REQ(packed); NF_REQ(x); NF_REQ(y); NF_REQ(ld);
+    NF_REQ(packed); NF_REQ(x); NF_REQ(ld);
+    if (!(inverse & NF_STACK_SKIP_Y)) NF_REQ(y);
     if (!aligned16(packed)) return NF_ERR_MISALIGNED;
     const int32_t* h = (const int32_t*)hdr_host;
     if (h[0] != NF_STACK_MAGIC_AFFINE_TC) return NF_ERR_BAD_SHAPE;

@@ -44,6 +44,88 @@ def compute_input(v):
     return v
 
 
+def on_input_device(fn):
+    """Run a module method under the CUDA device of its tensor argument.  The C ABI launches on the *current* device's
+    stream; a model that lives on cuda:1 while cuda:0 is current (plain `model.to('cuda:1')`, which works with the
+    reference) must therefore switch devices around the launches instead of passing device-1 pointers to device 0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, v, *args, **kwargs):
+        if isinstance(v, torch.Tensor) and v.is_cuda and v.device.index != torch.cuda.current_device():
+            with torch.cuda.device(v.device):
+                return fn(self, v, *args, **kwargs)
+        return fn(self, v, *args, **kwargs)
+    return wrapped
+
+
+_STD_NORMAL_CACHE = {}
+
+
+def is_std_normal(base_dist, D=None) -> bool:
+    """True when `base_dist` is N(0, I): torch.distributions Normal(0, 1) (scalar or [D] parameters), Independent of
+    it, or MultivariateNormal with zero mean and identity covariance -- the case every caller of the reference uses
+    (README.md:113-114, plots/_common.py:201-202).  Reading the parameters costs one device sync, so the verdict is
+    cached per distribution object (torch distributions are immutable)."""
+    if base_dist is None:
+        return True
+    key = id(base_dist)
+    hit = _STD_NORMAL_CACHE.get(key)
+    if hit is not None and hit[0]() is base_dist:
+        return hit[1]
+    import weakref
+    from torch import distributions as td
+    ok = False
+    try:
+        d = base_dist
+        if isinstance(d, td.Independent):
+            d = d.base_dist
+        if type(d) is td.Normal:
+            ok = bool((d.loc == 0).all()) and bool((d.scale == 1).all()) and d.loc.dim() <= 1
+            if ok and D is not None and d.loc.dim() == 1 and d.loc.numel() not in (1, D):
+                ok = False
+        elif type(d) is td.MultivariateNormal and d is base_dist:
+            n = d.loc.shape[-1]
+            eye = torch.eye(n, dtype=d.loc.dtype, device=d.loc.device)
+            ok = d.loc.dim() == 1 and bool((d.loc == 0).all()) and bool((d.scale_tril == eye).all())
+            if ok and D is not None and n != D:
+                ok = False
+    except Exception:
+        ok = False
+    if len(_STD_NORMAL_CACHE) > 64:
+        _STD_NORMAL_CACHE.clear()
+    try:
+        _STD_NORMAL_CACHE[key] = (weakref.ref(base_dist), ok)
+    except TypeError:
+        pass
+    return ok
+
+
+def _default_base(D, device, dtype=torch.float32):
+    from torch import distributions as td
+    return td.Normal(torch.zeros(D, device=device, dtype=dtype), torch.ones(D, device=device, dtype=dtype))
+
+
+def flow_log_prob(flow, x, base_dist, fused_head=None):
+    """Flow.log_prob (flow.py:56-73).  For a standard-normal base the head log N(z; 0, I) + log_det is one kernel
+    (nf_std_normal_log_prob_*, with a backward), or -- `fused_head`, no autograd graph needed -- part of the last
+    layer's epilogue of the fused stack launch; any other base goes through the torch distribution on the returned z."""
+    D = x.shape[-1] if x.dim() == 2 else None
+    std = x.is_cuda and x.dim() == 2 and is_std_normal(base_dist, D)
+    if std and fused_head is not None:
+        with torch.cuda.device(x.device):
+            lp = fused_head(x)
+        if lp is not None:
+            return lp
+    z, log_det_inv = flow.inverse(x)
+    if std and z.dtype in (torch.float32, torch.float64):
+        return ops.std_normal_log_prob(z, log_det_inv)
+    log_p_z = base_dist.log_prob(z)
+    if log_p_z.dim() > 1:
+        log_p_z = log_p_z.sum(dim=1)
+    return log_p_z + log_det_inv
+
+
 def _module_tensors(module: nn.Module):
     return list(module.parameters()) + list(module.buffers())
 
@@ -57,8 +139,8 @@ class _PackCache:
         self._tensors = None
         self._owner_ids = None
 
-    def get(self, tensors, build):
-        key = packing.tensors_key(tensors)
+    def get(self, tensors, build, extra=()):
+        key = packing.tensors_key(tensors, extra)
         if key != self._key:
             self._val = build()
             self._key = key
@@ -121,12 +203,9 @@ class Flow(nn.Module):
         return x
 
     def log_prob(self, x, base_dist):
-        """flow.py:56-73: log p(z) (summed over the event axis if the base is factorised) + log|det J_inv|."""
-        z, log_det_inv = self.inverse(x)
-        log_p_z = base_dist.log_prob(z)
-        if log_p_z.dim() > 1:
-            log_p_z = log_p_z.sum(dim=1)
-        return log_p_z + log_det_inv
+        """flow.py:56-73: log p(z) (summed over the event axis if the base is factorised) + log|det J_inv|.
+        A standard-normal base is detected (is_std_normal) and evaluated by the fused head kernels."""
+        return flow_log_prob(self, x, base_dist, getattr(self, "_log_prob_fused", None))
 
 
 class SequentialFlow(Flow):
@@ -139,6 +218,11 @@ class SequentialFlow(Flow):
         self.flows = nn.ModuleList(flows)
         self._chain = ChainPlan()
 
+    def _log_prob_fused(self, x):
+        out = self._chain.run(self.flows, None, self.training, x, True, head=True)
+        return None if out is None else out[1]
+
+    @on_input_device
     def _run(self, v, inverse):
         fused = self._chain.run(self.flows, None, self.training, v, inverse)
         if fused is not None:
@@ -208,6 +292,7 @@ class CouplingLayer(Flow):
         return (not self.training and v.dtype == torch.float32 and self.s_net[0].weight.dtype == torch.float32
                 and self.data_dim <= packing.DMAX and self.s_net[0].out_features <= 128)
 
+    @on_input_device
     def _run(self, v, inverse):
         v = compute_input(v)
         if not wants_grad(self, v) and self.fusable(v):
@@ -289,13 +374,14 @@ class SplineCouplingLayer(Flow):
             tlist = torch.nonzero(self.mask.detach().to("cpu") == 0).flatten().tolist()
             tidx = torch.tensor(tlist, dtype=torch.int32, device=v.device)
             return tidx, packing.rescale_tensors(self, self.data_dim, v.dtype, v.device), tlist
-        return self._aux.get([self.mask, torch.empty(0, dtype=v.dtype, device=v.device)], build)
+        return self._aux.get([self.mask], build, extra=(v.dtype, v.device))
 
     def fusable(self, v):
         return (v.dtype == torch.float32 and self.param_net[0].weight.dtype == torch.float32
                 and self.data_dim <= packing.DMAX and self.param_net[0].out_features <= 128
                 and 2 <= self.num_bins <= 16)
 
+    @on_input_device
     def _run(self, v, inverse):
         v = compute_input(v)
         if not wants_grad(self, v) and self.fusable(v):
@@ -371,6 +457,7 @@ class MaskedLinear(nn.Linear):
         super().__init__(in_features, out_features, bias)
         self.register_buffer("mask", mask)
 
+    @on_input_device
     def forward(self, input):
         return ops.linear(input, self.weight, self.bias, mask=self.mask)
 
@@ -472,6 +559,7 @@ class _AffineAutoregressive(Flow):
         self.dim = dim
         self.conditioner = MADE(dim, hidden_dim, 2, use_batch_norm=use_batch_norm)
 
+    @on_input_device
     def _parallel(self, v):
         v = compute_input(v)
         if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
@@ -480,6 +568,7 @@ class _AffineAutoregressive(Flow):
                 return ops.made_affine(v, f, self._mode_parallel)
         return ops.affine_ar(v, self.conditioner(v), self._mode_parallel)
 
+    @on_input_device
     def _sequential(self, v):
         v = compute_input(v)
         if not wants_grad(self, v) and not (self.conditioner.use_batch_norm and self.training):
@@ -554,6 +643,7 @@ class ARQS(Flow):
             return ops.feature_affine(v, lo, span, None, None)
         return ops.feature_affine(v, None, None, span, lo)
 
+    @on_input_device
     def _run(self, v, inverse):
         v = compute_input(v)
         vr = self._rescale(v, True)
@@ -577,41 +667,38 @@ class ARQS(Flow):
 USE_TENSOR_CORES = True      # tcgen05 stack kernels (3xTF32, fp32-accurate); False forces the FP32-pipe kernels
 
 
-def run_spline_stack(cache: _PackCache, tensors, flows, bns, v, inverse):
+def run_spline_stack(cache: _PackCache, tensors, flows, bns, v, inverse, head=False):
     """Spline-coupling stack in one launch: tcgen05 kernel when the configuration fits it, FP32-pipe kernel otherwise."""
     def build():
         tcp = packing.pack_spline_stack_tc(flows, bns) if USE_TENSOR_CORES else None
         return ("tc", tcp) if tcp is not None else ("simt", packing.pack_spline_stack(flows, bns))
-    kind, pk = cache.get(tensors + [_TC_FLAG[USE_TENSOR_CORES]], build)
+    kind, pk = cache.get(tensors, build, extra=(USE_TENSOR_CORES,))
     if pk is None:
         return None
     if kind == "tc":
-        out = ops.spline_stack_tc(pk[0], pk[1], v, inverse)
+        out = ops.spline_stack_tc(pk[0], pk[1], v, inverse, head)
         if out is not None:
             return out
         pk = packing.pack_spline_stack(flows, bns)
-        return None if pk is None else ops.spline_stack(pk[0], pk[1], v, inverse)
-    return ops.spline_stack(pk[0], pk[1], v, inverse)
+        return None if pk is None else ops.spline_stack(pk[0], pk[1], v, inverse, head)
+    return ops.spline_stack(pk[0], pk[1], v, inverse, head)
 
 
-def run_coupling_stack(cache: _PackCache, tensors, flows, bns, v, inverse):
+def run_coupling_stack(cache: _PackCache, tensors, flows, bns, v, inverse, head=False):
     """Eval-mode affine coupling stack in one launch: tcgen05 kernel when hidden_dim <= 64, FP32-pipe kernel otherwise."""
     def build():
         tcp = packing.pack_coupling_stack_tc(flows, bns) if USE_TENSOR_CORES else None
         return ("tc", tcp) if tcp is not None else ("simt", packing.pack_coupling_stack(flows, bns))
-    kind, pk = cache.get(tensors + [_TC_FLAG[USE_TENSOR_CORES]], build)
+    kind, pk = cache.get(tensors, build, extra=(USE_TENSOR_CORES,))
     if pk is None:
         return None
     if kind == "tc":
-        out = ops.coupling_stack_tc(pk[0], pk[1], v, inverse)
+        out = ops.coupling_stack_tc(pk[0], pk[1], v, inverse, head)
         if out is not None:
             return out
         pk = packing.pack_coupling_stack(flows, bns)
-        return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse)
-    return ops.coupling_stack(pk[0], pk[1], v, inverse)
-
-
-_TC_FLAG = {True: torch.zeros(1), False: torch.zeros(2)}     # distinct cache-key tensors for the two settings
+        return None if pk is None else ops.coupling_stack(pk[0], pk[1], v, inverse, head)
+    return ops.coupling_stack(pk[0], pk[1], v, inverse, head)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -625,8 +712,10 @@ class ChainPlan:
     def __init__(self):
         self._pack = _PackCache()
 
-    def run(self, flows, bns, training, v, inverse):
-        """(y, log_det) from one fused launch, or None when the chain must be walked layer by layer."""
+    def run(self, flows, bns, training, v, inverse, head=False):
+        """(y, log_det) from one fused launch, or None when the chain must be walked layer by layer.
+        head=True (inverse only): (None, log_prob) with the standard-normal Flow.log_prob head evaluated in the last
+        layer's epilogue -- z is never written."""
         flows = list(flows)
         v = compute_input(v)
         if not flows or not v.is_cuda or v.dim() != 2:
@@ -643,5 +732,5 @@ class ChainPlan:
         if torch.is_grad_enabled() and (v.requires_grad or any(t.requires_grad for t in tensors)):
             return None
         if kind is CouplingLayer:
-            return run_coupling_stack(self._pack, tensors, flows, bns, v, inverse)
-        return run_spline_stack(self._pack, tensors, flows, bns, v, inverse)
+            return run_coupling_stack(self._pack, tensors, flows, bns, v, inverse, head)
+        return run_spline_stack(self._pack, tensors, flows, bns, v, inverse, head)

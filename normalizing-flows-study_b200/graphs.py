@@ -14,6 +14,8 @@ from __future__ import annotations
 
 import torch
 
+from . import packing
+
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, loss_fn, example_input, warmup=3, sync_gradients=None):
@@ -47,4 +49,7 @@ class GraphedTrainStep:
         if x is not None:
             self.static_input.copy_(x, non_blocking=True)
         self.graph.replay()
+        # the replay moved the weights (and BatchNorm statistics) without running any Python: no version counter
+        # changed, so the derived weight layouts cached by the eval routes must be dropped explicitly
+        packing.invalidate_caches()
         return self.static_loss.detach()

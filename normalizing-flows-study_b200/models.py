@@ -10,10 +10,32 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .flows import ChainPlan, CouplingLayer, SplineCouplingLayer
+from .flows import ChainPlan, CouplingLayer, SplineCouplingLayer, _default_base, flow_log_prob, on_input_device
 
 
-class NormalizingFlowModel(nn.Module):
+class _DensityAPI:
+    """log_prob / sample on the model containers (north_star: `NormalizingFlowModel.log_prob/sample`; same meaning as
+    Flow.log_prob / Flow.sample, flow.py:40-73).  base_dist=None means the standard normal N(0, I); a standard-normal
+    base is evaluated by the fused head (one launch for a fused stack, z never written)."""
+
+    def _data_dim(self):
+        flows = self.flows if hasattr(self, "flows") else self.flow.flows
+        return getattr(flows[0], "data_dim", None)
+
+    def log_prob(self, x, base_dist=None):
+        return flow_log_prob(self, x, base_dist, getattr(self, "_log_prob_fused", None))
+
+    def sample(self, num_samples, base_dist=None, device=None):
+        if device is None:
+            device = next(self.parameters()).device
+        if base_dist is None:
+            base_dist = _default_base(self._data_dim(), device)
+        z = base_dist.sample((num_samples,)).to(device)
+        x, _ = self.forward(z)
+        return x
+
+
+class NormalizingFlowModel(_DensityAPI, nn.Module):
     """Chain of flow layers, optionally with an invertible BatchNorm affine between consecutive layers.
 
     The between-layer BatchNorm always transforms with its *running* statistics (so that forward, inverse and
@@ -56,6 +78,11 @@ class NormalizingFlowModel(nn.Module):
     def _bns(self):
         return self.batch_norms if self.batch_norm_between_layers else None
 
+    def _log_prob_fused(self, x):
+        out = self._chain.run(self.flows, self._bns(), self.training, x, True, head=True)
+        return None if out is None else out[1]
+
+    @on_input_device
     def forward(self, z):
         """Sampling direction z -> x (:25-46)."""
         fused = self._chain.run(self.flows, self._bns(), self.training, z, False)
@@ -72,6 +99,7 @@ class NormalizingFlowModel(nn.Module):
                 log_det_sum = log_det_sum + self._batch_norm_log_det_jacobian(bn, z)
         return z, log_det_sum
 
+    @on_input_device
     def inverse(self, x):
         """Density direction x -> z (:48-65)."""
         fused = self._chain.run(self.flows, self._bns(), self.training, x, True)
@@ -97,12 +125,15 @@ def _half_masks(data_dim, n_layers):
     return [first.clone() if i % 2 == 0 else 1 - first for i in range(n_layers)]
 
 
-class RealNVP(nn.Module):
+class RealNVP(_DensityAPI, nn.Module):
     def __init__(self, data_dim, n_layers, hidden_dim, batch_norm_between_layers=False):
         super().__init__()
         assert n_layers % 2 == 0, "Number of layers must be even to ensure all dimensions are transformed."
         layers = [CouplingLayer(data_dim, hidden_dim, m) for m in _half_masks(data_dim, n_layers)]
         self.flow = NormalizingFlowModel(layers, batch_norm_between_layers)
+
+    def _log_prob_fused(self, x):
+        return self.flow._log_prob_fused(x)
 
     def forward(self, z):
         return self.flow.forward(z)
@@ -111,12 +142,15 @@ class RealNVP(nn.Module):
         return self.flow.inverse(x)
 
 
-class RealNVPSpline(nn.Module):
+class RealNVPSpline(_DensityAPI, nn.Module):
     def __init__(self, data_dim, n_layers, hidden_dim, batch_norm_between_layers=False):
         super().__init__()
         assert n_layers % 2 == 0, "Number of layers must be even to ensure all dimensions are transformed."
         layers = [SplineCouplingLayer(data_dim, hidden_dim, m) for m in _half_masks(data_dim, n_layers)]
         self.flow = NormalizingFlowModel(layers, batch_norm_between_layers)
+
+    def _log_prob_fused(self, x):
+        return self.flow._log_prob_fused(x)
 
     def forward(self, z):
         return self.flow.forward(z)

@@ -12,6 +12,8 @@ current CUDA stream.  Nothing here has a CPU implementation.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -82,7 +84,7 @@ class MaskPlan:
     """Zero structure of a 2-D weight mask [N, K] (MaskedLinear.mask, masked_linear.py:10): the K ranges / tiles the
     tensor-core GEMMs of the layer may skip.  MADE masks are block lower-triangular once the hidden units are sorted
     by degree (they are for data_dim > 2, made.py:36), so ~44 % of the 128 x 128 tiles are exactly zero."""
-    __slots__ = ("k_extent", "k_begin_t", "tile_live", "live_fraction")
+    __slots__ = ("k_extent", "k_begin_t", "tile_live", "live_fraction", "owner")
 
 
 _MASK_PLANS = {}
@@ -91,8 +93,13 @@ _MASK_PLANS = {}
 def mask_plan(mask):
     if mask is None or mask.dim() != 2 or mask.shape[0] < 256 or mask.shape[1] < 256:
         return None
-    key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
+    from . import packing
+    key = (id(mask), packing.tensors_key([mask]), tuple(mask.shape))
     plan = _MASK_PLANS.get(key)
+    # the entry pins its mask through a weak reference: a freed mask's address (and id) may be handed to a new mask
+    # of the same shape with different degrees, whose zero structure must not be taken from the stale plan
+    if plan is not None and plan.owner() is not mask:
+        plan = None
     if plan is None:
         if len(_MASK_PLANS) > 256:
             _MASK_PLANS.clear()
@@ -116,6 +123,7 @@ def mask_plan(mask):
         live = padded.view(tn, 128, tk, 128).any(dim=3).any(dim=1)
         plan.tile_live = live.to(torch.uint8).contiguous().view(-1)
         plan.live_fraction = float(live.float().mean())
+        plan.owner = weakref.ref(mask)
         _MASK_PLANS[key] = plan
     return plan if plan.live_fraction < 0.95 else None
 
@@ -574,46 +582,55 @@ def std_normal_log_prob(z, log_det=None):
 # --------------------------------------------------------------------------------------------
 # fused inference launches
 # --------------------------------------------------------------------------------------------
-def spline_stack(packed, hdr_host, x, inverse):
+STACK_INVERSE, STACK_LOG_PROB_HEAD, STACK_SKIP_Y = 1, 2, 4      # csrc/stack_small.cuh
+
+
+def _stack_flags(inverse, head):
+    """Flag word of the fused stack entry points.  head=True: the per-row output is the Flow.log_prob value
+    log N(z; 0, I) + log_det (flow.py:56-73) computed in the last layer's epilogue, and z is not stored."""
+    return (STACK_INVERSE if inverse else 0) | ((STACK_LOG_PROB_HEAD | STACK_SKIP_Y) if head else 0)
+
+
+def spline_stack(packed, hdr_host, x, inverse, head=False):
     """Whole spline-coupling stack in one launch; returns None if the configuration is unsupported."""
     x = _c(x)
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = None if head else torch.empty_like(x)
     ld = torch.empty(B, dtype=x.dtype, device=x.device)
     ok = L.try_call("nf_spline_stack_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
-                    ptr(ld), B, int(inverse), stream())
+                    ptr(ld), B, _stack_flags(inverse, head), stream())
     return (y, ld) if ok else None
 
 
-def spline_stack_tc(packed, hdr_host, x, inverse):
+def spline_stack_tc(packed, hdr_host, x, inverse, head=False):
     """Tensor-core (tcgen05) variant of spline_stack; returns None if the configuration is unsupported."""
     x = _c(x)
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = None if head else torch.empty_like(x)
     ld = torch.empty(B, dtype=x.dtype, device=x.device)
     ok = L.try_call("nf_spline_stack_tc_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
-                    ptr(ld), B, int(inverse), stream())
+                    ptr(ld), B, _stack_flags(inverse, head), stream())
     return (y, ld) if ok else None
 
 
-def coupling_stack_tc(packed, hdr_host, x, inverse):
+def coupling_stack_tc(packed, hdr_host, x, inverse, head=False):
     """Tensor-core (tcgen05) variant of coupling_stack; returns None if the configuration is unsupported."""
     x = _c(x)
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = None if head else torch.empty_like(x)
     ld = torch.empty(B, dtype=x.dtype, device=x.device)
     ok = L.try_call("nf_coupling_stack_tc_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
-                    ptr(ld), B, int(inverse), stream())
+                    ptr(ld), B, _stack_flags(inverse, head), stream())
     return (y, ld) if ok else None
 
 
-def coupling_stack(packed, hdr_host, x, inverse):
+def coupling_stack(packed, hdr_host, x, inverse, head=False):
     x = _c(x)
     B, D = x.shape
-    y = torch.empty_like(x)
+    y = None if head else torch.empty_like(x)
     ld = torch.empty(B, dtype=x.dtype, device=x.device)
     ok = L.try_call("nf_coupling_stack_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x),
-                    ptr(y), ptr(ld), B, int(inverse), stream())
+                    ptr(y), ptr(ld), B, _stack_flags(inverse, head), stream())
     return (y, ld) if ok else None
 
 

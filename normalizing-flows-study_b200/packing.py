@@ -23,9 +23,28 @@ MAGIC_AFFINE_TC = 0x4E464132
 HDR, LAYER_HDR, DMAX = 16, 80, 8
 
 
-def tensors_key(tensors):
-    """Cache key that changes when any tensor is modified in place, re-assigned or moved."""
-    return tuple((t.data_ptr(), t._version, t.device.index, t.dtype) for t in tensors if t is not None)
+_generation = 0
+
+
+def invalidate_caches() -> None:
+    """Drop every derived weight layout (fused stack packs, folded MADE weights, TF32 splits, mask plans) at its next
+    use.  Needed after updates that autograd's version counters cannot see: a CUDA-graph replay that contains the
+    optimizer step (graphs.GraphedTrainStep calls this itself), `p.data.<op>_()` writes (the reference's EMA code,
+    consistency_flow.py:28), raw-pointer writes from another library."""
+    global _generation
+    _generation += 1
+
+
+def _version_of(t):
+    # inference tensors (created under torch.inference_mode) do not track a version counter
+    return -1 if t.is_inference() else t._version
+
+
+def tensors_key(tensors, extra=()):
+    """Cache key that changes when any tensor is modified in place, re-assigned or moved, or when
+    invalidate_caches() was called.  `extra`: plain hashable components (dtypes, devices, flags)."""
+    return (_generation, tuple(extra)) + tuple(
+        (t.data_ptr(), _version_of(t), t.device.index, t.dtype) for t in tensors if t is not None)
 
 
 def _np(t, dtype=np.float64):

@@ -13,6 +13,8 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import packing
+
 
 def shard_bounds(n_rows: int, rank: int, world: int):
     """Contiguous balanced row range [lo, hi) of `rank`: the first n_rows % world ranks get one extra row."""
@@ -79,7 +81,8 @@ class DataParallelFlow(nn.Module):
     def broadcast_parameters(self, src: int = 0):
         """Rank `src`'s parameters and buffers overwrite everyone's (start of training / after loading)."""
         for t in list(self.module.parameters()) + list(self.module.buffers()):
-            dist.broadcast(t.data, src=src, group=self.process_group)
+            dist.broadcast(t, src=src, group=self.process_group)      # on the tensor itself: bumps its version
+        packing.invalidate_caches()
 
     def _buckets(self):
         params = [p for p in reversed(list(self.module.parameters())) if p.requires_grad]
@@ -229,8 +232,9 @@ class DataParallelFlow(nn.Module):
             return
         for b in self.module.buffers():
             if b.is_floating_point() and ("running_mean" in _name_of(self.module, b) or "running_var" in _name_of(self.module, b)):
-                dist.all_reduce(b.data, op=dist.ReduceOp.SUM, group=self.process_group)
-                b.data.div_(world)
+                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.process_group)
+                b.div_(world)
+        packing.invalidate_caches()
 
 
 def _name_of(module, buf):
