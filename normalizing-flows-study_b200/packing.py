@@ -231,9 +231,15 @@ class FoldedMade:
 
 
 def fold_made(made) -> Optional[FoldedMade]:
-    if made.use_batch_norm or made.output_dim_multiplier != 2:
+    """Eval-mode BatchNorm (use_batch_norm=True, made.py:93-108) is a per-unit affine on running statistics: it is
+    folded into the rows of the preceding masked linear, which leaves the mask's zero structure untouched.  (Callers
+    take the layered route in train mode, where the statistics come from the batch.)"""
+    if made.output_dim_multiplier != 2:
         return None
     lin = [m for m in made.net if hasattr(m, "mask")]
+    bns = [m for m in made.net if isinstance(m, torch.nn.BatchNorm1d)]
+    if made.use_batch_norm and (len(bns) != 3 or any(bn.running_mean is None for bn in bns)):
+        return None
     D, H = made.input_dim, made.hidden_dim
     deg = np.asarray(made.m[0]).astype(np.int64)
     perm = np.argsort(deg, kind="stable")
@@ -242,10 +248,16 @@ def fold_made(made) -> Optional[FoldedMade]:
     p = torch.as_tensor(perm, device=dev)
     with torch.no_grad():
         eff = [l.weight * l.mask.to(l.weight.dtype) for l in lin]
+        bias = [l.bias for l in lin]
+        if made.use_batch_norm:
+            for i, bn in enumerate(bns):
+                sc = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                eff[i] = eff[i] * sc[:, None]
+                bias[i] = (bias[i] - bn.running_mean) * sc + bn.bias
         w = [eff[0][p].contiguous(), eff[1][p][:, p].contiguous(), eff[2][p][:, p].contiguous(),
              eff[3][:, p].contiguous()]
-        b = [lin[0].bias[p].contiguous(), lin[1].bias[p].contiguous(), lin[2].bias[p].contiguous(),
-             lin[3].bias.detach().contiguous()]
+        b = [bias[0][p].contiguous(), bias[1][p].contiguous(), bias[2][p].contiguous(),
+             bias[3].detach().contiguous()]
     gstart = np.searchsorted(sdeg, np.arange(D + 1), side="left").astype(np.int32)   # #units with degree < g
     # k-extents per 64 output columns
     def hh_ext():

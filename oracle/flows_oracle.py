@@ -275,15 +275,20 @@ def made_masks(D: int, H: int, mult: int = 2):
             torch.from_numpy(m2)]
 
 
-def made(sd: SD, p: str, x: Tensor) -> Tensor:
-    """MADE.forward with use_batch_norm=False: 4 masked linears, 3 ReLU
-    (made.py:81-140; keys net.{0,2,4,6}.{weight,bias,mask})."""
+def made(sd: SD, p: str, x: Tensor, training=False, update=False) -> Tensor:
+    """MADE.forward: 4 masked linears, 3 ReLU (made.py:81-140).  use_batch_norm=False: keys net.{0,2,4,6}.*;
+    use_batch_norm=True: a BatchNorm1d after each of the first three masked linears (made.py:93-108), keys
+    net.{0,3,6,9}.* for the linears and net.{1,4,7}.* for the BatchNorms -- detected from the state_dict."""
+    bn = f"{p}net.1.running_mean" in sd
+    idxs = (0, 3, 6, 9) if bn else (0, 2, 4, 6)
     h = x
-    for i, idx in enumerate((0, 2, 4, 6)):
+    for i, idx in enumerate(idxs):
         W = sd[f"{p}net.{idx}.weight"]
         mk = sd[f"{p}net.{idx}.mask"].to(dtype=W.dtype)             # masked_linear.py:17
         h = F.linear(h, W * mk, sd[f"{p}net.{idx}.bias"])           # masked_linear.py:18
         if i < 3:
+            if bn:
+                h = _bn1d(sd, f"{p}net.{idx + 1}", h, training, update)
             h = torch.relu(h)
     return h
 
@@ -291,8 +296,8 @@ def made(sd: SD, p: str, x: Tensor) -> Tensor:
 # --------------------------------------------------------------------------- #
 # a11/a12  MAF  (masked_autoregressive_flow.py:18-78)
 # --------------------------------------------------------------------------- #
-def maf_inverse(sd: SD, p: str, x: Tensor) -> Tuple[Tensor, Tensor]:
-    mu, alpha = made(sd, p + "conditioner.", x).chunk(2, dim=1)
+def maf_inverse(sd: SD, p: str, x: Tensor, training=False, update=False) -> Tuple[Tensor, Tensor]:
+    mu, alpha = made(sd, p + "conditioner.", x, training, update).chunk(2, dim=1)
     alpha = torch.clamp(alpha, min=-3, max=3)
     z = (x - mu) * torch.exp(torch.clamp(-alpha, min=-5, max=5))
     ld = _scrub_zero(-torch.sum(alpha, dim=1))
@@ -317,8 +322,8 @@ def maf_forward(sd: SD, p: str, z: Tensor) -> Tuple[Tensor, Tensor]:
 # --------------------------------------------------------------------------- #
 # a13  IAF  (inverse_autoregressive_flow.py:30-103)
 # --------------------------------------------------------------------------- #
-def iaf_forward(sd: SD, p: str, z: Tensor) -> Tuple[Tensor, Tensor]:
-    mu, alpha = made(sd, p + "conditioner.", z).chunk(2, dim=1)
+def iaf_forward(sd: SD, p: str, z: Tensor, training=False, update=False) -> Tuple[Tensor, Tensor]:
+    mu, alpha = made(sd, p + "conditioner.", z, training, update).chunk(2, dim=1)
     alpha = torch.clamp(alpha, min=-2, max=2)
     mu = torch.clamp(mu, min=-10, max=10)
     x = z * torch.exp(torch.clamp(alpha, min=-3, max=3)) + mu

@@ -33,10 +33,10 @@ def build(g, sd=None):
         m = N.CouplingLayer(g["D"], g["H"], sd["mask"].clone())
     elif k == "spline":
         m = N.SplineCouplingLayer(g["D"], g["H"], sd["mask"].clone(), num_bins=g["K"], **g["extra"])
-    elif k == "maf":
-        m = N.MaskedAutoregressiveFlow(g["D"], g["H"])
-    elif k == "iaf":
-        m = N.InverseAutoregressiveFlow(g["D"], g["H"])
+    elif k in ("maf", "maf_train"):
+        m = N.MaskedAutoregressiveFlow(g["D"], g["H"], use_batch_norm=g.get("use_batch_norm", False))
+    elif k in ("iaf", "iaf_train"):
+        m = N.InverseAutoregressiveFlow(g["D"], g["H"], use_batch_norm=g.get("use_batch_norm", False))
     elif k == "arqs":
         m = N.ARQS(g["D"], hidden_dim=g["H"], num_bins=g["K"], **g["extra"])
     elif k in ("realnvp", "realnvp_train"):

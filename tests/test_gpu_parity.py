@@ -2,6 +2,9 @@
   * the committed golden vectors produced by the unmodified reference (tests/golden), and
   * the CPU oracle on seeded inputs.
 Tolerances (north_star): z within 1e-5*max(1,|z|), row log-det within 1e-4 absolute; written at each assert."""
+import json
+import os
+
 import pytest
 import torch
 
@@ -70,25 +73,40 @@ def _conditioning(g, name, inverse):
     return _COND[key]
 
 
+FALLBACK_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_fallbacks.jsonl")
+MAX_FALLBACK_FRACTION = 1e-3     # at most 0.1 % of a comparison's elements (and never fewer than 2 allowed) may need a fallback clause
+
+
 def _within(mine, ref32, ref64, atol, rtol, what, cond=None):
-    """|mine-ref32| <= atol + rtol|ref32|; on ill-conditioned elements, where the reference's own float32 result is
-    already that far from the float64 truth, within tolerance + 2x the reference's own error (+ half its worst
-    error over the batch) of the float64 oracle; and, last, + 2x the element's measured 1-ulp weight-noise
-    sensitivity (`cond`, a callable evaluated only when needed)."""
+    """Per-element clauses only:
+      (1) strict      |mine-ref32| <= atol + rtol|ref32|                                       (north_star's bound)
+      (2) fallback A  ill-conditioned element, i.e. the reference's own float32 result is already e_ref away from its
+                      float64 result: |mine-ref64| <= atol + rtol|ref64| + 2*e_ref  (THIS element's e_ref);
+      (3) fallback B  |mine-ref32| <= atol + rtol|ref32| + 2*c with c = THIS element's measured sensitivity of the
+                      float32 oracle to 1-ulp weight noise (`cond`, a callable evaluated only when needed).
+    The number of elements that needed (2) or (3) is printed, logged to gpurun_out/parity_fallbacks.jsonl and bounded."""
     mine, ref32 = mine.double(), ref32.double()
     assert torch.equal(torch.isnan(mine), torch.isnan(ref32)), f"{what}: NaN pattern differs"
-    ok = ((mine - ref32).abs() <= atol + rtol * ref32.abs()) | (mine == ref32)       # equal infinities are equal
+    strict = ((mine - ref32).abs() <= atol + rtol * ref32.abs()) | (mine == ref32) | torch.isnan(mine)   # equal infinities are equal
     e_ref = (ref32 - ref64).abs().nan_to_num(0.0, posinf=0.0)
-    thr64 = atol + rtol * ref64.abs() + 2 * e_ref + 0.5 * e_ref.max()
-    ok |= (mine - ref64).abs() <= thr64
-    ok |= torch.isnan(mine)
+    ok = strict | ((mine - ref64).abs() <= atol + rtol * ref64.abs() + 2 * e_ref)
     if not bool(ok.all()) and cond is not None:
-        c = cond()
-        ok |= (mine - ref32).abs() <= atol + rtol * ref32.abs() + 2 * c
+        ok |= (mine - ref32).abs() <= atol + rtol * ref32.abs() + 2 * cond()
+    n, n_fb = strict.numel(), int((ok & ~strict).sum())
+    print(f"[parity] {what}: {n} elements, {n_fb} through a fallback clause, worst |mine-ref32| "
+          f"{(mine - ref32).abs().nan_to_num(0.0, posinf=0.0).max().item() if n else 0.0:.3e}")
+    try:
+        os.makedirs(os.path.dirname(FALLBACK_LOG), exist_ok=True)
+        with open(FALLBACK_LOG, "a") as f:
+            f.write(json.dumps({"what": what, "elements": n, "fallback": n_fb}) + "\n")
+    except OSError:
+        pass
     bad = ~ok
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())} elements off, worst |mine-ref32| "
                                  f"{(mine - ref32).abs()[bad].max().item():.3e}, reference's own fp32 error "
                                  f"max {e_ref.max().item():.3e}")
+    assert n_fb <= max(2, int(MAX_FALLBACK_FRACTION * n)), (
+        f"{what}: {n_fb} of {n} elements pass only through a fallback clause")
 
 
 def _compare(g, y, ld, key, tag, name):
@@ -185,6 +203,24 @@ def test_train_mode_coupling_batch_statistics(name):
         y, ld = m.forward(g["x"].to(_dev()))
     assert_close(y, g["fwd"], Z_ATOL, Z_RTOL, name + " z")
     assert_close(ld, g["fwd_ld"], LD_ATOL, LD_RTOL, name + " ld")
+    after = m.state_dict()
+    for k, v in g["sd_after"].items():
+        if v.is_floating_point():
+            assert_close(after[k], v, 1e-6, 1e-5, f"{name} {k}")
+        else:
+            assert torch.equal(after[k].cpu(), v), k
+
+
+@pytest.mark.parametrize("name", G.golden_names("mafbn_train") + G.golden_names("iafbn_train"))
+def test_train_mode_made_batch_norm(name):
+    """MAF / IAF with use_batch_norm=True in train mode, parallel direction: batch statistics + running-stat updates."""
+    g = G.load(name)
+    m = build(g).to(_dev())
+    m.train()
+    with torch.no_grad():
+        y, ld = m.inverse(g["x"].to(_dev())) if g["kind"] == "maf_train" else m.forward(g["x"].to(_dev()))
+    assert_close(y, g["out"], Z_ATOL, Z_RTOL, name + " z")
+    assert_close(ld, g["out_ld"], LD_ATOL, LD_RTOL, name + " ld")
     after = m.state_dict()
     for k, v in g["sd_after"].items():
         if v.is_floating_point():

@@ -194,3 +194,163 @@ def test_reference_flow_profiler_recipe(make, shape):
             assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(log_det).all())
         assert torch.cuda.max_memory_allocated() > 0
     assert sum(p.numel() for p in flow.parameters()) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: cache invalidation, inference mode, mask plans, fused log-prob head (VERDICT f1)
+# ------------------------------------------------------------------------------------------------
+def _nll(model, x):
+    z, ld = model.inverse(x)
+    return -(N.ops.std_normal_log_prob(z, ld)).mean()
+
+
+@pytest.mark.parametrize("kind", ["spline", "realnvp", "maf"])
+def test_eval_after_graph_replay_sees_the_new_weights(kind):
+    """eval (packs built) -> CUDA-graph replays that contain the optimizer step -> eval: the replay bumps no version
+    counter, so GraphedTrainStep must invalidate the derived weight layouts itself."""
+    torch.manual_seed(0)
+    m = {"spline": lambda: N.RealNVPSpline(2, 2, 16), "realnvp": lambda: N.RealNVP(2, 2, 16),
+         "maf": lambda: N.MaskedAutoregressiveFlow(8, 32)}[kind]().to(DEV)
+    D = 8 if kind == "maf" else 2
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(512, D, device=DEV)
+    xe = torch.randn(300, D, device=DEV)
+    m.eval()
+    with torch.no_grad():
+        z0, _ = m.inverse(xe)                                     # builds the fused packs from the initial weights
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-2, capturable=True)
+    step = N.graphs.GraphedTrainStep(m, opt, _nll, x)
+    for _ in range(5):
+        step(x)
+    m.eval()
+    with torch.no_grad():
+        z1, ld1 = m.inverse(xe)                                   # fused route, must use the replayed weights
+    xr = xe.clone().requires_grad_()
+    z2, ld2 = m.inverse(xr)                                       # layered route reads the parameters directly
+    assert not torch.allclose(z0, z1), "training did not move the model: the test would be vacuous"
+    assert torch.allclose(z1, z2.detach(), rtol=1e-5, atol=1e-5), (z1 - z2).abs().max().item()
+    assert torch.allclose(ld1, ld2.detach(), rtol=1e-5, atol=1e-4)
+
+
+def test_data_writes_are_covered_by_invalidate_caches():
+    """`p.data.add_()` (the reference's EMA pattern, consistency_flow.py:28) bumps no version counter either."""
+    torch.manual_seed(0)
+    m = N.RealNVPSpline(2, 2, 16).to(DEV).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(256, 2, device=DEV)
+    with torch.no_grad():
+        z0, _ = m.inverse(x)
+        for p in m.parameters():
+            p.data.add_(0.05 * torch.randn_like(p))
+        N.invalidate_caches()
+        z1, _ = m.inverse(x)
+    z2, _ = m.inverse(x.clone().requires_grad_())
+    assert not torch.allclose(z0, z1)
+    assert torch.allclose(z1, z2.detach(), rtol=1e-5, atol=1e-5)
+
+
+def test_inference_mode_on_every_route():
+    """torch.inference_mode tensors carry no version counter: the fused, wide (tcgen05 GEMM) and float64 layered routes
+    must all run there, as the reference does."""
+    torch.manual_seed(0)
+    wide = N.SplineCouplingLayer(16, 160, torch.tensor([1., 0.] * 8), num_bins=8).to(DEV).eval()      # D > 8: not fusable
+    small = N.RealNVPSpline(2, 2, 16).to(DEV).eval()
+    maf = N.MaskedAutoregressiveFlow(8, 32).to(DEV).eval()
+    with torch.no_grad():
+        for m in (wide, small, maf):
+            for p in m.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+    x16, x2, x8 = torch.randn(512, 16, device=DEV), torch.randn(512, 2, device=DEV), torch.randn(512, 8, device=DEV)
+    with torch.no_grad():
+        ref = [wide.inverse(x16), small.inverse(x2), maf.inverse(x8), maf.forward(x8)]
+    with torch.inference_mode():
+        got = [wide.inverse(x16.clone()), small.inverse(x2.clone()), maf.inverse(x8.clone()), maf.forward(x8.clone())]
+        w64 = copy.deepcopy(wide).double()
+        z64, _ = w64.inverse(x16.double())
+    for (a, b), (c, d) in zip(ref, got):
+        assert torch.equal(a, c) and torch.equal(b, d)
+    assert torch.allclose(z64.float(), ref[0][0], rtol=1e-4, atol=1e-4)
+
+
+def test_mask_plan_is_pinned_to_its_mask():
+    """A freed MADE mask's address can be handed to a new mask of the same shape with other degrees: the cached zero
+    structure must not be reused for it."""
+    from nfb200 import ops
+    a = N.MADE(64, 512).net[2].mask.to(DEV)                     # [512, 512], degrees of data_dim 64
+    pa = ops.mask_plan(a)
+    assert pa is not None
+    ext_a = pa.k_extent.clone()
+    ptr_a = a.data_ptr()
+    del a, pa
+    b = None
+    for _ in range(8):                                          # the caching allocator hands the block out again
+        b = N.MADE(16, 512).net[2].mask.to(DEV)
+        if b.data_ptr() == ptr_a:
+            break
+    pb = ops.mask_plan(b)
+    nz = b != 0
+    last = torch.where(nz, torch.arange(1, 513, device=DEV)[None, :], 0).amax(dim=1).view(-1, 64).amax(dim=1).to(torch.int32)
+    assert torch.equal(pb.k_extent, last)
+    assert not torch.equal(pb.k_extent, ext_a)
+
+
+@pytest.mark.parametrize("kind", ["spline_tc", "spline_simt", "coupling_tc", "coupling_simt", "spline_bn"])
+def test_fused_log_prob_head_matches_separate_head(kind, monkeypatch):
+    """Flow.log_prob with a standard-normal base: one launch, head in the last layer's epilogue, z not written."""
+    torch.manual_seed(0)
+    monkeypatch.setattr(N.flows, "USE_TENSOR_CORES", kind.endswith("_tc") or kind == "spline_bn")
+    if kind.startswith("spline"):
+        m = N.RealNVPSpline(2, 4, 64, batch_norm_between_layers=(kind == "spline_bn"))
+    else:
+        m = N.RealNVP(2, 4, 64)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        for name, b in m.named_buffers():                         # non-trivial between-layer BatchNorm statistics
+            if name.endswith("running_mean"):
+                b.add_(0.3 * torch.randn_like(b))
+            elif name.endswith("running_var"):
+                b.mul_(1.0 + 0.5 * torch.rand_like(b))
+    x = torch.randn(3000, 2, device=DEV)
+    base = torch.distributions.Normal(torch.zeros(2, device=DEV), torch.ones(2, device=DEV))
+    with torch.no_grad():
+        z, ld = m.inverse(x)
+        want = base.log_prob(z).sum(dim=1) + ld                   # the reference's formula in eager torch
+        before = N._lib.launch_count()
+        got = m.log_prob(x, base)
+        assert N._lib.launch_count() - before == 1, "log_prob must be ONE launch (head fused into the stack kernel)"
+        got_default = m.log_prob(x)
+        got_flow = m.flow.log_prob(x, torch.distributions.MultivariateNormal(torch.zeros(2, device=DEV), torch.eye(2, device=DEV)))
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (got - want).abs().max().item()
+    assert torch.equal(got, got_default) and torch.equal(got, got_flow)
+
+
+def test_log_prob_with_other_bases_and_gradients():
+    """Non-standard bases go through the torch distribution; a standard base with autograd uses the head kernel + backward."""
+    torch.manual_seed(0)
+    m = N.RealNVP(4, 2, 16).to(DEV)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    m.eval()
+    x = torch.randn(128, 4, device=DEV)
+    wide = torch.distributions.Normal(torch.zeros(4, device=DEV), 2 * torch.ones(4, device=DEV))
+    assert not N.flows.is_std_normal(wide, 4)
+    with torch.no_grad():
+        z, ld = m.inverse(x)
+        assert torch.allclose(m.log_prob(x, wide), wide.log_prob(z).sum(1) + ld, rtol=1e-6, atol=1e-6)
+    xr = x.clone().requires_grad_()
+    lp = m.log_prob(xr)
+    lp.sum().backward()
+    xr2 = x.clone().requires_grad_()
+    z2, ld2 = m.inverse(xr2)
+    ((-0.5 * z2 * z2).sum(1) - 2 * 1.8378770664093453 + ld2).sum().backward()
+    assert torch.allclose(xr.grad, xr2.grad, rtol=1e-5, atol=1e-6)
+    s = m.sample(77)
+    assert s.shape == (77, 4) and s.is_cuda and torch.isfinite(s).all()

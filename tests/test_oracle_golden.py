@@ -43,6 +43,20 @@ def test_oracle_train_mode_coupling(name):
         _same(sd[k], v)
 
 
+@pytest.mark.parametrize("name", G.golden_names("mafbn_train") + G.golden_names("iafbn_train"))
+def test_oracle_train_mode_made_batch_norm(name):
+    """MADE(use_batch_norm=True) in train mode: batch statistics + running-stat side effects (made.py:93-108)."""
+    g = G.load(name)
+    sd = {k: v.clone() for k, v in g["sd"].items()}
+    with torch.no_grad():
+        fn = O.maf_inverse if g["kind"] == "maf_train" else O.iaf_forward
+        y, ld = fn(sd, "", g["x"], training=True, update=True)
+    _same(y, g["out"])
+    _same(ld, g["out_ld"])
+    for k, v in g["sd_after"].items():
+        _same(sd[k], v)
+
+
 def test_oracle_train_mode_between_layer_bn():
     """normalizing_flow_model.py:74-79: running stats updated, affine uses running stats."""
     g = G.load("realnvp_4_4_16_bn_train")
