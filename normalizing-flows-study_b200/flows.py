@@ -196,13 +196,15 @@ class Flow(nn.Module):
     def inverse(self, x):
         raise NotImplementedError
 
-    def sample(self, num_samples, base_dist, device="cpu"):
-        """flow.py:40-54."""
+    def sample(self, num_samples, base_dist=None, device="cpu"):
+        """flow.py:40-54 (base_dist=None: standard normal over data_dim / dim)."""
+        if base_dist is None:
+            base_dist = _default_base(self.data_dim, device)
         z = base_dist.sample((num_samples,)).to(device)
         x, _ = self.forward(z)
         return x
 
-    def log_prob(self, x, base_dist):
+    def log_prob(self, x, base_dist=None):
         """flow.py:56-73: log p(z) (summed over the event axis if the base is factorised) + log|det J_inv|.
         A standard-normal base is detected (is_std_normal) and evaluated by the fused head kernels."""
         return flow_log_prob(self, x, base_dist, getattr(self, "_log_prob_fused", None))
@@ -491,7 +493,10 @@ class MADE(nn.Module):
         m_in = (d_in[None, :] <= d_h[:, None]).astype(np.float32)                  # [H, D]
         m_hh = (d_h[None, :] <= d_h[:, None]).astype(np.float32)                   # [H, H]
         m_out = np.tile((d_h[None, :] < d_out[:, None]).astype(np.float32), (self.output_dim_multiplier, 1))
-        return [torch.from_numpy(m_in), torch.from_numpy(m_hh), torch.from_numpy(m_out)]
+        # on torch's default device, like the nn.Linear parameters beside them (a model built under
+        # `with torch.device("cuda")` is then on one device as a whole)
+        dev = torch.get_default_device()
+        return [torch.from_numpy(m).to(dev) for m in (m_in, m_hh, m_out)]
 
     def create_network(self):
         """made.py:81-134 (xavier-normal gain 0.5 hidden layers, N(0, 0.01^2) final layer, zero biases)."""
