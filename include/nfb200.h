@@ -296,6 +296,21 @@ NF_API int nf_ar_blocked_forward(const void* v, const void* const* w, const void
                           void* out, void* ld, int64_t B, int D, int H, int mode, int block_degrees, nf_stream_t stream);
 NF_API int64_t nf_ar_blocked_workspace_floats(int64_t B, int D, int H);
 
+/* ---- a10 + a11 / a13 in ONE launch, bf16 tensor-core mode (csrc/made_chain_bf16.cu): MADE.forward (made.py:136-140, 4 masked
+ * linears + 3 ReLU) + MAF.inverse (masked_autoregressive_flow.py:18-44) / IAF.forward (inverse_autoregressive_flow.py:30-63)
+ * + row log-det; activations stay on the SM in bf16 (kind::f16 MMAs, fp32 accumulation), only x [B,D] fp32 is read and
+ * out [B,D] / ld [B] fp32 are written.  Reduced precision: bf16 operands (documented bounds in DESIGN.md) -- the fp32-parity
+ * path is nf_linear_tc x4 + nf_affine_ar_forward.
+ * w0 [H,64] (input layer, K zero-padded to 64), w1 / w2 [H,H], w3 [128,H] (rows 0..D-1 = mu rows, rows 64..64+D-1 = alpha
+ * rows, others zero): bf16, row-major, mask folded, hidden units sorted by degree; b0..b2 [H], b3 [128] (same row layout
+ * as w3): fp32.  kext16_host: HOST int32[16] = [layer][128-column block] number of 16-wide k-steps holding non-zero
+ * weights (the rest is skipped).  flags: bit 1 (2) = ld receives log N(out; 0, I) + log_det (Flow.log_prob head, flow.py:56-73);
+ * bit 2 (4) = out is not stored (may be NULL).  mode: NF_AR_MAF_INVERSE or NF_AR_IAF_FORWARD.
+ * NF_ERR_UNSUPPORTED unless D <= 64, D % 4 == 0, H % 128 == 0, H <= 512. */
+NF_API int nf_made_chain_bf16_forward(const void* x, const void* w0, const void* w1, const void* w2, const void* w3,
+                               const void* b0, const void* b1, const void* b2, const void* b3, const int32_t* kext16_host,
+                               void* out, void* ld, int64_t B, int D, int H, int mode, int flags, nf_stream_t stream);
+
 /* ---- unit-test hook of the tcgen05 tile primitive (csrc/tc_common.cuh): D[128,N] = A[128,64] * W[N,64]^T.
  * w_images: the hi then the lo K-major SWIZZLE_128B image of W (packing.umma_sw128_images); N % 16 == 0, <= 128;
  * passes: 3 = 3xTF32 (fp32-accurate), 1 = single TF32 pass; > 3 and nacc > 1 (independent accumulators) are for

@@ -25,7 +25,8 @@ def set_strict_fp32(flag: bool = True) -> None:
     ops.USE_TENSOR_CORE_GEMM = not flag
 
 
-_GEMM_PASSES = {"fp32": 3, "tf32": 1}
+_GEMM_PASSES = {"fp32": 3, "tf32": 1, "bf16": 1}
+GEMM_PRECISIONS = tuple(_GEMM_PASSES)
 _gemm_precision = "fp32"
 
 
@@ -37,11 +38,15 @@ def set_gemm_precision(mode: str = "fp32") -> None:
     bf16) with fp32 accumulation -- the reduced-precision conditioner-GEMM mode of BASELINE config C4 (what the reference
     reaches with `MixedPrecisionFlow` autocast, optimization/mixed_precision.py:89-105).  Spline / affine transform
     arithmetic, BatchNorm and log-det reductions stay fp32 in both modes; the fused data_dim <= 8 stacks are unaffected.
-    Measured bounds of the mode: DESIGN.md "Reduced-precision mode", tests/test_gpu_tensorcore.py."""
+    "bf16": the MADE-based flows (MAF.inverse / IAF.forward) run their whole parallel direction as ONE fused launch with
+    bf16 operands on the tensor cores (kind::f16 MMAs, fp32 accumulation, activations kept on the SM in bf16:
+    csrc/made_chain_bf16.cu); every other dense layer behaves as in "tf32".  Bounds: DESIGN.md, tests/test_gpu_bf16.py.
+    Measured bounds of the modes: DESIGN.md "Reduced-precision mode", tests/test_gpu_tensorcore.py."""
     global _gemm_precision
     if mode not in _GEMM_PASSES:
         raise ValueError(f"gemm precision must be one of {sorted(_GEMM_PASSES)}, got {mode!r}")
     _lib.call("nf_set_option", 7, _GEMM_PASSES[mode])
+    ops.MADE_CHAIN_BF16 = (mode == "bf16")
     _gemm_precision = mode
 
 

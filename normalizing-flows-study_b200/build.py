@@ -72,10 +72,12 @@ def build(force=False, verbose=True):
                 print(f"  nvcc {os.path.basename(obj)} {dt:.1f}s", flush=True)
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        # link beside the target and rename: a snapshot of the tree (gpurun) never sees a half-written library
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB + ".tmp"] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(LIB + ".tmp", LIB)
         if verbose:
             print(f"  linked {LIB}", flush=True)
     with open(lib_stamp, "w") as f:

@@ -1,0 +1,418 @@
+// made_chain_bf16.cu -- the whole parallel direction of an affine autoregressive flow in ONE persistent launch, bf16
+// operands on tcgen05 (kind::f16, fp32 accumulation in TMEM):
+//     MAF.inverse / IAF.forward  =  MADE (4 masked linears, 3 ReLU; made.py:136-140) + affine-AR transform + row log-det
+//     (masked_autoregressive_flow.py:18-44, inverse_autoregressive_flow.py:30-63) [+ the N(0,I) log-prob head, flow.py:56-73]
+// This is the reduced-precision ("bf16 conditioner GEMMs") mode; the fp32-parity default stays the 3xTF32 GEMM chain.
+//
+// Why one kernel: unfused, the chain moves the [B, H] activations through HBM between every pair of GEMMs (~12.8 KB per
+// row against 516 B of compulsory traffic at MAF(64, 512)).  Here a CTA owns 128 rows for the whole chain and the
+// activations never leave the SM:
+//     TMEM accumulator (fp32) -> tcgen05.ld -> +bias, ReLU, -> bf16 -> shared memory (K-major SWIZZLE_128B) = A operand
+//     of the next layer's MMAs;
+// only x (fp32, read once) and z / log-det (written once) touch HBM.  Weights (bf16, mask folded, hidden units sorted by
+// degree so that every masked weight is block lower-triangular) stream from L2 through a TMA ring.
+//
+// Activation buffer: KA + 2 slots of one K atom each ([128 rows x 64 bf16] = 16 KB), addressed through a ROTATING map
+//     slot(l, a) = (o + a + 2 l) mod (KA + 2)          (l = layer whose INPUT the atom is, a = atom, o = tile offset)
+// Output blocks (128 columns = 2 atoms) of a layer are produced in DESCENDING order and written two slots "ahead" of the
+// input atoms: block j's output lands where input atoms 2j+2, 2j+3 lived -- inputs that only output blocks >= j (+ the
+// few "spill" columns of degree groups that straddle a block boundary, read by block j itself) still need, and those
+// MMAs have completed when block j's accumulator is drained.  So the epilogue of block j overlaps the MMAs of block
+// j-1, and the NEXT layer's first (widest) block can start on atoms 7, 6, ... as soon as they are written: the MMA warp
+// issues one continuous stream of MMAs across layers and tiles.  The next tile's x goes to a slot that is free during the
+// last layer (o' = o + 4).
+//
+// Warp roles (320 threads, one CTA per SM, all 512 TMEM columns = four 128-column accumulators):
+//   warp 0      TMA producer: weight tiles [128 x 64] bf16, 4-stage ring, in (tile, layer, block desc., atom desc.) order
+//   warp 1      MMA issuer (whole warp convergent, one elected lane): waits x / block-ready / stage-full / accumulator-empty
+//   warps 2-9   epilogue: warp w drains TMEM lane quadrant w % 4, column half (w - 2) / 4 of each accumulator
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "nf_common.cuh"
+#include "stack_small.cuh"
+#include "tc_common.cuh"
+
+namespace nf {
+
+constexpr int kMcRows = 128;                 // rows per CTA tile (UMMA M)
+constexpr int kMcBN = 128;                   // output block width (UMMA N)
+constexpr int kMcAtom = 64;                  // bf16 elements per K atom (128 bytes: one swizzle span)
+constexpr int kMcAtomBytes = kMcRows * kMcAtom * 2;      // 16 KB: one activation slot = one weight stage
+constexpr int kMcStages = 4;
+constexpr int kMcMaxKA = 8;                  // hidden_dim <= 512
+constexpr int kMcThreads = 320;
+constexpr int kMcEpiWarps = 8;
+constexpr int kMcTmemCols = 512;
+
+struct McParams {
+    int kext16[4][4];       // [layer][block]: 16-wide k-steps the block's outputs depend on (monotone in block)
+    int NB;                 // 128-column blocks of the hidden layers (H / 128)
+    int KA;                 // K atoms of the hidden layers (H / 64)
+    int D;                  // data_dim (<= 64, multiple of 4)
+    int mode;               // NF_AR_MAF_INVERSE / NF_AR_IAF_FORWARD
+    int flags;              // NF_STACK_LOG_PROB_HEAD | NF_STACK_SKIP_Y semantics (bits 1, 2)
+    int64_t B;
+    int num_tiles;
+};
+
+__device__ __forceinline__ void mc_tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar)) : "memory");
+}
+// instruction descriptor: kind::f16, A = B = bf16, fp32 accumulate, both K-major, M = 128
+__host__ __device__ constexpr uint32_t mc_idesc_bf16(uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mc_mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t mc_pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);          // .x = lo (low 16 bits), .y = hi
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+// one 16-byte chunk (8 bf16) of row r of a K-major SWIZZLE_128B atom: chunk c sits at position c ^ (r % 8)
+__device__ __forceinline__ void mc_store_chunk(uint8_t* atom, int r, int c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint8_t* p = atom + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(p) = make_uint4(w0, w1, w2, w3);
+}
+
+__global__ void __launch_bounds__(kMcThreads, 1)
+made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+                       const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
+                       const float* __restrict__ x, const float* __restrict__ b0, const float* __restrict__ b1,
+                       const float* __restrict__ b2, const float* __restrict__ b3, float* __restrict__ out,
+                       float* __restrict__ ld_out, const __grid_constant__ McParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int NSLOT = P.KA + 2;
+    uint8_t* act = smem;                                           // NSLOT activation slots
+    uint8_t* wst = smem + (size_t)NSLOT * kMcAtomBytes;            // kMcStages weight stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)kMcStages * kMcAtomBytes);
+    uint64_t* w_full = bars;                    // [4]
+    uint64_t* w_empty = w_full + kMcStages;     // [4]
+    uint64_t* acc_full = w_empty + kMcStages;   // [4]
+    uint64_t* acc_empty = acc_full + 4;         // [4]
+    uint64_t* blk_ready = acc_empty + 4;        // [4] block jb of the current layer's input activations written
+    uint64_t* x_ready = blk_ready + 4;          // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+    float* row_part = reinterpret_cast<float*>(tmem_slot + 2);     // [2 tile parities][2 values][128 rows]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NB = P.NB;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kMcStages; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) {
+            tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], kMcEpiWarps); tc::mbar_init(&blk_ready[i], kMcEpiWarps);
+        }
+        tc::mbar_init(x_ready, kMcEpiWarps);
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, kMcTmemCols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            bool first_round = true;
+            for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x) {
+                for (int l = 0; l < 4; ++l) {
+                    const CUtensorMap* map = l == 0 ? &tm_w0 : (l == 1 ? &tm_w1 : (l == 2 ? &tm_w2 : &tm_w3));
+                    const int nblk = (l == 3) ? 1 : NB;
+                    for (int j = nblk - 1; j >= 0; --j) {
+                        const int na = (P.kext16[l][j] + 3) >> 2;
+                        for (int a = na - 1; a >= 0; --a) {
+                            if (!first_round) tc::mbar_wait(&w_empty[s], ph ^ 1u);
+                            tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)kMcAtomBytes);
+                            mc_tma_load_2d(wst + (size_t)s * kMcAtomBytes, map, a * kMcAtom, j * kMcBN, &w_full[s]);
+                            if (++s == kMcStages) { s = 0; ph ^= 1u; first_round = false; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = mc_idesc_bf16((uint32_t)kMcBN);
+        const bool leader = tc::elect_one();
+        int s = 0, u = 0, it = 0, o = 0;                   // weight stage, unit counter (accumulator ring), tile iteration, slot offset
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+            for (int l = 0; l < 4; ++l) {
+                const int nblk = (l == 3) ? 1 : NB;
+                uint32_t ready = 0;                            // input blocks of this layer already waited for
+                if (l == 0) tc::mbar_wait(x_ready, (uint32_t)(it & 1));
+                for (int j = nblk - 1; j >= 0; --j, ++u) {
+                    const int acc = u & 3;
+                    if (u >= 4) tc::mbar_wait(&acc_empty[acc], (uint32_t)(((u >> 2) & 1) ^ 1));
+                    const int k16 = P.kext16[l][j];
+                    const int na = (k16 + 3) >> 2;
+                    const uint32_t dcol = tb + (uint32_t)(acc * kMcBN);
+                    bool first = true;
+                    for (int a = na - 1; a >= 0; --a) {
+                        if (l > 0) {
+                            const int jb = a >> 1;
+                            if (!(ready & (1u << jb))) {
+                                // h_l block jb: completion number 3*it + (l-1) of blk_ready[jb]
+                                tc::mbar_wait(&blk_ready[jb], (uint32_t)((3 * it + (l - 1)) & 1));
+                                ready |= 1u << jb;
+                            }
+                        }
+                        tc::mbar_wait(&w_full[s], ph);
+                        tc::fence_after_sync();
+                        const int slot = (o + a + 2 * l) % NSLOT;
+                        const uint64_t da = tc::smem_desc_k_sw128(tc::smem_u32(act + (size_t)slot * kMcAtomBytes));
+                        const uint64_t db = tc::smem_desc_k_sw128(tc::smem_u32(wst + (size_t)s * kMcAtomBytes));
+                        const int nk = min(4, k16 - 4 * a);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < nk && leader)
+                                mc_mma_bf16_ss(dcol, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                        }
+                        first = false;
+                        if (leader) tc::mma_commit(&w_empty[s]);
+                        __syncwarp();
+                        if (++s == kMcStages) { s = 0; ph ^= 1u; }
+                    }
+                    if (leader) tc::mma_commit(&acc_full[acc]);      // na == 0 (all-zero block): completes at once, accumulator unread
+                    __syncwarp();
+                }
+            }
+            o = (o + 4) % NSLOT;
+        }
+    } else {
+        // ---------------- epilogue warps ----------------
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;                                   // row inside the tile = TMEM lane
+        const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
+        const int D = P.D;
+        const bool iaf = (P.mode == AR_IAF_FWD);
+        const float lim = iaf ? 50.f : 100.f;
+        const int c0 = half * 32;                                      // this thread's 32 data columns
+        float xc[32], xn[32];
+
+        auto load_x = [&](int tile, float (&v)[32]) {
+            const int64_t row = (int64_t)tile * kMcRows + r;
+            const bool ok = tile < P.num_tiles && row < P.B;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && c0 + 4 * i < D) f = __ldcs(reinterpret_cast<const float4*>(x + row * D + c0 + 4 * i));
+                v[4 * i + 0] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+            }
+        };
+        auto write_x = [&](const float (&v)[32], int slot) {
+            uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                mc_store_chunk(atom, r, half * 4 + c, mc_pack_bf16(v[8 * c + 0], v[8 * c + 1]), mc_pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                               mc_pack_bf16(v[8 * c + 4], v[8 * c + 5]), mc_pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(x_ready);
+        };
+
+        int u = 0, it = 0, o = 0;
+        load_x(blockIdx.x, xc);
+        if ((int)blockIdx.x < P.num_tiles) write_x(xc, 0);
+        for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
+            load_x(t + gridDim.x, xn);                                  // in flight during layers 0..2
+            for (int l = 0; l < 3; ++l) {
+                const float* bias = l == 0 ? b0 : (l == 1 ? b1 : b2);
+                for (int j = NB - 1; j >= 0; --j, ++u) {
+                    const int acc = u & 3;
+                    const bool live = P.kext16[l][j] > 0;
+                    tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1));
+                    tc::fence_after_sync();
+                    uint32_t v[4][16];
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + half * 64 + c * 16), v[c]);
+                        tc::wait_ld();
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[c][i] = 0u;
+                    }
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+                    // h_{l+1} atom 2j + half of this row: bias, ReLU (NaN stays NaN), bf16
+                    const int slot = (o + (2 * j + half) + 2 * (l + 1)) % NSLOT;
+                    uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
+                    const float* bp = bias + j * kMcBN + half * 64;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(bp + 8 * c));
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bp + 8 * c + 4));
+                        const uint32_t* vv = &v[c >> 1][(c & 1) * 8];
+                        float f[8];
+                        f[0] = __uint_as_float(vv[0]) + ba.x; f[1] = __uint_as_float(vv[1]) + ba.y;
+                        f[2] = __uint_as_float(vv[2]) + ba.z; f[3] = __uint_as_float(vv[3]) + ba.w;
+                        f[4] = __uint_as_float(vv[4]) + bb.x; f[5] = __uint_as_float(vv[5]) + bb.y;
+                        f[6] = __uint_as_float(vv[6]) + bb.z; f[7] = __uint_as_float(vv[7]) + bb.w;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = (f[i] < 0.f) ? 0.f : f[i];
+                        mc_store_chunk(atom, r, c, mc_pack_bf16(f[0], f[1]), mc_pack_bf16(f[2], f[3]), mc_pack_bf16(f[4], f[5]),
+                                       mc_pack_bf16(f[6], f[7]));
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&blk_ready[j]);
+                }
+            }
+            // every MMA of layers 0..2 has completed: the next tile's x may take the slot that is free during layer 3
+            const int o_next = (o + 4) % NSLOT;
+            if (t + (int)gridDim.x < P.num_tiles) write_x(xn, o_next);
+            // ---- layer 3: [mu | alpha] -> affine autoregressive transform, row log-det (+ head) ----
+            {
+                const int acc = u & 3;
+                tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1));
+                tc::fence_after_sync();
+                uint32_t vm[2][16], va[2][16];
+                if (P.kext16[3][0] > 0) {
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0), vm[0]);
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0 + 16), vm[1]);
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0), va[0]);
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0 + 16), va[1]);
+                    tc::wait_ld();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { vm[0][i] = vm[1][i] = va[0][i] = va[1][i] = 0u; }
+                }
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+                ++u;
+                const int64_t row = (int64_t)t * kMcRows + r;
+                float lsum = 0.f, sq = 0.f, o32[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int d = c0 + i;
+                    float ov = 0.f;
+                    if (d < D) {
+                        const float mu = __uint_as_float(vm[i >> 4][i & 15]) + __ldg(b3 + d);
+                        const float al = __uint_as_float(va[i >> 4][i & 15]) + __ldg(b3 + 64 + d);
+                        float tt;
+                        affine_ar_elem<float>(P.mode, xc[i], mu, al, ov, tt);
+                        if (!is_finite(ov)) ov = iaf ? xc[i] : 0.f;          // IAF scrubs to the input (:53)
+                        lsum += tt;
+                        sq += -0.5f * ov * ov;
+                    }
+                    o32[i] = ov;
+                }
+                if (row < P.B && !(P.flags & NF_STACK_SKIP_Y)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (c0 + 4 * i < D)
+                            __stcs(reinterpret_cast<float4*>(out + row * D + c0 + 4 * i),
+                                   make_float4(o32[4 * i], o32[4 * i + 1], o32[4 * i + 2], o32[4 * i + 3]));
+                }
+                // the two column halves of a row live in two warps: combine through shared memory (fixed order)
+                float* part = row_part + (it & 1) * 256;
+                if (half == 1) { part[r] = lsum; part[128 + r] = sq; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && row < P.B) {
+                    const float tot = clamp_mm(scrub0(lsum + part[r]), -lim, lim);
+                    float res = tot;
+                    if (P.flags & NF_STACK_LOG_PROB_HEAD)
+                        res = (sq + part[128 + r]) - (float)(0.5 * (double)D * 1.8378770664093453) + tot;
+                    __stcs(ld_out + row, res);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xc[i] = xn[i];
+            o = o_next;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tb, kMcTmemCols);
+}
+
+typedef CUresult (*McEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static McEncodeFn mc_encode_fn() {
+    static McEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<McEncodeFn>(p);
+    }
+    return fn;
+}
+
+// bf16 weight [rows, K] row-major (K % 64 == 0, rows % 128 == 0): boxes of [128 rows x 64 k] = one SWIZZLE_128B atom block
+static bool mc_make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t K) {
+    McEncodeFn fn = mc_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kMcAtom, (cuuint32_t)kMcBN};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace nf
+
+using namespace nf;
+#define NF_REQ(p) do { if ((p) == nullptr) return NF_ERR_NULL; } while (0)
+
+extern "C" int nf_made_chain_bf16_forward(const void* x, const void* w0, const void* w1, const void* w2, const void* w3,
+                                          const void* b0, const void* b1, const void* b2, const void* b3,
+                                          const int32_t* kext16_host, void* out, void* ld, int64_t B, int D, int H, int mode,
+                                          int flags, nf_stream_t stream) {
+    if (B < 0 || D < 1 || H < 1) return NF_ERR_BAD_SHAPE;
+    if (mode != NF_AR_MAF_INVERSE && mode != NF_AR_IAF_FORWARD) return NF_ERR_UNSUPPORTED;
+    if (D > 64 || (D % 4) != 0 || (H % 128) != 0 || H > kMcMaxKA * kMcAtom) return NF_ERR_UNSUPPORTED;
+    NF_REQ(kext16_host);
+    if (B == 0) return NF_OK;
+    NF_REQ(x); NF_REQ(w0); NF_REQ(w1); NF_REQ(w2); NF_REQ(w3); NF_REQ(b0); NF_REQ(b1); NF_REQ(b2); NF_REQ(b3); NF_REQ(ld);
+    if (!(flags & NF_STACK_SKIP_Y)) NF_REQ(out);
+    if (!aligned16(x) || (out && !aligned16(out)) || !aligned16(b0) || !aligned16(b1) || !aligned16(b2)) return NF_ERR_MISALIGNED;
+    McParams P;
+    P.NB = H / kMcBN; P.KA = H / kMcAtom; P.D = D; P.mode = mode; P.flags = flags; P.B = B;
+    const int64_t tiles = cdiv(B, kMcRows);
+    if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
+    P.num_tiles = (int)tiles;
+    for (int l = 0; l < 4; ++l) {
+        const int kmax = (l == 0 ? kMcAtom : H) / 16;
+        int prev = 0;
+        for (int j = 0; j < 4; ++j) {
+            int v = kext16_host[l * 4 + j];
+            if (v < 0 || v > kmax) return NF_ERR_BAD_SHAPE;
+            if (j >= (l == 3 ? 1 : P.NB)) v = 0;
+            else { v = v > prev ? v : prev; prev = v; }            // monotone in the block index (block-triangular weights)
+            P.kext16[l][j] = v;
+        }
+    }
+    alignas(64) CUtensorMap t0, t1, t2, t3;
+    if (!mc_make_map(&t0, w0, H, kMcAtom) || !mc_make_map(&t1, w1, H, H) || !mc_make_map(&t2, w2, H, H) ||
+        !mc_make_map(&t3, w3, kMcBN, H))
+        return NF_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)(P.KA + 2 + kMcStages) * kMcAtomBytes + 256 + 2 * 256 * sizeof(float);
+    if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
+    NF_CUDA(cudaFuncSetAttribute(made_chain_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    made_chain_bf16_kernel<<<grid, kMcThreads, smem, (cudaStream_t)stream>>>(
+        t0, t1, t2, t3, (const float*)x, (const float*)b0, (const float*)b1, (const float*)b2, (const float*)b3, (float*)out,
+        (float*)ld, P);
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}

@@ -601,6 +601,18 @@ class MaskedAutoregressiveFlow(_AffineAutoregressive):
     def forward(self, z):
         return self._sequential(z)
 
+    def _log_prob_fused(self, x):
+        """bf16 fused-chain mode: the N(0,I) head is part of the chain kernel's last epilogue (one launch, z not stored)."""
+        x = compute_input(x)
+        if (not ops.MADE_CHAIN_BF16 or wants_grad(self, x) or x.shape[0] < 128
+                or (self.conditioner.use_batch_norm and self.training)):
+            return None
+        f = self.conditioner.folded()
+        if f is None or f.w[0].dtype != x.dtype:
+            return None
+        out = ops.made_chain_bf16(x, f, self._mode_parallel, head=True)
+        return None if out is None else out[1]
+
 
 class InverseAutoregressiveFlow(_AffineAutoregressive):
     """IAF: `forward` (sampling) is one parallel pass, `inverse` (density) is sequential

@@ -634,12 +634,42 @@ def coupling_stack(packed, hdr_host, x, inverse, head=False):
     return (y, ld) if ok else None
 
 
+MADE_CHAIN_BF16 = False          # set by nfb200.set_gemm_precision("bf16"): the fused bf16 chain kernel for MAF / IAF
+
+
+def made_chain_bf16(v, folded, mode, head=False):
+    """Whole parallel direction in ONE launch on bf16 tensor cores (csrc/made_chain_bf16.cu); None when the shape is
+    outside the kernel's envelope (data_dim <= 64 and a multiple of 4, hidden_dim a multiple of 128 and <= 512).
+    head=True: returns (None, log N(z;0,I) + log_det) without storing z."""
+    from . import packing
+    if v.dtype != torch.float32:
+        return None
+    if folded.bf16 is None:
+        folded.bf16 = packing.made_bf16_pack(folded)
+    pk = folded.bf16
+    if pk is False:
+        return None
+    v = _c(v)
+    B, D = v.shape
+    out = None if head else torch.empty_like(v)
+    ld = torch.empty(B, dtype=v.dtype, device=v.device)
+    ok = L.try_call("nf_made_chain_bf16_forward", ptr(v), ptr(pk.w[0]), ptr(pk.w[1]), ptr(pk.w[2]), ptr(pk.w[3]),
+                    ptr(pk.b[0]), ptr(pk.b[1]), ptr(pk.b[2]), ptr(pk.b[3]), pk.kext16_host.ctypes.data, ptr(out), ptr(ld),
+                    B, D, folded.H, mode, (STACK_LOG_PROB_HEAD | STACK_SKIP_Y) if head else 0, stream())
+    return (out, ld) if ok else None
+
+
 def made_affine(v, folded, mode):
     """MADE chain + MAF.inverse / IAF.forward.  folded: packing.FoldedMade.  float32: four tcgen05 GEMMs (3xTF32,
-    bias/ReLU epilogues, masked-out K tiles skipped) + the transform kernel; float64 or tiny shapes: FP32/FP64-pipe chain."""
+    bias/ReLU epilogues, masked-out K tiles skipped) + the transform kernel; float64 or tiny shapes: FP32/FP64-pipe chain.
+    In the bf16 mode (set_gemm_precision("bf16")) the whole direction is one fused launch."""
     v = _c(v)
     B, D = v.shape
     H = folded.H
+    if MADE_CHAIN_BF16 and USE_TENSOR_CORE_GEMM and B >= 128:
+        res = made_chain_bf16(v, folded, mode)
+        if res is not None:
+            return res
     if USE_TENSOR_CORE_GEMM and folded.w_split is not None and v.dtype == torch.float32 and B >= 128:
         h, ok = v, True
         for i in range(4):

@@ -228,6 +228,7 @@ class FoldedMade:
     gstart: torch.Tensor
     w_split: Optional[list] = None      # [(hi, lo)] x 4: 3xTF32 operands of the tensor-core GEMM (float32 only)
     gstart_host: Optional[np.ndarray] = None
+    bf16: Optional[object] = None       # made_bf16_pack(self), built on first use of the bf16 fused chain (False: unsupported)
 
 
 def fold_made(made) -> Optional[FoldedMade]:
@@ -281,6 +282,53 @@ def fold_made(made) -> Optional[FoldedMade]:
         from . import ops
         folded.w_split = [ops.split_tf32(t) for t in w]
     return folded
+
+
+@dataclass
+class MadeBf16Pack:
+    """Operands of nf_made_chain_bf16_forward (csrc/made_chain_bf16.cu): bf16 weights with the input layer's K padded to
+    64 and the output layer laid out as [mu rows 0..D-1 | zero | alpha rows 64..64+D-1 | zero] (128 rows), fp32 biases
+    (output bias padded the same way), and per (layer, 128-column block) the number of 16-wide k-steps that hold a
+    non-zero weight (block lower-triangular masks: everything beyond is exactly zero and is neither loaded nor multiplied)."""
+    w: list
+    b: list
+    kext16_host: np.ndarray
+
+
+def made_bf16_pack(folded: FoldedMade):
+    D, H = folded.D, folded.H
+    if D > 64 or D % 4 or H % 128 or H > 512 or folded.w[0].dtype != torch.float32 or not folded.w[0].is_cuda:
+        return False
+    dev = folded.w[0].device
+    bf = torch.bfloat16
+    with torch.no_grad():
+        w0 = torch.zeros(H, 64, dtype=bf, device=dev)
+        w0[:, :D] = folded.w[0].to(bf)
+        w1, w2 = folded.w[1].to(bf).contiguous(), folded.w[2].to(bf).contiguous()
+        w3 = torch.zeros(128, H, dtype=bf, device=dev)
+        w3[:D] = folded.w[3][:D].to(bf)
+        w3[64:64 + D] = folded.w[3][D:].to(bf)
+        b3 = torch.zeros(128, dtype=torch.float32, device=dev)
+        b3[:D] = folded.b[3][:D]
+        b3[64:64 + D] = folded.b[3][D:]
+        ws = [w0, w1, w2, w3]
+        # last non-zero column (+1) of every 128-row block, in 16-wide k-steps
+        lasts = []
+        for wm in ws:
+            nz = (wm != 0)
+            K = wm.shape[1]
+            last = torch.where(nz, torch.arange(1, K + 1, device=dev)[None, :], 0).amax(dim=1)        # per row
+            pad = (-last.numel()) % 128
+            if pad:
+                last = torch.cat([last, last.new_zeros(pad)])
+            lasts.append(last.view(-1, 128).amax(dim=1))
+        host = [t.cpu().numpy() for t in lasts]
+    kext = np.zeros((4, 4), dtype=np.int32)
+    for l, v in enumerate(host):
+        n = min(4, len(v))
+        kext[l, :n] = (v[:n] + 15) // 16
+    return MadeBf16Pack(ws, [folded.b[0].contiguous(), folded.b[1].contiguous(), folded.b[2].contiguous(), b3],
+                        np.ascontiguousarray(kext.reshape(-1)))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -119,8 +119,14 @@ def test_gemm_precision_switch_is_host_only_and_validated():
     finally:
         N.set_gemm_precision("fp32")
     assert N.get_gemm_precision() == "fp32"
+    try:
+        N.set_gemm_precision("bf16")                      # round 2: the fused bf16 MADE-chain mode
+        assert N.get_gemm_precision() == "bf16" and N.ops.MADE_CHAIN_BF16
+    finally:
+        N.set_gemm_precision("fp32")
+    assert not N.ops.MADE_CHAIN_BF16
     with pytest.raises(ValueError):
-        N.set_gemm_precision("bf16")
+        N.set_gemm_precision("fp8")
     assert N._lib.lib().nf_set_option(7, 2) != 0          # only 1 and 3 passes exist
     assert N._lib.lib().nf_set_option(7, 3) == 0
     assert N._lib.lib().nf_set_option(99, 0) != 0         # unknown key
