@@ -516,7 +516,7 @@ def run_product(args):
     # the other log_prob+sample config of BASELINE.json (the tensor-pipe one) in the same line
     if wl == "c2" and not args.no_also:
         also = {}
-        modes = ["fp32"] + (["bf16"] if "bf16" in getattr(N, "GEMM_PRECISIONS", ()) else [])
+        modes = ["fp32"] + (["bf16"] if "bf16" in getattr(N, "GEMM_PRECISIONS", ()) and not os.environ.get("NF_SKIP_BF16") else [])
         for mode in modes:
             try:
                 a = measure("c3", args, N, dev, world, rank, barrier, min(steps, 10), 3, precision=mode, with_clocks=False)
