@@ -152,6 +152,25 @@ NF_API int nf_batchnorm_backward(const void* x, const void* y, const void* gamma
                           const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta, void* workspace,
                           int64_t B, int H, int relu, int training, int dtype, nf_stream_t stream);
 
+/* BatchNorm1d with statistics synchronised over data-parallel ranks (CouplingLayer's train-mode BatchNorm,
+ * coupling_layer.py:18-35, is the one cross-row reduction of the path; per-shard statistics make N GPUs != 1 GPU).
+ * forward  stage 1: workspace[2H] doubles <- this shard's (sum x, sum x^2); nothing else is touched.  The caller all-reduces
+ *          the workspace (and the row count) over the ranks.
+ *          stage 2: statistics from the workspace over `count` rows (= all ranks' rows), running-stat update (unbiased
+ *          variance with `count`), normalisation of this shard's B rows.
+ * backward stage 1: workspace[2H] doubles <- this shard's (sum g*xhat, sum g) = its ggamma / gbeta (g = gy masked by ReLU).
+ *          stage 2: gx of this shard's rows from the all-reduced sums in the workspace over `count` rows; ggamma / gbeta
+ *          receive the GLOBAL sums (the caller keeps the local ones from stage 1 as the parameter gradients).
+ * B may be 0 (empty shard). */
+NF_API int nf_batchnorm_forward_staged(const void* x, const void* gamma, const void* beta, void* running_mean,
+                                void* running_var, void* y, void* save_mean, void* save_rstd, void* workspace, int64_t B,
+                                int H, double momentum, double eps, int relu, int stage, int64_t count, int dtype,
+                                nf_stream_t stream);
+NF_API int nf_batchnorm_backward_staged(const void* x, const void* y, const void* gamma, const void* save_mean,
+                                 const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
+                                 void* workspace, int64_t B, int H, int relu, int stage, int64_t count, int dtype,
+                                 nf_stream_t stream);
+
 /* ---- fused inference stacks (small data_dim): whole NormalizingFlowModel in one launch --------------------
  * a4-a6 + a14/a15: L SplineCouplingLayers (+ optional between-layer BatchNorm affine using running stats,
  * normalizing_flow_model.py:25-128) for data_dim<=8, hidden_dim<=128, num_bins<=16; fp32 only.

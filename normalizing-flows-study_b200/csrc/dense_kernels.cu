@@ -394,9 +394,9 @@ template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ gamma,
                                     const T* __restrict__ mean, const T* __restrict__ rstd, const T* __restrict__ gy,
                                     const T* __restrict__ ggamma, const T* __restrict__ gbeta, T* __restrict__ gx,
-                                    int64_t B, int H, int relu, int training) {
+                                    int64_t B, int H, int relu, int training, int64_t count) {
     const int64_t n = B * H, stride = (int64_t)gridDim.x * blockDim.x;
-    const T invB = T(1) / (T)B;
+    const T invB = T(1) / (T)count;            // rows behind the statistics: B, or the global count with synchronised statistics
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = (int)(i % H);
         T g = gy[i];
@@ -544,14 +544,14 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gy,
                          const float* __restrict__ ggamma, const float* __restrict__ gbeta, float* __restrict__ gx, int64_t B,
-                         int H, int relu, int training, int64_t rpc, int tx) {
+                         int H, int relu, int training, int64_t rpc, int tx, int64_t count) {
     const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
     const int col = (blockIdx.x * tx + cx) * 4;
     if (col >= H) return;
     const float4 mu4 = ld4(mean + col), rs4 = ld4(rstd + col), ga4 = ld4(gamma + col), gg4 = ld4(ggamma + col), gb4 = ld4(gbeta + col);
     const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
     const float gg[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, gb[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
-    const float invB = 1.0f / (float)B;
+    const float invB = 1.0f / (float)count;
     const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
 #pragma unroll 2
     for (int64_t r = r0 + ry; r < r1; r += ty) {
@@ -593,30 +593,40 @@ static inline int ew_grid(int64_t n) {
 }
 
 template <typename T>
+// stage 0: the whole pass.  Synchronised statistics (data-parallel training, SURVEY 8e: exact N-GPU == 1-GPU equivalence
+// of CouplingLayer's train-mode BatchNorm needs the (sum x, sum x^2, n) triples all-reduced): stage 1 = this shard's sums
+// into ws and return; the caller all-reduces ws; stage 2 = statistics from ws over `count` rows, running-stat update,
+// apply to this shard's B rows.
 static int bn_forward(const void* x, const void* gamma, const void* beta, void* rm, void* rv, void* y, void* sm,
                       void* sr, void* ws, int64_t B, int H, int training, double momentum, double eps, int relu,
-                      cudaStream_t st) {
-    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, y, gamma, beta) && aligned16(sm) && aligned16(sr);
+                      cudaStream_t st, int stage = 0, int64_t count = 0) {
+    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, y ? y : x, gamma ? gamma : x, beta ? beta : x) &&
+                     (sm == nullptr || aligned16(sm)) && (sr == nullptr || aligned16(sr));
     const BnVecGeom vg = bn_vec_geom(B, H);
+    if (count <= 0) count = B;
     if (training) {
-        NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
-        int chunks; int64_t rpc;
-        bn_chunking(B, H, chunks, rpc);
-        dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
-        if (vec)
-            bn_partial_sums_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
-                (const float*)x, (double*)ws, B, H, vg.rpc, vg.tx);
-        else
-        bn_partial_sums_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (double*)ws, B, H, rpc);
-        count_launch();
-        NF_LAUNCH_CHECK();
-        bn_finish_stats_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)rm, (T*)rv, (T*)sm, (T*)sr, B, H,
+        if (stage != 2) {
+            NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
+            int chunks; int64_t rpc;
+            bn_chunking(B, H, chunks, rpc);
+            dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
+            if (vec)
+                bn_partial_sums_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
+                    (const float*)x, (double*)ws, B, H, vg.rpc, vg.tx);
+            else
+                bn_partial_sums_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (double*)ws, B, H, rpc);
+            count_launch();
+            NF_LAUNCH_CHECK();
+            if (stage == 1) return NF_OK;
+        }
+        bn_finish_stats_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)rm, (T*)rv, (T*)sm, (T*)sr, count, H,
                                                                   momentum, eps);
     } else {
         bn_eval_stats_kernel<T><<<(H + 255) / 256, 256, 0, st>>>((const T*)rm, (const T*)rv, (T*)sm, (T*)sr, H, eps);
     }
     count_launch();
     NF_LAUNCH_CHECK();
+    if (B == 0) return NF_OK;                    // empty shard of a synchronised pass: statistics only
     if (vec)
         bn_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
             (const float*)x, (const float*)gamma, (const float*)beta, (const float*)sm, (const float*)sr, (float*)y, B, H, relu, vg.rpc, vg.tx);
@@ -629,34 +639,42 @@ static int bn_forward(const void* x, const void* gamma, const void* beta, void* 
 }
 
 template <typename T>
+// stage 0: the whole pass.  Synchronised statistics: stage 1 = this shard's (sum g*xhat, sum g) into ws and return (they
+// are also this shard's ggamma / gbeta); the caller all-reduces a copy; stage 2 = gx of this shard's rows from the
+// all-reduced sums in ws over `count` rows (gg / gb receive the GLOBAL sums as a by-product).
 static int bn_backward(const void* x, const void* y, const void* gamma, const void* sm, const void* sr, const void* gy,
-                       void* gx, void* gg, void* gb, void* ws, int64_t B, int H, int relu, int training, cudaStream_t st) {
-    NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
+                       void* gx, void* gg, void* gb, void* ws, int64_t B, int H, int relu, int training, cudaStream_t st,
+                       int stage = 0, int64_t count = 0) {
     int chunks; int64_t rpc;
     bn_chunking(B, H, chunks, rpc);
     dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
-    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, gy, y, gx) && aligned16(sm) && aligned16(sr) && aligned16(gamma) &&
-                     aligned16(gg) && aligned16(gb);
+    const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, gy, y, gx ? gx : x) && aligned16(sm) && aligned16(sr) &&
+                     (gamma == nullptr || aligned16(gamma)) && (gg == nullptr || aligned16(gg)) && (gb == nullptr || aligned16(gb));
     const BnVecGeom vg = bn_vec_geom(B, H);
-    if (vec)
-        bn_bwd_partial_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
-            (const float*)x, (const float*)y, (const float*)sm, (const float*)sr, (const float*)gy, (double*)ws, B, H, relu, vg.rpc, vg.tx);
-    else
-    bn_bwd_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr, (const T*)gy,
-                                                   (double*)ws, B, H, relu, rpc);
-    count_launch();
-    NF_LAUNCH_CHECK();
+    if (count <= 0) count = B;
+    if (stage != 2) {
+        NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
+        if (vec)
+            bn_bwd_partial_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
+                (const float*)x, (const float*)y, (const float*)sm, (const float*)sr, (const float*)gy, (double*)ws, B, H, relu, vg.rpc, vg.tx);
+        else
+            bn_bwd_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr, (const T*)gy,
+                                                           (double*)ws, B, H, relu, rpc);
+        count_launch();
+        NF_LAUNCH_CHECK();
+        if (stage == 1) return NF_OK;
+    }
     bn_bwd_finish_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)gg, (T*)gb, H);
     count_launch();
     NF_LAUNCH_CHECK();
     if (vec)
         bn_bwd_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
             (const float*)x, (const float*)y, (const float*)gamma, (const float*)sm, (const float*)sr, (const float*)gy,
-            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx);
+            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx, count);
     else
     bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
                                                            (const T*)sr, (const T*)gy, (const T*)gg, (const T*)gb,
-                                                           (T*)gx, B, H, relu, training);
+                                                           (T*)gx, B, H, relu, training, count);
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;
@@ -770,6 +788,53 @@ extern "C" int nf_batchnorm_forward(const void* x, const void* gamma, const void
         return bn_forward<float>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, training, momentum, eps, relu, st);
     if (dtype == NF_F64)
         return bn_forward<double>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, training, momentum, eps, relu, st);
+    return NF_ERR_UNSUPPORTED;
+}
+
+extern "C" int nf_batchnorm_forward_staged(const void* x, const void* gamma, const void* beta, void* running_mean,
+                                           void* running_var, void* y, void* save_mean, void* save_rstd, void* workspace,
+                                           int64_t B, int H, double momentum, double eps, int relu, int stage, int64_t count,
+                                           int dtype, nf_stream_t stream) {
+    if (B < 0 || H < 1 || (stage != 1 && stage != 2)) return NF_ERR_BAD_SHAPE;
+    NF_REQ(workspace);
+    if (stage == 2) {
+        if (count < 1) return NF_ERR_BAD_SHAPE;
+        NF_REQ(gamma); NF_REQ(beta); NF_REQ(save_mean); NF_REQ(save_rstd);
+        if (B > 0) { NF_REQ(x); NF_REQ(y); }
+    } else if (B > 0) {
+        NF_REQ(x);
+    }
+    if ((running_mean == nullptr) != (running_var == nullptr)) return NF_ERR_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0 && stage == 1) return cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * H, st) == cudaSuccess ? NF_OK : NF_ERR_CUDA;
+    if (dtype == NF_F32)
+        return bn_forward<float>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, 1, momentum, eps, relu, st, stage, count);
+    if (dtype == NF_F64)
+        return bn_forward<double>(x, gamma, beta, running_mean, running_var, y, save_mean, save_rstd, workspace, B, H, 1, momentum, eps, relu, st, stage, count);
+    return NF_ERR_UNSUPPORTED;
+}
+
+extern "C" int nf_batchnorm_backward_staged(const void* x, const void* y, const void* gamma, const void* save_mean,
+                                            const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
+                                            void* workspace, int64_t B, int H, int relu, int stage, int64_t count, int dtype,
+                                            nf_stream_t stream) {
+    if (B < 0 || H < 1 || (stage != 1 && stage != 2)) return NF_ERR_BAD_SHAPE;
+    NF_REQ(workspace); NF_REQ(save_mean); NF_REQ(save_rstd);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stage == 2) {
+        if (count < 1) return NF_ERR_BAD_SHAPE;
+        NF_REQ(gamma); NF_REQ(ggamma); NF_REQ(gbeta);
+    }
+    if (B == 0) {
+        if (stage == 1) return cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * H, st) == cudaSuccess ? NF_OK : NF_ERR_CUDA;
+        return NF_OK;
+    }
+    NF_REQ(x); NF_REQ(y); NF_REQ(gy);
+    if (stage == 2) NF_REQ(gx);
+    if (dtype == NF_F32)
+        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, 1, st, stage, count);
+    if (dtype == NF_F64)
+        return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, 1, st, stage, count);
     return NF_ERR_UNSUPPORTED;
 }
 

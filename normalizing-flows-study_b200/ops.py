@@ -267,9 +267,100 @@ class _BatchNormFn(Function):
         return gx, gg, gb, None, None, None, None, None, None
 
 
+# Synchronised batch statistics.  CouplingLayer's train-mode BatchNorm (coupling_layer.py:18-35) is the one
+# cross-row reduction of the path: with per-shard statistics an N-GPU data-parallel step differs from the 1-GPU step on
+# the same global batch.  When a process group is registered here (parallel.DataParallelFlow(sync_batchnorm=True) or
+# parallel.enable_sync_batchnorm()), every train-mode BatchNorm all-reduces its [2H + 1] triple (sum x, sum x^2, n)
+# between the statistics pass and the normalisation, and the two batch sums of its backward.
+_SYNC_BN = {"group": None, "enabled": False}
+
+
+def set_sync_batchnorm(enabled: bool, group=None):
+    _SYNC_BN["enabled"], _SYNC_BN["group"] = bool(enabled), group
+
+
+def _sync_bn_world():
+    if not _SYNC_BN["enabled"]:
+        return 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(_SYNC_BN["group"])
+
+
+def allreduce_bn_sums(ws, count, group=None):
+    """ws: float64 [2H] local sums; count: local row count.  Returns (global sums in ws, global count); one collective."""
+    import torch.distributed as dist
+    packed = torch.cat([ws, ws.new_tensor([float(count)])])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    ws.copy_(packed[:-1])
+    return ws, int(round(float(packed[-1])))
+
+
+class _SyncBatchNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, group):
+        import torch.distributed as dist
+        x = _c(x)
+        B, H = x.shape
+        y = torch.empty_like(x)
+        sm = torch.empty(H, dtype=x.dtype, device=x.device)
+        sr = torch.empty(H, dtype=x.dtype, device=x.device)
+        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
+        code = L.dtype_code(x)
+        call("nf_batchnorm_forward_staged", ptr(x), None, None, None, None, None, None, None, ptr(ws), B, H, 0.0, float(eps),
+             int(relu), 1, 0, code, stream())
+        packed = torch.cat([ws, ws.new_tensor([float(B)])])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        count = int(round(float(packed[-1])))            # one host read per BatchNorm: the row count of the global batch
+        ws = packed[:-1].contiguous()
+        call("nf_batchnorm_forward_staged", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
+             ptr(y), ptr(sm), ptr(sr), ptr(ws), B, H, float(momentum), float(eps), int(relu), 2, count, code, stream())
+        ctx.relu, ctx.group, ctx.count = relu, group, count
+        ctx.save_for_backward(x, y, gamma, sm, sr)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        import torch.distributed as dist
+        x, y, gamma, sm, sr = ctx.saved_tensors
+        B, H = x.shape
+        code = L.dtype_code(x)
+        gy = _c(gy)
+        gx = torch.empty_like(x)
+        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
+        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), None, ptr(sm), ptr(sr), ptr(gy), None, None, None, ptr(ws), B, H,
+             int(ctx.relu), 1, 0, code, stream())
+        gg = ws[:H].to(x.dtype)                           # this shard's ggamma / gbeta: the gradient all-reduce sums them
+        gb = ws[H:].to(x.dtype)
+        glob = ws.clone()
+        dist.all_reduce(glob, op=dist.ReduceOp.SUM, group=ctx.group)
+        gg_g = torch.empty(H, dtype=x.dtype, device=x.device)
+        gb_g = torch.empty(H, dtype=x.dtype, device=x.device)
+        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(gy), ptr(gx), ptr(gg_g),
+             ptr(gb_g), ptr(glob), B, H, int(ctx.relu), 2, ctx.count, code, stream())
+        return gx, gg, gb, None, None, None, None, None, None
+
+
 def batchnorm_relu(x, bn: torch.nn.BatchNorm1d, relu=True):
     """nn.BatchNorm1d forward (train: batch stats + running-stat update, eval: running stats) fused with ReLU."""
     training = bn.training or bn.running_mean is None
+    if training and _sync_bn_world() > 1 and x.dtype in (torch.float32, torch.float64):
+        momentum = 0.0
+        if bn.track_running_stats and bn.running_mean is not None:
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            momentum = (1.0 / float(bn.num_batches_tracked)) if bn.momentum is None else bn.momentum
+        rm, rv = bn.running_mean, bn.running_var
+        if rm is not None and rm.dtype != x.dtype:
+            rm32, rv32 = rm.to(x.dtype), rv.to(x.dtype)
+            y = _SyncBatchNormFn.apply(x, bn.weight.to(x.dtype), bn.bias.to(x.dtype), rm32, rv32, momentum, bn.eps, relu,
+                                       _SYNC_BN["group"])
+            rm.copy_(rm32)
+            rv.copy_(rv32)
+            return y
+        return _SyncBatchNormFn.apply(x, bn.weight, bn.bias, rm, rv, momentum, bn.eps, relu, _SYNC_BN["group"])
     momentum = 0.0
     if training and bn.track_running_stats and bn.running_mean is not None:
         if bn.num_batches_tracked is not None:

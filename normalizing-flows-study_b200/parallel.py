@@ -33,6 +33,13 @@ def shard_rows(x: torch.Tensor, rank: int = None, world: int = None):
     return x[lo:hi]
 
 
+def enable_sync_batchnorm(enabled: bool = True, process_group=None) -> None:
+    """Process-wide switch: every train-mode BatchNorm1d of the flow layers all-reduces its batch sums over
+    `process_group` (ops._SyncBatchNormFn).  No effect without an initialised process group or at world size 1."""
+    from . import ops
+    ops.set_sync_batchnorm(enabled, process_group)
+
+
 class DataParallelFlow(nn.Module):
     """Wraps a flow module for data-parallel training.  forward / inverse / log_prob delegate to the wrapped
     module on the local shard; call `sync_gradients()` between `backward()` and `optimizer.step()`.
@@ -45,10 +52,14 @@ class DataParallelFlow(nn.Module):
     Gradient accumulation over micro-batches: wrap all but the last backward in `no_sync()`."""
 
     def __init__(self, module: nn.Module, process_group=None, bucket_bytes: int = 64 << 20, broadcast: bool = True,
-                 overlap: bool = True):
+                 overlap: bool = True, sync_batchnorm: bool = True):
         super().__init__()
         self.module = module
         self.process_group = process_group
+        # train-mode BatchNorm of the coupling conditioners: all-reduce the (sum x, sum x^2, n) triples so that N ranks
+        # on shards of a batch compute what one rank computes on the whole batch (SURVEY 8e)
+        enable_sync_batchnorm(sync_batchnorm and any(isinstance(m, nn.BatchNorm1d) for m in module.modules()),
+                              process_group)
         self.bucket_bytes = int(bucket_bytes)
         self.overlap = bool(overlap)
         self._bucket_list = None

@@ -354,3 +354,62 @@ def test_log_prob_with_other_bases_and_gradients():
     assert torch.allclose(xr.grad, xr2.grad, rtol=1e-5, atol=1e-6)
     s = m.sample(77)
     assert s.shape == (77, 4) and s.is_cuda and torch.isfinite(s).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: synchronised BatchNorm statistics -- two "ranks" emulated on one GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,relu", [(64, True), (48, True), (30, False)])
+def test_staged_batchnorm_on_two_shards_equals_one_batch(H, relu):
+    """The staged entry points (stage 1: shard sums; all-reduce = a plain add here; stage 2: statistics over the global
+    count, apply / input gradient) on two uneven shards reproduce the unsharded train-mode BatchNorm: outputs, running
+    statistics, gx, and ggamma / gbeta as the SUM of the shards' local sums."""
+    from nfb200 import _lib as L
+    torch.manual_seed(0)
+    B, cut = 3000, 1234
+    x = torch.randn(B, H, device=DEV) * 1.7 + 0.3
+    gy = torch.randn(B, H, device=DEV)
+    bn = torch.nn.BatchNorm1d(H).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    # unsharded reference through the ordinary op
+    bn_ref = copy.deepcopy(bn).train()
+    xr = x.clone().requires_grad_()
+    yr = N.ops.batchnorm_relu(xr, bn_ref, relu=relu)
+    yr.backward(gy)
+    # two shards through the staged C ABI
+    call, ptr, stream = L.call, L.ptr, L.stream
+    shards = [x[:cut].contiguous(), x[cut:].contiguous()]
+    gys = [gy[:cut].contiguous(), gy[cut:].contiguous()]
+    ws = [torch.empty(2 * H, dtype=torch.float64, device=DEV) for _ in shards]
+    for xs, w in zip(shards, ws):
+        call("nf_batchnorm_forward_staged", ptr(xs), None, None, None, None, None, None, None, ptr(w), xs.shape[0], H, 0.0, bn.eps,
+             int(relu), 1, 0, 0, stream())
+    glob = ws[0] + ws[1]                                             # the all-reduce
+    ys, sms, srs, rms, rvs = [], [], [], [], []
+    for xs in shards:
+        y = torch.empty_like(xs)
+        sm, sr = torch.empty(H, device=DEV), torch.empty(H, device=DEV)
+        rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+        call("nf_batchnorm_forward_staged", ptr(xs), ptr(bn.weight), ptr(bn.bias), ptr(rm), ptr(rv), ptr(y), ptr(sm), ptr(sr),
+             ptr(glob.clone()), xs.shape[0], H, 0.1, bn.eps, int(relu), 2, B, 0, stream())
+        ys.append(y); sms.append(sm); srs.append(sr); rms.append(rm); rvs.append(rv)
+    assert torch.allclose(torch.cat(ys), yr.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(rms[0], rms[1]) and torch.allclose(rms[0], bn_ref.running_mean, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(rvs[0], bn_ref.running_var, rtol=1e-6, atol=1e-7)
+    wsb = [torch.empty(2 * H, dtype=torch.float64, device=DEV) for _ in shards]
+    for xs, y, g, w in zip(shards, ys, gys, wsb):
+        call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), None, ptr(sms[0]), ptr(srs[0]), ptr(g), None, None, None, ptr(w),
+             xs.shape[0], H, int(relu), 1, 0, 0, stream())
+    globb = wsb[0] + wsb[1]
+    gxs = []
+    for xs, y, g in zip(shards, ys, gys):
+        gx = torch.empty_like(xs)
+        gg, gb = torch.empty(H, device=DEV), torch.empty(H, device=DEV)
+        call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), ptr(bn.weight), ptr(sms[0]), ptr(srs[0]), ptr(g), ptr(gx), ptr(gg),
+             ptr(gb), ptr(globb.clone()), xs.shape[0], H, int(relu), 2, B, 0, stream())
+        gxs.append(gx)
+    assert torch.allclose(torch.cat(gxs), xr.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(globb[:H].float(), bn_ref.weight.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(globb[H:].float(), bn_ref.bias.grad, rtol=1e-5, atol=1e-5)

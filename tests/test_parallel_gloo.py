@@ -175,3 +175,42 @@ def test_overlapped_gradient_allreduce_world2(bucket_bytes):
         assert all(results), (rank, results)
         assert launched == nb                                # every bucket was started before sync_gradients()
     assert out[0][2] == (1 if bucket_bytes > 1000 else out[0][2]) and out[0][2] >= 1
+
+
+def _bn_sums_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nfb200 import ops
+        H = 6
+        torch.manual_seed(0)
+        x = torch.randn(11, H, dtype=torch.float64)                 # the global batch, identical on every rank
+        lo, hi = P.shard_bounds(11, rank, world)
+        mine = x[lo:hi]
+        ws = torch.cat([mine.sum(0), (mine * mine).sum(0)])
+        ws, count = ops.allreduce_bn_sums(ws, mine.shape[0])
+        mean = ws[:H] / count
+        var = ws[H:] / count - mean * mean
+        ok = count == 11 and torch.allclose(mean, x.mean(0)) and torch.allclose(var, x.var(0, unbiased=False))
+        # the switch the layers consult: on only with an initialised group and world > 1
+        P.enable_sync_batchnorm(True)
+        on = ops._sync_bn_world()
+        P.enable_sync_batchnorm(False)
+        off = ops._sync_bn_world()
+        dp = P.DataParallelFlow(N.RealNVP(4, 2, 8))                 # has BatchNorm1d layers: the wrapper switches it on
+        wrapped = ops._sync_bn_world()
+        P.enable_sync_batchnorm(False)
+        out[rank] = (bool(ok), on, off, wrapped)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_batchnorm_host_logic_world2():
+    """(sum x, sum x^2, n) all-reduce of the synchronised BatchNorm: global mean / biased variance from two uneven shards."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_bn_sums_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        ok, on, off, wrapped = out[rank]
+        assert ok and on == 2 and off == 1 and wrapped == 2
