@@ -35,6 +35,47 @@ feature_affine_fwd_kernel(const T* __restrict__ x, const T* __restrict__ sub, co
     }
 }
 
+// float32, 16-byte aligned x / y, D % 4 == 0 or D in {1, 2}: 128-bit loads / stores, two chunks in flight per thread, the
+// per-column constants of a chunk fetched as one float4 (the scalar kernel above takes a 64-bit `i % D` and an IEEE
+// division per 4-byte access: 40 % of HBM).  PERIOD = 4 (D % 4 == 0: the chunk's columns are col..col+3), 2 (D == 2:
+// columns 0,1,0,1), 1 (D == 1).  Same operation order per element: ((x - sub) / div) * mul + add.
+template <int PERIOD>
+__global__ void __launch_bounds__(256)
+feature_affine_fwd_vec4_kernel(const float* __restrict__ x, const float* __restrict__ sub, const float* __restrict__ div,
+                               const float* __restrict__ mul, const float* __restrict__ add, float add_scalar,
+                               float* __restrict__ y, int64_t nchunks, int D) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto col_of = [&](int64_t c) -> int { return PERIOD == 4 ? (int)((c * 4) % D) : 0; };
+    auto params = [&](const float* p, int col, float dflt, float (&o)[4]) {
+        if (!p) { o[0] = o[1] = o[2] = o[3] = dflt; return; }
+        if (PERIOD == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p + col)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+        else if (PERIOD == 2) { o[0] = o[2] = __ldg(p); o[1] = o[3] = __ldg(p + 1); }
+        else { o[0] = o[1] = o[2] = o[3] = __ldg(p); }
+    };
+    auto apply = [&](const float4 v, int col) -> float4 {
+        float s4[4], d4[4], m4[4], a4[4], e[4] = {v.x, v.y, v.z, v.w};
+        params(sub, col, 0.f, s4); params(div, col, 1.f, d4); params(mul, col, 1.f, m4); params(add, col, add_scalar, a4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = e[j];
+            if (sub) t = t - s4[j];
+            if (div) t = t / d4[j];
+            if (mul) t = t * m4[j];
+            e[j] = t + a4[j];
+        }
+        return make_float4(e[0], e[1], e[2], e[3]);
+    };
+    int64_t c = c0;
+    for (; c + stride < nchunks; c += 2 * stride) {
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(x) + c);
+        const float4 v1 = __ldcs(reinterpret_cast<const float4*>(x) + c + stride);
+        __stcs(reinterpret_cast<float4*>(y) + c, apply(v0, col_of(c)));
+        __stcs(reinterpret_cast<float4*>(y) + c + stride, apply(v1, col_of(c + stride)));
+    }
+    if (c < nchunks) __stcs(reinterpret_cast<float4*>(y) + c, apply(__ldcs(reinterpret_cast<const float4*>(x) + c), col_of(c)));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 feature_affine_bwd_x_kernel(const T* __restrict__ div, const T* __restrict__ mul, const T* __restrict__ gy,
@@ -79,6 +120,86 @@ col_moments_kernel(const T* __restrict__ x, const T* __restrict__ sub, const T* 
         atomicAdd(acc + col, ta);
         atomicAdd(acc + D + col, tb);
     }
+}
+
+// Column moments for narrow matrices (D <= 8): the 32-column x 8-row block above keeps D of its 32 column lanes busy
+// (D = 2: 6.7 % of HBM).  Here a thread owns whole rows -- 16 / 32-byte row loads, D running sums in registers, four
+// rows in flight -- and a block combines through warp shuffles and one double atomic per column.  Same sums as
+// col_moments_kernel (double accumulation; the order of the additions differs).
+template <int DM>
+__global__ void __launch_bounds__(256)
+col_moments_rows_kernel(const float* __restrict__ x, const float* __restrict__ sub, const float* __restrict__ w,
+                        double* __restrict__ acc, int64_t B, int D, int square) {
+    double a[DM], b[DM];
+    float sb[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) { a[d] = 0.0; b[d] = 0.0; sb[d] = (sub && d < D) ? __ldg(sub + d) : 0.f; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = (D == DM) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (!w || (reinterpret_cast<uintptr_t>(w) & 15) == 0) && DM >= 2;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += stride) {
+        float xv[DM], wv[DM];
+        if (vec) {
+            if (DM == 2) {
+                const float2 t = __ldcs(reinterpret_cast<const float2*>(x) + r); xv[0] = t.x; xv[1] = t.y;
+                if (w) { const float2 u = __ldcs(reinterpret_cast<const float2*>(w) + r); wv[0] = u.x; wv[1] = u.y; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < DM / 4; ++q) {
+                    const float4 t = __ldcs(reinterpret_cast<const float4*>(x) + r * (DM / 4) + q);
+                    xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+                    if (w) {
+                        const float4 u = __ldcs(reinterpret_cast<const float4*>(w) + r * (DM / 4) + q);
+                        wv[4 * q] = u.x; wv[4 * q + 1] = u.y; wv[4 * q + 2] = u.z; wv[4 * q + 3] = u.w;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DM; ++d) {
+                xv[d] = d < D ? x[r * D + d] : 0.f;
+                wv[d] = (w && d < D) ? w[r * D + d] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < DM; ++d) {
+            const double xd = (double)xv[d] - (double)sb[d];
+            const double wd = w ? (double)wv[d] : 1.0;
+            if (square) { a[d] += xd; b[d] += xd * xd; }
+            else        { a[d] += wd; b[d] += wd * xd; }
+        }
+    }
+    __shared__ double red[8][2 * DM];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+        double ta = a[d], tb = b[d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tb += __shfl_xor_sync(0xffffffffu, tb, o); }
+        if (lane == 0) { red[wp][d] = ta; red[wp][DM + d] = tb; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * DM) {
+        const int d = threadIdx.x % DM, which = threadIdx.x / DM;
+        if (d < D) {
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[i][which * DM + d];
+            atomicAdd(acc + which * D + d, t);
+        }
+    }
+}
+
+// returns true when the narrow-matrix kernel took the launch
+static bool col_moments_rows_launch(const float* x, const float* sub, const float* w, double* acc, int64_t B, int D, int square,
+                                    cudaStream_t st) {
+    if (D > 8) return false;
+    int64_t need = cdiv(B, 256 * 4);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+    if (D <= 2) col_moments_rows_kernel<2><<<grid, 256, 0, st>>>(x, sub, w, acc, B, D, square);
+    else if (D <= 4) col_moments_rows_kernel<4><<<grid, 256, 0, st>>>(x, sub, w, acc, B, D, square);
+    else col_moments_rows_kernel<8><<<grid, 256, 0, st>>>(x, sub, w, acc, B, D, square);
+    return true;
 }
 
 template <typename T>
@@ -213,6 +334,61 @@ std_normal_log_prob_fwd_kernel(const T* __restrict__ z, const T* __restrict__ ld
     }
 }
 
+// float32, 16-byte aligned z: D % 4 == 0 -> G lanes per row (G = pow2 >= D/4, <= 32), each lane sums float4 chunks, two
+// row groups in flight; D == 2 -> one thread per PAIR of rows (one float4).  (The scalar kernel keeps one 4-byte load in
+// flight per lane: 28-31 % of HBM at D <= 64.)  Same per-element arithmetic; the order of the D additions differs.
+template <int G>
+__global__ void __launch_bounds__(256)
+std_normal_log_prob_vec4_kernel(const float* __restrict__ z, const float* __restrict__ ld, float* __restrict__ lp, int64_t B,
+                                int D, float norm_const) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, g = lane % G, sub = lane / G;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nblk = (B + RPW - 1) / RPW;
+    const int nch = D >> 2;
+    auto row_sum = [&](int64_t row) -> float {
+        float acc = 0.f;
+        if (row < B) {
+            const float4* p = reinterpret_cast<const float4*>(z + row * D);
+            for (int c = g; c < nch; c += G) {
+                const float4 v = __ldcs(p + c);
+                acc += -0.5f * v.x * v.x; acc += -0.5f * v.y * v.y; acc += -0.5f * v.z * v.z; acc += -0.5f * v.w * v.w;
+            }
+        }
+        return acc;
+    };
+    for (int64_t blk = warp; blk < nblk; blk += 2 * nwarps) {
+        const int64_t r0 = blk * RPW + sub, r1 = (blk + nwarps) * RPW + sub;
+        const bool second = blk + nwarps < nblk;
+        float a0 = row_sum(r0), a1 = second ? row_sum(r1) : 0.f;
+        a0 = group_sum<float, G>(a0);
+        a1 = group_sum<float, G>(a1);
+        if (g == 0 && r0 < B) lp[r0] = a0 - norm_const + (ld ? ld[r0] : 0.f);
+        if (g == 0 && second && r1 < B) lp[r1] = a1 - norm_const + (ld ? ld[r1] : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+std_normal_log_prob_d2_kernel(const float* __restrict__ z, const float* __restrict__ ld, float* __restrict__ lp, int64_t B,
+                              float norm_const) {
+    const int64_t npair = B >> 1, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npair; p += stride) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(z) + p);
+        float a = 0.f, b = 0.f;
+        a += -0.5f * v.x * v.x; a += -0.5f * v.y * v.y;
+        b += -0.5f * v.z * v.z; b += -0.5f * v.w * v.w;
+        lp[2 * p] = a - norm_const + (ld ? ld[2 * p] : 0.f);
+        lp[2 * p + 1] = b - norm_const + (ld ? ld[2 * p + 1] : 0.f);
+    }
+    if ((B & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t r = B - 1;
+        float a = 0.f;
+        a += -0.5f * z[2 * r] * z[2 * r]; a += -0.5f * z[2 * r + 1] * z[2 * r + 1];
+        lp[r] = a - norm_const + (ld ? ld[r] : 0.f);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 std_normal_log_prob_bwd_kernel(const T* __restrict__ z, const T* __restrict__ glp, T* __restrict__ gz, int64_t B, int D) {
@@ -232,6 +408,7 @@ static int feature_affine_bwd(const void* x, const void* sub, const void* div, c
     int chunks; int64_t rpc;
     chunking(B, chunks, rpc);
     dim3 grid((unsigned)cdiv(D, 32), (unsigned)chunks);
+    if (!(sizeof(T) == 4 && col_moments_rows_launch((const float*)x, (const float*)sub, (const float*)gy, (double*)ws, B, D, 0, st)))
     col_moments_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)sub, (const T*)gy, (double*)ws, B, D, rpc, 0);
     count_launch();
     NF_LAUNCH_CHECK();
@@ -248,6 +425,7 @@ static int col_stats(const void* x, void* mean, void* var, void* ws, int64_t B, 
     int chunks; int64_t rpc;
     chunking(B, chunks, rpc);
     dim3 grid((unsigned)cdiv(D, 32), (unsigned)chunks);
+    if (!(sizeof(T) == 4 && col_moments_rows_launch((const float*)x, nullptr, nullptr, (double*)ws, B, D, 1, st)))
     col_moments_kernel<T><<<grid, 256, 0, st>>>((const T*)x, nullptr, nullptr, (double*)ws, B, D, rpc, 1);
     count_launch();
     NF_LAUNCH_CHECK();
@@ -276,6 +454,21 @@ extern "C" int nf_feature_affine_forward(const void* x, const void* sub, const v
     NF_REQ(x); NF_REQ(y);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ew_grid(B * D);
+    const int64_t n = B * D;
+    const bool pal = (D % 4 != 0) || ((!sub || aligned16(sub)) && (!div || aligned16(div)) && (!mul || aligned16(mul)) && (!add || aligned16(add)));
+    if (dtype == NF_F32 && (n % 4) == 0 && aligned16(x) && aligned16(y) && pal && (D % 4 == 0 || D == 2 || D == 1)) {
+        const int64_t nch = n / 4;
+        int64_t need = cdiv(nch, 256 * 2);
+        const int64_t cap = (int64_t)kNumSMs * 16;
+        const int g4 = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+#define NF_FA(PER) feature_affine_fwd_vec4_kernel<PER><<<g4, 256, 0, st>>>((const float*)x, (const float*)sub, (const float*)div, \
+            (const float*)mul, (const float*)add, (float)add_scalar, (float*)y, nch, D)
+        if (D % 4 == 0) NF_FA(4); else if (D == 2) NF_FA(2); else NF_FA(1);
+#undef NF_FA
+        count_launch();
+        NF_LAUNCH_CHECK();
+        return NF_OK;
+    }
     NF_DISPATCH(
         (feature_affine_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)sub, (const float*)div,
             (const float*)mul, (const float*)add, (float)add_scalar, (float*)y, B, D)),
@@ -401,6 +594,25 @@ extern "C" int nf_std_normal_log_prob_forward(const void* z, const void* ld, voi
     NF_REQ(z); NF_REQ(lp);
     cudaStream_t st = (cudaStream_t)stream;
     const double nc = 0.5 * (double)D * 1.8378770664093453;   // D/2 * log(2 pi)
+    if (dtype == NF_F32 && aligned16(z) && (D == 2 || (D % 4 == 0))) {
+        const int64_t cap4 = (int64_t)kNumSMs * 16;
+        if (D == 2) {
+            int64_t need4 = cdiv(B / 2 + 1, 256);
+            const int g4 = (int)(need4 < 1 ? 1 : (need4 < cap4 ? need4 : cap4));
+            std_normal_log_prob_d2_kernel<<<g4, 256, 0, st>>>((const float*)z, (const float*)ld, (float*)lp, B, (float)nc);
+        } else {
+            int G4 = 1; while (G4 < D / 4 && G4 < 32) G4 <<= 1;
+            int64_t need4 = cdiv(cdiv(B, 32 / G4), 8 * 2);
+            const int g4 = (int)(need4 < 1 ? 1 : (need4 < cap4 ? need4 : cap4));
+#define NF_LP4(GG) std_normal_log_prob_vec4_kernel<GG><<<g4, 256, 0, st>>>((const float*)z, (const float*)ld, (float*)lp, B, D, (float)nc)
+            switch (G4) { case 1: NF_LP4(1); break; case 2: NF_LP4(2); break; case 4: NF_LP4(4); break; case 8: NF_LP4(8); break;
+                          case 16: NF_LP4(16); break; default: NF_LP4(32); break; }
+#undef NF_LP4
+        }
+        count_launch();
+        NF_LAUNCH_CHECK();
+        return NF_OK;
+    }
     int G = 1; while (G < D && G < 32) G <<= 1;
     int64_t need = cdiv(cdiv(B, 32 / G), 8), cap = (int64_t)kNumSMs * 32;
     const int grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));

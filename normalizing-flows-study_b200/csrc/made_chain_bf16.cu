@@ -23,7 +23,7 @@
 // last layer (o' = o + 4).
 //
 // Warp roles (320 threads, one CTA per SM, all 512 TMEM columns = four 128-column accumulators):
-//   warp 0      TMA producer: weight tiles [128 x 64] bf16, 4-stage ring, in (tile, layer, block desc., atom desc.) order
+//   warp 0      TMA producer: weight tiles [128 x 64] bf16, 3-stage ring, in (tile, layer, block desc., atom desc.) order
 //   warp 1      MMA issuer (whole warp convergent, one elected lane): waits x / block-ready / stage-full / accumulator-empty
 //   warps 2-9   epilogue: warp w drains TMEM lane quadrant w % 4, column half (w - 2) / 4 of each accumulator
 #include <cuda.h>
@@ -38,7 +38,7 @@ constexpr int kMcRows = 128;                 // rows per CTA tile (UMMA M)
 constexpr int kMcBN = 128;                   // output block width (UMMA N)
 constexpr int kMcAtom = 64;                  // bf16 elements per K atom (128 bytes: one swizzle span)
 constexpr int kMcAtomBytes = kMcRows * kMcAtom * 2;      // 16 KB: one activation slot = one weight stage
-constexpr int kMcStages = 4;
+constexpr int kMcStages = 3;                 // 3 x 16 KB weight stages: the 4th stage's room holds the biases (see below)
 constexpr int kMcMaxKA = 8;                  // hidden_dim <= 512
 constexpr int kMcThreads = 320;
 constexpr int kMcEpiWarps = 8;
@@ -78,6 +78,20 @@ __device__ __forceinline__ void mc_store_chunk(uint8_t* atom, int r, int c, uint
     *reinterpret_cast<uint4*>(p) = make_uint4(w0, w1, w2, w3);
 }
 
+// (o + k) mod nslot for o < nslot, k <= 3 * nslot: conditional subtractions (a run-time `%` is a ~25-instruction division)
+__device__ __forceinline__ int mc_slot(int o, int k, int nslot) {
+    int s = o + k;
+    if (s >= 2 * nslot) s -= 2 * nslot;
+    if (s >= nslot) s -= nslot;
+    if (s >= nslot) s -= nslot;
+    return s;
+}
+__device__ __forceinline__ float mc_relu_keepnan(float x) {      // torch.relu: NaN stays NaN
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __global__ void __launch_bounds__(kMcThreads, 1)
 made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
                        const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
@@ -88,9 +102,14 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
     const int NSLOT = P.KA + 2;
     uint8_t* act = smem;                                           // NSLOT activation slots
     uint8_t* wst = smem + (size_t)NSLOT * kMcAtomBytes;            // kMcStages weight stages
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)kMcStages * kMcAtomBytes);
-    uint64_t* w_full = bars;                    // [4]
-    uint64_t* w_empty = w_full + kMcStages;     // [4]
+    // all biases (b0 | b1 | b2 | b3: 3 H + 128 floats) staged once: the first version fetched them with __ldg in front of
+    // every use -- two 16-byte loads at a time for want of registers -- and the epilogue warps, the critical path of the
+    // kernel, spent a quarter of their samples waiting on those loads (profiles/r02b_made_chain_bf16_ncu.txt)
+    float* bias_s = reinterpret_cast<float*>(wst + (size_t)kMcStages * kMcAtomBytes);
+    const int H = P.KA * kMcAtom;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 3 * H + 128);
+    uint64_t* w_full = bars;                    // [kMcStages]
+    uint64_t* w_empty = w_full + kMcStages;     // [kMcStages]
     uint64_t* acc_full = w_empty + kMcStages;   // [4]
     uint64_t* acc_empty = acc_full + 4;         // [4]
     uint64_t* blk_ready = acc_empty + 4;        // [4] block jb of the current layer's input activations written
@@ -110,6 +129,8 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         tc::fence_mbar_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, kMcTmemCols);
+    for (int i = tid; i < 3 * H + 128; i += kMcThreads)
+        bias_s[i] = i < H ? __ldg(b0 + i) : (i < 2 * H ? __ldg(b1 + i - H) : (i < 3 * H ? __ldg(b2 + i - 2 * H) : __ldg(b3 + i - 3 * H)));
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -166,7 +187,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                         }
                         tc::mbar_wait(&w_full[s], ph);
                         tc::fence_after_sync();
-                        const int slot = (o + a + 2 * l) % NSLOT;
+                        const int slot = mc_slot(o, a + 2 * l, NSLOT);
                         const uint64_t da = tc::smem_desc_k_sw128(tc::smem_u32(act + (size_t)slot * kMcAtomBytes));
                         const uint64_t db = tc::smem_desc_k_sw128(tc::smem_u32(wst + (size_t)s * kMcAtomBytes));
                         const int nk = min(4, k16 - 4 * a);
@@ -184,7 +205,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     __syncwarp();
                 }
             }
-            o = (o + 4) % NSLOT;
+            o = mc_slot(o, 4, NSLOT);
         }
     } else {
         // ---------------- epilogue warps ----------------
@@ -224,7 +245,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
             load_x(t + gridDim.x, xn);                                  // in flight during layers 0..2
             for (int l = 0; l < 3; ++l) {
-                const float* bias = l == 0 ? b0 : (l == 1 ? b1 : b2);
+                const float* bias = bias_s + l * H;
                 for (int j = NB - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
                     const bool live = P.kext16[l][j] > 0;
@@ -245,13 +266,13 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
                     // h_{l+1} atom 2j + half of this row: bias, ReLU (NaN stays NaN), bf16
-                    const int slot = (o + (2 * j + half) + 2 * (l + 1)) % NSLOT;
+                    const int slot = mc_slot(o, (2 * j + half) + 2 * (l + 1), NSLOT);
                     uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
                     const float* bp = bias + j * kMcBN + half * 64;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 ba = __ldg(reinterpret_cast<const float4*>(bp + 8 * c));
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bp + 8 * c + 4));
+                        const float4 ba = *reinterpret_cast<const float4*>(bp + 8 * c);
+                        const float4 bb = *reinterpret_cast<const float4*>(bp + 8 * c + 4);
                         const uint32_t* vv = &v[c >> 1][(c & 1) * 8];
                         float f[8];
                         f[0] = __uint_as_float(vv[0]) + ba.x; f[1] = __uint_as_float(vv[1]) + ba.y;
@@ -259,7 +280,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                         f[4] = __uint_as_float(vv[4]) + bb.x; f[5] = __uint_as_float(vv[5]) + bb.y;
                         f[6] = __uint_as_float(vv[6]) + bb.z; f[7] = __uint_as_float(vv[7]) + bb.w;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = (f[i] < 0.f) ? 0.f : f[i];
+                        for (int i = 0; i < 8; ++i) f[i] = mc_relu_keepnan(f[i]);
                         mc_store_chunk(atom, r, c, mc_pack_bf16(f[0], f[1]), mc_pack_bf16(f[2], f[3]), mc_pack_bf16(f[4], f[5]),
                                        mc_pack_bf16(f[6], f[7]));
                     }
@@ -269,7 +290,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 }
             }
             // every MMA of layers 0..2 has completed: the next tile's x may take the slot that is free during layer 3
-            const int o_next = (o + 4) % NSLOT;
+            const int o_next = mc_slot(o, 4, NSLOT);
             if (t + (int)gridDim.x < P.num_tiles) write_x(xn, o_next);
             // ---- layer 3: [mu | alpha] -> affine autoregressive transform, row log-det (+ head) ----
             {
@@ -298,8 +319,8 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     const int d = c0 + i;
                     float ov = 0.f;
                     if (d < D) {
-                        const float mu = __uint_as_float(vm[i >> 4][i & 15]) + __ldg(b3 + d);
-                        const float al = __uint_as_float(va[i >> 4][i & 15]) + __ldg(b3 + 64 + d);
+                        const float mu = __uint_as_float(vm[i >> 4][i & 15]) + bias_s[3 * H + d];
+                        const float al = __uint_as_float(va[i >> 4][i & 15]) + bias_s[3 * H + 64 + d];
                         float tt;
                         affine_ar_elem<float>(P.mode, xc[i], mu, al, ov, tt);
                         if (!is_finite(ov)) ov = iaf ? xc[i] : 0.f;          // IAF scrubs to the input (:53)
@@ -405,7 +426,8 @@ extern "C" int nf_made_chain_bf16_forward(const void* x, const void* w0, const v
     if (!mc_make_map(&t0, w0, H, kMcAtom) || !mc_make_map(&t1, w1, H, H) || !mc_make_map(&t2, w2, H, H) ||
         !mc_make_map(&t3, w3, kMcBN, H))
         return NF_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)(P.KA + 2 + kMcStages) * kMcAtomBytes + 256 + 2 * 256 * sizeof(float);
+    const size_t smem = (size_t)(P.KA + 2 + kMcStages) * kMcAtomBytes + (size_t)(3 * H + 128) * sizeof(float) + 256 +
+                        2 * 256 * sizeof(float);
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
     NF_CUDA(cudaFuncSetAttribute(made_chain_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
