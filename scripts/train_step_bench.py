@@ -38,8 +38,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="capture the whole step (fwd, bwd, Adam) in one CUDA graph (1 GPU)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"],
                     help="dense-layer precision: fp32 = 3xTF32 (reference tolerances), tf32 = one TF32 pass (reduced-precision mode)")
+    ap.add_argument("--micro", type=int, default=1,
+                    help="micro-batches of --batch rows per optimizer step; all but the last run under no_sync() (gradient accumulation)")
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce after backward instead of during it (A/B for the overlap)")
+    ap.add_argument("--no-sync-bn", action="store_true", help="per-shard BatchNorm statistics (what DistributedDataParallel would do)")
     a = ap.parse_args()
     N.set_gemm_precision(a.precision)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -52,16 +56,25 @@ def main():
     torch.manual_seed(1234 + rank)            # different init per rank: the wrapper must broadcast rank 0's weights
     model, D = MODELS[a.model]()
     model.to(dev).train()
-    dp = N.parallel.DataParallelFlow(model)
+    dp = N.parallel.DataParallelFlow(model, overlap=not a.no_overlap, sync_batchnorm=not a.no_sync_bn)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=a.graph)
     gen = torch.Generator(device=dev).manual_seed(rank)
-    x = torch.randn(a.batch, D, device=dev, generator=gen)
+    xs = [torch.randn(a.batch, D, device=dev, generator=gen) for _ in range(min(a.micro, 4))]
+    x = xs[0]
+
+    def micro_step(xb):
+        z, ld = dp.inverse(xb)
+        loss = -N.ops.std_normal_log_prob(z, ld).mean() / a.micro
+        loss.backward()
+        return loss
 
     def step():
         opt.zero_grad(set_to_none=True)
-        z, ld = dp.inverse(x)
-        loss = -N.ops.std_normal_log_prob(z, ld).mean()
-        loss.backward()
+        if a.micro > 1:
+            with dp.no_sync():
+                for i in range(a.micro - 1):
+                    micro_step(xs[i % len(xs)])
+        loss = micro_step(xs[(a.micro - 1) % len(xs)])
         dp.sync_gradients()
         opt.step()
         return loss
@@ -106,8 +119,10 @@ def main():
         in_sync = bool(flag.item())
     if rank == 0:
         nparam = sum(p.numel() for p in model.parameters())
-        print(json.dumps({"model": a.model, "n_gpus": world, "batch_per_gpu": a.batch, "ms_per_step": ms.item(),
-                          "samples_per_s": a.batch * world / (ms.item() * 1e-3), "loss": float(loss),
+        print(json.dumps({"model": a.model, "n_gpus": world, "batch_per_gpu": a.batch, "micro_batches": a.micro,
+                          "global_rows_per_step": a.batch * a.micro * world, "ms_per_step": ms.item(),
+                          "samples_per_s": a.batch * a.micro * world / (ms.item() * 1e-3), "loss": float(loss),
+                          "overlap": not a.no_overlap, "sync_batchnorm": not a.no_sync_bn,
                           "params": nparam, "allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
                           "cuda_graph": bool(a.graph), "gemm_precision": a.precision, "replicas_in_sync": in_sync, "launches_per_step": (N._lib.launch_count() - l0) / a.steps,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
