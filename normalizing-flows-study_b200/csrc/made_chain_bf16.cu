@@ -44,6 +44,19 @@ constexpr int kMcThreads = 320;
 constexpr int kMcEpiWarps = 8;
 constexpr int kMcTmemCols = 512;
 
+#ifdef NF_MC_PROFILE
+// debug builds only (-DNF_MC_PROFILE): cycles CTA 0 spends waiting, per role and barrier
+__device__ long long g_mc_prof[16];
+#define MC_PROF_DECL long long pf_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long pf_start_ = clock64();
+#define MC_WAIT(i, stmt) do { const long long t__ = clock64(); stmt; pf_[i] += clock64() - t__; } while (0)
+#define MC_PROF_STORE(base, n) do { if (blockIdx.x == 0 && lane == 0) { for (int i__ = 0; i__ < (n); ++i__) g_mc_prof[(base) + i__] = pf_[i__]; \
+                                                                      g_mc_prof[(base) + (n)] = clock64() - pf_start_; } } while (0)
+#else
+#define MC_PROF_DECL
+#define MC_WAIT(i, stmt) do { stmt; } while (0)
+#define MC_PROF_STORE(base, n) do { } while (0)
+#endif
+
 struct McParams {
     int kext16[4][4];       // [layer][block]: 16-wide k-steps the block's outputs depend on (monotone in block)
     int NB;                 // 128-column blocks of the hidden layers (H / 128)
@@ -139,6 +152,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
     if (warp == 0) {
         // ---------------- weight producer ----------------
         if (lane == 0) {
+            MC_PROF_DECL
             int s = 0;
             uint32_t ph = 0;
             bool first_round = true;
@@ -149,7 +163,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     for (int j = nblk - 1; j >= 0; --j) {
                         const int na = (P.kext16[l][j] + 3) >> 2;
                         for (int a = na - 1; a >= 0; --a) {
-                            if (!first_round) tc::mbar_wait(&w_empty[s], ph ^ 1u);
+                            if (!first_round) MC_WAIT(0, tc::mbar_wait(&w_empty[s], ph ^ 1u));
                             tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)kMcAtomBytes);
                             mc_tma_load_2d(wst + (size_t)s * kMcAtomBytes, map, a * kMcAtom, j * kMcBN, &w_full[s]);
                             if (++s == kMcStages) { s = 0; ph ^= 1u; first_round = false; }
@@ -157,21 +171,23 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     }
                 }
             }
+            MC_PROF_STORE(0, 1);           // [0] producer waits for a free stage, [1] producer total
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         const uint32_t idesc = mc_idesc_bf16((uint32_t)kMcBN);
         const bool leader = tc::elect_one();
+        MC_PROF_DECL
         int s = 0, u = 0, it = 0, o = 0;                   // weight stage, unit counter (accumulator ring), tile iteration, slot offset
         uint32_t ph = 0;
         for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
             for (int l = 0; l < 4; ++l) {
                 const int nblk = (l == 3) ? 1 : NB;
                 uint32_t ready = 0;                            // input blocks of this layer already waited for
-                if (l == 0) tc::mbar_wait(x_ready, (uint32_t)(it & 1));
+                if (l == 0) MC_WAIT(0, tc::mbar_wait(x_ready, (uint32_t)(it & 1)));
                 for (int j = nblk - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
-                    if (u >= 4) tc::mbar_wait(&acc_empty[acc], (uint32_t)(((u >> 2) & 1) ^ 1));
+                    if (u >= 4) MC_WAIT(1, tc::mbar_wait(&acc_empty[acc], (uint32_t)(((u >> 2) & 1) ^ 1)));
                     const int k16 = P.kext16[l][j];
                     const int na = (k16 + 3) >> 2;
                     const uint32_t dcol = tb + (uint32_t)(acc * kMcBN);
@@ -181,11 +197,11 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                             const int jb = a >> 1;
                             if (!(ready & (1u << jb))) {
                                 // h_l block jb: completion number 3*it + (l-1) of blk_ready[jb]
-                                tc::mbar_wait(&blk_ready[jb], (uint32_t)((3 * it + (l - 1)) & 1));
+                                MC_WAIT(2, tc::mbar_wait(&blk_ready[jb], (uint32_t)((3 * it + (l - 1)) & 1)));
                                 ready |= 1u << jb;
                             }
                         }
-                        tc::mbar_wait(&w_full[s], ph);
+                        MC_WAIT(3, tc::mbar_wait(&w_full[s], ph));
                         tc::fence_after_sync();
                         const int slot = mc_slot(o, a + 2 * l, NSLOT);
                         const uint64_t da = tc::smem_desc_k_sw128(tc::smem_u32(act + (size_t)slot * kMcAtomBytes));
@@ -207,6 +223,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
             }
             o = mc_slot(o, 4, NSLOT);
         }
+        MC_PROF_STORE(2, 4);               // [2] x ready, [3] accumulator empty, [4] input block ready, [5] weight stage full, [6] MMA warp total
     } else {
         // ---------------- epilogue warps ----------------
         const int q = warp & 3, half = (warp - 2) >> 2;
@@ -239,6 +256,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
             if (lane == 0) tc::mbar_arrive(x_ready);
         };
 
+        MC_PROF_DECL
         int u = 0, it = 0, o = 0;
         load_x(blockIdx.x, xc);
         if ((int)blockIdx.x < P.num_tiles) write_x(xc, 0);
@@ -249,7 +267,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 for (int j = NB - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
                     const bool live = P.kext16[l][j] > 0;
-                    tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1));
+                    MC_WAIT(0, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                     tc::fence_after_sync();
                     uint32_t v[4][16];
                     if (live) {
@@ -295,7 +313,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
             // ---- layer 3: [mu | alpha] -> affine autoregressive transform, row log-det (+ head) ----
             {
                 const int acc = u & 3;
-                tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1));
+                MC_WAIT(1, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                 tc::fence_after_sync();
                 uint32_t vm[2][16], va[2][16];
                 if (P.kext16[3][0] > 0) {
@@ -352,6 +370,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
             for (int i = 0; i < 32; ++i) xc[i] = xn[i];
             o = o_next;
         }
+        if (warp == 2) MC_PROF_STORE(8, 2);    // [8] hidden-layer accumulator full, [9] last-layer accumulator full, [10] epilogue warp total
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -393,6 +412,12 @@ static bool mc_make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t 
 
 using namespace nf;
 #define NF_REQ(p) do { if ((p) == nullptr) return NF_ERR_NULL; } while (0)
+
+#ifdef NF_MC_PROFILE
+extern "C" __attribute__((visibility("default"))) int nf_debug_mc_profile(long long* out) {
+    return cudaMemcpyFromSymbol(out, nf::g_mc_prof, sizeof(long long) * 16) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 extern "C" int nf_made_chain_bf16_forward(const void* x, const void* w0, const void* w1, const void* w2, const void* w3,
                                           const void* b0, const void* b1, const void* b2, const void* b3,
