@@ -22,10 +22,10 @@
 // issues one continuous stream of MMAs across layers and tiles.  The next tile's x goes to a slot that is free during the
 // last layer (o' = o + 4).
 //
-// Warp roles (320 threads, one CTA per SM, all 512 TMEM columns = four 128-column accumulators):
+// Warp roles (576 threads, one CTA per SM, all 512 TMEM columns = four 128-column accumulators):
 //   warp 0      TMA producer: weight tiles [128 x 64] bf16, 3-stage ring, in (tile, layer, block desc., atom desc.) order
 //   warp 1      MMA issuer (whole warp convergent, one elected lane): waits x / block-ready / stage-full / accumulator-empty
-//   warps 2-9   epilogue: warp w drains TMEM lane quadrant w % 4, column half (w - 2) / 4 of each accumulator
+//   warps 2-17  epilogue: warp w drains TMEM lane quadrant w % 4, column quarter (w - 2) / 4 of each accumulator
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "nf_common.cuh"
@@ -40,8 +40,8 @@ constexpr int kMcAtom = 64;                  // bf16 elements per K atom (128 by
 constexpr int kMcAtomBytes = kMcRows * kMcAtom * 2;      // 16 KB: one activation slot = one weight stage
 constexpr int kMcStages = 3;                 // 3 x 16 KB weight stages: the 4th stage's room holds the biases (see below)
 constexpr int kMcMaxKA = 8;                  // hidden_dim <= 512
-constexpr int kMcThreads = 320;
-constexpr int kMcEpiWarps = 8;
+constexpr int kMcEpiWarps = 16;
+constexpr int kMcThreads = 64 + 32 * kMcEpiWarps;
 constexpr int kMcTmemCols = 512;
 
 #ifdef NF_MC_PROFILE
@@ -128,7 +128,9 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
     uint64_t* blk_ready = acc_empty + 4;        // [4] block jb of the current layer's input activations written
     uint64_t* x_ready = blk_ready + 4;          // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
-    float* row_part = reinterpret_cast<float*>(tmem_slot + 2);     // [2 tile parities][2 values][128 rows]
+    float* row_part = reinterpret_cast<float*>(tmem_slot + 2);     // [2 tile parities][3 column quarters][2 values][128 rows]
+    int* kext_s = reinterpret_cast<int*>(row_part + 2 * 3 * 256);  // [4 layers][4 blocks]: P.kext16 (dynamic indexing of a
+                                                                   // __grid_constant__ struct member goes through local memory)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NB = P.NB;
@@ -142,6 +144,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         tc::fence_mbar_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, kMcTmemCols);
+    if (tid < 16) kext_s[tid] = P.kext16[tid >> 2][tid & 3];
     for (int i = tid; i < 3 * H + 128; i += kMcThreads)
         bias_s[i] = i < H ? __ldg(b0 + i) : (i < 2 * H ? __ldg(b1 + i - H) : (i < 3 * H ? __ldg(b2 + i - 2 * H) : __ldg(b3 + i - 3 * H)));
     tc::fence_before_sync();
@@ -161,7 +164,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     const CUtensorMap* map = l == 0 ? &tm_w0 : (l == 1 ? &tm_w1 : (l == 2 ? &tm_w2 : &tm_w3));
                     const int nblk = (l == 3) ? 1 : NB;
                     for (int j = nblk - 1; j >= 0; --j) {
-                        const int na = (P.kext16[l][j] + 3) >> 2;
+                        const int na = (kext_s[l * 4 + j] + 3) >> 2;
                         for (int a = na - 1; a >= 0; --a) {
                             if (!first_round) MC_WAIT(0, tc::mbar_wait(&w_empty[s], ph ^ 1u));
                             tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)kMcAtomBytes);
@@ -188,7 +191,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 for (int j = nblk - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
                     if (u >= 4) MC_WAIT(1, tc::mbar_wait(&acc_empty[acc], (uint32_t)(((u >> 2) & 1) ^ 1)));
-                    const int k16 = P.kext16[l][j];
+                    const int k16 = kext_s[l * 4 + j];
                     const int na = (k16 + 3) >> 2;
                     const uint32_t dcol = tb + (uint32_t)(acc * kMcBN);
                     bool first = true;
@@ -226,30 +229,34 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         MC_PROF_STORE(2, 4);               // [2] x ready, [3] accumulator empty, [4] input block ready, [5] weight stage full, [6] MMA warp total
     } else {
         // ---------------- epilogue warps ----------------
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        // 16 warps: warp w drains TMEM lane quadrant w % 4, column quarter cq = (w - 2) / 4 (32 of a block's 128 columns).
+        // The first version had 8 warps with 64 columns each: ~220 dependent instructions per unit at two warps per
+        // scheduler took ~2 400 clk per unit against ~1 000 clk of MMAs -- the MMA warp spent a third of its time waiting
+        // for a free accumulator (profiles/r02d_chain_phase.log).
+        const int q = warp & 3, cq = (warp - 2) >> 2;
         const int r = q * 32 + lane;                                   // row inside the tile = TMEM lane
         const uint32_t lane_addr = tb + ((uint32_t)(q * 32) << 16);
         const int D = P.D;
         const bool iaf = (P.mode == AR_IAF_FWD);
         const float lim = iaf ? 50.f : 100.f;
-        const int c0 = half * 32;                                      // this thread's 32 data columns
-        float xc[32], xn[32];
+        const int c0 = cq * 16;                                        // this thread's 16 data columns
+        float xc[16], xn[16];
 
-        auto load_x = [&](int tile, float (&v)[32]) {
+        auto load_x = [&](int tile, float (&v)[16]) {
             const int64_t row = (int64_t)tile * kMcRows + r;
             const bool ok = tile < P.num_tiles && row < P.B;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && c0 + 4 * i < D) f = __ldcs(reinterpret_cast<const float4*>(x + row * D + c0 + 4 * i));
                 v[4 * i + 0] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
             }
         };
-        auto write_x = [&](const float (&v)[32], int slot) {
+        auto write_x = [&](const float (&v)[16], int slot) {
             uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                mc_store_chunk(atom, r, half * 4 + c, mc_pack_bf16(v[8 * c + 0], v[8 * c + 1]), mc_pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+            for (int c = 0; c < 2; ++c)
+                mc_store_chunk(atom, r, cq * 2 + c, mc_pack_bf16(v[8 * c + 0], v[8 * c + 1]), mc_pack_bf16(v[8 * c + 2], v[8 * c + 3]),
                                mc_pack_bf16(v[8 * c + 4], v[8 * c + 5]), mc_pack_bf16(v[8 * c + 6], v[8 * c + 7]));
             tc::fence_proxy_async_smem();
             __syncwarp();
@@ -266,41 +273,41 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 const float* bias = bias_s + l * H;
                 for (int j = NB - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
-                    const bool live = P.kext16[l][j] > 0;
+                    const bool live = kext_s[l * 4 + j] > 0;
                     MC_WAIT(0, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                     tc::fence_after_sync();
-                    uint32_t v[4][16];
+                    uint32_t v[2][16];
                     if (live) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + half * 64 + c * 16), v[c]);
+                        tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32), v[0]);
+                        tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32 + 16), v[1]);
                         tc::wait_ld();
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[c][i] = 0u;
+                        for (int i = 0; i < 16; ++i) { v[0][i] = 0u; v[1][i] = 0u; }
                     }
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
-                    // h_{l+1} atom 2j + half of this row: bias, ReLU (NaN stays NaN), bf16
-                    const int slot = mc_slot(o, (2 * j + half) + 2 * (l + 1), NSLOT);
+                    // columns [32 cq, 32 cq + 32) of h_{l+1} block j = chunks 4 (cq & 1) .. + 3 of atom 2j + cq / 2:
+                    // bias, ReLU (NaN stays NaN), bf16
+                    const int slot = mc_slot(o, (2 * j + (cq >> 1)) + 2 * (l + 1), NSLOT);
                     uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
-                    const float* bp = bias + j * kMcBN + half * 64;
+                    const float* bp = bias + j * kMcBN + cq * 32;
+                    float4 bb[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float4 ba = *reinterpret_cast<const float4*>(bp + 8 * c);
-                        const float4 bb = *reinterpret_cast<const float4*>(bp + 8 * c + 4);
+                    for (int c = 0; c < 8; ++c) bb[c] = *reinterpret_cast<const float4*>(bp + 4 * c);     // all bias loads first
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
                         const uint32_t* vv = &v[c >> 1][(c & 1) * 8];
                         float f[8];
-                        f[0] = __uint_as_float(vv[0]) + ba.x; f[1] = __uint_as_float(vv[1]) + ba.y;
-                        f[2] = __uint_as_float(vv[2]) + ba.z; f[3] = __uint_as_float(vv[3]) + ba.w;
-                        f[4] = __uint_as_float(vv[4]) + bb.x; f[5] = __uint_as_float(vv[5]) + bb.y;
-                        f[6] = __uint_as_float(vv[6]) + bb.z; f[7] = __uint_as_float(vv[7]) + bb.w;
+                        f[0] = __uint_as_float(vv[0]) + bb[2 * c].x; f[1] = __uint_as_float(vv[1]) + bb[2 * c].y;
+                        f[2] = __uint_as_float(vv[2]) + bb[2 * c].z; f[3] = __uint_as_float(vv[3]) + bb[2 * c].w;
+                        f[4] = __uint_as_float(vv[4]) + bb[2 * c + 1].x; f[5] = __uint_as_float(vv[5]) + bb[2 * c + 1].y;
+                        f[6] = __uint_as_float(vv[6]) + bb[2 * c + 1].z; f[7] = __uint_as_float(vv[7]) + bb[2 * c + 1].w;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = mc_relu_keepnan(f[i]);
-                        mc_store_chunk(atom, r, c, mc_pack_bf16(f[0], f[1]), mc_pack_bf16(f[2], f[3]), mc_pack_bf16(f[4], f[5]),
-                                       mc_pack_bf16(f[6], f[7]));
+                        mc_store_chunk(atom, r, (cq & 1) * 4 + c, mc_pack_bf16(f[0], f[1]), mc_pack_bf16(f[2], f[3]),
+                                       mc_pack_bf16(f[4], f[5]), mc_pack_bf16(f[6], f[7]));
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
@@ -315,59 +322,58 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 const int acc = u & 3;
                 MC_WAIT(1, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                 tc::fence_after_sync();
-                uint32_t vm[2][16], va[2][16];
-                if (P.kext16[3][0] > 0) {
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0), vm[0]);
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0 + 16), vm[1]);
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0), va[0]);
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0 + 16), va[1]);
+                uint32_t vm[16], va[16];
+                if (kext_s[12] > 0) {
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0), vm);
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0), va);
                     tc::wait_ld();
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { vm[0][i] = vm[1][i] = va[0][i] = va[1][i] = 0u; }
+                    for (int i = 0; i < 16; ++i) { vm[i] = 0u; va[i] = 0u; }
                 }
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
                 ++u;
                 const int64_t row = (int64_t)t * kMcRows + r;
-                float lsum = 0.f, sq = 0.f, o32[32];
+                float lsum = 0.f, sq = 0.f, o16[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const int d = c0 + i;
                     float ov = 0.f;
                     if (d < D) {
-                        const float mu = __uint_as_float(vm[i >> 4][i & 15]) + bias_s[3 * H + d];
-                        const float al = __uint_as_float(va[i >> 4][i & 15]) + bias_s[3 * H + 64 + d];
+                        const float mu = __uint_as_float(vm[i]) + bias_s[3 * H + d];
+                        const float al = __uint_as_float(va[i]) + bias_s[3 * H + 64 + d];
                         float tt;
                         affine_ar_elem<float>(P.mode, xc[i], mu, al, ov, tt);
                         if (!is_finite(ov)) ov = iaf ? xc[i] : 0.f;          // IAF scrubs to the input (:53)
                         lsum += tt;
                         sq += -0.5f * ov * ov;
                     }
-                    o32[i] = ov;
+                    o16[i] = ov;
                 }
                 if (row < P.B && !(P.flags & NF_STACK_SKIP_Y)) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 4; ++i)
                         if (c0 + 4 * i < D)
                             __stcs(reinterpret_cast<float4*>(out + row * D + c0 + 4 * i),
-                                   make_float4(o32[4 * i], o32[4 * i + 1], o32[4 * i + 2], o32[4 * i + 3]));
+                                   make_float4(o16[4 * i], o16[4 * i + 1], o16[4 * i + 2], o16[4 * i + 3]));
                 }
-                // the two column halves of a row live in two warps: combine through shared memory (fixed order)
-                float* part = row_part + (it & 1) * 256;
-                if (half == 1) { part[r] = lsum; part[128 + r] = sq; }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && row < P.B) {
-                    const float tot = clamp_mm(scrub0(lsum + part[r]), -lim, lim);
+                // the four column quarters of a row live in four warps: combine through shared memory in a fixed order
+                float* part = row_part + (it & 1) * (3 * 256);
+                if (cq > 0) { part[(cq - 1) * 256 + r] = lsum; part[(cq - 1) * 256 + 128 + r] = sq; }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (cq == 0 && row < P.B) {
+                    const float tot = clamp_mm(scrub0(((lsum + part[r]) + part[256 + r]) + part[512 + r]), -lim, lim);
                     float res = tot;
                     if (P.flags & NF_STACK_LOG_PROB_HEAD)
-                        res = (sq + part[128 + r]) - (float)(0.5 * (double)D * 1.8378770664093453) + tot;
+                        res = (((sq + part[128 + r]) + part[256 + 128 + r]) + part[512 + 128 + r]) -
+                              (float)(0.5 * (double)D * 1.8378770664093453) + tot;
                     __stcs(ld_out + row, res);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xc[i] = xn[i];
+            for (int i = 0; i < 16; ++i) xc[i] = xn[i];
             o = o_next;
         }
         if (warp == 2) MC_PROF_STORE(8, 2);    // [8] hidden-layer accumulator full, [9] last-layer accumulator full, [10] epilogue warp total
@@ -452,7 +458,7 @@ extern "C" int nf_made_chain_bf16_forward(const void* x, const void* w0, const v
         !mc_make_map(&t3, w3, kMcBN, H))
         return NF_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(P.KA + 2 + kMcStages) * kMcAtomBytes + (size_t)(3 * H + 128) * sizeof(float) + 256 +
-                        2 * 256 * sizeof(float);
+                        (2 * 3 * 256 + 16) * sizeof(float);
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
     NF_CUDA(cudaFuncSetAttribute(made_chain_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
