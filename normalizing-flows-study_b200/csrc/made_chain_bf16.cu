@@ -240,7 +240,7 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         const bool iaf = (P.mode == AR_IAF_FWD);
         const float lim = iaf ? 50.f : 100.f;
         const int c0 = cq * 16;                                        // this thread's 16 data columns
-        float xc[16], xn[16];
+        float xn[16];                                                  // the NEXT tile's x, in flight during layers 0..2
 
         auto load_x = [&](int tile, float (&v)[16]) {
             const int64_t row = (int64_t)tile * kMcRows + r;
@@ -265,8 +265,8 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
 
         MC_PROF_DECL
         int u = 0, it = 0, o = 0;
-        load_x(blockIdx.x, xc);
-        if ((int)blockIdx.x < P.num_tiles) write_x(xc, 0);
+        load_x(blockIdx.x, xn);
+        if ((int)blockIdx.x < P.num_tiles) write_x(xn, 0);
         for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
             load_x(t + gridDim.x, xn);                                  // in flight during layers 0..2
             for (int l = 0; l < 3; ++l) {
@@ -274,6 +274,16 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 for (int j = NB - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
                     const bool live = kext_s[l * 4 + j] > 0;
+                    // everything that does not depend on the accumulator goes in front of the wait: the destination of
+                    // columns [32 cq, 32 cq + 32) of h_{l+1} block j (chunks 4 (cq & 1) .. + 3 of atom 2j + cq / 2) and the
+                    // 32 bias values (the epilogue is the critical path of the kernel: ~2 000 clk per unit against ~1 000
+                    // clk of MMAs, profiles/r02e_chain_phase.log)
+                    const int slot = mc_slot(o, (2 * j + (cq >> 1)) + 2 * (l + 1), NSLOT);
+                    uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
+                    const float* bp = bias + j * kMcBN + cq * 32;
+                    float4 bb[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) bb[c] = *reinterpret_cast<const float4*>(bp + 4 * c);
                     MC_WAIT(0, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                     tc::fence_after_sync();
                     uint32_t v[2][16];
@@ -288,14 +298,6 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
-                    // columns [32 cq, 32 cq + 32) of h_{l+1} block j = chunks 4 (cq & 1) .. + 3 of atom 2j + cq / 2:
-                    // bias, ReLU (NaN stays NaN), bf16
-                    const int slot = mc_slot(o, (2 * j + (cq >> 1)) + 2 * (l + 1), NSLOT);
-                    uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
-                    const float* bp = bias + j * kMcBN + cq * 32;
-                    float4 bb[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) bb[c] = *reinterpret_cast<const float4*>(bp + 4 * c);     // all bias loads first
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const uint32_t* vv = &v[c >> 1][(c & 1) * 8];
@@ -336,6 +338,8 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
                 ++u;
                 const int64_t row = (int64_t)t * kMcRows + r;
+                float xc[16];                       // this tile's x in fp32 again (L2 hit: read at the start of the tile)
+                load_x(t, xc);
                 float lsum = 0.f, sq = 0.f, o16[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -372,8 +376,6 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     __stcs(ld_out + row, res);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xc[i] = xn[i];
             o = o_next;
         }
         if (warp == 2) MC_PROF_STORE(8, 2);    // [8] hidden-layer accumulator full, [9] last-layer accumulator full, [10] epilogue warp total
