@@ -334,7 +334,7 @@ std_normal_log_prob_fwd_kernel(const T* __restrict__ z, const T* __restrict__ ld
     }
 }
 
-// float32, 16-byte aligned z: D % 4 == 0 -> G lanes per row (G = pow2 >= D/4, <= 32), each lane sums float4 chunks, two
+// float32, 16-byte aligned z: D % 4 == 0 -> G lanes per row (G = pow2 >= D/4, <= 32), each lane sums float4 chunks, four
 // row groups in flight; D == 2 -> one thread per PAIR of rows (one float4).  (The scalar kernel keeps one 4-byte load in
 // flight per lane: 28-31 % of HBM at D <= 64.)  Same per-element arithmetic; the order of the D additions differs.
 template <int G>
@@ -358,14 +358,20 @@ std_normal_log_prob_vec4_kernel(const float* __restrict__ z, const float* __rest
         }
         return acc;
     };
-    for (int64_t blk = warp; blk < nblk; blk += 2 * nwarps) {
-        const int64_t r0 = blk * RPW + sub, r1 = (blk + nwarps) * RPW + sub;
-        const bool second = blk + nwarps < nblk;
-        float a0 = row_sum(r0), a1 = second ? row_sum(r1) : 0.f;
-        a0 = group_sum<float, G>(a0);
-        a1 = group_sum<float, G>(a1);
-        if (g == 0 && r0 < B) lp[r0] = a0 - norm_const + (ld ? ld[r0] : 0.f);
-        if (g == 0 && second && r1 < B) lp[r1] = a1 - norm_const + (ld ? ld[r1] : 0.f);
+    constexpr int U = 4;                                   // row groups in flight per warp
+    for (int64_t blk = warp; blk < nblk; blk += U * nwarps) {
+        int64_t rr[U];
+        float a[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            rr[k] = (blk + k * nwarps) * RPW + sub;
+            a[k] = (blk + k * nwarps < nblk) ? row_sum(rr[k]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            a[k] = group_sum<float, G>(a[k]);
+            if (g == 0 && blk + k * nwarps < nblk && rr[k] < B) lp[rr[k]] = a[k] - norm_const + (ld ? ld[rr[k]] : 0.f);
+        }
     }
 }
 
@@ -602,7 +608,7 @@ extern "C" int nf_std_normal_log_prob_forward(const void* z, const void* ld, voi
             std_normal_log_prob_d2_kernel<<<g4, 256, 0, st>>>((const float*)z, (const float*)ld, (float*)lp, B, (float)nc);
         } else {
             int G4 = 1; while (G4 < D / 4 && G4 < 32) G4 <<= 1;
-            int64_t need4 = cdiv(cdiv(B, 32 / G4), 8 * 2);
+            int64_t need4 = cdiv(cdiv(B, 32 / G4), 8 * 4);
             const int g4 = (int)(need4 < 1 ? 1 : (need4 < cap4 ? need4 : cap4));
 #define NF_LP4(GG) std_normal_log_prob_vec4_kernel<GG><<<g4, 256, 0, st>>>((const float*)z, (const float*)ld, (float*)lp, B, D, (float)nc)
             switch (G4) { case 1: NF_LP4(1); break; case 2: NF_LP4(2); break; case 4: NF_LP4(4); break; case 8: NF_LP4(8); break;

@@ -85,6 +85,13 @@ __device__ __forceinline__ uint32_t mc_pack_bf16(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);          // .x = lo (low 16 bits), .y = hi
     return *reinterpret_cast<const uint32_t*>(&v);
 }
+// max(x, 0) with NaN kept (torch.relu) and round-to-nearest bf16, two values per instruction (F2FP.RELU.BF16.F32.PACK_AB;
+// cvt's .relu maps NaN to the canonical NaN and -0 / negatives to +0)
+__device__ __forceinline__ uint32_t mc_pack_relu_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // one 16-byte chunk (8 bf16) of row r of a K-major SWIZZLE_128B atom: chunk c sits at position c ^ (r % 8)
 __device__ __forceinline__ void mc_store_chunk(uint8_t* atom, int r, int c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     uint8_t* p = atom + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4);
@@ -240,7 +247,12 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
         const bool iaf = (P.mode == AR_IAF_FWD);
         const float lim = iaf ? 50.f : 100.f;
         const int c0 = cq * 16;                                        // this thread's 16 data columns
-        float xn[16];                                                  // the NEXT tile's x, in flight during layers 0..2
+        float xc[16], xn[16];
+        // byte offsets of this thread's row and of its four 16-byte chunks inside a SWIZZLE_128B atom (constant per thread)
+        const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        uint32_t chunk_off[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk_off[c] = (uint32_t)((((cq & 1) * 4 + c) ^ (r & 7)) << 4);
 
         auto load_x = [&](int tile, float (&v)[16]) {
             const int64_t row = (int64_t)tile * kMcRows + r;
@@ -265,51 +277,42 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
 
         MC_PROF_DECL
         int u = 0, it = 0, o = 0;
-        load_x(blockIdx.x, xn);
-        if ((int)blockIdx.x < P.num_tiles) write_x(xn, 0);
+        load_x(blockIdx.x, xc);
+        if ((int)blockIdx.x < P.num_tiles) write_x(xc, 0);
         for (int t = blockIdx.x; t < P.num_tiles; t += gridDim.x, ++it) {
             load_x(t + gridDim.x, xn);                                  // in flight during layers 0..2
             for (int l = 0; l < 3; ++l) {
                 const float* bias = bias_s + l * H;
                 for (int j = NB - 1; j >= 0; --j, ++u) {
                     const int acc = u & 3;
-                    const bool live = kext_s[l * 4 + j] > 0;
-                    // everything that does not depend on the accumulator goes in front of the wait: the destination of
-                    // columns [32 cq, 32 cq + 32) of h_{l+1} block j (chunks 4 (cq & 1) .. + 3 of atom 2j + cq / 2) and the
-                    // 32 bias values (the epilogue is the critical path of the kernel: ~2 000 clk per unit against ~1 000
-                    // clk of MMAs, profiles/r02e_chain_phase.log)
-                    const int slot = mc_slot(o, (2 * j + (cq >> 1)) + 2 * (l + 1), NSLOT);
-                    uint8_t* atom = act + (size_t)slot * kMcAtomBytes;
-                    const float* bp = bias + j * kMcBN + cq * 32;
-                    float4 bb[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) bb[c] = *reinterpret_cast<const float4*>(bp + 4 * c);
+                    // The epilogue is the critical path (13 units x ~2 000 clk per tile against ~1 000 clk of MMAs per unit,
+                    // profiles/r02e_chain_phase.log) and it is ISSUE-bound: 16 warps x ~180 instructions per unit over four
+                    // schedulers.  So the unit body is pared down: per-thread store offsets precomputed, bias added with
+                    // packed f32x2 adds (FADD2), ReLU folded into the bf16 pack (F2FP.RELU), no zero-fill path (the host
+                    // guarantees at least one k-step per block).
                     MC_WAIT(0, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                     tc::fence_after_sync();
                     uint32_t v[2][16];
-                    if (live) {
-                        tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32), v[0]);
-                        tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32 + 16), v[1]);
-                        tc::wait_ld();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { v[0][i] = 0u; v[1][i] = 0u; }
-                    }
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32), v[0]);
+                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + cq * 32 + 16), v[1]);
+                    tc::wait_ld();
                     tc::fence_before_sync();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
+                    // columns [32 cq, 32 cq + 32) of h_{l+1} block j = chunks 4 (cq & 1) .. + 3 of atom 2j + cq / 2
+                    uint8_t* dst = act + (size_t)mc_slot(o, (2 * j + (cq >> 1)) + 2 * (l + 1), NSLOT) * kMcAtomBytes + row_off;
+                    const float4* bp = reinterpret_cast<const float4*>(bias + j * kMcBN + cq * 32);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
+                        const float4 b0 = bp[2 * c], b1 = bp[2 * c + 1];
                         const uint32_t* vv = &v[c >> 1][(c & 1) * 8];
-                        float f[8];
-                        f[0] = __uint_as_float(vv[0]) + bb[2 * c].x; f[1] = __uint_as_float(vv[1]) + bb[2 * c].y;
-                        f[2] = __uint_as_float(vv[2]) + bb[2 * c].z; f[3] = __uint_as_float(vv[3]) + bb[2 * c].w;
-                        f[4] = __uint_as_float(vv[4]) + bb[2 * c + 1].x; f[5] = __uint_as_float(vv[5]) + bb[2 * c + 1].y;
-                        f[6] = __uint_as_float(vv[6]) + bb[2 * c + 1].z; f[7] = __uint_as_float(vv[7]) + bb[2 * c + 1].w;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = mc_relu_keepnan(f[i]);
-                        mc_store_chunk(atom, r, (cq & 1) * 4 + c, mc_pack_bf16(f[0], f[1]), mc_pack_bf16(f[2], f[3]),
-                                       mc_pack_bf16(f[4], f[5]), mc_pack_bf16(f[6], f[7]));
+                        const float2 f0 = __fadd2_rn(make_float2(__uint_as_float(vv[0]), __uint_as_float(vv[1])), make_float2(b0.x, b0.y));
+                        const float2 f1 = __fadd2_rn(make_float2(__uint_as_float(vv[2]), __uint_as_float(vv[3])), make_float2(b0.z, b0.w));
+                        const float2 f2 = __fadd2_rn(make_float2(__uint_as_float(vv[4]), __uint_as_float(vv[5])), make_float2(b1.x, b1.y));
+                        const float2 f3 = __fadd2_rn(make_float2(__uint_as_float(vv[6]), __uint_as_float(vv[7])), make_float2(b1.z, b1.w));
+                        *reinterpret_cast<uint4*>(dst + chunk_off[c]) =
+                            make_uint4(mc_pack_relu_bf16(f0.x, f0.y), mc_pack_relu_bf16(f1.x, f1.y), mc_pack_relu_bf16(f2.x, f2.y),
+                                       mc_pack_relu_bf16(f3.x, f3.y));
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
@@ -325,21 +328,14 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                 MC_WAIT(1, tc::mbar_wait(&acc_full[acc], (uint32_t)((u >> 2) & 1)));
                 tc::fence_after_sync();
                 uint32_t vm[16], va[16];
-                if (kext_s[12] > 0) {
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0), vm);
-                    tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0), va);
-                    tc::wait_ld();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { vm[i] = 0u; va[i] = 0u; }
-                }
+                tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + c0), vm);
+                tc::tmem_ld16(lane_addr + (uint32_t)(acc * kMcBN + 64 + c0), va);
+                tc::wait_ld();
                 tc::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[acc]);
                 ++u;
                 const int64_t row = (int64_t)t * kMcRows + r;
-                float xc[16];                       // this tile's x in fp32 again (L2 hit: read at the start of the tile)
-                load_x(t, xc);
                 float lsum = 0.f, sq = 0.f, o16[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -376,6 +372,8 @@ made_chain_bf16_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_c
                     __stcs(ld_out + row, res);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xc[i] = xn[i];
             o = o_next;
         }
         if (warp == 2) MC_PROF_STORE(8, 2);    // [8] hidden-layer accumulator full, [9] last-layer accumulator full, [10] epilogue warp total
@@ -451,7 +449,8 @@ extern "C" int nf_made_chain_bf16_forward(const void* x, const void* w0, const v
             int v = kext16_host[l * 4 + j];
             if (v < 0 || v > kmax) return NF_ERR_BAD_SHAPE;
             if (j >= (l == 3 ? 1 : P.NB)) v = 0;
-            else { v = v > prev ? v : prev; prev = v; }            // monotone in the block index (block-triangular weights)
+            else { v = v > prev ? v : prev; v = v < 1 ? 1 : v; prev = v; }   // monotone in the block index (block-triangular
+                                                                   // weights); >= 1: every accumulator is written by an MMA
             P.kext16[l][j] = v;
         }
     }
