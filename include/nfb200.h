@@ -161,7 +161,8 @@ NF_API int nf_batchnorm_backward(const void* x, const void* y, const void* gamma
  * backward stage 1: workspace[2H] doubles <- this shard's (sum g*xhat, sum g) = its ggamma / gbeta (g = gy masked by ReLU).
  *          stage 2: gx of this shard's rows from the all-reduced sums in the workspace over `count` rows; ggamma / gbeta
  *          receive the GLOBAL sums (the caller keeps the local ones from stage 1 as the parameter gradients).
- * B may be 0 (empty shard). */
+ * count = -1 in stage 2: the row count is read from workspace[2H] on the device (the caller all-reduces [2H + 1] doubles:
+ * the sums and its row count), so the pass needs no host read.  B may be 0 (empty shard). */
 NF_API int nf_batchnorm_forward_staged(const void* x, const void* gamma, const void* beta, void* running_mean,
                                 void* running_var, void* y, void* save_mean, void* save_rstd, void* workspace, int64_t B,
                                 int H, double momentum, double eps, int relu, int stage, int64_t count, int dtype,

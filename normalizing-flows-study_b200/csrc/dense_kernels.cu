@@ -306,9 +306,10 @@ bn_partial_sums_kernel(const T* __restrict__ x, double* __restrict__ acc, int64_
 template <typename T>
 __global__ void bn_finish_stats_kernel(const double* __restrict__ acc, T* __restrict__ running_mean, T* __restrict__ running_var,
                                        T* __restrict__ save_mean, T* __restrict__ save_rstd, int64_t B, int H,
-                                       double momentum, double eps) {
+                                       double momentum, double eps, const double* __restrict__ count_dev) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= H) return;
+    if (count_dev) B = (int64_t)(*count_dev + 0.5);          // synchronised statistics: the global row count, all-reduced with the sums
     const double mean = acc[col] / (double)B;
     double var = acc[H + col] / (double)B - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -394,9 +395,11 @@ template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ gamma,
                                     const T* __restrict__ mean, const T* __restrict__ rstd, const T* __restrict__ gy,
                                     const T* __restrict__ ggamma, const T* __restrict__ gbeta, T* __restrict__ gx,
-                                    int64_t B, int H, int relu, int training, int64_t count) {
+                                    int64_t B, int H, int relu, int training, int64_t count,
+                                    const double* __restrict__ count_dev) {
     const int64_t n = B * H, stride = (int64_t)gridDim.x * blockDim.x;
-    const T invB = T(1) / (T)count;            // rows behind the statistics: B, or the global count with synchronised statistics
+    // rows behind the statistics: B, or the global count with synchronised statistics (host value or all-reduced on the device)
+    const T invB = count_dev ? (T)(1.0 / *count_dev) : T(1) / (T)count;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = (int)(i % H);
         T g = gy[i];
@@ -544,14 +547,14 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gy,
                          const float* __restrict__ ggamma, const float* __restrict__ gbeta, float* __restrict__ gx, int64_t B,
-                         int H, int relu, int training, int64_t rpc, int tx, int64_t count) {
+                         int H, int relu, int training, int64_t rpc, int tx, int64_t count, const double* __restrict__ count_dev) {
     const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
     const int col = (blockIdx.x * tx + cx) * 4;
     if (col >= H) return;
     const float4 mu4 = ld4(mean + col), rs4 = ld4(rstd + col), ga4 = ld4(gamma + col), gg4 = ld4(ggamma + col), gb4 = ld4(gbeta + col);
     const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
     const float gg[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, gb[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
-    const float invB = 1.0f / (float)count;
+    const float invB = count_dev ? (float)(1.0 / *count_dev) : 1.0f / (float)count;
     const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
 #pragma unroll 2
     for (int64_t r = r0 + ry; r < r1; r += ty) {
@@ -603,6 +606,7 @@ static int bn_forward(const void* x, const void* gamma, const void* beta, void* 
     const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, y ? y : x, gamma ? gamma : x, beta ? beta : x) &&
                      (sm == nullptr || aligned16(sm)) && (sr == nullptr || aligned16(sr));
     const BnVecGeom vg = bn_vec_geom(B, H);
+    const bool count_on_device = (stage == 2 && count < 0);     // workspace[2H] holds the all-reduced row count (no host read)
     if (count <= 0) count = B;
     if (training) {
         if (stage != 2) {
@@ -620,7 +624,7 @@ static int bn_forward(const void* x, const void* gamma, const void* beta, void* 
             if (stage == 1) return NF_OK;
         }
         bn_finish_stats_kernel<T><<<(H + 127) / 128, 128, 0, st>>>((const double*)ws, (T*)rm, (T*)rv, (T*)sm, (T*)sr, count, H,
-                                                                  momentum, eps);
+                                                                  momentum, eps, count_on_device ? (const double*)ws + 2 * H : nullptr);
     } else {
         bn_eval_stats_kernel<T><<<(H + 255) / 256, 256, 0, st>>>((const T*)rm, (const T*)rv, (T*)sm, (T*)sr, H, eps);
     }
@@ -651,6 +655,7 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
     const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, gy, y, gx ? gx : x) && aligned16(sm) && aligned16(sr) &&
                      (gamma == nullptr || aligned16(gamma)) && (gg == nullptr || aligned16(gg)) && (gb == nullptr || aligned16(gb));
     const BnVecGeom vg = bn_vec_geom(B, H);
+    const double* count_dev = (stage == 2 && count < 0) ? (const double*)ws + 2 * H : nullptr;
     if (count <= 0) count = B;
     if (stage != 2) {
         NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
@@ -670,11 +675,11 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
     if (vec)
         bn_bwd_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
             (const float*)x, (const float*)y, (const float*)gamma, (const float*)sm, (const float*)sr, (const float*)gy,
-            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx, count);
+            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx, count, count_dev);
     else
     bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
                                                            (const T*)sr, (const T*)gy, (const T*)gg, (const T*)gb,
-                                                           (T*)gx, B, H, relu, training, count);
+                                                           (T*)gx, B, H, relu, training, count, count_dev);
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;
@@ -798,7 +803,7 @@ extern "C" int nf_batchnorm_forward_staged(const void* x, const void* gamma, con
     if (B < 0 || H < 1 || (stage != 1 && stage != 2)) return NF_ERR_BAD_SHAPE;
     NF_REQ(workspace);
     if (stage == 2) {
-        if (count < 1) return NF_ERR_BAD_SHAPE;
+        if (count < 1 && count != -1) return NF_ERR_BAD_SHAPE;
         NF_REQ(gamma); NF_REQ(beta); NF_REQ(save_mean); NF_REQ(save_rstd);
         if (B > 0) { NF_REQ(x); NF_REQ(y); }
     } else if (B > 0) {
@@ -822,7 +827,7 @@ extern "C" int nf_batchnorm_backward_staged(const void* x, const void* y, const 
     NF_REQ(workspace); NF_REQ(save_mean); NF_REQ(save_rstd);
     cudaStream_t st = (cudaStream_t)stream;
     if (stage == 2) {
-        if (count < 1) return NF_ERR_BAD_SHAPE;
+        if (count < 1 && count != -1) return NF_ERR_BAD_SHAPE;
         NF_REQ(gamma); NF_REQ(ggamma); NF_REQ(gbeta);
     }
     if (B == 0) {

@@ -374,6 +374,7 @@ constexpr int kWgCols = 128, kWgAhi = 0, kWgAlo = 32, kWgD = 64;
 template <int DM>
 __device__ __forceinline__ void layer1_chunk(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], int u0,
                                              uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+    float t16[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float* w1 = sW1k + (u0 + j) * W1S;
@@ -391,8 +392,10 @@ __device__ __forceinline__ void layer1_chunk(const float* __restrict__ sW1k, int
             t = fmaf(v0.x, xa[0], t); t = fmaf(v0.y, xa[1], t); t = fmaf(v0.z, xa[2], t); t = fmaf(v0.w, xa[3], t);
             t = fmaf(v1.x, xa[4], t); t = fmaf(v1.y, xa[5], t); t = fmaf(v1.z, xa[6], t); t = fmaf(v1.w, xa[7], t);
         }
-        tc::split_tf32(relu_keepnan(t), hi[j], lo[j]);
+        t16[j] = relu_keepnan(t);
     }
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) tc::split_tf32_x2(t16[j], t16[j + 1], hi[j], hi[j + 1], lo[j], lo[j + 1]);
 }
 
 // 16 raw layer-2 accumulators + bias -> relu -> split
@@ -400,10 +403,11 @@ __device__ __forceinline__ void hidden2_chunk(const uint32_t (&v)[16], const flo
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
         const float4 b = *reinterpret_cast<const float4*>(sb2 + j4 * 4);
-        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
-        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
-        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
-        tc::split_tf32(relu_keepnan(__uint_as_float(v[j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+        // packed fp32 (FADD2 / FMUL2 / FFMA2): bias add and the hi/lo split two values per instruction
+        const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v[j4 * 4 + 0]), __uint_as_float(v[j4 * 4 + 1])), make_float2(b.x, b.y));
+        const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v[j4 * 4 + 2]), __uint_as_float(v[j4 * 4 + 3])), make_float2(b.z, b.w));
+        tc::split_tf32_x2(relu_keepnan(s0.x), relu_keepnan(s0.y), hi[j4 * 4 + 0], hi[j4 * 4 + 1], lo[j4 * 4 + 0], lo[j4 * 4 + 1]);
+        tc::split_tf32_x2(relu_keepnan(s1.x), relu_keepnan(s1.y), hi[j4 * 4 + 2], hi[j4 * 4 + 3], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
     }
 }
 

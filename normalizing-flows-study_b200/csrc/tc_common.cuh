@@ -176,6 +176,19 @@ __device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) 
     hi = (__float_as_uint(a) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(a - __uint_as_float(hi));
 }
+// Two values at once on the packed fp32 pipe (Blackwell FMUL2 / FFMA2: 3 instructions per PAIR instead of the 6 integer / FP
+// ones above -- the fused stack kernels are issue-bound and split 128 activations per row and layer).  Veltkamp's split
+// with C = 2^13 + 1:  c = fl(C a);  hi = c - 2^13 a  (2^13 a is exact and the difference has at most 11 significant bits,
+// so the FMA does not round: hi = a rounded to the nearest TF32);  lo = a - hi exactly.  Same guarantees as split_tf32
+// (ties may round the other way, which lo absorbs); |a| > 2^114 overflows c, Inf / NaN give NaN in both as before the MMA.
+__device__ __forceinline__ void split_tf32_x2(float a0, float a1, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
+    const float2 a = make_float2(a0, a1);
+    const float2 c = __fmul2_rn(a, make_float2(8193.0f, 8193.0f));
+    const float2 h = __ffma2_rn(a, make_float2(-8192.0f, -8192.0f), c);
+    const float2 l = __ffma2_rn(h, make_float2(-1.0f, -1.0f), a);
+    hi0 = __float_as_uint(h.x); hi1 = __float_as_uint(h.y);
+    lo0 = __float_as_uint(l.x); lo1 = __float_as_uint(l.y);
+}
 // weights (split once per weight version): lo is additionally rounded to TF32 so that the hardware truncation is exact
 __device__ __forceinline__ void split_tf32_weight(float a, uint32_t& hi, uint32_t& lo) {
     split_tf32(a, hi, lo);

@@ -298,6 +298,10 @@ def allreduce_bn_sums(ws, count, group=None):
 
 
 class _SyncBatchNormFn(Function):
+    """Train-mode BatchNorm1d (+ReLU) with statistics over all ranks' rows.  One all-reduce of [2H + 1] doubles in the
+    forward (sum x, sum x^2, row count) and one of [2H] in the backward; the global row count stays on the device
+    (`count = -1`: the kernels read it from workspace[2H]), so the pass has no host synchronisation."""
+
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, relu, group):
         import torch.distributed as dist
@@ -306,40 +310,38 @@ class _SyncBatchNormFn(Function):
         y = torch.empty_like(x)
         sm = torch.empty(H, dtype=x.dtype, device=x.device)
         sr = torch.empty(H, dtype=x.dtype, device=x.device)
-        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
+        packed = torch.empty(2 * H + 1, dtype=torch.float64, device=x.device)
         code = L.dtype_code(x)
-        call("nf_batchnorm_forward_staged", ptr(x), None, None, None, None, None, None, None, ptr(ws), B, H, 0.0, float(eps),
+        call("nf_batchnorm_forward_staged", ptr(x), None, None, None, None, None, None, None, ptr(packed), B, H, 0.0, float(eps),
              int(relu), 1, 0, code, stream())
-        packed = torch.cat([ws, ws.new_tensor([float(B)])])
+        packed[2 * H:].fill_(float(B))
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-        count = int(round(float(packed[-1])))            # one host read per BatchNorm: the row count of the global batch
-        ws = packed[:-1].contiguous()
         call("nf_batchnorm_forward_staged", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
-             ptr(y), ptr(sm), ptr(sr), ptr(ws), B, H, float(momentum), float(eps), int(relu), 2, count, code, stream())
-        ctx.relu, ctx.group, ctx.count = relu, group, count
-        ctx.save_for_backward(x, y, gamma, sm, sr)
+             ptr(y), ptr(sm), ptr(sr), ptr(packed), B, H, float(momentum), float(eps), int(relu), 2, -1, code, stream())
+        ctx.relu, ctx.group = relu, group
+        ctx.save_for_backward(x, y, gamma, sm, sr, packed[2 * H:])
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         import torch.distributed as dist
-        x, y, gamma, sm, sr = ctx.saved_tensors
+        x, y, gamma, sm, sr, count = ctx.saved_tensors
         B, H = x.shape
         code = L.dtype_code(x)
         gy = _c(gy)
         gx = torch.empty_like(x)
-        ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
-        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), None, ptr(sm), ptr(sr), ptr(gy), None, None, None, ptr(ws), B, H,
+        glob = torch.empty(2 * H + 1, dtype=torch.float64, device=x.device)
+        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), None, ptr(sm), ptr(sr), ptr(gy), None, None, None, ptr(glob), B, H,
              int(ctx.relu), 1, 0, code, stream())
-        gg = ws[:H].to(x.dtype)                           # this shard's ggamma / gbeta: the gradient all-reduce sums them
-        gb = ws[H:].to(x.dtype)
-        glob = ws.clone()
-        dist.all_reduce(glob, op=dist.ReduceOp.SUM, group=ctx.group)
+        gg = glob[:H].to(x.dtype)                         # this shard's ggamma / gbeta: the gradient all-reduce sums them
+        gb = glob[H:2 * H].to(x.dtype)
+        dist.all_reduce(glob[:2 * H], op=dist.ReduceOp.SUM, group=ctx.group)
+        glob[2 * H:].copy_(count)
         gg_g = torch.empty(H, dtype=x.dtype, device=x.device)
         gb_g = torch.empty(H, dtype=x.dtype, device=x.device)
         call("nf_batchnorm_backward_staged", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(gy), ptr(gx), ptr(gg_g),
-             ptr(gb_g), ptr(glob), B, H, int(ctx.relu), 2, ctx.count, code, stream())
+             ptr(gb_g), ptr(glob), B, H, int(ctx.relu), 2, -1, code, stream())
         return gx, gg, gb, None, None, None, None, None, None
 
 

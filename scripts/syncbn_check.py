@@ -27,17 +27,22 @@ def nll(model, x):
 def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    # NF_DIST_BACKEND=gloo: several ranks on ONE GPU (gloo copies CUDA tensors through the host), for 1-GPU boxes
+    backend = os.environ.get("NF_DIST_BACKEND", "nccl")
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)
     res = {}
     for D, H, B in ((2, 64, 10001), (16, 128, 4096)):
         torch.manual_seed(0)
         base = N.RealNVP(D, 4, H)
         with torch.no_grad():
             for p in base.parameters():
-                p.add_(0.05 * torch.randn_like(p))
+                p.add_(0.02 * torch.randn_like(p))
         x = torch.randn(B, D, generator=torch.Generator().manual_seed(1)).to(dev)
         # single-process step on the whole batch
         ref = copy.deepcopy(base).to(dev).train()
@@ -50,8 +55,10 @@ def main():
             loss = nll(dp, x[lo:hi].contiguous())
             loss.backward()
             dp.sync_gradients()                              # averages: multiply back by world to compare sums
-            gerr = max(float(((p.grad * world - q.grad).abs() / (1e-6 + q.grad.abs().max())).max())
-                       for p, q in zip(m.parameters(), ref.parameters()))
+            # relative to the largest gradient entry of the whole model: the biases of the Linears that feed a BatchNorm
+            # have an exactly-zero true gradient, so a per-parameter relative error would compare rounding noise
+            gmax = max(float(q.grad.abs().max()) for q in ref.parameters())
+            gerr = max(float((p.grad * world - q.grad).abs().max()) for p, q in zip(m.parameters(), ref.parameters())) / gmax
             serr = max(float((a - b).abs().max()) for (n, a), (_, b) in zip(m.named_buffers(), ref.named_buffers())
                        if "running" in n)
             res[f"D{D}_H{H}_sync{int(sync)}"] = {"grad_rel_err": gerr, "running_stat_err": serr}

@@ -388,12 +388,15 @@ def test_staged_batchnorm_on_two_shards_equals_one_batch(H, relu):
              int(relu), 1, 0, 0, stream())
     glob = ws[0] + ws[1]                                             # the all-reduce
     ys, sms, srs, rms, rvs = [], [], [], [], []
-    for xs in shards:
+    for si, xs in enumerate(shards):
         y = torch.empty_like(xs)
         sm, sr = torch.empty(H, device=DEV), torch.empty(H, device=DEV)
         rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+        # shard 0: global count from the host; shard 1: count = -1, read from workspace[2H] on the device (what
+        # ops._SyncBatchNormFn does: the count is all-reduced with the sums, no host read)
+        wsg = torch.cat([glob, glob.new_tensor([float(B)])])
         call("nf_batchnorm_forward_staged", ptr(xs), ptr(bn.weight), ptr(bn.bias), ptr(rm), ptr(rv), ptr(y), ptr(sm), ptr(sr),
-             ptr(glob.clone()), xs.shape[0], H, 0.1, bn.eps, int(relu), 2, B, 0, stream())
+             ptr(wsg), xs.shape[0], H, 0.1, bn.eps, int(relu), 2, B if si == 0 else -1, 0, stream())
         ys.append(y); sms.append(sm); srs.append(sr); rms.append(rm); rvs.append(rv)
     assert torch.allclose(torch.cat(ys), yr.detach(), rtol=1e-6, atol=1e-6)
     assert torch.equal(rms[0], rms[1]) and torch.allclose(rms[0], bn_ref.running_mean, rtol=1e-6, atol=1e-7)
@@ -404,11 +407,12 @@ def test_staged_batchnorm_on_two_shards_equals_one_batch(H, relu):
              xs.shape[0], H, int(relu), 1, 0, 0, stream())
     globb = wsb[0] + wsb[1]
     gxs = []
-    for xs, y, g in zip(shards, ys, gys):
+    for si, (xs, y, g) in enumerate(zip(shards, ys, gys)):
         gx = torch.empty_like(xs)
         gg, gb = torch.empty(H, device=DEV), torch.empty(H, device=DEV)
+        wsg = torch.cat([globb, globb.new_tensor([float(B)])])
         call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), ptr(bn.weight), ptr(sms[0]), ptr(srs[0]), ptr(g), ptr(gx), ptr(gg),
-             ptr(gb), ptr(globb.clone()), xs.shape[0], H, int(relu), 2, B, 0, stream())
+             ptr(gb), ptr(wsg), xs.shape[0], H, int(relu), 2, B if si == 0 else -1, 0, stream())
         gxs.append(gx)
     assert torch.allclose(torch.cat(gxs), xr.grad, rtol=1e-5, atol=1e-6)
     assert torch.allclose(globb[:H].float(), bn_ref.weight.grad, rtol=1e-5, atol=1e-5)
