@@ -65,30 +65,46 @@ __device__ __forceinline__ void bn_between_tc(const float* __restrict__ sL, int 
     tot = inverse ? tot - bn_ld : tot + bn_ld;
 }
 
+// Layer 1 for data_dim <= 3 (W1S == 4), two hidden units per packed-fp32 FMA.  The host stores the units in pairs:
+// [w0a w0b | w1a w1b | w2a w2b | ba bb] (packing._tc_net_block), i.e. two LDS.128 per pair like the unit-major layout, and
+// every FFMA2 operand pair sits in adjacent registers.  Returns relu(W1 x + b1) of units 2p, 2p+1.
+template <int DM>
+__device__ __forceinline__ float2 layer1_pair(const float* __restrict__ sW1k, int p, const float (&xa)[DM]) {
+    const float4 wa = *reinterpret_cast<const float4*>(sW1k + p * 8);          // w0a w0b w1a w1b
+    const float4 wb = *reinterpret_cast<const float4*>(sW1k + p * 8 + 4);      // w2a w2b ba  bb
+    float2 t = make_float2(wb.z, wb.w);
+    t = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(xa[0], xa[0]), t);
+    if constexpr (DM > 1) t = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(xa[1], xa[1]), t);
+    if constexpr (DM > 2) t = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(xa[2], xa[2]), t);
+    return make_float2(relu_keepnan(t.x), relu_keepnan(t.y));
+}
+
 // (a): hidden layer 1 of one conditioner for this thread's row -> TMEM A operand (hi at kColAhi, lo at kColAlo)
 template <int DM>
 __device__ __forceinline__ void layer1_to_tmem(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], uint32_t lane_addr) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t hi[16], lo[16];
+        if constexpr (DM <= 4) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float* w1 = sW1k + (c * 16 + j) * W1S;
-            float t;
-            if constexpr (DM <= 4) {
-                const float4 v = *reinterpret_cast<const float4*>(w1);     // {w0, w1, w2, b1}
-                t = v.w;
-                t = fmaf(v.x, xa[0], t);
-                if constexpr (DM > 1) t = fmaf(v.y, xa[1], t);
-                if constexpr (DM > 2) t = fmaf(v.z, xa[2], t);
-            } else {
+            for (int j = 0; j < 16; j += 2) {
+                const float2 t = layer1_pair<DM>(sW1k, (c * 16 + j) >> 1, xa);
+                tc::split_tf32_x2(t.x, t.y, hi[j], hi[j + 1], lo[j], lo[j + 1]);
+            }
+        } else {
+            float t16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float* w1 = sW1k + (c * 16 + j) * W1S;
                 const float4 v0 = *reinterpret_cast<const float4*>(w1);
                 const float4 v1 = *reinterpret_cast<const float4*>(w1 + 4);
-                t = w1[W1S - 1];
+                float t = w1[W1S - 1];
                 t = fmaf(v0.x, xa[0], t); t = fmaf(v0.y, xa[1], t); t = fmaf(v0.z, xa[2], t); t = fmaf(v0.w, xa[3], t);
                 t = fmaf(v1.x, xa[4], t); t = fmaf(v1.y, xa[5], t); t = fmaf(v1.z, xa[6], t); t = fmaf(v1.w, xa[7], t);
+                t16[j] = relu_keepnan(t);
             }
-            tc::split_tf32(relu_keepnan(t), hi[j], lo[j]);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) tc::split_tf32_x2(t16[j], t16[j + 1], hi[j], hi[j + 1], lo[j], lo[j + 1]);
         }
         tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
         tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
@@ -107,10 +123,10 @@ __device__ __forceinline__ void hidden2_to_tmem(const float* __restrict__ sb2, u
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b = *reinterpret_cast<const float4*>(sb2 + c * 16 + j4 * 4);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 0]) + b.x), hi[j4 * 4 + 0], lo[j4 * 4 + 0]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 1]) + b.y), hi[j4 * 4 + 1], lo[j4 * 4 + 1]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 2]) + b.z), hi[j4 * 4 + 2], lo[j4 * 4 + 2]);
-            tc::split_tf32(relu_keepnan(__uint_as_float(v[c][j4 * 4 + 3]) + b.w), hi[j4 * 4 + 3], lo[j4 * 4 + 3]);
+            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 0]), __uint_as_float(v[c][j4 * 4 + 1])), make_float2(b.x, b.y));
+            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 2]), __uint_as_float(v[c][j4 * 4 + 3])), make_float2(b.z, b.w));
+            tc::split_tf32_x2(relu_keepnan(s0.x), relu_keepnan(s0.y), hi[j4 * 4 + 0], hi[j4 * 4 + 1], lo[j4 * 4 + 0], lo[j4 * 4 + 1]);
+            tc::split_tf32_x2(relu_keepnan(s1.x), relu_keepnan(s1.y), hi[j4 * 4 + 2], hi[j4 * 4 + 3], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
         }
         tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
         tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
@@ -305,7 +321,15 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
                         const float* b3 = net + off.b3 + t * 32;
                         float prm[32];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { prm[j] = __uint_as_float(p0[j]) + b3[j]; prm[16 + j] = __uint_as_float(p1[j]) + b3[16 + j]; }
+                        for (int j = 0; j < 16; j += 4) {             // packed fp32 bias adds (FADD2), bias fetched 16 bytes at a time
+                            const float4 ba = *reinterpret_cast<const float4*>(b3 + j), bb = *reinterpret_cast<const float4*>(b3 + 16 + j);
+                            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(p0[j]), __uint_as_float(p0[j + 1])), make_float2(ba.x, ba.y));
+                            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(p0[j + 2]), __uint_as_float(p0[j + 3])), make_float2(ba.z, ba.w));
+                            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(p1[j]), __uint_as_float(p1[j + 1])), make_float2(bb.x, bb.y));
+                            const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(p1[j + 2]), __uint_as_float(p1[j + 3])), make_float2(bb.z, bb.w));
+                            prm[j] = s0.x; prm[j + 1] = s0.y; prm[j + 2] = s1.x; prm[j + 3] = s1.y;
+                            prm[16 + j] = s2.x; prm[16 + j + 1] = s2.y; prm[16 + j + 2] = s3.x; prm[16 + j + 3] = s3.y;
+                        }
                         // columns of one transformed dim: [uw: KMAX slots | uh: KMAX slots | ud: KMAX-1 slots] (host packing)
                         float uw[KMAX], uh[KMAX], ud[KMAX];
 #pragma unroll
@@ -374,28 +398,27 @@ constexpr int kWgCols = 128, kWgAhi = 0, kWgAlo = 32, kWgD = 64;
 template <int DM>
 __device__ __forceinline__ void layer1_chunk(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], int u0,
                                              uint32_t (&hi)[16], uint32_t (&lo)[16]) {
-    float t16[16];
+    if constexpr (DM <= 4) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float* w1 = sW1k + (u0 + j) * W1S;
-        float t;
-        if constexpr (DM <= 4) {
-            const float4 v = *reinterpret_cast<const float4*>(w1);
-            t = v.w;
-            t = fmaf(v.x, xa[0], t);
-            if constexpr (DM > 1) t = fmaf(v.y, xa[1], t);
-            if constexpr (DM > 2) t = fmaf(v.z, xa[2], t);
-        } else {
+        for (int j = 0; j < 16; j += 2) {
+            const float2 t = layer1_pair<DM>(sW1k, (u0 + j) >> 1, xa);
+            tc::split_tf32_x2(t.x, t.y, hi[j], hi[j + 1], lo[j], lo[j + 1]);
+        }
+    } else {
+        float t16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float* w1 = sW1k + (u0 + j) * W1S;
             const float4 v0 = *reinterpret_cast<const float4*>(w1);
             const float4 v1 = *reinterpret_cast<const float4*>(w1 + 4);
-            t = w1[W1S - 1];
+            float t = w1[W1S - 1];
             t = fmaf(v0.x, xa[0], t); t = fmaf(v0.y, xa[1], t); t = fmaf(v0.z, xa[2], t); t = fmaf(v0.w, xa[3], t);
             t = fmaf(v1.x, xa[4], t); t = fmaf(v1.y, xa[5], t); t = fmaf(v1.z, xa[6], t); t = fmaf(v1.w, xa[7], t);
+            t16[j] = relu_keepnan(t);
         }
-        t16[j] = relu_keepnan(t);
-    }
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) tc::split_tf32_x2(t16[j], t16[j + 1], hi[j], hi[j + 1], lo[j], lo[j + 1]);
+        for (int j = 0; j < 16; j += 2) tc::split_tf32_x2(t16[j], t16[j + 1], hi[j], hi[j + 1], lo[j], lo[j + 1]);
+    }
 }
 
 // 16 raw layer-2 accumulators + bias -> relu -> split
@@ -573,7 +596,15 @@ spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restric
                         const float* b3 = net + off.b3 + t * 32;
                         float prm[32];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { prm[j] = __uint_as_float(p0[j]) + b3[j]; prm[16 + j] = __uint_as_float(p1[j]) + b3[16 + j]; }
+                        for (int j = 0; j < 16; j += 4) {             // packed fp32 bias adds (FADD2), bias fetched 16 bytes at a time
+                            const float4 ba = *reinterpret_cast<const float4*>(b3 + j), bb = *reinterpret_cast<const float4*>(b3 + 16 + j);
+                            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(p0[j]), __uint_as_float(p0[j + 1])), make_float2(ba.x, ba.y));
+                            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(p0[j + 2]), __uint_as_float(p0[j + 3])), make_float2(ba.z, ba.w));
+                            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(p1[j]), __uint_as_float(p1[j + 1])), make_float2(bb.x, bb.y));
+                            const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(p1[j + 2]), __uint_as_float(p1[j + 3])), make_float2(bb.z, bb.w));
+                            prm[j] = s0.x; prm[j + 1] = s0.y; prm[j + 2] = s1.x; prm[j + 3] = s1.y;
+                            prm[16 + j] = s2.x; prm[16 + j + 1] = s2.y; prm[16 + j + 2] = s3.x; prm[16 + j + 3] = s3.y;
+                        }
                         float uw[KMAX], uh[KMAX], ud[KMAX];
 #pragma unroll
                         for (int j = 0; j < KMAX; ++j) {

@@ -373,11 +373,15 @@ def _pad256(n):
 
 def _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, lead_words):
     """One conditioner block of the tensor-core stack layout (csrc/stack_tc.cu: blk_offsets):
-    W1k[64][W1S] | b2[64] | b3[NO3] | pad to a 256-word boundary (counting `lead_words` in front) |
+    W1k[64][W1S] (W1S == 4: pair-interleaved, see below) | b2[64] | b3[NO3] | pad to a 256-word boundary (counting `lead_words` in front) |
     W2 hi image | W2 lo image | W3 hi image | W3 lo image.  W3rows/b3rows: [NO3, H] / [NO3] already in head-column order."""
     w1k = np.zeros((64, W1S))
     w1k[:H, :D] = W1
     w1k[:H, W1S - 1] = b1
+    if W1S == 4:
+        # data_dim <= 3: units are stored in PAIRS, [w0a w0b | w1a w1b | w2a w2b | ba bb] per pair (a = unit 2p, b = 2p+1),
+        # so that the kernel's packed-fp32 FMAs (FFMA2) find both units' operands in adjacent registers
+        w1k = w1k.reshape(32, 2, 4).transpose(0, 2, 1).reshape(64, 4)
     b2p = np.zeros(64)
     b2p[:H] = b2
     small = np.concatenate([w1k.ravel(), b2p, b3rows]).astype(np.float32)
