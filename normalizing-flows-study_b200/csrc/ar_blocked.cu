@@ -183,11 +183,11 @@ template <int NCH, int NUP>
 __device__ __forceinline__ void warp_units_chunk(const float* __restrict__ wt, const float* __restrict__ bias,
                                                  const float* __restrict__ in, int nv, float* __restrict__ out, int cu, int ub0,
                                                  int ub1, int lane) {
-    float acc[NCH][4];
+    // accumulators as register pairs: packed fp32 FMAs (FFMA2), two units per instruction -- the weights of a pair are
+    // adjacent in the broadcast LDS.128, the lane's activation is duplicated into a pair; same operations and order
+    float2 acc2[NCH][2];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+    for (int c = 0; c < NCH; ++c) { acc2[c][0] = make_float2(0.f, 0.f); acc2[c][1] = make_float2(0.f, 0.f); }
     // compile-time row pitches (NUP, kBlkPad): the unrolled body addresses everything with immediate offsets
     const float* ap = in + lane;
     const float* wp = wt + cu;
@@ -196,23 +196,28 @@ __device__ __forceinline__ void warp_units_chunk(const float* __restrict__ wt, c
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float a = ap[k * kBlkPad];
+            const float2 aa = make_float2(a, a);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const float4 w = *reinterpret_cast<const float4*>(wp + k * NUP + 4 * c);    // rows padded by 4*kWarpChunks floats
-                acc[c][0] = fmaf(w.x, a, acc[c][0]); acc[c][1] = fmaf(w.y, a, acc[c][1]);
-                acc[c][2] = fmaf(w.z, a, acc[c][2]); acc[c][3] = fmaf(w.w, a, acc[c][3]);
+                acc2[c][0] = __ffma2_rn(make_float2(w.x, w.y), aa, acc2[c][0]);
+                acc2[c][1] = __ffma2_rn(make_float2(w.z, w.w), aa, acc2[c][1]);
             }
         }
     }
     for (; v < nv; ++v, ap += kBlkPad, wp += NUP) {
         const float a = *ap;
+        const float2 aa = make_float2(a, a);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(wp + 4 * c);
-            acc[c][0] = fmaf(w.x, a, acc[c][0]); acc[c][1] = fmaf(w.y, a, acc[c][1]);
-            acc[c][2] = fmaf(w.z, a, acc[c][2]); acc[c][3] = fmaf(w.w, a, acc[c][3]);
+            acc2[c][0] = __ffma2_rn(make_float2(w.x, w.y), aa, acc2[c][0]);
+            acc2[c][1] = __ffma2_rn(make_float2(w.z, w.w), aa, acc2[c][1]);
         }
     }
+    float acc[NCH][4];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { acc[c][0] = acc2[c][0].x; acc[c][1] = acc2[c][0].y; acc[c][2] = acc2[c][1].x; acc[c][3] = acc2[c][1].y; }
     float* op = out + cu * kBlkPad + lane;
     const float* bp = bias + cu;
 #pragma unroll

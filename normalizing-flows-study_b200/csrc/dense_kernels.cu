@@ -113,10 +113,25 @@ gemm_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ C
 #pragma unroll
                 for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
             }
+            if constexpr (sizeof(T) == 4) {
+                // packed fp32 FMAs (Blackwell FFMA2): two output columns per instruction, a[i] duplicated into a pair; the
+                // accumulators of a column pair are adjacent registers.  Same operations per element, bit-identical.
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
+                for (int i = 0; i < TM; ++i) {
+                    const float2 aa = make_float2((float)a[i], (float)a[i]);
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+                    for (int j = 0; j < TN; j += 2) {
+                        const float2 r = __ffma2_rn(aa, make_float2((float)b[j], (float)b[j + 1]),
+                                                    make_float2((float)acc[i][j], (float)acc[i][j + 1]));
+                        acc[i][j] = (T)r.x; acc[i][j + 1] = (T)r.y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+            }
         }
     }
 

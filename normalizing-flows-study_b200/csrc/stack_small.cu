@@ -44,16 +44,20 @@ template <int HP, int R, int DM>
 __device__ __forceinline__ void mlp_hidden(const float* __restrict__ sW1k, const float* __restrict__ sW2t,
                                            const float* __restrict__ sb2, int W1S, const float (&xa)[R][DM],
                                            float (&acc)[R][HP]) {
+    // layer-2 accumulators as register PAIRS: the inner product runs on the packed fp32 pipe (FFMA2: two outputs per
+    // instruction, the weights of a pair adjacent in the LDS.128, h broadcast into a pair) -- 64 FFMA2 + 32 LDS.128 per k
+    // at HP = 128 instead of 128 FFMA + 32 LDS.128; same operations, bit-identical results
+    float2 a2[R][HP / 2];
 #pragma unroll
     for (int j4 = 0; j4 < HP / 4; ++j4) {
         const float4 b = *reinterpret_cast<const float4*>(sb2 + 4 * j4);
 #pragma unroll
-        for (int i = 0; i < R; ++i) { acc[i][4 * j4] = b.x; acc[i][4 * j4 + 1] = b.y; acc[i][4 * j4 + 2] = b.z; acc[i][4 * j4 + 3] = b.w; }
+        for (int i = 0; i < R; ++i) { a2[i][2 * j4] = make_float2(b.x, b.y); a2[i][2 * j4 + 1] = make_float2(b.z, b.w); }
     }
 #pragma unroll 2
     for (int k = 0; k < HP; ++k) {
         const float* w1 = sW1k + k * W1S;
-        float h[R];
+        float2 h[R];
         if constexpr (DM <= 4) {       // D<=3 (W1S=4): one LDS.128 {w0,w1,w2,b1}
             const float4 v = *reinterpret_cast<const float4*>(w1);
 #pragma unroll
@@ -62,7 +66,8 @@ __device__ __forceinline__ void mlp_hidden(const float* __restrict__ sW1k, const
                 t = fmaf(v.x, xa[i][0], t);
                 if (DM > 1) t = fmaf(v.y, xa[i][1], t);
                 if (DM > 2) t = fmaf(v.z, xa[i][2], t);
-                h[i] = relu_nan(t);
+                t = relu_nan(t);
+                h[i] = make_float2(t, t);
             }
         } else {                        // 4<=D<=8 (W1S=12): {w0..w7, 0, 0, 0, b1}
             const float4 v0 = *reinterpret_cast<const float4*>(w1);
@@ -73,7 +78,8 @@ __device__ __forceinline__ void mlp_hidden(const float* __restrict__ sW1k, const
                 float t = bb;
                 t = fmaf(v0.x, xa[i][0], t); t = fmaf(v0.y, xa[i][1], t); t = fmaf(v0.z, xa[i][2], t); t = fmaf(v0.w, xa[i][3], t);
                 t = fmaf(v1.x, xa[i][4], t); t = fmaf(v1.y, xa[i][5], t); t = fmaf(v1.z, xa[i][6], t); t = fmaf(v1.w, xa[i][7], t);
-                h[i] = relu_nan(t);
+                t = relu_nan(t);
+                h[i] = make_float2(t, t);
             }
         }
         const float4* w2 = reinterpret_cast<const float4*>(sW2t + k * HP);
@@ -82,17 +88,15 @@ __device__ __forceinline__ void mlp_hidden(const float* __restrict__ sW1k, const
             const float4 w = w2[j4];
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                acc[i][4 * j4]     = fmaf(w.x, h[i], acc[i][4 * j4]);
-                acc[i][4 * j4 + 1] = fmaf(w.y, h[i], acc[i][4 * j4 + 1]);
-                acc[i][4 * j4 + 2] = fmaf(w.z, h[i], acc[i][4 * j4 + 2]);
-                acc[i][4 * j4 + 3] = fmaf(w.w, h[i], acc[i][4 * j4 + 3]);
+                a2[i][2 * j4]     = __ffma2_rn(make_float2(w.x, w.y), h[i], a2[i][2 * j4]);
+                a2[i][2 * j4 + 1] = __ffma2_rn(make_float2(w.z, w.w), h[i], a2[i][2 * j4 + 1]);
             }
         }
     }
 #pragma unroll
     for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < HP; ++j) acc[i][j] = relu_nan(acc[i][j]);
+        for (int j = 0; j < HP / 2; ++j) { acc[i][2 * j] = relu_nan(a2[i][j].x); acc[i][2 * j + 1] = relu_nan(a2[i][j].y); }
 }
 
 // one chunk of 4 head outputs: o[i][q] = b3[4c+q] + sum_j W3[4c+q][j] * h2[i][j]
@@ -100,20 +104,22 @@ template <int HP, int R>
 __device__ __forceinline__ void head_chunk(const float* __restrict__ sW3c, const float* __restrict__ sb3, int c,
                                            const float (&h2)[R][HP], float (&o)[R][4]) {
     const float4 b = *reinterpret_cast<const float4*>(sb3 + 4 * c);
+    float2 o01[R], o23[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) { o[i][0] = b.x; o[i][1] = b.y; o[i][2] = b.z; o[i][3] = b.w; }
+    for (int i = 0; i < R; ++i) { o01[i] = make_float2(b.x, b.y); o23[i] = make_float2(b.z, b.w); }
     const float4* w3 = reinterpret_cast<const float4*>(sW3c) + (size_t)c * HP;
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
         const float4 w = w3[j];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            o[i][0] = fmaf(w.x, h2[i][j], o[i][0]);
-            o[i][1] = fmaf(w.y, h2[i][j], o[i][1]);
-            o[i][2] = fmaf(w.z, h2[i][j], o[i][2]);
-            o[i][3] = fmaf(w.w, h2[i][j], o[i][3]);
+        for (int i = 0; i < R; ++i) {                     // packed fp32: two head outputs per FFMA2
+            const float2 hh = make_float2(h2[i][j], h2[i][j]);
+            o01[i] = __ffma2_rn(make_float2(w.x, w.y), hh, o01[i]);
+            o23[i] = __ffma2_rn(make_float2(w.z, w.w), hh, o23[i]);
         }
     }
+#pragma unroll
+    for (int i = 0; i < R; ++i) { o[i][0] = o01[i].x; o[i][1] = o01[i].y; o[i][2] = o23[i].x; o[i][3] = o23[i].y; }
 }
 
 // between-layer BatchNorm as an invertible affine on running stats (normalizing_flow_model.py:67-128)
