@@ -306,11 +306,16 @@ NF_API int nf_arqs_step_backward(const void* v, const void* params, int64_t ldp,
                           double min_bin_width, double min_bin_height, double min_derivative, int dtype,
                           nf_stream_t stream);
 
-/* ---- a12/a13 sequential directions, blocked: dense contributions of previous degree blocks on tcgen05
- * (nf_linear_tc on column slices), in-block dependent steps in a small-footprint kernel (csrc/ar_blocked.cu).
- * w / w_hi / w_lo / b: arrays of 4 device pointers (mask-folded, degree-sorted weights of the 4 MADE layers, their
- * TF32 splits, biases); gstart: int32[D+1] (device and host copies); workspace: nf_ar_blocked_workspace_floats()
- * floats; block_degrees: consecutive degrees per block (8).  float32; D % 4 == 0 and H % 4 == 0. */
+/* ---- a12/a13 sequential directions, blocked (csrc/ar_blocked.cu): hidden pre-activations of a block of degrees PULL
+ * the contributions of all previous blocks as dense products on tcgen05 (column slices of the activation buffers),
+ * the in-block dependent steps run in a persistent small-footprint kernel, and every finished block PUSHES its
+ * layer-3 units into the output-layer pre-activations of all later dims (one narrow-K product, accumulated).
+ * w / b: arrays of 4 device pointers, mask-folded degree-sorted weights and biases of the 4 MADE layers (output layer
+ * as made.py:136-140 lays it out, [mu rows | alpha rows]); w_hi / w_lo: their TF32 splits, the output layer's rows
+ * INTERLEAVED (row 2g = mu_g, row 2g+1 = alpha_g).  gstart: int32[D+1], first unit of degree >= g (device and host
+ * copies); every block of `block_degrees` degrees must start at a multiple of 8 units (pad the blocks with dead units:
+ * zero weights and biases -- packing.blocked_made_pack does), H is that padded width.  workspace:
+ * nf_ar_blocked_workspace_floats() floats.  float32; D % 4 == 0, H % 8 == 0, block_degrees % 4 == 0 (8). */
 NF_API int nf_ar_blocked_forward(const void* v, const void* const* w, const void* const* w_hi, const void* const* w_lo,
                           const void* const* b, const int32_t* gstart_dev, const int32_t* gstart_host, void* workspace,
                           void* out, void* ld, int64_t B, int D, int H, int mode, int block_degrees, nf_stream_t stream);

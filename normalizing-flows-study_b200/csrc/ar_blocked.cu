@@ -18,6 +18,21 @@ extern "C" int nf_ar_finish_forward(const void*, const void*, const void*, void*
 
 namespace nf {
 
+int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
+                    int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
+                    cudaStream_t st, int accumulate);
+
+// Y[M,N] (+)= X[M,K] W[N,K]^T for K <= 128 through the persistent direct-epilogue kernel of gemm_tc2.cu
+static int linear_tc_push(const float* x, const float* w_hi, const float* w_lo, float* y, int64_t M, int64_t N, int64_t K,
+                          int64_t ldx, int64_t ldw, int64_t ldy, int accumulate, cudaStream_t st) {
+    if (!aligned16(x) || !aligned16(w_hi) || !aligned16(w_lo) || (ldx % 4) != 0 || (ldw % 4) != 0) return NF_ERR_UNSUPPORTED;
+    const int rc = gemm_tc2_launch(x, w_hi, w_lo, nullptr, y, M, N, K, ldx, ldw, ldy, 0, nullptr, nullptr, st, accumulate);
+    if (rc != NF_OK) return rc;
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
 constexpr int kBlkRows = 32;
 constexpr int kBlkWarps = 4;
 constexpr int kBlkPad = 33;          // [unit][row] tiles padded to 33 rows: conflict-free transposed fills and lane reads
@@ -91,7 +106,7 @@ ar_block_kernel(const float* __restrict__ vin, float* __restrict__ xcur, const f
         if (warp == 0) {
             float mu = __ldg(b3 + g) + dot_tile(w3 + (size_t)g * H + u0, a3, ub0, lane);
             float al = __ldg(b3 + D + g) + dot_tile(w3 + (size_t)(D + g) * H + u0, a3, ub0, lane);
-            if (preo && lane < nrow) { mu += preo[(r0 + lane) * 2 * D + g]; al += preo[(r0 + lane) * 2 * D + D + g]; }
+            if (preo && lane < nrow) { mu += preo[(r0 + lane) * 2 * D + 2 * g]; al += preo[(r0 + lane) * 2 * D + 2 * g + 1]; }
             float o, t;
             affine_ar_elem<float>(mode, sx[(g - g0) * kBlkPad + lane], mu, al, o, t);
             if (sbad[lane]) { o = __int_as_float(0x7fc00000); t = o; }
@@ -191,21 +206,47 @@ __device__ __forceinline__ void warp_units_chunk(const float* __restrict__ wt, c
     // compile-time row pitches (NUP, kBlkPad): the unrolled body addresses everything with immediate offsets
     const float* ap = in + lane;
     const float* wp = wt + cu;
-    int v = 0;
-    for (; v + 4 <= nv; v += 4, ap += 4 * kBlkPad, wp += 4 * NUP) {
+    // groups of four inputs, software-pipelined by hand: the operands of group i+1 are requested before the FMAs of group
+    // i issue.  A warp shares its scheduler with at most one other warp here (shared memory bounds the CTA at 5-6 warps),
+    // so nothing else covers the ~30-cycle LDS latency: the straight loop sat on the short scoreboard for 40 % of its
+    // samples (profiles/r02l_c3_ar_block_warp_ncu.txt).  Same FMAs in the same order.
+    auto load = [&](int grp, float (&a)[4], float4 (&w)[4][NCH]) {
+        const float* a_ = ap + grp * 4 * kBlkPad;
+        const float* w_ = wp + grp * 4 * NUP;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float a = ap[k * kBlkPad];
-            const float2 aa = make_float2(a, a);
+            a[k] = a_[k * kBlkPad];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) w[k][c] = *reinterpret_cast<const float4*>(w_ + k * NUP + 4 * c);   // rows padded by 4*kWarpChunks floats
+        }
+    };
+    auto fma = [&](const float (&a)[4], const float4 (&w)[4][NCH]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 aa = make_float2(a[k], a[k]);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                const float4 w = *reinterpret_cast<const float4*>(wp + k * NUP + 4 * c);    // rows padded by 4*kWarpChunks floats
-                acc2[c][0] = __ffma2_rn(make_float2(w.x, w.y), aa, acc2[c][0]);
-                acc2[c][1] = __ffma2_rn(make_float2(w.z, w.w), aa, acc2[c][1]);
+                acc2[c][0] = __ffma2_rn(make_float2(w[k][c].x, w[k][c].y), aa, acc2[c][0]);
+                acc2[c][1] = __ffma2_rn(make_float2(w[k][c].z, w[k][c].w), aa, acc2[c][1]);
             }
         }
+    };
+    const int ngrp = nv >> 2;
+    if (ngrp > 0) {
+        float aA[4], aB[4];
+        float4 wA[4][NCH], wB[4][NCH];
+        load(0, aA, wA);
+        int g = 0;
+        for (; g + 2 <= ngrp; g += 2) {
+            load(g + 1, aB, wB);
+            fma(aA, wA);
+            if (g + 2 < ngrp) load(g + 2, aA, wA);
+            fma(aB, wB);
+        }
+        if (g < ngrp) fma(aA, wA);
     }
-    for (; v < nv; ++v, ap += kBlkPad, wp += NUP) {
+    ap += ngrp * 4 * kBlkPad; wp += ngrp * 4 * NUP;
+    for (int v = ngrp * 4; v < nv; ++v, ap += kBlkPad, wp += NUP) {
         const float a = *ap;
         const float2 aa = make_float2(a, a);
 #pragma unroll
@@ -242,6 +283,13 @@ __device__ __forceinline__ void warp_units(const float* __restrict__ wt, const f
     }
 }
 
+constexpr int kBlkMaxDeg = 8;        // degrees per block the warp kernel takes (compile-time pitch of its W3 tile)
+
+// PERSISTENT: the block's weights are staged once per CTA (one CTA per SM) and every warp then walks over row tiles on
+// its own -- no CTA barrier after the staging, so one warp's tile fill / drain overlaps the other warps' step loops.  (As
+// one CTA per 6 row tiles, each of the ~9 CTAs an SM ran in turn re-staged ~58 KB of weights and sat alone on the SM
+// while they and the tiles arrived: a third of the kernel's stall samples, profiles/r02l_c3_ar_block_warp_ncu.txt.)
+// preo: [B, 2D] with (mu, alpha) of a dim adjacent -- the layout the push GEMMs of nf_ar_blocked_forward accumulate into.
 template <int NUP>
 __global__ void __launch_bounds__(256)
 ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, const float* __restrict__ pre1,
@@ -255,16 +303,20 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
     extern __shared__ __align__(16) float sm[];
     const int nd = g1 - g0, nu = u1 - u0;
     constexpr int nup = NUP;                                     // padded row length of the transposed weight tiles
+    constexpr int p3 = 2 * kBlkMaxDeg;                           // row pitch of the W3 tile
     const int nwarps = blockDim.x >> 5;
-    // shared weights: W0t [nd][nup], W1t / W2t [nu][nup], W3t [nu][2*nd] (mu, alpha interleaved per dim), biases [3][nu]
+    // shared weights: W0t [nd][nup], W1t / W2t [nu][nup], W3t [nu][p3] (mu, alpha interleaved per dim), biases [3][nu],
+    // output biases [p3] (mu, alpha interleaved), in-block unit boundaries of the block's degrees [kBlkMaxDeg + 2]
     float* W0t = sm;
     float* W1t = W0t + nd * nup;
     float* W2t = W1t + nu * nup;
     float* W3t = W2t + nu * nup;
-    float* bs = W3t + nu * 2 * nd;
-    float* tiles = bs + ((3 * nu + 3) & ~3);
+    float* bs = W3t + nu * p3;
+    float* b3s = bs + ((3 * nu + 3) & ~3);
+    int* gsm = reinterpret_cast<int*>(b3s + p3);
+    float* tiles = b3s + p3 + 16;
     const int tile_floats = (nd + 3 * nu) * kBlkPad;
-    for (int i = threadIdx.x; i < (nd + 2 * nu) * nup; i += blockDim.x) W0t[i] = 0.f;      // padding columns must be finite
+    for (int i = threadIdx.x; i < (nd + 2 * nu) * nup + nu * p3; i += blockDim.x) W0t[i] = 0.f;      // padding columns must be finite
     __syncthreads();
     {
         const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, nw_ = blockDim.x >> 5;
@@ -279,86 +331,91 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
         for (int d = warp_; d < nd; d += nw_) {
             const float* rm = w3 + (size_t)(g0 + d) * H + u0;
             const float* ra = w3 + (size_t)(D + g0 + d) * H + u0;
-            for (int v = lane_; v < nu; v += 32) { NF_CPA4(W3t + v * 2 * nd + 2 * d, rm + v); NF_CPA4(W3t + v * 2 * nd + 2 * d + 1, ra + v); }
+            for (int v = lane_; v < nu; v += 32) { NF_CPA4(W3t + v * p3 + 2 * d, rm + v); NF_CPA4(W3t + v * p3 + 2 * d + 1, ra + v); }
         }
 #undef NF_CPA4
     }
     for (int i = threadIdx.x; i < nu; i += blockDim.x) { bs[i] = b0[u0 + i]; bs[nu + i] = b1[u0 + i]; bs[2 * nu + i] = b2[u0 + i]; }
+    if (threadIdx.x < nd) { b3s[2 * threadIdx.x] = b3[g0 + threadIdx.x]; b3s[2 * threadIdx.x + 1] = b3[D + g0 + threadIdx.x]; }
+    if (threadIdx.x <= nd + 1) gsm[threadIdx.x] = (g0 + (int)threadIdx.x <= D ? gstart[g0 + threadIdx.x] : gstart[D]) - u0;
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();                                 // the weights (all warps' copies) have landed; no CTA barrier below
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t r0 = ((int64_t)blockIdx.x * nwarps + warp) * kBlkRows;
-    const bool idle = r0 >= B;                       // keeps going to the barrier below, touches nothing
-    if (idle) r0 = 0;
-    const int nrow = idle ? 0 : (int)((B - r0) < kBlkRows ? (B - r0) : kBlkRows);
     const bool first = (g0 == 0);
     float* sx = tiles + (size_t)warp * tile_floats;
     float* a1 = sx + nd * kBlkPad;
     float* a2 = a1 + nu * kBlkPad;
     float* a3 = a2 + nu * kBlkPad;
-    warp_fill_tile(sx, vin, r0, nrow, D, g0, nd, lane);
-    warp_fill_tile(a1, pre1, r0, nrow, H, u0, nu, lane);
-    warp_fill_tile(a2, pre2, r0, nrow, H, u0, nu, lane);
-    warp_fill_tile(a3, pre3, r0, nrow, H, u0, nu, lane);
-    asm volatile("cp.async.commit_group;\n" ::);
-    const bool ok = lane < nrow;
-    float ld = (!first && ok) ? ldacc[r0 + lane] : 0.f;
-    int poisoned = (!first && ok) ? bad[r0 + lane] : 0;
-    // previous blocks' contributions to the parameters of this block's dims, and the degree boundaries, up front:
-    // inside the step loop every global load would sit on the critical path of a warp that is alone on its scheduler
-    const float* prow = (preo && ok) ? preo + (r0 + lane) * 2 * D : nullptr;
-    float cmu = prow ? prow[g0] : 0.f, cal = prow ? prow[D + g0] : 0.f;      // consumed by the first step
-    int ub_lo = gstart[g0] - u0, ub_hi = gstart[g0 + 1] - u0;
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();                                 // weights (all warps' copies) and this warp's tiles have landed
-    if (idle) return;
+    const int64_t ntiles = (B + kBlkRows - 1) / kBlkRows;
+    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+        const int64_t r0 = tile * kBlkRows;
+        const int nrow = (int)((B - r0) < kBlkRows ? (B - r0) : kBlkRows);
+        warp_fill_tile(sx, vin, r0, nrow, D, g0, nd, lane);
+        warp_fill_tile(a1, pre1, r0, nrow, H, u0, nu, lane);
+        warp_fill_tile(a2, pre2, r0, nrow, H, u0, nu, lane);
+        warp_fill_tile(a3, pre3, r0, nrow, H, u0, nu, lane);
+        asm volatile("cp.async.commit_group;\n" ::);
+        const bool ok = lane < nrow;
+        float ld = (!first && ok) ? ldacc[r0 + lane] : 0.f;
+        int poisoned = (!first && ok) ? bad[r0 + lane] : 0;
+        // previous blocks' contributions to the parameters of this block's dims, up front: inside the step loop every
+        // global load would sit on the critical path of a warp that is nearly alone on its scheduler
+        const float2* prow = (preo && ok) ? reinterpret_cast<const float2*>(preo + (r0 + lane) * 2 * D) + g0 : nullptr;
+        float2 cpar = prow ? prow[0] : make_float2(0.f, 0.f);                 // consumed by the first step
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
 
-    for (int g = g0; g < g1; ++g) {
-        const int ub0 = ub_lo, ub1 = ub_hi;                           // in-block units of degree g
-        // next step's global operands are requested now and consumed one iteration later
-        const bool more = g + 1 < g1;
-        const float nmu = (more && prow) ? prow[g + 1] : 0.f, nal = (more && prow) ? prow[D + g + 1] : 0.f;
-        const int nub = more ? gstart[g + 2] - u0 : ub_hi;
-        // (A) parameters of dim g: previous blocks (preo) + in-block layer-3 units of degree < g
-        {
-            float mu0 = __ldg(b3 + g), al0 = __ldg(b3 + D + g), mu1 = 0.f, al1 = 0.f;
-            const float* wq = W3t + 2 * (g - g0);
-            int v = 0;
-            for (; v + 2 <= ub0; v += 2) {
-                const float2 wa = *reinterpret_cast<const float2*>(wq + v * 2 * nd);
-                const float2 wb = *reinterpret_cast<const float2*>(wq + (v + 1) * 2 * nd);
-                const float xa = a3[v * kBlkPad + lane], xb = a3[(v + 1) * kBlkPad + lane];
-                mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
-                mu1 = fmaf(wb.x, xb, mu1); al1 = fmaf(wb.y, xb, al1);
+        for (int g = g0; g < g1; ++g) {
+            const int ub0 = gsm[g - g0], ub1 = gsm[g - g0 + 1];               // in-block units of degree g
+            // next step's global operand is requested now and consumed one iteration later
+            const float2 npar = (g + 1 < g1 && prow) ? prow[g + 1 - g0] : make_float2(0.f, 0.f);
+            // (A) parameters of dim g: previous blocks (preo) + in-block layer-3 units of degree < g
+            {
+                const float2 bq = *reinterpret_cast<const float2*>(b3s + 2 * (g - g0));
+                float mu0 = bq.x, al0 = bq.y, mu1 = 0.f, al1 = 0.f;
+                const float* wq = W3t + 2 * (g - g0);
+                const float* aq = a3 + lane;
+                int v = 0;
+                for (; v + 2 <= ub0; v += 2) {
+                    const float2 wa = *reinterpret_cast<const float2*>(wq + v * p3);
+                    const float2 wb = *reinterpret_cast<const float2*>(wq + (v + 1) * p3);
+                    const float xa = aq[v * kBlkPad], xb = aq[(v + 1) * kBlkPad];
+                    mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
+                    mu1 = fmaf(wb.x, xb, mu1); al1 = fmaf(wb.y, xb, al1);
+                }
+                if (v < ub0) {
+                    const float2 wa = *reinterpret_cast<const float2*>(wq + v * p3);
+                    const float xa = aq[v * kBlkPad];
+                    mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
+                }
+                float mu = mu0 + mu1, al = al0 + al1;
+                mu += cpar.x; al += cpar.y;
+                float o, t;
+                affine_ar_elem<float>(mode, sx[(g - g0) * kBlkPad + lane], mu, al, o, t);
+                if (poisoned) { o = __int_as_float(0x7fc00000); t = o; }
+                if (!is_finite(o)) poisoned = 1;        // 0*NaN of the dense reference poisons every later dim
+                sx[(g - g0) * kBlkPad + lane] = o;
+                ld += t;
             }
-            if (v < ub0) {
-                const float2 wa = *reinterpret_cast<const float2*>(wq + v * 2 * nd);
-                const float xa = a3[v * kBlkPad + lane];
-                mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
-            }
-            float mu = mu0 + mu1, al = al0 + al1;
-            mu += cmu; al += cal;
-            float o, t;
-            affine_ar_elem<float>(mode, sx[(g - g0) * kBlkPad + lane], mu, al, o, t);
-            if (poisoned) { o = __int_as_float(0x7fc00000); t = o; }
-            if (!is_finite(o)) poisoned = 1;        // 0*NaN of the dense reference poisons every later dim
-            sx[(g - g0) * kBlkPad + lane] = o;
-            ld += t;
+            if (g == D - 1) break;
+            // (B) hidden units of degree g, layer by layer (all lane-private: no synchronisation)
+            warp_units<NUP>(W0t, bs, sx, g - g0 + 1, a1, ub0, ub1, lane);
+            warp_units<NUP>(W1t, bs + nu, a1, ub1, a2, ub0, ub1, lane);
+            warp_units<NUP>(W2t, bs + 2 * nu, a2, ub1, a3, ub0, ub1, lane);
+            cpar = npar;
         }
-        if (g == D - 1) break;
-        // (B) hidden units of degree g, layer by layer (all lane-private: no synchronisation)
-        warp_units<NUP>(W0t, bs, sx, g - g0 + 1, a1, ub0, ub1, lane);
-        warp_units<NUP>(W1t, bs + nu, a1, ub1, a2, ub0, ub1, lane);
-        warp_units<NUP>(W2t, bs + 2 * nu, a2, ub1, a3, ub0, ub1, lane);
-        cmu = nmu; cal = nal; ub_lo = ub_hi; ub_hi = nub;
+        __syncwarp();
+        warp_drain_tile(sx, xcur, r0, nrow, D, g0, nd, lane);
+        if (g1 < D) {
+            warp_drain_tile(a1, act1, r0, nrow, H, u0, nu, lane);
+            warp_drain_tile(a2, act2, r0, nrow, H, u0, nu, lane);
+            warp_drain_tile(a3, act3, r0, nrow, H, u0, nu, lane);
+        }
+        if (ok) { ldacc[r0 + lane] = ld; bad[r0 + lane] = poisoned; }
+        __syncwarp();                                // the drain's reads of the tile are done before the next fill lands
     }
-    __syncwarp();
-    warp_drain_tile(sx, xcur, r0, nrow, D, g0, nd, lane);
-    if (g1 < D) {
-        warp_drain_tile(a1, act1, r0, nrow, H, u0, nu, lane);
-        warp_drain_tile(a2, act2, r0, nrow, H, u0, nu, lane);
-        warp_drain_tile(a3, act3, r0, nrow, H, u0, nu, lane);
-    }
-    if (ok) { ldacc[r0 + lane] = ld; bad[r0 + lane] = poisoned; }
 }
 
 int g_ar_block_variant = 1;          // nf_set_option(3, v): 0 = first in-block kernel (CTA barriers), 1 = warp-private tiles
@@ -382,7 +439,11 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
     if (B == 0) return NF_OK;
     NF_REQ(v); NF_REQ(w); NF_REQ(w_hi); NF_REQ(w_lo); NF_REQ(b); NF_REQ(gstart_dev); NF_REQ(gstart_host);
     NF_REQ(workspace); NF_REQ(out); NF_REQ(ld);
-    if ((D % 4) != 0 || (H % 4) != 0) return NF_ERR_UNSUPPORTED;      // TMA row pitches of the slice GEMMs
+    if ((D % 4) != 0 || (H % 8) != 0 || (block_degrees % 4) != 0) return NF_ERR_UNSUPPORTED;      // TMA row pitches of the slice GEMMs
+    // every block of hidden units starts at a multiple of 8 (packing.blocked_made_pack pads the blocks with dead units):
+    // TMA bases of the push products' column slices, 256-bit row stores of the pull products
+    for (int g0 = 0; g0 < D; g0 += block_degrees)
+        if (gstart_host[g0] % 8) return NF_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = (float*)workspace;
     const size_t BH = (size_t)B * H, BD = (size_t)B * D;
@@ -393,6 +454,7 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
     const float* w0 = (const float*)w[0]; const float* w1 = (const float*)w[1];
     const float* w2 = (const float*)w[2]; const float* w3 = (const float*)w[3];
     const int grid = (int)cdiv(B, kBlkRows);
+    bool pushed = false;
     for (int g0 = 0; g0 < D; g0 += block_degrees) {
         const int g1 = (g0 + block_degrees < D) ? g0 + block_degrees : D;
         const int u0 = gstart_host[g0], u1 = gstart_host[g1];
@@ -401,65 +463,71 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
         if (smem > 160 * 1024) return NF_ERR_UNSUPPORTED;
         const bool prev = g0 > 0;
         int rc;
-        if (prev) {
-            // contributions of dims < g0 / units < u0 (all final) to this block, dense over the whole batch
-            if (nu > 0) {
-                rc = nf_linear_tc(xcur, (const float*)w_hi[0] + (size_t)u0 * D, (const float*)w_lo[0] + (size_t)u0 * D, nullptr,
-                                  pre1 + u0, B, nu, g0, D, D, H, 0, nullptr, stream);
-                if (rc) return rc;
-                if (u0 > 0) {
-                    rc = nf_linear_tc(act1, (const float*)w_hi[1] + (size_t)u0 * H, (const float*)w_lo[1] + (size_t)u0 * H, nullptr,
-                                      pre2 + u0, B, nu, u0, H, H, H, 0, nullptr, stream);
-                    if (rc) return rc;
-                    rc = nf_linear_tc(act2, (const float*)w_hi[2] + (size_t)u0 * H, (const float*)w_lo[2] + (size_t)u0 * H, nullptr,
-                                      pre3 + u0, B, nu, u0, H, H, H, 0, nullptr, stream);
-                    if (rc) return rc;
-                }
-            }
+        if (prev && nu > 0) {
+            // PULL: contributions of dims < g0 / units < u0 (all final) to the block's hidden pre-activations, dense over
+            // the whole batch (the output layer's share arrives by PUSH, below)
+            rc = nf_linear_tc(xcur, (const float*)w_hi[0] + (size_t)u0 * D, (const float*)w_lo[0] + (size_t)u0 * D, nullptr,
+                              pre1 + u0, B, nu, g0, D, D, H, 0, nullptr, stream);
+            if (rc) return rc;
             if (u0 > 0) {
-                rc = nf_linear_tc(act3, (const float*)w_hi[3] + (size_t)g0 * H, (const float*)w_lo[3] + (size_t)g0 * H, nullptr,
-                                  preo + g0, B, nd, u0, H, H, 2 * D, 0, nullptr, stream);
+                rc = nf_linear_tc(act1, (const float*)w_hi[1] + (size_t)u0 * H, (const float*)w_lo[1] + (size_t)u0 * H, nullptr,
+                                  pre2 + u0, B, nu, u0, H, H, H, 0, nullptr, stream);
                 if (rc) return rc;
-                rc = nf_linear_tc(act3, (const float*)w_hi[3] + (size_t)(D + g0) * H, (const float*)w_lo[3] + (size_t)(D + g0) * H,
-                                  nullptr, preo + D + g0, B, nd, u0, H, H, 2 * D, 0, nullptr, stream);
+                rc = nf_linear_tc(act2, (const float*)w_hi[2] + (size_t)u0 * H, (const float*)w_lo[2] + (size_t)u0 * H, nullptr,
+                                  pre3 + u0, B, nu, u0, H, H, H, 0, nullptr, stream);
                 if (rc) return rc;
             }
         }
         const bool hp = prev && u0 > 0;
+        const bool have_preo = pushed;               // some earlier block pushed into preo (it covers every later dim)
+        bool launched = false;
         {
             // warp-private variant: shared transposed weights + one tile per warp; as many warps as fit in 220 KB
             const int need = ((nu + 3) & ~3) + 4 * kWarpChunks;
-            const int nup = need <= 48 ? 48 : (need <= 96 ? 96 : 160);       // compile-time pitches of ar_block_warp_kernel
-            const size_t wfl = (size_t)(nd + 2 * nu) * nup + (size_t)nu * 2 * nd + ((3 * nu + 3) & ~3);
+            const int nup = need <= 48 ? 48 : (need <= 80 ? 80 : (need <= 96 ? 96 : 160));   // compile-time pitches of ar_block_warp_kernel
+            const size_t wfl = (size_t)(nd + 2 * nu) * nup + (size_t)nu * 2 * kBlkMaxDeg + ((3 * nu + 3) & ~3) + 2 * kBlkMaxDeg + 16;
             const size_t tfl = (size_t)(nd + 3 * nu) * kBlkPad;
             int nw = wfl * sizeof(float) < 200 * 1024 ? (int)((220 * 1024 / sizeof(float) - wfl) / tfl) : 0;
             if (nw > 8) nw = 8;
-            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= 8) {
+            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= kBlkMaxDeg) {
                 const size_t smem2 = sizeof(float) * (wfl + (size_t)nw * tfl);
-                const int grid2 = (int)cdiv(B, (int64_t)kBlkRows * nw);
+                const int64_t ctas = cdiv(cdiv(B, (int64_t)kBlkRows), (int64_t)nw);
+                const int grid2 = (int)(ctas < kNumSMs ? ctas : kNumSMs);              // persistent: one CTA per SM
 #define NF_ABW(NUPV)                                                                                                          \
                 do {                                                                                                          \
                     NF_CUDA(cudaFuncSetAttribute(ar_block_warp_kernel<NUPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
                     ar_block_warp_kernel<NUPV><<<grid2, 32 * nw, smem2, st>>>(                                                 \
-                        (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr, hp ? preo : nullptr, \
-                        act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2, (const float*)b[2], w3,           \
-                        (const float*)b[3], gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, u1, mode);                            \
+                        (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr,                \
+                        have_preo ? preo : nullptr, act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2,      \
+                        (const float*)b[2], w3, (const float*)b[3], gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, u1, mode);    \
                 } while (0)
-                if (nup == 48) NF_ABW(48); else if (nup == 96) NF_ABW(96); else NF_ABW(160);
+                if (nup == 48) NF_ABW(48); else if (nup == 80) NF_ABW(80); else if (nup == 96) NF_ABW(96); else NF_ABW(160);
 #undef NF_ABW
                 count_launch();
                 NF_LAUNCH_CHECK();
-                continue;
+                launched = true;
             }
         }
-        if (smem > 48 * 1024)
-            NF_CUDA(cudaFuncSetAttribute(ar_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ar_block_kernel<<<grid, kBlkRows * kBlkWarps, smem, st>>>(
-            (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr, hp ? preo : nullptr,
-            act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2, (const float*)b[2], w3, (const float*)b[3],
-            gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, u1, mode);
-        count_launch();
-        NF_LAUNCH_CHECK();
+        if (!launched) {
+            if (smem > 48 * 1024)
+                NF_CUDA(cudaFuncSetAttribute(ar_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ar_block_kernel<<<grid, kBlkRows * kBlkWarps, smem, st>>>(
+                (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr, have_preo ? preo : nullptr,
+                act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2, (const float*)b[2], w3, (const float*)b[3],
+                gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, u1, mode);
+            count_launch();
+            NF_LAUNCH_CHECK();
+        }
+        // PUSH: the block's layer-3 units are final -> their share of the output-layer pre-activations of ALL later dims in
+        // one narrow-K product, accumulated into preo ([B, 2D], (mu, alpha) of a dim adjacent; w_hi[3] / w_lo[3] hold the
+        // output layer's rows in that order).  Pulling per block instead re-read act3[:, :u0] for 2 x 8 outputs every time:
+        // 1.85 ms of the 8.3 ms pass at [262144, 64] x 512 (profiles/r01z_c3_launches.csv).
+        if (g1 < D && nu > 0) {
+            rc = linear_tc_push(act3 + u0, (const float*)w_hi[3] + (size_t)2 * g1 * H + u0, (const float*)w_lo[3] + (size_t)2 * g1 * H + u0,
+                                preo + 2 * g1, B, 2 * (D - g1), nu, H, H, 2 * D, pushed ? 1 : 0, st);
+            if (rc) return rc;
+            pushed = true;
+        }
     }
     return nf_ar_finish_forward(xcur, v, ldacc, out, ld, B, D, mode, NF_F32, stream);
 }

@@ -249,7 +249,7 @@ extern int g_gemm_tc_small_k;
 extern int g_tc_passes;
 int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                     int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
-                    cudaStream_t st);
+                    cudaStream_t st, int accumulate);
 
 }  // namespace nf
 
@@ -289,7 +289,7 @@ extern "C" int nf_linear_tc_range(const void* x, const void* w_hi, const void* w
     // contractions longer than 128 go to the short-chain kernel (gemm_tc2.cu: chains of 4 K blocks folded into registers
     // with round-to-nearest adds); up to K = 128 the single chain here is just as short and two CTAs per SM are faster
     if (g_gemm_tc_variant == 1 && (K > 128 || g_gemm_tc_small_k)) {
-        const int rc = gemm_tc2_launch(x, w_hi, w_lo, bias, y, M, N, K, ldx, ldw, ldy, relu, k_begin, k_extent, (cudaStream_t)stream);
+        const int rc = gemm_tc2_launch(x, w_hi, w_lo, bias, y, M, N, K, ldx, ldw, ldy, relu, k_begin, k_extent, (cudaStream_t)stream, 0);
         if (rc == NF_OK) { count_launch(); NF_LAUNCH_CHECK(); return NF_OK; }
         if (rc != NF_ERR_UNSUPPORTED) return rc;
     }

@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                 int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
-                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec, int ss) {
+                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec, int ss, int accumulate) {
+    // accumulate (DIRECT + vec only, checked on the host): Y += X W^T instead of Y = ... (the blocked sampler's push of a
+    // finished block of layer-3 units into the output-layer pre-activations of all later dims)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int chain_kb = passes == 1 ? k2ChainKBFast : k2ChainKB;
     const int n_stages = passes == 1 ? k2StagesFast : k2Stages;
@@ -156,7 +158,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (whole warp, convergent; one elected lane issues) ----------------
-        const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)k2BN);
         const bool leader = tc::elect_one();
         int it = 0, s = 0, ic = 0, cb = 0;               // K-block counter, stage, position in the chain, accumulator
         uint32_t ph = 0, dph = 0;                        // parity of the stage round / of the accumulator round
@@ -167,6 +168,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             (void)m0;
             int kb_first, nkb;
             tile_k_range(n0, N, K, k_extent, k_begin, kb_first, nkb);
+            // narrow tiles (column slices of the blocked sampler, 2*D-wide heads): the MMA covers only the live columns,
+            // rounded up to the instruction's N granularity of 16 -- its cost is proportional to N
+            const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)((min(k2BN, N - n0) + 15) & ~15));
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int a = it & (kAStages - 1);
                 if (ic == 0 && !first_acc_round) tc::mbar_wait(&d_empty[cb], dph ^ 1u);
@@ -283,17 +287,46 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             }
             const int row = m0 + q * 32 + lane;
             float* yrow = Y + (int64_t)row * ldc;
+            const int n_live = min(k2BN, N - n0);                 // columns past it are neither multiplied nor stored
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                const bool live = c * 32 < n_live;                // CTA-uniform
                 uint32_t v0[16], v1[16];
+                float old[32];
+                if (live && accumulate) {
+                    // requested ahead of the accumulator wait; rows past M / columns past N read as zero
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int col = n0 + c * 32 + 8 * h;
+                        if (row < M && col + 8 <= N) {
+                            const float4 o0 = *reinterpret_cast<const float4*>(yrow + col);
+                            const float4 o1 = *reinterpret_cast<const float4*>(yrow + col + 4);
+                            old[8 * h + 0] = o0.x; old[8 * h + 1] = o0.y; old[8 * h + 2] = o0.z; old[8 * h + 3] = o0.w;
+                            old[8 * h + 4] = o1.x; old[8 * h + 5] = o1.y; old[8 * h + 6] = o1.z; old[8 * h + 7] = o1.w;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) old[8 * h + i] = (row < M && col + i < N) ? yrow[col + i] : 0.f;
+                        }
+                    }
+                }
                 if (nkb > 0) {
-                    tc::tmem_ld16(lane_addr + cb * 128 + c * 32, v0);
-                    tc::tmem_ld16(lane_addr + cb * 128 + c * 32 + 16, v1);
-                    tc::wait_ld();
+                    if (live) {
+                        tc::tmem_ld16(lane_addr + cb * 128 + c * 32, v0);
+                        tc::tmem_ld16(lane_addr + cb * 128 + c * 32 + 16, v1);
+                        tc::wait_ld();
+                    }
                     if (c == 3) { tc::fence_before_sync(); tc::mbar_arrive(&d_empty[cb]); }     // accumulator free again
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { v0[j] = 0u; v1[j] = 0u; }
+                }
+                if (!live) continue;
+                if (accumulate) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v0[j] = __float_as_uint(__uint_as_float(v0[j]) + old[j]);
+                        v1[j] = __float_as_uint(__uint_as_float(v1[j]) + old[16 + j]);
+                    }
                 }
                 if (vec) {
                     if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, true);
@@ -331,11 +364,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 128; ++j) acc[j] = 0.f;
             }
+            const int n_live = min(k2BN, N - n0);                 // columns past it are neither multiplied nor stored
             for (int c = 0; c < nchains; ++c) {
                 tc::mbar_wait(&d_full[cb], dph);
                 tc::fence_after_sync();
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
+                    if (ch * 16 >= n_live) break;
                     uint32_t v[16];
                     tc::tmem_ld16(lane_addr + cb * 128 + ch * 16, v);
                     tc::wait_ld();
@@ -408,7 +443,7 @@ static bool make_map2(CUtensorMap* m, const void* base, int64_t rows, int64_t co
 // returns NF_OK when launched; NF_ERR_UNSUPPORTED when the caller should use gemm_tc.cu
 int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const void* bias, void* y, int64_t M, int64_t N, int64_t K,
                     int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
-                    cudaStream_t st) {
+                    cudaStream_t st, int accumulate) {
     alignas(64) CUtensorMap tx, twh, twl;
     if (!make_map2(&tx, x, M, K, ldx, k2BM) || !make_map2(&twh, w_hi, N, K, ldw, k2BN) || !make_map2(&twl, w_lo, N, K, ldw, k2BN))
         return NF_ERR_UNSUPPORTED;
@@ -418,21 +453,22 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     // 256-bit row stores in the epilogue: 32-byte aligned rows of Y
     const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : 0;
     const int ss = (g_tc_passes == 1 && g_gemm_tc2_ss) ? 1 : 0;
+    if (accumulate && (K > 4 * k2BK || !vec || bias != nullptr || relu)) return NF_ERR_UNSUPPORTED;
     if (K <= 4 * k2BK) {
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc2_kernel<true, k2NAcc><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
-                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
+                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
     } else {
         const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
         if (g_gemm_tc2_nacc == 2) {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, 2><<<grid, k2Threads, smem, st>>>((tx), twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
+                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
         } else {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, k2NAcc><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss);
+                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
         }
     }
     return NF_OK;

@@ -796,21 +796,25 @@ def _ptr_array(tensors):
 
 def ar_sequential_blocked(v, folded, mode):
     """MAF.forward / IAF.inverse, blocked: previous-block contributions on tcgen05, in-block steps in ar_block_warp_kernel.
-    Returns None when the configuration is not taken (no TF32 splits, D or H not a multiple of 4)."""
-    if folded.w_split is None or v.dtype != torch.float32 or folded.D % 4 or folded.H % 4:
+    Returns None when the configuration is not taken (no TF32 splits, D not a multiple of 4)."""
+    if folded.w_split is None or v.dtype != torch.float32 or folded.D % 4 or AR_BLOCK_DEGREES % 4:
+        return None
+    pk = folded.blocked
+    if pk is None or (pk is not False and pk.block_degrees != AR_BLOCK_DEGREES):
+        from . import packing
+        pk = packing.blocked_made_pack(folded, AR_BLOCK_DEGREES) or False
+        folded.blocked = pk
+    if pk is False:
         return None
     v = _c(v)
     B, D = v.shape
-    H = folded.H
+    H = pk.H
     nws = L.lib().nf_ar_blocked_workspace_floats(B, D, H)
     ws = torch.empty(nws, dtype=torch.float32, device=v.device)
     out = torch.empty_like(v)
     ld = torch.empty(B, dtype=v.dtype, device=v.device)
-    w = _ptr_array(folded.w)
-    whi = _ptr_array([s[0] for s in folded.w_split])
-    wlo = _ptr_array([s[1] for s in folded.w_split])
-    bb = _ptr_array(folded.b)
-    ok = L.try_call("nf_ar_blocked_forward", ptr(v), w, whi, wlo, bb, ptr(folded.gstart), folded.gstart_host.ctypes.data,
+    ok = L.try_call("nf_ar_blocked_forward", ptr(v), _ptr_array(pk.w), _ptr_array(pk.w_hi), _ptr_array(pk.w_lo),
+                    _ptr_array(pk.b), ptr(pk.gstart), pk.gstart_host.ctypes.data,
                     ptr(ws), ptr(out), ptr(ld), B, D, H, mode, AR_BLOCK_DEGREES, stream())
     return (out, ld) if ok else None
 

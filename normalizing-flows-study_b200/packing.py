@@ -229,6 +229,7 @@ class FoldedMade:
     w_split: Optional[list] = None      # [(hi, lo)] x 4: 3xTF32 operands of the tensor-core GEMM (float32 only)
     gstart_host: Optional[np.ndarray] = None
     bf16: Optional[object] = None       # made_bf16_pack(self), built on first use of the bf16 fused chain (False: unsupported)
+    blocked: Optional[object] = None    # blocked_made_pack(self, .), built on first use of the blocked sequential direction
 
 
 def fold_made(made) -> Optional[FoldedMade]:
@@ -282,6 +283,67 @@ def fold_made(made) -> Optional[FoldedMade]:
         from . import ops
         folded.w_split = [ops.split_tf32(t) for t in w]
     return folded
+
+
+@dataclass
+class BlockedMadePack:
+    """Operands of nf_ar_blocked_forward (csrc/ar_blocked.cu).  The degree-sorted hidden units are laid out in blocks of
+    `block_degrees` consecutive degrees, every block starting at a multiple of 8 units: the gaps are dead units (zero
+    weights and biases, so they hold relu(0) = 0 and feed nothing).  H is the padded width; gstart[g] the padded index of
+    the first unit of degree >= g (a block's dead units count with its last degree).  w / b: fp32 operands of the
+    in-block kernel (output layer as [mu rows | alpha rows], like made.py:136-140); w_hi / w_lo: 3xTF32 operands of the
+    slice products, the output layer's rows INTERLEAVED (row 2g = mu_g, row 2g+1 = alpha_g) to match the [B, D, 2]
+    layout of the pushed output pre-activations."""
+    block_degrees: int
+    H: int
+    w: list
+    b: list
+    w_hi: list
+    w_lo: list
+    gstart: torch.Tensor
+    gstart_host: np.ndarray
+
+
+def blocked_layout(gstart: np.ndarray, block_degrees: int, align: int = 8):
+    """(pos, pgstart, Hp): padded index of every sorted unit, padded degree boundaries, padded width."""
+    D = len(gstart) - 1
+    H = int(gstart[D])
+    pos = np.zeros(H, dtype=np.int64)
+    pgstart = np.zeros(D + 1, dtype=np.int32)
+    at = 0
+    for g0 in range(0, D, block_degrees):
+        g1 = min(g0 + block_degrees, D)
+        u0, u1 = int(gstart[g0]), int(gstart[g1])
+        pos[u0:u1] = at + np.arange(u1 - u0)
+        for g in range(g0, g1):
+            pgstart[g] = at + int(gstart[g]) - u0
+        at = (at + (u1 - u0) + align - 1) // align * align
+    pgstart[D] = at
+    return pos, pgstart, max(at, align)
+
+
+def blocked_made_pack(folded: "FoldedMade", block_degrees: int) -> Optional[BlockedMadePack]:
+    w, b = folded.w, folded.b
+    if w[0].dtype != torch.float32 or not w[0].is_cuda or folded.gstart_host is None:
+        return None
+    from . import ops
+    D, H = folded.D, folded.H
+    pos, pgstart, Hp = blocked_layout(folded.gstart_host, block_degrees)
+    dev = w[0].device
+    p = torch.as_tensor(pos, device=dev)
+    with torch.no_grad():
+        w0 = torch.zeros(Hp, D, device=dev); w0[p] = w[0]
+        w1 = torch.zeros(Hp, Hp, device=dev); w1[p[:, None], p[None, :]] = w[1]
+        w2 = torch.zeros(Hp, Hp, device=dev); w2[p[:, None], p[None, :]] = w[2]
+        w3 = torch.zeros(2 * D, Hp, device=dev); w3[:, p] = w[3]
+        bb = []
+        for i in range(3):
+            t = torch.zeros(Hp, device=dev); t[p] = b[i]; bb.append(t)
+        bb.append(b[3].contiguous())
+        w3i = w3.reshape(2, D, Hp).transpose(0, 1).reshape(2 * D, Hp).contiguous()
+        splits = [ops.split_tf32(t) for t in (w0, w1, w2, w3i)]
+    return BlockedMadePack(block_degrees, Hp, [w0, w1, w2, w3], bb, [s_[0] for s_ in splits], [s_[1] for s_ in splits],
+                           torch.as_tensor(pgstart, device=dev), np.ascontiguousarray(pgstart, dtype=np.int32))
 
 
 @dataclass
