@@ -313,9 +313,9 @@ NF_API int nf_arqs_step_backward(const void* v, const void* params, int64_t ldp,
  * w / b: arrays of 4 device pointers, mask-folded degree-sorted weights and biases of the 4 MADE layers (output layer
  * as made.py:136-140 lays it out, [mu rows | alpha rows]); w_hi / w_lo: their TF32 splits, the output layer's rows
  * INTERLEAVED (row 2g = mu_g, row 2g+1 = alpha_g).  gstart: int32[D+1], first unit of degree >= g (device and host
- * copies); every block of `block_degrees` degrees must start at a multiple of 8 units (pad the blocks with dead units:
+ * copies); every block of `block_degrees` degrees must start at a multiple of 4 units (pad the blocks with dead units:
  * zero weights and biases -- packing.blocked_made_pack does), H is that padded width.  workspace:
- * nf_ar_blocked_workspace_floats() floats.  float32; D % 4 == 0, H % 8 == 0, block_degrees % 4 == 0 (8). */
+ * nf_ar_blocked_workspace_floats() floats.  float32; D % 4 == 0, H % 4 == 0, block_degrees % 4 == 0 (8). */
 NF_API int nf_ar_blocked_forward(const void* v, const void* const* w, const void* const* w_hi, const void* const* w_lo,
                           const void* const* b, const int32_t* gstart_dev, const int32_t* gstart_host, void* workspace,
                           void* out, void* ld, int64_t B, int D, int H, int mode, int block_degrees, nf_stream_t stream);

@@ -285,6 +285,111 @@ __device__ __forceinline__ void warp_units(const float* __restrict__ wt, const f
 
 constexpr int kBlkMaxDeg = 8;        // degrees per block the warp kernel takes (compile-time pitch of its W3 tile)
 
+// Layer 3 of the in-block step: the units [ub0, ub1) of the current degree, evaluated like warp_units_chunk (inputs: the
+// layer-2 tile), but their values never go to shared memory.  Nothing in the block reads a layer-3 activation except the
+// output layer, so each finished unit is PUSHED straight into the (mu, alpha) partial sums of the block's dims, held in
+// registers (par[d]; the output weights of dims the unit does not feed are exact zeros of the folded mask), and written
+// to the global activation buffer for the later blocks' pull / push products.  The partial pre-activation (previous
+// blocks' pull product) comes straight from global memory -- requested before the contraction loop, used after it.
+// Without the layer-3 tile a warp's tile is a third smaller: eight warps per SM instead of five or six.
+template <int NCH, int NUP>
+__device__ __forceinline__ void warp_units_l3_chunk(const float* __restrict__ wt, const float* __restrict__ bias,
+                                                    const float* __restrict__ in, int nv, const float* __restrict__ pre_row,
+                                                    float* __restrict__ act_row, const float* __restrict__ w3t,
+                                                    float2 (&par)[kBlkMaxDeg], int cu, int ub0, int ub1, int lane) {
+    float4 pre[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+        pre[c] = pre_row ? *reinterpret_cast<const float4*>(pre_row + cu + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 acc2[NCH][2];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { acc2[c][0] = make_float2(0.f, 0.f); acc2[c][1] = make_float2(0.f, 0.f); }
+    const float* ap = in + lane;
+    const float* wp = wt + cu;
+    auto load = [&](int grp, float (&a)[4], float4 (&w)[4][NCH]) {
+        const float* a_ = ap + grp * 4 * kBlkPad;
+        const float* w_ = wp + grp * 4 * NUP;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = a_[k * kBlkPad];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) w[k][c] = *reinterpret_cast<const float4*>(w_ + k * NUP + 4 * c);
+        }
+    };
+    auto fma = [&](const float (&a)[4], const float4 (&w)[4][NCH]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 aa = make_float2(a[k], a[k]);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                acc2[c][0] = __ffma2_rn(make_float2(w[k][c].x, w[k][c].y), aa, acc2[c][0]);
+                acc2[c][1] = __ffma2_rn(make_float2(w[k][c].z, w[k][c].w), aa, acc2[c][1]);
+            }
+        }
+    };
+    const int ngrp = nv >> 2;
+    if (ngrp > 0) {
+        float aA[4], aB[4];
+        float4 wA[4][NCH], wB[4][NCH];
+        load(0, aA, wA);
+        int g = 0;
+        for (; g + 2 <= ngrp; g += 2) {
+            load(g + 1, aB, wB);
+            fma(aA, wA);
+            if (g + 2 < ngrp) load(g + 2, aA, wA);
+            fma(aB, wB);
+        }
+        if (g < ngrp) fma(aA, wA);
+    }
+    ap += ngrp * 4 * kBlkPad; wp += ngrp * 4 * NUP;
+    for (int v = ngrp * 4; v < nv; ++v, ap += kBlkPad, wp += NUP) {
+        const float a = *ap;
+        const float2 aa = make_float2(a, a);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(wp + 4 * c);
+            acc2[c][0] = __ffma2_rn(make_float2(w.x, w.y), aa, acc2[c][0]);
+            acc2[c][1] = __ffma2_rn(make_float2(w.z, w.w), aa, acc2[c][1]);
+        }
+    }
+    const float* bp = bias + cu;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const float accv[4] = {acc2[c][0].x, acc2[c][0].y, acc2[c][1].x, acc2[c][1].y};
+        const float prev[4] = {pre[c].x, pre[c].y, pre[c].z, pre[c].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = cu + 4 * c + j;
+            if (u >= ub0 && u < ub1) {                               // warp-uniform
+                const float h = relu_nan(prev[j] + bp[4 * c + j] + accv[j]);
+                if (act_row) act_row[u] = h;
+                const float2 hh = make_float2(h, h);
+                const float4* wr = reinterpret_cast<const float4*>(w3t + u * (2 * kBlkMaxDeg));
+#pragma unroll
+                for (int q = 0; q < kBlkMaxDeg / 2; ++q) {
+                    const float4 w = wr[q];                           // (mu, alpha) weights of dims 2q, 2q + 1
+                    par[2 * q] = __ffma2_rn(make_float2(w.x, w.y), hh, par[2 * q]);
+                    par[2 * q + 1] = __ffma2_rn(make_float2(w.z, w.w), hh, par[2 * q + 1]);
+                }
+            }
+        }
+    }
+}
+
+template <int NUP>
+__device__ __forceinline__ void warp_units_l3(const float* __restrict__ wt, const float* __restrict__ bias,
+                                              const float* __restrict__ in, int nv, const float* __restrict__ pre_row,
+                                              float* __restrict__ act_row, const float* __restrict__ w3t,
+                                              float2 (&par)[kBlkMaxDeg], int ub0, int ub1, int lane) {
+    int cu = ub0 & ~3;
+    while (cu < ub1) {
+        const int left = (ub1 - cu + 3) >> 2;
+        if (left >= 3) { warp_units_l3_chunk<3, NUP>(wt, bias, in, nv, pre_row, act_row, w3t, par, cu, ub0, ub1, lane); cu += 12; }
+        else if (left == 2) { warp_units_l3_chunk<2, NUP>(wt, bias, in, nv, pre_row, act_row, w3t, par, cu, ub0, ub1, lane); cu += 8; }
+        else { warp_units_l3_chunk<1, NUP>(wt, bias, in, nv, pre_row, act_row, w3t, par, cu, ub0, ub1, lane); cu += 4; }
+    }
+}
+
 // PERSISTENT: the block's weights are staged once per CTA (one CTA per SM) and every warp then walks over row tiles on
 // its own -- no CTA barrier after the staging, so one warp's tile fill / drain overlaps the other warps' step loops.  (As
 // one CTA per 6 row tiles, each of the ~9 CTAs an SM ran in turn re-staged ~58 KB of weights and sat alone on the SM
@@ -315,7 +420,7 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
     float* b3s = bs + ((3 * nu + 3) & ~3);
     int* gsm = reinterpret_cast<int*>(b3s + p3);
     float* tiles = b3s + p3 + 16;
-    const int tile_floats = (nd + 3 * nu) * kBlkPad;
+    const int tile_floats = (nd + 2 * nu) * kBlkPad;             // inputs/outputs of the dims, layer-1 and layer-2 units
     for (int i = threadIdx.x; i < (nd + 2 * nu) * nup + nu * p3; i += blockDim.x) W0t[i] = 0.f;      // padding columns must be finite
     __syncthreads();
     {
@@ -347,7 +452,6 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
     float* sx = tiles + (size_t)warp * tile_floats;
     float* a1 = sx + nd * kBlkPad;
     float* a2 = a1 + nu * kBlkPad;
-    float* a3 = a2 + nu * kBlkPad;
     const int64_t ntiles = (B + kBlkRows - 1) / kBlkRows;
     for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
         const int64_t r0 = tile * kBlkRows;
@@ -355,63 +459,53 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
         warp_fill_tile(sx, vin, r0, nrow, D, g0, nd, lane);
         warp_fill_tile(a1, pre1, r0, nrow, H, u0, nu, lane);
         warp_fill_tile(a2, pre2, r0, nrow, H, u0, nu, lane);
-        warp_fill_tile(a3, pre3, r0, nrow, H, u0, nu, lane);
         asm volatile("cp.async.commit_group;\n" ::);
         const bool ok = lane < nrow;
         float ld = (!first && ok) ? ldacc[r0 + lane] : 0.f;
         int poisoned = (!first && ok) ? bad[r0 + lane] : 0;
         // previous blocks' contributions to the parameters of this block's dims, up front: inside the step loop every
         // global load would sit on the critical path of a warp that is nearly alone on its scheduler
-        const float2* prow = (preo && ok) ? reinterpret_cast<const float2*>(preo + (r0 + lane) * 2 * D) + g0 : nullptr;
-        float2 cpar = prow ? prow[0] : make_float2(0.f, 0.f);                 // consumed by the first step
+        const float4* prow = (preo && ok) ? reinterpret_cast<const float4*>(preo + (r0 + lane) * 2 * D + 2 * g0) : nullptr;
+        float2 par[kBlkMaxDeg];                      // (mu, alpha) partial sums of the block's dims
+#pragma unroll
+        for (int q = 0; q < kBlkMaxDeg / 2; ++q) {
+            const float4 pv = (prow && 2 * q < nd) ? prow[q] : make_float4(0.f, 0.f, 0.f, 0.f);      // nd is a multiple of 4
+            par[2 * q] = make_float2(pv.x, pv.y); par[2 * q + 1] = make_float2(pv.z, pv.w);
+        }
+        const float* pre3_row = (pre3 && ok) ? pre3 + (r0 + lane) * (int64_t)H + u0 : nullptr;
+        float* act3_row = (g1 < D && ok) ? act3 + (r0 + lane) * (int64_t)H + u0 : nullptr;
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncwarp();
 
         for (int g = g0; g < g1; ++g) {
-            const int ub0 = gsm[g - g0], ub1 = gsm[g - g0 + 1];               // in-block units of degree g
-            // next step's global operand is requested now and consumed one iteration later
-            const float2 npar = (g + 1 < g1 && prow) ? prow[g + 1 - g0] : make_float2(0.f, 0.f);
-            // (A) parameters of dim g: previous blocks (preo) + in-block layer-3 units of degree < g
+            const int gi = g - g0;
+            const int ub0 = gsm[gi], ub1 = gsm[gi + 1];                       // in-block units of degree g
+            // (A) parameters of dim g: bias + previous blocks (preo) + the in-block layer-3 units of degree < g, all
+            //     already folded into par[gi] by the pushes of the earlier steps
             {
-                const float2 bq = *reinterpret_cast<const float2*>(b3s + 2 * (g - g0));
-                float mu0 = bq.x, al0 = bq.y, mu1 = 0.f, al1 = 0.f;
-                const float* wq = W3t + 2 * (g - g0);
-                const float* aq = a3 + lane;
-                int v = 0;
-                for (; v + 2 <= ub0; v += 2) {
-                    const float2 wa = *reinterpret_cast<const float2*>(wq + v * p3);
-                    const float2 wb = *reinterpret_cast<const float2*>(wq + (v + 1) * p3);
-                    const float xa = aq[v * kBlkPad], xb = aq[(v + 1) * kBlkPad];
-                    mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
-                    mu1 = fmaf(wb.x, xb, mu1); al1 = fmaf(wb.y, xb, al1);
-                }
-                if (v < ub0) {
-                    const float2 wa = *reinterpret_cast<const float2*>(wq + v * p3);
-                    const float xa = aq[v * kBlkPad];
-                    mu0 = fmaf(wa.x, xa, mu0); al0 = fmaf(wa.y, xa, al0);
-                }
-                float mu = mu0 + mu1, al = al0 + al1;
-                mu += cpar.x; al += cpar.y;
+                float2 pq = par[0];
+#pragma unroll
+                for (int d = 1; d < kBlkMaxDeg; ++d) if (gi == d) pq = par[d];
+                const float2 bq = *reinterpret_cast<const float2*>(b3s + 2 * gi);
+                const float mu = bq.x + pq.x, al = bq.y + pq.y;
                 float o, t;
-                affine_ar_elem<float>(mode, sx[(g - g0) * kBlkPad + lane], mu, al, o, t);
+                affine_ar_elem<float>(mode, sx[gi * kBlkPad + lane], mu, al, o, t);
                 if (poisoned) { o = __int_as_float(0x7fc00000); t = o; }
                 if (!is_finite(o)) poisoned = 1;        // 0*NaN of the dense reference poisons every later dim
-                sx[(g - g0) * kBlkPad + lane] = o;
+                sx[gi * kBlkPad + lane] = o;
                 ld += t;
             }
             if (g == D - 1) break;
             // (B) hidden units of degree g, layer by layer (all lane-private: no synchronisation)
-            warp_units<NUP>(W0t, bs, sx, g - g0 + 1, a1, ub0, ub1, lane);
+            warp_units<NUP>(W0t, bs, sx, gi + 1, a1, ub0, ub1, lane);
             warp_units<NUP>(W1t, bs + nu, a1, ub1, a2, ub0, ub1, lane);
-            warp_units<NUP>(W2t, bs + 2 * nu, a2, ub1, a3, ub0, ub1, lane);
-            cpar = npar;
+            warp_units_l3<NUP>(W2t, bs + 2 * nu, a2, ub1, pre3_row, act3_row, W3t, par, ub0, ub1, lane);
         }
         __syncwarp();
         warp_drain_tile(sx, xcur, r0, nrow, D, g0, nd, lane);
         if (g1 < D) {
             warp_drain_tile(a1, act1, r0, nrow, H, u0, nu, lane);
             warp_drain_tile(a2, act2, r0, nrow, H, u0, nu, lane);
-            warp_drain_tile(a3, act3, r0, nrow, H, u0, nu, lane);
         }
         if (ok) { ldacc[r0 + lane] = ld; bad[r0 + lane] = poisoned; }
         __syncwarp();                                // the drain's reads of the tile are done before the next fill lands
@@ -439,11 +533,12 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
     if (B == 0) return NF_OK;
     NF_REQ(v); NF_REQ(w); NF_REQ(w_hi); NF_REQ(w_lo); NF_REQ(b); NF_REQ(gstart_dev); NF_REQ(gstart_host);
     NF_REQ(workspace); NF_REQ(out); NF_REQ(ld);
-    if ((D % 4) != 0 || (H % 8) != 0 || (block_degrees % 4) != 0) return NF_ERR_UNSUPPORTED;      // TMA row pitches of the slice GEMMs
-    // every block of hidden units starts at a multiple of 8 (packing.blocked_made_pack pads the blocks with dead units):
-    // TMA bases of the push products' column slices, 256-bit row stores of the pull products
+    if ((D % 4) != 0 || (H % 4) != 0 || (block_degrees % 4) != 0) return NF_ERR_UNSUPPORTED;      // TMA row pitches of the slice GEMMs
+    // every block of hidden units starts at a multiple of 4 (packing.blocked_made_pack pads the blocks with dead units):
+    // 16-byte TMA bases of the push products' column slices, 128-bit row stores of the pull products.  (Multiples of 8
+    // would allow 256-bit stores, but a 65-unit block padded to 72 costs the in-block kernel one of its six warps.)
     for (int g0 = 0; g0 < D; g0 += block_degrees)
-        if (gstart_host[g0] % 8) return NF_ERR_UNSUPPORTED;
+        if (gstart_host[g0] % 4) return NF_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = (float*)workspace;
     const size_t BH = (size_t)B * H, BD = (size_t)B * D;
@@ -486,10 +581,10 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
             const int need = ((nu + 3) & ~3) + 4 * kWarpChunks;
             const int nup = need <= 48 ? 48 : (need <= 80 ? 80 : (need <= 96 ? 96 : 160));   // compile-time pitches of ar_block_warp_kernel
             const size_t wfl = (size_t)(nd + 2 * nu) * nup + (size_t)nu * 2 * kBlkMaxDeg + ((3 * nu + 3) & ~3) + 2 * kBlkMaxDeg + 16;
-            const size_t tfl = (size_t)(nd + 3 * nu) * kBlkPad;
+            const size_t tfl = (size_t)(nd + 2 * nu) * kBlkPad;
             int nw = wfl * sizeof(float) < 200 * 1024 ? (int)((220 * 1024 / sizeof(float) - wfl) / tfl) : 0;
             if (nw > 8) nw = 8;
-            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= kBlkMaxDeg) {
+            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= kBlkMaxDeg && (nd % 4) == 0) {
                 const size_t smem2 = sizeof(float) * (wfl + (size_t)nw * tfl);
                 const int64_t ctas = cdiv(cdiv(B, (int64_t)kBlkRows), (int64_t)nw);
                 const int grid2 = (int)(ctas < kNumSMs ? ctas : kNumSMs);              // persistent: one CTA per SM

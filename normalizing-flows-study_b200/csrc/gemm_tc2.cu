@@ -329,7 +329,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                     }
                 }
                 if (vec) {
-                    if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, true);
+                    if (row < M) tc::epilogue_store32(yrow, n0 + c * 32, N, v0, v1, bias_s + c * 32, relu, vec);
                 } else {
                     tc::epilogue_store32_transposed(Y, ldc, m0 + q * 32, M, n0 + c * 32, N, v0, v1, bias, relu, tbuf, lane);
                 }
@@ -391,7 +391,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                         float a[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a[i] = acc[j * 8 + i];
-                        tc::epilogue_store8(yrow, n0 + j * 8, N, a, relu, true);
+                        tc::epilogue_store8(yrow, n0 + j * 8, N, a, relu, vec);
                     }
                 }
             } else {
@@ -450,8 +450,8 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
     const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
     if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
     const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-    // 256-bit row stores in the epilogue: 32-byte aligned rows of Y
-    const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : 0;
+    // row stores in the epilogue: 256-bit for 32-byte aligned rows of Y, 2 x 128-bit for 16-byte aligned ones
+    const int vec = (aligned32(y) && (ldy % 8) == 0) ? 1 : ((aligned16(y) && (ldy % 4) == 0) ? 2 : 0);
     const int ss = (g_tc_passes == 1 && g_gemm_tc2_ss) ? 1 : 0;
     if (accumulate && (K > 4 * k2BK || !vec || bias != nullptr || relu)) return NF_ERR_UNSUPPORTED;
     if (K <= 4 * k2BK) {

@@ -209,13 +209,17 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&o)[8]) {
 // 8 consecutive outputs of one row starting at column col (col % 8 == 0), bias already added: ReLU + store.  No loads
 // in here: the callers fetch the bias (from the shared-memory tile staged by stage_bias_tile) in one batch BEFORE the
 // stores -- a bias load in front of every store waited ~370 clk each behind the queued 1 KB stores (measured).
-// vec: &yrow[col] is 32-byte aligned (checked on the host); ragged column tails take the scalar path.
-__device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int col, int N, const float (&a)[8], int relu, bool vec) {
+// vec (checked on the host): 1 = &yrow[col] is 32-byte aligned (one 256-bit store), 2 = only 16-byte aligned (two 128-bit
+// stores: column slices that start at a multiple of 4 units); ragged column tails take the scalar path.
+__device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int col, int N, const float (&a)[8], int relu, int vec) {
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = (relu && a[i] < 0.f) ? 0.f : a[i];          // NaN stays NaN (torch.relu)
-    if (vec && col + 8 <= N) {
+    if (vec == 1 && col + 8 <= N) {
         st_global_v8(yrow + col, o);
+    } else if (vec == 2 && col + 8 <= N) {
+        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yrow + col), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]));
+        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yrow + col + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]));
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -225,7 +229,7 @@ __device__ __forceinline__ void epilogue_store8(float* __restrict__ yrow, int co
 // 32 columns [c0, c0 + 32) of one row held as the raw tcgen05.ld words v0 (first 16) / v1 (last 16); bias32 = the 32 bias
 // values of these columns in shared memory (16-byte aligned), read in one batch ahead of the stores
 __device__ __forceinline__ void epilogue_store32(float* __restrict__ yrow, int c0, int N, const uint32_t (&v0)[16],
-                                                 const uint32_t (&v1)[16], const float* __restrict__ bias32, int relu, bool vec) {
+                                                 const uint32_t (&v1)[16], const float* __restrict__ bias32, int relu, int vec) {
     float o[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

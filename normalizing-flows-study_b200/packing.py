@@ -288,9 +288,9 @@ def fold_made(made) -> Optional[FoldedMade]:
 @dataclass
 class BlockedMadePack:
     """Operands of nf_ar_blocked_forward (csrc/ar_blocked.cu).  The degree-sorted hidden units are laid out in blocks of
-    `block_degrees` consecutive degrees, every block starting at a multiple of 8 units: the gaps are dead units (zero
+    `block_degrees` consecutive degrees, every block starting at a multiple of 4 units: the gaps are dead units (zero
     weights and biases, so they hold relu(0) = 0 and feed nothing).  H is the padded width; gstart[g] the padded index of
-    the first unit of degree >= g (a block's dead units count with its last degree).  w / b: fp32 operands of the
+    the first unit of degree >= g (dead units count with the degree in front of them).  w / b: fp32 operands of the
     in-block kernel (output layer as [mu rows | alpha rows], like made.py:136-140); w_hi / w_lo: 3xTF32 operands of the
     slice products, the output layer's rows INTERLEAVED (row 2g = mu_g, row 2g+1 = alpha_g) to match the [B, D, 2]
     layout of the pushed output pre-activations."""
@@ -304,21 +304,26 @@ class BlockedMadePack:
     gstart_host: np.ndarray
 
 
-def blocked_layout(gstart: np.ndarray, block_degrees: int, align: int = 8):
-    """(pos, pgstart, Hp): padded index of every sorted unit, padded degree boundaries, padded width."""
+def blocked_layout(gstart: np.ndarray, block_degrees: int, align: int = 4):
+    """(pos, pgstart, Hp): padded index of every sorted unit, padded degree boundaries, padded width.  Blocks always
+    start at a multiple of `align`; when it costs at most 10 % more units every DEGREE does (the in-block kernel then
+    evaluates a degree's units in exact 4-unit chunks instead of the chunks straddling its neighbours)."""
     D = len(gstart) - 1
     H = int(gstart[D])
+    counts = np.diff(gstart).astype(np.int64)
+    per_degree = int(((counts + align - 1) // align * align).sum()) <= 1.10 * H
     pos = np.zeros(H, dtype=np.int64)
     pgstart = np.zeros(D + 1, dtype=np.int32)
     at = 0
-    for g0 in range(0, D, block_degrees):
-        g1 = min(g0 + block_degrees, D)
-        u0, u1 = int(gstart[g0]), int(gstart[g1])
-        pos[u0:u1] = at + np.arange(u1 - u0)
-        for g in range(g0, g1):
-            pgstart[g] = at + int(gstart[g]) - u0
-        at = (at + (u1 - u0) + align - 1) // align * align
+    for g in range(D):
+        if g % block_degrees == 0 or per_degree:
+            at = (at + align - 1) // align * align
+        pgstart[g] = at
+        pos[gstart[g]:gstart[g + 1]] = at + np.arange(counts[g])
+        at += int(counts[g])
+    at = (at + align - 1) // align * align
     pgstart[D] = at
+    # a degree's dead units are the gap up to the next degree's start
     return pos, pgstart, max(at, align)
 
 

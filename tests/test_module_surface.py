@@ -135,7 +135,7 @@ def test_gemm_precision_switch_is_host_only_and_validated():
 @pytest.mark.parametrize("D,H,gb", [(64, 512, 8), (16, 128, 8), (12, 100, 4), (784, 1024, 8), (8, 16, 8)])
 def test_blocked_sampler_layout_pads_blocks_to_aligned_starts(D, H, gb):
     """packing.blocked_layout (host logic of the blocked sequential direction, csrc/ar_blocked.cu): every block of `gb`
-    degrees starts at a multiple of 8 units, the sorted order of the live units is kept, the dead units sit at the end of
+    degrees starts at a multiple of 4 units, the sorted order of the live units is kept, the dead units sit at the end of
     their block (counted with its last degree), and the padded boundaries delimit exactly the live units of each degree
     except there."""
     import numpy as np
@@ -143,15 +143,12 @@ def test_blocked_sampler_layout_pads_blocks_to_aligned_starts(D, H, gb):
     deg = np.sort(np.arange(H) % (D - 1) + 1)                      # made.py:31-33 hidden degrees, sorted
     gstart = np.searchsorted(deg, np.arange(D + 1), side="left").astype(np.int32)
     pos, pg, Hp = packing.blocked_layout(gstart, gb)
-    assert Hp % 8 == 0 and pg[D] == Hp and len(pos) == H
+    assert Hp % 4 == 0 and pg[D] == Hp and len(pos) == H
     assert np.all(np.diff(pos) > 0) and pos[-1] < Hp
-    assert np.all(np.diff(pg) >= 0)
-    for g0 in range(0, D, gb):
-        g1 = min(g0 + gb, D)
-        assert pg[g0] % 8 == 0
-        u0, u1 = gstart[g0], gstart[g1]
-        if u1 > u0:
-            assert pos[u0] == pg[g0] and np.array_equal(pos[u0:u1] - pos[u0], np.arange(u1 - u0))
-        assert 0 <= pg[g1] - pg[g0] - (u1 - u0) < 8              # dead units of the block
-        for g in range(g0, g1 - 1):
-            assert pg[g + 1] - pg[g] == gstart[g + 1] - gstart[g]
+    assert Hp <= 1.10 * H + 4 * ((D + gb - 1) // gb)              # per-degree padding only when it is cheap
+    for g in range(D):
+        n = gstart[g + 1] - gstart[g]
+        assert np.array_equal(pos[gstart[g]:gstart[g + 1]], pg[g] + np.arange(n))
+        assert 0 <= pg[g + 1] - pg[g] - n < 4                     # dead units behind the degree's live ones
+        if g % gb == 0:
+            assert pg[g] % 4 == 0
