@@ -67,7 +67,9 @@ NF_API int64_t nf_launch_count(void);
  *         reference reaches with autocast, optimization/mixed_precision.py:89-105; w_lo is not read);
  * key 9 = nf_linear_tc* (K > 128): TMEM split of gemm_tc2.cu, 3 chain accumulators + 2 A stages (default) or 2 + 4;
  * key 10 = nf_linear_tc* in the one-pass mode: 1 = A operand straight from shared memory (x truncated to TF32 by the tensor
- *         core instead of rounded by the converter warps); default 0 */
+ *         core instead of rounded by the converter warps); default 0;
+ * key 11 = nf_spline_transform_* (float32, compact layout, 8 / 10 bins): 1 = TMA-staged kernels (spline_stream.cu,
+ *         default), 0 = the first-version cp.async kernels */
 NF_API int nf_set_option(int key, int value);
 
 /* ---- a7: rational_quadratic_spline(inputs, widths, heights, derivatives, inverse, ...) ----------

@@ -69,4 +69,16 @@ __host__ inline RqsCfg<T> make_rqs_cfg(bool bounded, int K, double bound, double
     return c;
 }
 
+// spline_stream.cu: TMA-staged float32 kernels of the compact spline coupling transform (K = 8 / 10).  Returns
+// NF_ERR_UNSUPPORTED when the shape is outside its envelope (the caller then takes the first-version kernels).
+struct SplineStreamArgs {
+    const float* x; const float* params; const float* mask; const int32_t* tidx;
+    float* y; float* ld;                                              // forward outputs
+    const float* gy; const float* gld; float* gx; float* gparams;     // backward
+    int64_t B; int D, Dt;
+    RqsCfg<float> c;
+    const float* r_in; const float* r_lo; const float* r_out;
+};
+int spline_stream_launch(const SplineStreamArgs& a, int K, bool bwd, int inverse, cudaStream_t st);
+
 }  // namespace nf

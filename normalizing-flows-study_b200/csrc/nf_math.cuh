@@ -46,7 +46,7 @@ NF_HD double t_abs(double x)   { return fabs(x); }
 NF_HD double sm_exp(double x) { return exp(x); }
 NF_HD float sm_exp(float x) {
 #if defined(__CUDA_ARCH__)
-    x = (x < -87.0f) ? -87.0f : x;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(x) : "f"(x), "f"(-87.0f));
     const float magic = 12582912.0f;                                  // 1.5 * 2^23: integer part lands in the low mantissa bits
     const float tm = fmaf(x, 1.4426950408889634f, magic);
     const float n = tm - magic;
@@ -85,6 +85,21 @@ NF_HD float t_logf(float x) {
 template <typename T> NF_HD bool is_finite(T x) { return (x - x) == T(0); }       // false for NaN and +-Inf
 template <typename T> NF_HD T clamp_min(T x, T lo) { return x < lo ? lo : x; }    // NaN stays NaN (torch.clamp)
 template <typename T> NF_HD T clamp_mm(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+#if defined(__CUDA_ARCH__)
+// device float: the NaN-propagating min / max of the FMNMX unit, one instruction per bound instead of a compare + select
+// pair (same value for every input; the only visible difference is clamp(-0.0, 0, .) = +0.0 instead of -0.0)
+__device__ __forceinline__ float clamp_min(float x, float lo) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float clamp_mm(float x, float lo, float hi) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+    return r;
+}
+#endif
 template <typename T> NF_HD T relu_nan(T x) { return x < T(0) ? T(0) : x; }       // torch.relu(NaN) = NaN
 template <typename T> NF_HD bool pass_min(T x, T lo) { return x >= lo; }          // clamp backward mask
 template <typename T> NF_HD bool pass_mm(T x, T lo, T hi) { return x >= lo && x <= hi; }
@@ -232,7 +247,7 @@ template <typename T, int N> NF_HD void inclusive_scan(T* a) {      // Hillis-St
 // KMAX <= 16: max / sum / cumulative sum as trees (the per-row dependent chain is what bounds the fused stack
 // kernels; summation order differs from torch.cumsum by a few ulp).  KMAX > 16 (generic path): sequential loops.
 template <typename T, int KMAX, bool BOUNDED>
-NF_HD void rqs_knots(const T* u, int K, T floor_, T scale, const RqsCfg<T>& c, T* wn, T* kn) {
+NF_HD void rqs_knots(const T* u, int K, T floor_, T scale, const RqsCfg<T>& c, T* wn, T* kn, T* smx = nullptr) {
     if constexpr (KMAX <= 16) {
         T m[KMAX];
 NF_UNROLL
@@ -244,7 +259,9 @@ NF_UNROLL
         T run[KMAX];
 NF_UNROLL
         for (int j = 0; j < KMAX; ++j) {
-            T w = floor_ + scale * (wn[j] * inv);
+            const T p = wn[j] * inv;                       // softmax value (kept for the reverse sweep when asked for)
+            if (smx) smx[j] = p;
+            T w = floor_ + scale * p;
             w = clamp_min(w, c.eps);
             wn[j] = w;
             run[j] = (j < K) ? w : T(0);
@@ -265,7 +282,9 @@ NF_UNROLL
         kn[0] = BOUNDED ? c.lo : T(0);
 NF_UNROLL
         for (int j = 0; j < KMAX; ++j) if (j < K) {
-            T w = floor_ + scale * (wn[j] * inv);
+            const T p = wn[j] * inv;
+            if (smx) smx[j] = p;
+            T w = floor_ + scale * p;
             w = clamp_min(w, c.eps);
             wn[j] = w;
             run += w;
@@ -290,7 +309,8 @@ template <int N> __device__ __forceinline__ float2 tree_sum2(const float2* a) {
 }
 template <int KMAX, bool BOUNDED>
 __device__ __forceinline__ void rqs_knots_pair(const float* uw, const float* uh, int K, const RqsCfg<float>& c,
-                                               float* wn, float* hn, float* cw, float* ch) {
+                                               float* wn, float* hn, float* cw, float* ch, float* smw = nullptr,
+                                               float* smh = nullptr) {
     float mw[KMAX], mh[KMAX];
 NF_UNROLL
     for (int j = 0; j < KMAX; ++j) { mw[j] = (j < K) ? uw[j] : uw[0]; mh[j] = (j < K) ? uh[j] : uh[0]; }
@@ -307,7 +327,9 @@ NF_UNROLL
     float2 run[KMAX];
 NF_UNROLL
     for (int j = 0; j < KMAX; ++j) {
-        float2 w = __ffma2_rn(scale2, __fmul2_rn(e[j], inv), floor2);
+        const float2 p = __fmul2_rn(e[j], inv);
+        if (smw) { smw[j] = p.x; smh[j] = p.y; }
+        float2 w = __ffma2_rn(scale2, p, floor2);
         w.x = clamp_min(w.x, c.eps); w.y = clamp_min(w.y, c.eps);
         wn[j] = w.x; hn[j] = w.y;
         run[j] = (j < K) ? w : make_float2(0.f, 0.f);
@@ -464,73 +486,96 @@ NF_HD void rqs_eval(T v, const T* uw, const T* uh, const T* ud, int K, bool inve
 }
 
 // ------------------------------------------------------------------------------------------
-// Reverse mode.  Given upstream (g_out, g_lad) of one element, produce g_v and ACCUMULATE the
-// raw-parameter gradients into guw[K], guh[K], gud[K-1] (caller zero-initialises).
-// Forward intermediates are recomputed (the element is 3K-1 parameters; nothing is stashed).
+// Reverse mode.  Given upstream (g_out, g_lad) of one element, produce g_v and the raw-parameter gradients
+// guw[K], guh[K], gud[K-1].  Forward intermediates are recomputed ONCE (the element is 3K-1 parameters; nothing
+// is stashed): the knots keep their softmax values for the softmax backward, the bin evaluation yields the
+// element's own output (needed for the scrubs) and its reverse sweep from the same intermediates, every
+// division is one reciprocal shared by its uses.  (The first version evaluated the element three times --
+// scrub check, forward recomputation, softmax backward -- with IEEE divisions: 2 360 instructions per element.)
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct RqsBinGrad { T gv, gxk, gyk, gwk, ghk, gdk, gdk1; };
 
+// How the element's own forward result (out, lad of the selected bin, BEFORE the scrubs of :306-307) adjusts the
+// upstream gradients: a replaced output passes its gradient straight to the input (gv_direct), a replaced log-det
+// term receives none.  Kernels with a layer-level scrub / rescale supply their own functor.
 template <typename T, bool BOUNDED>
-NF_HD void rqs_bin_eval_bwd(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, T eps,
-                            T g_out, T g_lad, RqsBinGrad<T>& g) {
+struct RqsScrubAdj {
+    NF_HD void operator()(T out, T lad, T& g_out, T& g_lad, T& gv_direct) const {
+        if (BOUNDED) {
+            if (!is_finite(lad)) g_lad = T(0);
+            if (!is_finite(out)) { gv_direct = g_out; g_out = T(0); }
+        }
+    }
+};
+
+// value, log|derivative| and reverse sweep inside the selected bin.  Same formulas as rqs_bin_eval; a / b is
+// written a * (1 / b) with the reciprocal shared (float device: rcp.approx, 1 ulp; double / host: exact).
+template <typename T, bool BOUNDED, typename Adj>
+NF_HD void rqs_bin_fwdbwd(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inverse, T eps, T g_out, T g_lad,
+                          const Adj& adj, RqsBinGrad<T>& g, T& gv_direct) {
     const T wkc = clamp_min(wk, eps);
     const bool p_wkc = pass_min(wk, eps);
-    const T s = hk / wkc;
-    T g_s = T(0), g_xi = T(0), g_om = T(0), g_A = T(0), g_wkc = T(0);
-    g.gv = g.gxk = g.gyk = g.gwk = g.ghk = g.gdk = g.gdk1 = T(0);
+    const T rw = t_div(T(1), wkc);
+    const T s = hk * rw;
+    const T A = dk1 + dk - T(2) * s;
+    T g_s, g_xi, g_om, g_A, g_wkc;
+    gv_direct = T(0);
     if (!inverse) {
-        const T xi0 = (v - xk) / wkc;
+        const T xi0 = (v - xk) * rw;
         const T xi = clamp_mm(xi0, T(0), T(1));
         const T om = T(1) - xi;
-        const T A = dk1 + dk - T(2) * s;
-        const T den0 = s + A * xi * om;
+        const T xo = xi * om, xx = xi * xi, oo = om * om;
+        const T den0 = s + A * xo;
         const T denc = clamp_min(den0, eps);
-        const T N1 = s * (xi * xi) + dk * xi * om;
-        const T Q = dk1 * (xi * xi) + T(2) * s * xi * om + dk * (om * om);
+        const T rden = t_div(T(1), denc);
+        const T N1 = s * xx + dk * xo;
+        const T Q = dk1 * xx + T(2) * s * xo + dk * oo;
         const T num = (s * s) * Q;
         const T den2 = BOUNDED ? denc * denc : den0 * den0;
         const T den2c = clamp_min(den2, eps);
-        const T der = num / den2c;
+        const T rden2 = t_div(T(1), den2c);
+        const T der = num * rden2;
         const T derc = clamp_min(der, eps);
-        // lad = log(derc)
-        const T g_der = pass_min(der, eps) ? g_lad / derc : T(0);
-        const T g_num = g_der / den2c;
-        const T g_den2 = pass_min(den2, eps) ? -g_der * num / (den2c * den2c) : T(0);
+        const T hr = hk * rden;                         // d out / d N1
+        const T nr = N1 * rden;                         // d out / d hk
+        adj(yk + hk * nr, t_logf(derc), g_out, g_lad, gv_direct);
+        // lad = log(derc), der = num / den2c
+        const T g_der = pass_min(der, eps) ? g_lad * t_div(T(1), derc) : T(0);
+        const T g_num = g_der * rden2;
+        const T g_den2 = pass_min(den2, eps) ? -(g_der * der) * rden2 : T(0);
         T g_denc = T(0), g_den0 = T(0);
-        if (BOUNDED) g_denc += T(2) * denc * g_den2; else g_den0 += T(2) * den0 * g_den2;
+        if (BOUNDED) g_denc = T(2) * denc * g_den2; else g_den0 = T(2) * den0 * g_den2;
         // num = s^2 Q
-        g_s += T(2) * s * Q * g_num;
         const T g_Q = (s * s) * g_num;
-        g.gdk1 += (xi * xi) * g_Q;
-        g.gdk += (om * om) * g_Q;
-        g_s += T(2) * xi * om * g_Q;
-        g_xi += (T(2) * dk1 * xi + T(2) * s * om) * g_Q;
-        g_om += (T(2) * s * xi + T(2) * dk * om) * g_Q;
-        // out = yk + hk*N1/denc
-        g.gyk += g_out;
-        g.ghk += N1 / denc * g_out;
-        const T g_N1 = hk / denc * g_out;
-        g_denc += -hk * N1 / (denc * denc) * g_out;
-        g_s += (xi * xi) * g_N1;
+        g_s = T(2) * s * Q * g_num + T(2) * xo * g_Q;
+        g.gdk1 = xx * g_Q;
+        g.gdk = oo * g_Q;
+        g_xi = T(2) * (dk1 * xi + s * om) * g_Q;
+        g_om = T(2) * (s * xi + dk * om) * g_Q;
+        // out = yk + hk * N1 / denc
+        g.gyk = g_out;
+        g.ghk = nr * g_out;
+        const T g_N1 = hr * g_out;
+        g_denc -= hr * nr * g_out;
+        g_s += xx * g_N1;
         g_xi += (T(2) * s * xi + dk * om) * g_N1;
-        g.gdk += xi * om * g_N1;
+        g.gdk += xo * g_N1;
         g_om += dk * xi * g_N1;
-        // denc = clamp(den0)
+        // denc = clamp(den0), den0 = s + A xi om
         if (pass_min(den0, eps)) g_den0 += g_denc;
         g_s += g_den0;
-        g_A += xi * om * g_den0;
+        g_A = xo * g_den0;
         g_xi += A * om * g_den0;
         g_om += A * xi * g_den0;
-        g.gdk1 += g_A; g.gdk += g_A; g_s += -T(2) * g_A;
-        g_xi += -g_om;
+        g_xi -= g_om;
         const T g_xi0 = pass_mm(xi0, T(0), T(1)) ? g_xi : T(0);
-        g.gv += g_xi0 / wkc;
-        g.gxk += -g_xi0 / wkc;
-        g_wkc += -xi0 / wkc * g_xi0;
+        g.gv = g_xi0 * rw;
+        g.gxk = -g.gv;
+        g_wkc = -xi0 * g.gv;
+        g.gwk = T(0);
     } else {
         const T t0 = v - yk;
-        const T A = dk + dk1 - T(2) * s;
         const T t = t0 * A;
         const T a = t + hk * (s - dk);
         const T b = hk * dk - t;
@@ -541,137 +586,137 @@ NF_HD void rqs_bin_eval_bwd(T v, T xk, T yk, T wk, T hk, T dk, T dk1, bool inver
         const T q0 = -b - sq;
         const bool q_small = BOUNDED && (t_abs(q0) < eps);
         const T q = q_small ? eps : q0;
-        const T xi0 = (T(2) * c) / q;
+        const T rq = t_div(T(1), q);
+        const T xi0 = (T(2) * c) * rq;
         const T xi = clamp_mm(xi0, T(0), T(1));
         const T om = T(1) - xi;
-        const T Q = dk1 * (xi * xi) + T(2) * s * (xi * om) + dk * (om * om);
+        const T xo = xi * om, xx = xi * xi, oo = om * om;
+        const T Q = dk1 * xx + T(2) * s * xo + dk * oo;
         const T num = (s * s) * Q;
-        const T den0 = s + A * xi * om;
-        T g_num = T(0), g_den0 = T(0);
+        const T den0 = s + A * xo;
+        T g_num, g_den0;
         if (BOUNDED) {
             const T numc = clamp_min(num, eps), denc = clamp_min(den0, eps);
-            if (pass_min(num, eps)) g_num = -g_lad / numc;
-            if (pass_min(den0, eps)) g_den0 = T(2) * g_lad / denc;
+            adj(xi * wk + xk, -t_logf(numc) + T(2) * t_logf(denc), g_out, g_lad, gv_direct);
+            g_num = pass_min(num, eps) ? -g_lad * t_div(T(1), numc) : T(0);
+            g_den0 = pass_min(den0, eps) ? T(2) * g_lad * t_div(T(1), denc) : T(0);
         } else {
             const T den2 = den0 * den0;
             const T den2c = clamp_min(den2, eps);
-            const T der = num / den2c;
+            const T rden2 = t_div(T(1), den2c);
+            const T der = num * rden2;
             const T derc = clamp_min(der, eps);
-            const T g_der = pass_min(der, eps) ? -g_lad / derc : T(0);
-            g_num = g_der / den2c;
-            if (pass_min(den2, eps)) g_den0 = T(2) * den0 * (-g_der * num / (den2c * den2c));
+            adj(xi * wk + xk, -t_logf(derc), g_out, g_lad, gv_direct);
+            const T g_der = pass_min(der, eps) ? -g_lad * t_div(T(1), derc) : T(0);
+            g_num = g_der * rden2;
+            g_den0 = pass_min(den2, eps) ? T(2) * den0 * (-(g_der * der) * rden2) : T(0);
         }
-        g_s += T(2) * s * Q * g_num;
         const T g_Q = (s * s) * g_num;
-        g.gdk1 += (xi * xi) * g_Q;
-        g.gdk += (om * om) * g_Q;
-        g_s += T(2) * xi * om * g_Q;
-        g_xi += (T(2) * dk1 * xi + T(2) * s * om) * g_Q;
-        g_om += (T(2) * s * xi + T(2) * dk * om) * g_Q;
-        g_s += g_den0;
-        g_A += xi * om * g_den0;
-        g_xi += A * om * g_den0;
-        g_om += A * xi * g_den0;
-        // out = xi*wk + xk
+        g_s = T(2) * s * Q * g_num + T(2) * xo * g_Q + g_den0;
+        g.gdk1 = xx * g_Q;
+        g.gdk = oo * g_Q;
+        g_xi = T(2) * (dk1 * xi + s * om) * g_Q + A * om * g_den0;
+        g_om = T(2) * (s * xi + dk * om) * g_Q + A * xi * g_den0;
+        g_A = xo * g_den0;
+        // out = xi * wk + xk
         g_xi += wk * g_out;
-        g.gwk += xi * g_out;
-        g.gxk += g_out;
-        g_xi += -g_om;
+        g.gwk = xi * g_out;
+        g.gxk = g_out;
+        g_xi -= g_om;
         const T g_xi0 = pass_mm(xi0, T(0), T(1)) ? g_xi : T(0);
-        T g_c = T(2) / q * g_xi0;
-        const T g_q = -xi0 / q * g_xi0;
-        const T g_q0 = q_small ? T(0) : g_q;
-        T g_b = -g_q0;
-        const T g_sq = -g_q0;
-        const T g_disc = (sq > T(0)) ? g_sq / (T(2) * sq) : T(0);
+        // xi0 = 2 c / q, q = -b - sqrt(disc)
+        T g_c = T(2) * rq * g_xi0;
+        const T g_q0 = q_small ? T(0) : -xi0 * rq * g_xi0;
+        const T g_disc = (sq > T(0)) ? -g_q0 * t_div(T(0.5), sq) : T(0);
         const T g_disc0 = pass_min(disc0, T(0)) ? g_disc : T(0);
-        g_b += T(2) * b * g_disc0;
+        const T g_b = -g_q0 + T(2) * b * g_disc0;
         const T g_a = -T(4) * c * g_disc0;
-        g_c += -T(4) * a * g_disc0;
-        g_s += -t0 * g_c;
-        T g_t0 = -s * g_c;
-        g.ghk += dk * g_b;
-        g.gdk += hk * g_b;
-        T g_t = -g_b;
-        g_t += g_a;
-        g.ghk += (s - dk) * g_a;
+        g_c -= T(4) * a * g_disc0;
+        g_s -= t0 * g_c;
+        // b = hk dk - t, a = t + hk (s - dk), t = t0 A
+        g.ghk = dk * g_b + (s - dk) * g_a;
+        g.gdk += hk * (g_b - g_a);
         g_s += hk * g_a;
-        g.gdk += -hk * g_a;
-        g_t0 += A * g_t;
+        const T g_t = g_a - g_b;
+        const T g_t0 = A * g_t - s * g_c;
         g_A += t0 * g_t;
-        g.gdk += g_A; g.gdk1 += g_A; g_s += -T(2) * g_A;
-        g.gv += g_t0;
-        g.gyk += -g_t0;
+        g.gv = g_t0;
+        g.gyk = -g_t0;
+        g_wkc = T(0);
     }
-    // s = hk / wkc
-    g.ghk += g_s / wkc;
-    g_wkc += -s / wkc * g_s;
+    // A = dk1 + dk - 2 s;  s = hk / wkc
+    g.gdk1 += g_A; g.gdk += g_A; g_s -= T(2) * g_A;
+    g.ghk += g_s * rw;
+    g_wkc -= s * rw * g_s;
     if (p_wkc) g.gwk += g_wkc;
 }
 
-// push d(loss)/d(normalised bin sizes) through floor+clamp and the softmax:  gu += J^T gw
+// push d(loss)/d(normalised bin sizes) through floor+clamp and the softmax:  gu = J^T gw, with the softmax values sm
+// kept from the knot computation
 template <typename T, int KMAX>
-NF_HD void rqs_softmax_bwd(const T* u, int K, T floor_, T scale, T eps, const T* gw, T* gu) {
-    T mx = u[0];
-NF_UNROLL
-    for (int j = 1; j < KMAX; ++j) if (j < K) mx = (u[j] > mx) ? u[j] : mx;
-    T e[KMAX];
-    T sum = T(0);
-NF_UNROLL
-    for (int j = 0; j < KMAX; ++j) if (j < K) { e[j] = sm_exp(u[j] - mx); sum += e[j]; }
-    const T inv = t_rcp(sum);
+NF_HD void rqs_softmax_bwd(const T* sm, int K, T floor_, T scale, T eps, const T* gw, T* gu) {
     T dot = T(0);
     T gs[KMAX];
 NF_UNROLL
     for (int j = 0; j < KMAX; ++j) if (j < K) {
-        const T sm = e[j] * inv;
-        const T w = floor_ + scale * sm;
+        const T w = floor_ + scale * sm[j];
         gs[j] = pass_min(w, eps) ? scale * gw[j] : T(0);
-        e[j] = sm;
-        dot += gs[j] * sm;
+        dot += gs[j] * sm[j];
     }
 NF_UNROLL
-    for (int j = 0; j < KMAX; ++j) if (j < K) gu[j] += e[j] * (gs[j] - dot);
+    for (int j = 0; j < KMAX; ++j) gu[j] = (j < K) ? sm[j] * (gs[j] - dot) : T(0);
 }
 
-template <typename T, int KMAX, bool BOUNDED>
-NF_HD void rqs_eval_bwd(T v, const T* uw, const T* uh, const T* ud, int K, bool inverse, const RqsCfg<T>& c,
-                        T g_out, T g_lad, T& g_v, T* guw, T* guh, T* gud) {
+// ASSIGNS g_v, guw[0..KMAX), guh[0..KMAX), gud[0..KMAX-1) (zeros beyond the live bins).
+template <typename T, int KMAX, bool BOUNDED, typename Adj>
+NF_HD void rqs_eval_grad(T v, const T* uw, const T* uh, const T* ud, int K, bool inverse, const RqsCfg<T>& c,
+                         T g_out, T g_lad, const Adj& adj, T& g_v, T* guw, T* guh, T* gud) {
     if (BOUNDED) {
         const bool inside = (v >= c.lo) && (v <= c.hi);
-        if (!inside) { g_v = g_out; return; }
+        if (!inside) {                                      // identity tails: out = v, lad = 0
+            T gvd = T(0);
+            adj(v, T(0), g_out, g_lad, gvd);
+            g_v = g_out + gvd;
+NF_UNROLL
+            for (int j = 0; j < KMAX; ++j) { guw[j] = T(0); guh[j] = T(0); }
+NF_UNROLL
+            for (int j = 0; j < KMAX - 1; ++j) gud[j] = T(0);
+            return;
+        }
     }
-    T wn[KMAX], hn[KMAX], cw[KMAX + 1], ch[KMAX + 1];
-    rqs_knots<T, KMAX, BOUNDED>(uw, K, c.min_w, c.scale_w, c, wn, cw);
-    rqs_knots<T, KMAX, BOUNDED>(uh, K, c.min_h, c.scale_h, c, hn, ch);
+    T wn[KMAX], hn[KMAX], cw[KMAX + 1], ch[KMAX + 1], smw[KMAX], smh[KMAX];
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(T) == 4 && KMAX <= 16) {
+        rqs_knots_pair<KMAX, BOUNDED>(reinterpret_cast<const float*>(uw), reinterpret_cast<const float*>(uh), K,
+                                      reinterpret_cast<const RqsCfg<float>&>(c), reinterpret_cast<float*>(wn),
+                                      reinterpret_cast<float*>(hn), reinterpret_cast<float*>(cw), reinterpret_cast<float*>(ch),
+                                      reinterpret_cast<float*>(smw), reinterpret_cast<float*>(smh));
+    } else
+#endif
+    {
+        rqs_knots<T, KMAX, BOUNDED>(uw, K, c.min_w, c.scale_w, c, wn, cw, smw);
+        rqs_knots<T, KMAX, BOUNDED>(uh, K, c.min_h, c.scale_h, c, hn, ch, smh);
+    }
     RqsBin<T> b;
     rqs_select<T, KMAX>(v, inverse ? ch : cw, cw, ch, wn, hn, ud, K, b);
-    const T dk_pre  = c.min_d + softplus(b.udk);
-    const T dk1_pre = c.min_d + softplus(b.udk1);
+    // derivatives at the two knots: softplus and its slope from one exponential each
+    const T zk = sm_exp(b.udk > T(20) ? T(20) : b.udk), zk1 = sm_exp(b.udk1 > T(20) ? T(20) : b.udk1);
+    const T dk_pre  = c.min_d + (b.udk > T(20) ? b.udk : t_log1p(zk));
+    const T dk1_pre = c.min_d + (b.udk1 > T(20) ? b.udk1 : t_log1p(zk1));
     const T dk  = b.lo_edge ? T(1) : clamp_min(dk_pre, c.eps);
     const T dk1 = b.hi_edge ? T(1) : clamp_min(dk1_pre, c.eps);
     T wk, hk;
     if (BOUNDED) { wk = clamp_min(b.xk1 - b.xk, c.eps); hk = clamp_min(b.yk1 - b.yk, c.eps); }
     else         { wk = b.wn; hk = b.hn; }
-    T gv_direct = T(0);
-    if (BOUNDED) {                       // scrubs (:306-307): a replaced output passes its gradient to the input
-        T out, lad;
-        rqs_bin_eval<T, BOUNDED>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, out, lad);
-        if (!is_finite(lad)) g_lad = T(0);
-        if (!is_finite(out)) { gv_direct = g_out; g_out = T(0); }
-    }
     RqsBinGrad<T> g;
-    rqs_bin_eval_bwd<T, BOUNDED>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, g_out, g_lad, g);
+    T gv_direct;
+    rqs_bin_fwdbwd<T, BOUNDED, Adj>(v, b.xk, b.yk, wk, hk, dk, dk1, inverse, c.eps, g_out, g_lad, adj, g, gv_direct);
     g_v = g.gv + gv_direct;
-    // derivatives
-    if (!b.lo_edge && pass_min(dk_pre, c.eps)) {
+    // derivative parameters: ud[j] belongs to knot j + 1
+    const T sk  = (!b.lo_edge && pass_min(dk_pre, c.eps)) ? g.gdk * (b.udk > T(20) ? T(1) : zk * t_div(T(1), zk + T(1))) : T(0);
+    const T sk1 = (!b.hi_edge && pass_min(dk1_pre, c.eps)) ? g.gdk1 * (b.udk1 > T(20) ? T(1) : zk1 * t_div(T(1), zk1 + T(1))) : T(0);
 NF_UNROLL
-        for (int j = 0; j < KMAX - 1; ++j) if (j == b.k - 1) gud[j] += g.gdk * softplus_grad(b.udk);
-    }
-    if (!b.hi_edge && pass_min(dk1_pre, c.eps)) {
-NF_UNROLL
-        for (int j = 0; j < KMAX - 1; ++j) if (j == b.k) gud[j] += g.gdk1 * softplus_grad(b.udk1);
-    }
+    for (int j = 0; j < KMAX - 1; ++j) gud[j] = (j == b.k - 1 ? sk : T(0)) + (j == b.k ? sk1 : T(0));
     // bin sizes: map (gxk, gwk) / (gyk, ghk) onto d/d(normalised widths / heights)
     T gw[KMAX], gh[KMAX];
     if (BOUNDED) {
@@ -683,20 +728,33 @@ NF_UNROLL
         const T bw = (b.k + 1 <= K - 1) ? c.span * gxk1 : T(0);   // knot k+1 interior?
         const T ah = (b.k >= 1) ? c.span * gyk : T(0);
         const T bh = (b.k + 1 <= K - 1) ? c.span * gyk1 : T(0);
+        const T abw = aw + bw, abh = ah + bh;
 NF_UNROLL
-        for (int j = 0; j < KMAX; ++j) if (j < K) {
-            gw[j] = (j <= b.k - 1 ? aw : T(0)) + (j <= b.k ? bw : T(0));
-            gh[j] = (j <= b.k - 1 ? ah : T(0)) + (j <= b.k ? bh : T(0));
+        for (int j = 0; j < KMAX; ++j) {
+            gw[j] = (j < b.k) ? abw : (j == b.k ? bw : T(0));
+            gh[j] = (j < b.k) ? abh : (j == b.k ? bh : T(0));
         }
     } else {
 NF_UNROLL
-        for (int j = 0; j < KMAX; ++j) if (j < K) {
-            gw[j] = (j < b.k ? g.gxk : T(0)) + (j == b.k ? g.gwk : T(0));
-            gh[j] = (j < b.k ? g.gyk : T(0)) + (j == b.k ? g.ghk : T(0));
+        for (int j = 0; j < KMAX; ++j) {
+            gw[j] = (j < b.k) ? g.gxk : (j == b.k ? g.gwk : T(0));
+            gh[j] = (j < b.k) ? g.gyk : (j == b.k ? g.ghk : T(0));
         }
     }
-    rqs_softmax_bwd<T, KMAX>(uw, K, c.min_w, c.scale_w, c.eps, gw, guw);
-    rqs_softmax_bwd<T, KMAX>(uh, K, c.min_h, c.scale_h, c.eps, gh, guh);
+    rqs_softmax_bwd<T, KMAX>(smw, K, c.min_w, c.scale_w, c.eps, gw, guw);
+    rqs_softmax_bwd<T, KMAX>(smh, K, c.min_h, c.scale_h, c.eps, gh, guh);
+}
+
+// accumulating form (caller zero-initialises guw / guh / gud), default scrub handling
+template <typename T, int KMAX, bool BOUNDED>
+NF_HD void rqs_eval_bwd(T v, const T* uw, const T* uh, const T* ud, int K, bool inverse, const RqsCfg<T>& c,
+                        T g_out, T g_lad, T& g_v, T* guw, T* guh, T* gud) {
+    T a[KMAX], b[KMAX], d[KMAX];
+    rqs_eval_grad<T, KMAX, BOUNDED>(v, uw, uh, ud, K, inverse, c, g_out, g_lad, RqsScrubAdj<T, BOUNDED>(), g_v, a, b, d);
+NF_UNROLL
+    for (int j = 0; j < KMAX; ++j) if (j < K) { guw[j] += a[j]; guh[j] += b[j]; }
+NF_UNROLL
+    for (int j = 0; j < KMAX - 1; ++j) if (j < K - 1) gud[j] += d[j];
 }
 
 }  // namespace nf

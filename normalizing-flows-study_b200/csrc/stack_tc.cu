@@ -934,8 +934,9 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
 // key 2 = weight-gradient kernel: maximum number of 32-row K blocks accumulated in TMEM per split (wgrad_tc.cu);
 // key 3 = in-block kernel of the blocked sequential direction (ar_blocked.cu): 0 = CTA-barrier version, 1 = warp-private tiles
 // key 5 / 6 = dense-layer kernel selection (gemm_tc2.cu); key 7 = tensor-core passes per product of the dense-layer and
-// weight-gradient kernels: 3 = 3xTF32 (fp32 parity, default), 1 = one TF32 pass (reduced-precision mode)
-namespace nf { int g_wgrad_max_kb = 64; extern int g_ar_block_variant; extern int g_gemm_tc_variant; extern int g_gemm_tc_small_k; extern int g_tc_passes; extern int g_gemm_tc2_nacc; extern int g_gemm_tc2_ss; }
+// weight-gradient kernels: 3 = 3xTF32 (fp32 parity, default), 1 = one TF32 pass (reduced-precision mode);
+// key 11 = compact spline transform: 1 = TMA-staged kernels of spline_stream.cu (default), 0 = first-version kernels
+namespace nf { int g_wgrad_max_kb = 64; extern int g_ar_block_variant; extern int g_gemm_tc_variant; extern int g_gemm_tc_small_k; extern int g_tc_passes; extern int g_gemm_tc2_nacc; extern int g_gemm_tc2_ss; extern int g_spline_stream; }
 extern "C" int nf_set_option(int key, int value) {
     if (key == 1) { nf::g_tc_two_warpgroups = value != 0; return NF_OK; }
     if (key == 2) { if (value < 1) return NF_ERR_BAD_SHAPE; nf::g_wgrad_max_kb = value; return NF_OK; }
@@ -944,6 +945,7 @@ extern "C" int nf_set_option(int key, int value) {
     if (key == 6) { nf::g_gemm_tc_small_k = value != 0; return NF_OK; }
     if (key == 10) { nf::g_gemm_tc2_ss = value != 0; return NF_OK; }
     if (key == 9) { if (value != 2 && value != 3) return NF_ERR_BAD_SHAPE; nf::g_gemm_tc2_nacc = value; return NF_OK; }
+    if (key == 11) { nf::g_spline_stream = value != 0; return NF_OK; }
     if (key == 7) { if (value != 1 && value != 3) return NF_ERR_BAD_SHAPE; nf::g_tc_passes = value; return NF_OK; }
     return NF_ERR_UNSUPPORTED;
 }

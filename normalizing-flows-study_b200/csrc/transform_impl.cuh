@@ -551,6 +551,14 @@ static inline int pick_group_pow2(int n) { int g = 1; while (g < n && g < 32) g 
 
 template <typename T, bool GENERIC>
 int spline_transform_compact_fwd_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4 && !GENERIC) {
+        SplineStreamArgs sa{(const float*)a.x, (const float*)a.params, (const float*)a.mask, a.tidx, (float*)a.y, (float*)a.ld,
+                            (const float*)a.gy, (const float*)a.gld, (float*)a.gx, (float*)a.gparams, a.B, a.D, a.Dt,
+                            reinterpret_cast<const RqsCfg<float>&>(a.c), (const float*)a.r_in, (const float*)a.r_lo,
+                            (const float*)a.r_out};
+        const int rc = spline_stream_launch(sa, a.K, false, a.inverse, st);
+        if (rc != NF_ERR_UNSUPPORTED) return rc;
+    }
     const int G = pick_group_pow2(a.Dt);
     const int P = 3 * a.K - 1;
     const size_t smem = (size_t)8 * 32 * P * sizeof(T);
@@ -583,6 +591,14 @@ int spline_transform_compact_fwd_launch(const SplineTfArgs<T>& a, cudaStream_t s
 
 template <typename T, bool GENERIC>
 int spline_transform_compact_bwd_launch(const SplineTfArgs<T>& a, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4 && !GENERIC) {
+        SplineStreamArgs sa{(const float*)a.x, (const float*)a.params, (const float*)a.mask, a.tidx, (float*)a.y, (float*)a.ld,
+                            (const float*)a.gy, (const float*)a.gld, (float*)a.gx, (float*)a.gparams, a.B, a.D, a.Dt,
+                            reinterpret_cast<const RqsCfg<float>&>(a.c), (const float*)a.r_in, (const float*)a.r_lo,
+                            (const float*)a.r_out};
+        const int rc = spline_stream_launch(sa, a.K, true, a.inverse, st);
+        if (rc != NF_ERR_UNSUPPORTED) return rc;
+    }
     const int G = pick_group_pow2(a.Dt);
     const int P = 3 * a.K - 1;
     const size_t smem = (size_t)4 * 32 * P * sizeof(T);

@@ -263,15 +263,45 @@ def bench_stacks():
         report("MAF(64,512).forward sequential B=262144", ms, 262144 * 516, 1245184 * 262144)
 
 
+def bench_spline_tf_ncu():
+    """one launch of each compact spline transform kernel (forward, inverse, backward) on two shapes + rqs_unit:
+    the target of the ncu --set full capture (scripts/gpu_r02p.sh)"""
+    for (B, D, K) in ((1 << 22, 2, 8), (8192, 784, 10), (1 << 18, 16, 10)):
+        P = 3 * K - 1
+        mask = torch.zeros(D)
+        mask[: D // 2] = 1
+        Dt = int((mask == 0).sum())
+        tidx = torch.nonzero(mask == 0).flatten().to(torch.int32).to(DEV)
+        x = torch.randn(B, D, device=DEV) * 2
+        maskd = mask.to(DEV)
+        params = torch.randn(B, Dt * P, device=DEV)
+        gy, gl = torch.randn(B, D, device=DEV), torch.randn(B, device=DEV)
+        gx, gp = torch.empty_like(x), torch.zeros_like(params)
+        with torch.no_grad():
+            for inv in (False, True):
+                ops.spline_transform(x, params, maskd, tidx, K, inv, 5.0, (1e-3, 1e-3, 1e-3), None, True)
+        N._lib.call("nf_spline_transform_backward", x.data_ptr(), params.data_ptr(), maskd.data_ptr(), tidx.data_ptr(),
+                    gy.data_ptr(), gl.data_ptr(), gx.data_ptr(), gp.data_ptr(), B, D, Dt, K, 0, 5.0, 1e-3, 1e-3, 1e-3,
+                    None, None, None, 1, 0, N._lib.stream())
+        torch.cuda.synchronize()
+    n, K = 1 << 22, 8
+    xx = torch.rand(n, device=DEV)
+    w, h, d = torch.randn(n, K, device=DEV), torch.randn(n, K, device=DEV), torch.randn(n, K - 1, device=DEV)
+    with torch.no_grad():
+        ops.rqs_unit(xx, w, h, d, False, (1e-3, 1e-3, 1e-3))
+    torch.cuda.synchronize()
+    print("spline_tf_ncu: done")
+
+
 ALL = {"peaks": bench_peaks, "rqs": bench_rqs, "spline_tf": bench_spline_tf, "affine": bench_affine, "bn": bench_bn, "gemm": bench_gemm,
-       "stacks": bench_stacks}
+       "stacks": bench_stacks, "spline_tf_ncu": bench_spline_tf_ncu}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
-    names = [n for n in a.only.split(",") if n] or list(ALL)
+    names = [n for n in a.only.split(",") if n] or [n for n in ALL if not n.endswith("_ncu")]
     print(f"peaks: HBM {HBM} GB/s, bf16 {TF} TFLOP/s ({'measured' if PEAKS else 'fallback'})")
     for n in names:
         ALL[n]()
