@@ -46,7 +46,8 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 enum { kModeGroup = 0, kModeD2 = 1, kModeWide = 2 };
 
 struct ChunkState {
-    int64_t row;            // first row of the item (MODE 0 / 1) or the row (MODE 2)
+    int row;                // first row of the item (MODE 0 / 1) or the row (MODE 2); the launcher bounds B below 2^31
+
     const float* src;       // the chunk's parameter blocks
     int ch;                 // chunk within the row (MODE 2)
     int nfl;                // floats in the chunk
@@ -54,17 +55,17 @@ struct ChunkState {
 
 template <int P, int RPW, int MODE>
 struct ChunkWalk {
-    int64_t B, row_stride, src_stride;
-    int Dt, nch, full_fl;
+    int64_t src_stride;
+    int B, row_stride, Dt, nch, full_fl;
     __device__ __forceinline__ bool live(const ChunkState& c) const { return c.row < B; }
     __device__ __forceinline__ void start(ChunkState& c, const float* params, int64_t warp) const {
-        c.row = warp * RPW; c.ch = 0;
+        c.row = (int)warp * RPW; c.ch = 0;
         c.src = params + warp * (MODE == kModeWide ? (int64_t)Dt * P : (int64_t)full_fl);
         size(c);
     }
     __device__ __forceinline__ void size(ChunkState& c) const {
         if (MODE == kModeWide) { const int tn = Dt - c.ch * 32; c.nfl = (tn < 32 ? tn : 32) * P; }
-        else { const int64_t left = B - c.row; c.nfl = left >= RPW ? full_fl : (int)left * Dt * P; }
+        else { const int left = B - c.row; c.nfl = left >= RPW ? full_fl : left * Dt * P; }
     }
     __device__ __forceinline__ void advance(ChunkState& c) const {
         if (MODE == kModeWide) {
@@ -98,8 +99,10 @@ __device__ __forceinline__ void eval_elem(float v, const float* pp, const RqsCfg
     const float xk = mux<float, KMAX>(cw, k), xk1 = mux<float, KMAX>(cw + 1, k);
     const float yk = mux<float, KMAX>(ch, k), yk1 = mux<float, KMAX>(ch + 1, k);
     const float udk = pp[2 * K + (k >= 1 ? k - 1 : 0)], udk1 = pp[2 * K + (k < K - 1 ? k : K - 2)];
-    const float dk = (k == 0) ? 1.f : clamp_min(c.min_d + softplus(udk), c.eps);
-    const float dk1 = (k == K - 1) ? 1.f : clamp_min(c.min_d + softplus(udk1), c.eps);
+    float spk, spk1;
+    softplus_x2(udk, udk1, spk, spk1);
+    const float dk = (k == 0) ? 1.f : clamp_min(c.min_d + spk, c.eps);
+    const float dk1 = (k == K - 1) ? 1.f : clamp_min(c.min_d + spk1, c.eps);
     const float wk = clamp_min(xk1 - xk, c.eps), hk = clamp_min(yk1 - yk, c.eps);
     rqs_bin_eval<float, true>(v, xk, yk, wk, hk, dk, dk1, INV, c.eps, out, lad);
     if (!is_finite(out)) out = v;
@@ -107,7 +110,7 @@ __device__ __forceinline__ void eval_elem(float v, const float* pp, const RqsCfg
 #endif
 }
 
-constexpr int kIdU = 2;       // identity dims per lane and chunk held in registers (more go through a plain loop)
+constexpr int kIdU = 4;       // identity dims per lane in flight at once
 
 template <int KMAX, int G, bool INV, int MODE>
 __global__ void __launch_bounds__(128, 8)
@@ -122,41 +125,29 @@ spline_stream_fwd_kernel(const SplineStreamArgs a) {
     __syncwarp();
     const int g = lane % G, rsub = lane / G;
     const int D = a.D, Dt = a.Dt;
-    const int64_t B = a.B;
+    const int B = (int)a.B;
     const int64_t warp = (int64_t)blockIdx.x * nwc + wib, nwarps = (int64_t)gridDim.x * nwc;
     ChunkWalk<P, RPW, MODE> walk;
     walk.B = B; walk.Dt = Dt; walk.nch = WIDE ? (Dt + 31) >> 5 : 1; walk.full_fl = RPW * Dt * P;
-    walk.row_stride = nwarps * RPW; walk.src_stride = nwarps * (WIDE ? (int64_t)Dt * P : (int64_t)walk.full_fl);
+    walk.row_stride = (int)nwarps * RPW; walk.src_stride = nwarps * (WIDE ? (int64_t)Dt * P : (int64_t)walk.full_fl);
     const RqsCfg<float> c = a.c;
     const bool resc = a.r_in != nullptr;
-    // identity dims handled by this lane per chunk: dd = id0 + ch * idw + u * idstep, u = 0 .. idn - 1
-    const int idstep = WIDE ? 32 : G;
-    const int idn = WIDE ? (D + 32 * walk.nch - 1) / (32 * walk.nch) : (D + G - 1) / G;
-    const int idw = idn * 32;
-
     auto issue = [&](const ChunkState& cs, uint32_t q) {             // one lane: bulk copy of the chunk into slab q & 1
         if (walk.live(cs) && (cs.nfl & 3) == 0 && lane == 0) {
             mbar_arrive_expect_tx(&bars[q & 1], (uint32_t)cs.nfl * 4u);
             bulk_g2s(slab + (q & 1) * SLAB, cs.src, (uint32_t)cs.nfl * 4u, &bars[q & 1]);
         }
     };
-    struct In { float2 x; float idv[kIdU]; int dim; };
+    struct In { float2 x; int dim; };
     const int dim_fixed = D2 ? __ldg(a.tidx) : ((!WIDE && g < Dt) ? __ldg(a.tidx + g) : 0);
     auto fetch = [&](const ChunkState& cs, In& in) {                 // this lane's inputs of the chunk, requested early
         in.x = make_float2(0.f, 0.f); in.dim = dim_fixed;
-#pragma unroll
-        for (int u = 0; u < kIdU; ++u) in.idv[u] = 0.f;
-        const int64_t row = cs.row + rsub;
+        const int row = cs.row + rsub;
         if (!walk.live(cs) || row >= B) return;
         if (D2) { in.x = __ldcs(reinterpret_cast<const float2*>(a.x) + row); return; }
-        const float* xr = a.x + row * D;
+        const float* xr = a.x + (int64_t)row * D;
         const int t = WIDE ? cs.ch * 32 + g : g;
         if (t < Dt) { if (WIDE) in.dim = __ldg(a.tidx + t); in.x.x = xr[in.dim]; }
-#pragma unroll
-        for (int u = 0; u < kIdU; ++u) {
-            const int dd = (WIDE ? cs.ch * idw + lane : g) + u * idstep;
-            if (u < idn && dd < D && __ldg(a.mask + dd) != 0.f) in.idv[u] = xr[dd];
-        }
     };
 
     ChunkState cur, nxt;
@@ -172,8 +163,24 @@ spline_stream_fwd_kernel(const SplineStreamArgs a) {
         issue(nxt, q + 1);
         In inn;
         fetch(nxt, inn);
-        const int64_t row = cur.row + rsub;
+        const int row = cur.row + rsub;
         const bool vrow = row < B;
+        if (!D2 && vrow && (!WIDE || cur.ch == 0)) {     // identity dims of the row (layer-level scrub, :130), the row's
+            const float* xr = a.x + (int64_t)row * D;    // G lanes side by side, four dims per lane in flight
+            float* yr = a.y + (int64_t)row * D;
+            for (int dd0 = g; dd0 < D; dd0 += kIdU * G) {
+                float xi[kIdU];
+                bool on[kIdU];
+#pragma unroll
+                for (int u = 0; u < kIdU; ++u) {
+                    const int dd = dd0 + u * G;
+                    on[u] = dd < D && __ldg(a.mask + dd) != 0.f;
+                    xi[u] = on[u] ? xr[dd] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kIdU; ++u) if (on[u]) yr[dd0 + u * G] = scrub0(xi[u]);
+            }
+        }
         float* sl = slab + (q & 1) * SLAB;
         if ((cur.nfl & 3) == 0) {
             mbar_wait(&bars[q & 1], (q >> 1) & 1);
@@ -194,22 +201,9 @@ spline_stream_fwd_kernel(const SplineStreamArgs a) {
                 const float keep = scrub0(dim_fixed ? in.x.x : in.x.y);
                 __stcs(reinterpret_cast<float2*>(a.y) + row, dim_fixed ? make_float2(keep, out) : make_float2(out, keep));
             } else {
-                a.y[row * D + in.dim] = out;
+                a.y[(int64_t)row * D + in.dim] = out;
             }
             acc += lad;
-        }
-        if (!D2 && vrow) {                               // identity dims (layer-level scrub, :130)
-            float* yr = a.y + row * D;
-            const int dd0 = WIDE ? cur.ch * idw + lane : g;
-#pragma unroll
-            for (int u = 0; u < kIdU; ++u) {
-                const int dd = dd0 + u * idstep;
-                if (u < idn && dd < D && __ldg(a.mask + dd) != 0.f) yr[dd] = scrub0(in.idv[u]);
-            }
-            for (int u = kIdU; u < idn; ++u) {
-                const int dd = dd0 + u * idstep;
-                if (dd < D && __ldg(a.mask + dd) != 0.f) yr[dd] = scrub0(a.x[row * D + dd]);
-            }
         }
         if (!WIDE || cur.ch == walk.nch - 1) {
             acc = group_sum<float, G>(acc);
@@ -249,16 +243,13 @@ spline_stream_bwd_kernel(const SplineStreamArgs a) {
     __syncwarp();
     const int g = lane % G, rsub = lane / G;
     const int D = a.D, Dt = a.Dt;
-    const int64_t B = a.B;
+    const int B = (int)a.B;
     const int64_t warp = (int64_t)blockIdx.x * nwc + wib, nwarps = (int64_t)gridDim.x * nwc;
     ChunkWalk<P, RPW, MODE> walk;
     walk.B = B; walk.Dt = Dt; walk.nch = WIDE ? (Dt + 31) >> 5 : 1; walk.full_fl = RPW * Dt * P;
-    walk.row_stride = nwarps * RPW; walk.src_stride = nwarps * (WIDE ? (int64_t)Dt * P : (int64_t)walk.full_fl);
+    walk.row_stride = (int)nwarps * RPW; walk.src_stride = nwarps * (WIDE ? (int64_t)Dt * P : (int64_t)walk.full_fl);
     const RqsCfg<float> c = a.c;
     const bool resc = a.r_in != nullptr;
-    const int idstep = WIDE ? 32 : G;
-    const int idn = WIDE ? (D + 32 * walk.nch - 1) / (32 * walk.nch) : (D + G - 1) / G;
-    const int idw = idn * 32;
     const int64_t gdelta = a.gparams - a.params;         // the gradient block sits where the parameter block does
 
     auto issue = [&](const ChunkState& cs, uint32_t q) {
@@ -267,13 +258,11 @@ spline_stream_bwd_kernel(const SplineStreamArgs a) {
             bulk_g2s(slab + (q & 1) * SLAB, cs.src, (uint32_t)cs.nfl * 4u, &bars[q & 1]);
         }
     };
-    struct In { float2 x, gy; float gl; float idg[kIdU]; int dim; };
+    struct In { float2 x, gy; float gl; int dim; };
     const int dim_fixed = D2 ? __ldg(a.tidx) : ((!WIDE && g < Dt) ? __ldg(a.tidx + g) : 0);
     auto fetch = [&](const ChunkState& cs, In& in) {
         in.x = make_float2(0.f, 0.f); in.gy = in.x; in.gl = 0.f; in.dim = dim_fixed;
-#pragma unroll
-        for (int u = 0; u < kIdU; ++u) in.idg[u] = 0.f;
-        const int64_t row = cs.row + rsub;
+        const int row = cs.row + rsub;
         if (!walk.live(cs) || row >= B) return;
         in.gl = __ldg(a.gld + row);
         if (D2) {
@@ -281,15 +270,10 @@ spline_stream_bwd_kernel(const SplineStreamArgs a) {
             in.gy = __ldcs(reinterpret_cast<const float2*>(a.gy) + row);
             return;
         }
-        const float* xr = a.x + row * D;
-        const float* gr = a.gy + row * D;
+        const float* xr = a.x + (int64_t)row * D;
+        const float* gr = a.gy + (int64_t)row * D;
         const int t = WIDE ? cs.ch * 32 + g : g;
         if (t < Dt) { if (WIDE) in.dim = __ldg(a.tidx + t); in.x.x = xr[in.dim]; in.gy.x = gr[in.dim]; }
-#pragma unroll
-        for (int u = 0; u < kIdU; ++u) {                 // identity dims: the layer-level scrub zeroes non-finite inputs
-            const int dd = (WIDE ? cs.ch * idw + lane : g) + u * idstep;
-            if (u < idn && dd < D && __ldg(a.mask + dd) != 0.f) in.idg[u] = is_finite(xr[dd]) ? gr[dd] : 0.f;
-        }
     };
 
     ChunkState cur, nxt;
@@ -304,8 +288,26 @@ spline_stream_bwd_kernel(const SplineStreamArgs a) {
         issue(nxt, q + 1);
         In inn;
         fetch(nxt, inn);
-        const int64_t row = cur.row + rsub;
+        const int row = cur.row + rsub;
         const bool vrow = row < B;
+        if (!D2 && vrow && (!WIDE || cur.ch == 0)) {     // identity dims: the layer-level scrub zeroes non-finite inputs
+            const float* xr = a.x + (int64_t)row * D;
+            const float* gr = a.gy + (int64_t)row * D;
+            float* gxr = a.gx + (int64_t)row * D;
+            for (int dd0 = g; dd0 < D; dd0 += kIdU * G) {
+                float xi[kIdU], gi[kIdU];
+                bool on[kIdU];
+#pragma unroll
+                for (int u = 0; u < kIdU; ++u) {
+                    const int dd = dd0 + u * G;
+                    on[u] = dd < D && __ldg(a.mask + dd) != 0.f;
+                    xi[u] = on[u] ? xr[dd] : 0.f;
+                    gi[u] = on[u] ? gr[dd] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kIdU; ++u) if (on[u]) gxr[dd0 + u * G] = is_finite(xi[u]) ? gi[u] : 0.f;
+            }
+        }
         const bool bulk = (cur.nfl & 3) == 0;
         float* sl = slab + (q & 1) * SLAB;
         if (bulk) {
@@ -342,20 +344,7 @@ spline_stream_bwd_kernel(const SplineStreamArgs a) {
                 const float keep = is_finite(o) ? go_o : 0.f;
                 __stcs(reinterpret_cast<float2*>(a.gx) + row, dim_fixed ? make_float2(keep, gv) : make_float2(gv, keep));
             } else {
-                a.gx[row * D + in.dim] = gv;
-            }
-        }
-        if (!D2 && vrow) {
-            float* gxr = a.gx + row * D;
-            const int dd0 = WIDE ? cur.ch * idw + lane : g;
-#pragma unroll
-            for (int u = 0; u < kIdU; ++u) {
-                const int dd = dd0 + u * idstep;
-                if (u < idn && dd < D && __ldg(a.mask + dd) != 0.f) gxr[dd] = in.idg[u];
-            }
-            for (int u = kIdU; u < idn; ++u) {
-                const int dd = dd0 + u * idstep;
-                if (dd < D && __ldg(a.mask + dd) != 0.f) gxr[dd] = is_finite(a.x[row * D + dd]) ? a.gy[row * D + dd] : 0.f;
+                a.gx[(int64_t)row * D + in.dim] = gv;
             }
         }
         float* dst = const_cast<float*>(cur.src) + gdelta;
@@ -411,7 +400,7 @@ static int stream_launch_g(const SplineStreamArgs& a, bool bwd, int inverse, cud
 
 // NF_ERR_UNSUPPORTED = not taken (the caller falls back to the first-version kernels)
 int spline_stream_launch(const SplineStreamArgs& a, int K, bool bwd, int inverse, cudaStream_t st) {
-    if (!g_spline_stream || (K != 8 && K != 10) || a.Dt < 1) return NF_ERR_UNSUPPORTED;
+    if (!g_spline_stream || (K != 8 && K != 10) || a.Dt < 1 || a.B > (int64_t)0x7ff00000) return NF_ERR_UNSUPPORTED;
     if (!aligned16(a.params) || (bwd && !aligned16(a.gparams))) return NF_ERR_UNSUPPORTED;
     int G = 1;
     while (G < a.Dt && G < 32) G <<= 1;
