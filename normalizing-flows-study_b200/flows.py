@@ -163,21 +163,29 @@ def _fold_bn_eval(W, b, bn):
 
 
 def _tc_layer(W, b, relu):
-    hi, lo = ops.split_tf32(W.detach().float().contiguous())
-    return hi, lo, b.detach().float().contiguous(), relu
+    W = W.detach().float().contiguous()
+    hi, lo = ops.split_tf32(W)
+    return hi, lo, b.detach().float().contiguous(), relu, W
 
 
 def _tc_mlp(v, layers):
-    """relu?(... relu?(v W0^T + b0) ...) through the tcgen05 GEMM with cached TF32 splits; None if a layer is refused."""
+    """relu?(... relu?(v W0^T + b0) ...) with cached folded weights: the tcgen05 GEMM (TF32 splits) for every layer it
+    takes, the streaming FP32 kernels of nf_gemm for the skinny ones (reduction dimension or output width of a few
+    columns: the first / last Linear of a low-dimensional conditioner) -- a 128-wide tensor-core tile would waste > 90 %
+    of its work there, and K % 4 != 0 has no TMA row pitch."""
     h = v
-    for hi, lo, b, relu in layers:
-        h = ops.linear_tc(h, hi, lo, b, relu)
-        if h is None:
-            return None
+    for hi, lo, b, relu, W in layers:
+        N, K = W.shape
+        out = ops.linear_tc(h, hi, lo, b, relu) if (K % 4 == 0 and K >= 16 and N >= 16) else None
+        h = out if out is not None else ops.linear_raw(h, W, b, relu)
     return h
 
 
 WIDE_TC_MIN_ROWS = 256
+# hidden_dim in (64, 128] is outside the tcgen05 stack kernels; the FP32-pipe stack kernels hold the layer's weights in
+# shared memory at one 4-warp CTA per SM there (RealNVP(2, 10, 128), the reference's first published config: 57 ms per
+# 2^20 rows, profiles/r02v_published.jsonl) -- from this many rows on the GEMM route is several times faster
+WIDE_OVER_STACK_MIN_ROWS = 16384
 
 
 # ------------------------------------------------------------------------------------------------
@@ -291,8 +299,11 @@ class CouplingLayer(Flow):
         return ops.linear(h, net[6].weight, net[6].bias)
 
     def fusable(self, v):
+        H = self.s_net[0].out_features
+        if H > 64 and v.shape[0] >= WIDE_OVER_STACK_MIN_ROWS and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM:
+            return False
         return (not self.training and v.dtype == torch.float32 and self.s_net[0].weight.dtype == torch.float32
-                and self.data_dim <= packing.DMAX and self.s_net[0].out_features <= 128)
+                and self.data_dim <= packing.DMAX and H <= 128)
 
     @on_input_device
     def _run(self, v, inverse):
@@ -302,14 +313,11 @@ class CouplingLayer(Flow):
             if out is not None:
                 return out
         if (not wants_grad(self, v) and not self.training and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM and v.dtype == torch.float32
-                and self.s_net[0].weight.dtype == torch.float32 and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0):
+                and self.s_net[0].weight.dtype == torch.float32 and v.shape[0] >= WIDE_TC_MIN_ROWS):
             # wide eval route: mask and eval-mode BatchNorm folded into the Linears once per weight version, TF32 splits
             # cached, three tensor-core GEMMs per net (the layered route re-folds and re-splits on every call)
             nets = self._wide.get(self._wide.tensors_of([self]), self._fold_wide)
-            s_raw = _tc_mlp(v, nets[0])
-            b_raw = _tc_mlp(v, nets[1]) if s_raw is not None else None
-            if b_raw is not None:
-                return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
+            return ops.affine_coupling(v, _tc_mlp(v, nets[0]), _tc_mlp(v, nets[1]), self.mask, inverse)
         s_raw = self._conditioner(self.s_net, v)
         b_raw = self._conditioner(self.b_net, v)
         return ops.affine_coupling(v, s_raw, b_raw, self.mask, inverse)
@@ -379,9 +387,11 @@ class SplineCouplingLayer(Flow):
         return self._aux.get([self.mask], build, extra=(v.dtype, v.device))
 
     def fusable(self, v):
+        H = self.param_net[0].out_features
+        if H > 64 and v.shape[0] >= WIDE_OVER_STACK_MIN_ROWS and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM:
+            return False                              # see WIDE_OVER_STACK_MIN_ROWS
         return (v.dtype == torch.float32 and self.param_net[0].weight.dtype == torch.float32
-                and self.data_dim <= packing.DMAX and self.param_net[0].out_features <= 128
-                and 2 <= self.num_bins <= 16)
+                and self.data_dim <= packing.DMAX and H <= 128 and 2 <= self.num_bins <= 16)
 
     @on_input_device
     def _run(self, v, inverse):
@@ -396,12 +406,10 @@ class SplineCouplingLayer(Flow):
         if rescale is not None:                       # conditioner sees the rescaled input (:101-102)
             vin = ops.feature_affine(v, rescale[1], None, rescale[0], -float(self.bound))
         if (not wants_grad(self, v) and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM and v.dtype == torch.float32 and net[0].weight.dtype == torch.float32
-                and v.shape[0] >= WIDE_TC_MIN_ROWS and self.data_dim % 4 == 0 and tlist):
+                and v.shape[0] >= WIDE_TC_MIN_ROWS and tlist):
             layers = self._wide.get(self._wide.tensors_of([self]), lambda: self._fold_wide(tlist))
-            params = _tc_mlp(vin, layers)
-            if params is not None:
-                return ops.spline_transform(v, params, self.mask, tidx, self.num_bins, inverse, self.bound, self._mins,
-                                            rescale, compact=True)
+            return ops.spline_transform(v, _tc_mlp(vin, layers), self.mask, tidx, self.num_bins, inverse, self.bound,
+                                        self._mins, rescale, compact=True)
         h = ops.linear(vin, net[0].weight, net[0].bias, mask=self.mask, relu=True)
         h = ops.linear(h, net[2].weight, net[2].bias, relu=True)
         # head restricted to the transformed dims: the reference evaluates all D*(3K-1) outputs and discards the rows

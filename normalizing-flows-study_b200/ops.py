@@ -764,18 +764,21 @@ def made_affine(v, folded, mode):
         if res is not None:
             return res
     if USE_TENSOR_CORE_GEMM and folded.w_split is not None and v.dtype == torch.float32 and B >= 128:
-        h, ok = v, True
+        # layer by layer: the tensor-core GEMM where the shape has a TMA row pitch and a tile's worth of columns, the
+        # streaming FP32 kernels of nf_gemm for the skinny first / last layer of a low-dimensional MADE (MADE(2, 64):
+        # K = 2 in, 4 out) -- refusing the whole chain for them sent the two 64 x 64 layers to the FP32-pipe GEMM too
+        h = v
         for i in range(4):
             hi, lo = folded.w_split[i]
-            h = linear_tc(h, hi, lo, folded.b[i], relu=(i < 3), k_extent=(folded.kext[i - 1] if i > 0 else None))
-            if h is None:
-                ok = False
-                break
-        if ok:
-            out = torch.empty_like(v)
-            ld = torch.empty(B, dtype=v.dtype, device=v.device)
-            call("nf_affine_ar_forward", ptr(v), ptr(h), ptr(out), ptr(ld), B, D, mode, L.dtype_code(v), stream())
-            return out, ld
+            N_, K_ = folded.w[i].shape
+            y = None
+            if K_ % 4 == 0 and K_ >= 16 and N_ >= 16:
+                y = linear_tc(h, hi, lo, folded.b[i], relu=(i < 3), k_extent=(folded.kext[i - 1] if i > 0 else None))
+            h = y if y is not None else linear_raw(h, folded.w[i], folded.b[i], relu=(i < 3))
+        out = torch.empty_like(v)
+        ld = torch.empty(B, dtype=v.dtype, device=v.device)
+        call("nf_affine_ar_forward", ptr(v), ptr(h), ptr(out), ptr(ld), B, D, mode, L.dtype_code(v), stream())
+        return out, ld
     ws = torch.empty(2 * B * max(H, 2 * D), dtype=v.dtype, device=v.device)
     out = torch.empty_like(v)
     ld = torch.empty(B, dtype=v.dtype, device=v.device)

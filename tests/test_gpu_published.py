@@ -1,0 +1,85 @@
+"""GPU: the reference's four published configs (plots/_common.py:158-170) at a batch size that takes the large-batch
+routes -- RealNVP(2, 10, 128) (hidden_dim 128: folded tensor-core GEMMs + streaming first / last layers instead of the
+FP32-pipe stack kernel), RealNVPSpline(2, 8, 64), 6 x MAF(2, 64), 6 x IAF(2, 64) (mixed tensor-core / streaming MADE
+chain) -- against the CPU oracle in both directions, at the plain north_star bound."""
+import pytest
+import torch
+
+import nfb200 as N
+from oracle import flows_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROWS = 20000           # >= flows.WIDE_OVER_STACK_MIN_ROWS, not a multiple of any tile size
+
+
+def _compare(what, got, ref, atol, rtol, max_frac=1e-3, hard=20.0):
+    got, ref = got.detach().cpu().double(), ref.double()
+    assert torch.equal(torch.isnan(got), torch.isnan(ref)), what
+    err = (got - ref).abs() - (atol + rtol * ref.abs())
+    frac = (err > 0).double().mean().item()
+    print(f"[published] {what}: {frac:.2e} of the elements outside the plain bound, worst excess {err.max().item():.2e}")
+    assert frac <= max_frac, f"{what}: {frac:.2e} outside"
+    assert ((got - ref).abs() <= hard * (atol + rtol * ref.abs())).all(), what
+
+
+def _perturbed(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.add_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.add_(0.2 * torch.rand(m.running_var.shape, generator=g))
+    return model.eval()
+
+
+@pytest.mark.parametrize("bn_between", [False, True])
+def test_realnvp_hidden_128_large_batch_route(bn_between):
+    torch.manual_seed(0)
+    model = _perturbed(N.RealNVP(2, 10, 128, batch_norm_between_layers=bn_between), 1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    specs = [dict(kind="coupling")] * 10
+    model.to(DEV)
+    x = torch.randn(ROWS, 2) * 1.5
+    assert not model.flow.flows[0].fusable(x.to(DEV))
+    with torch.no_grad():
+        for inverse in (False, True):
+            ry, rld = O.flow_model(sd, "flow.", specs, x, inverse, bn_between=bn_between)
+            y, ld = model.inverse(x.to(DEV)) if inverse else model.forward(x.to(DEV))
+            _compare(f"RealNVP(2,10,128) bn={bn_between} inv={inverse} z", y, ry, 1e-5, 1e-5)
+            _compare(f"RealNVP(2,10,128) bn={bn_between} inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+
+
+def test_spline_hidden_128_large_batch_route():
+    torch.manual_seed(0)
+    masks = O.realnvp_masks(2, 4)
+    model = _perturbed(N.NormalizingFlowModel([N.SplineCouplingLayer(2, 128, m.clone(), num_bins=8) for m in masks]), 2)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    specs = [dict(kind="spline", num_bins=8)] * 4
+    model.to(DEV)
+    x = torch.randn(ROWS, 2) * 2.0
+    with torch.no_grad():
+        for inverse in (False, True):
+            ry, rld = O.flow_model(sd, "", specs, x, inverse)
+            y, ld = model.inverse(x.to(DEV)) if inverse else model.forward(x.to(DEV))
+            _compare(f"spline hidden 128 inv={inverse} z", y, ry, 1e-5, 1e-5)
+            _compare(f"spline hidden 128 inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("kind", ["maf", "iaf"])
+def test_six_layer_autoregressive_2d_large_batch(kind):
+    torch.manual_seed(0)
+    cls = N.MaskedAutoregressiveFlow if kind == "maf" else N.InverseAutoregressiveFlow
+    model = _perturbed(N.NormalizingFlowModel([cls(2, 64) for _ in range(6)]), 3)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    specs = [dict(kind=kind)] * 6
+    model.to(DEV)
+    x = torch.randn(ROWS, 2) * 1.5
+    with torch.no_grad():
+        for inverse in (False, True):
+            ry, rld = O.flow_model(sd, "", specs, x, inverse)
+            y, ld = model.inverse(x.to(DEV)) if inverse else model.forward(x.to(DEV))
+            _compare(f"6 x {kind}(2,64) inv={inverse} z", y, ry, 1e-5, 1e-5)
+            _compare(f"6 x {kind}(2,64) inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
