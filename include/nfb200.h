@@ -253,11 +253,14 @@ NF_API int nf_std_normal_log_prob_backward(const void* z, const void* glp, void*
  * follows the tensor-core layout (csrc/stack_tc.cu; magic 'NFS2').  NF_ERR_UNSUPPORTED otherwise. */
 NF_API int nf_spline_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
                                void* ld, int64_t B, int inverse, nf_stream_t stream);
-/* affine coupling stack (eval mode) on the tensor cores: same contract as nf_coupling_stack_forward for hidden_dim <= 64;
+/* affine coupling stack (eval mode) on the tensor cores: same contract as nf_coupling_stack_forward for hidden_dim <= 128
+ * (hidden units padded to 64, two CTAs per SM, or to 128, one CTA per SM with all 512 TMEM columns);
  * `packed` in the tensor-core layout (magic 'NFA2': two net blocks per layer, csrc/stack_tc.cu). */
 NF_API int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
                                  void* y, void* ld, int64_t B, int inverse, nf_stream_t stream);
 NF_API int64_t nf_coupling_stack_tc_block_words(int D);
+/* words per NET block of that layout for hidden_dim H (<= 64: same as above; <= 128: the 128-wide layout); -1 = unsupported */
+NF_API int64_t nf_coupling_stack_tc_block_words_hidden(int D, int H);
 /* words per layer block of that layout (-1 if the configuration is not supported) */
 NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
 

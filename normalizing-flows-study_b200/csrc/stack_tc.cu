@@ -80,10 +80,11 @@ __device__ __forceinline__ float2 layer1_pair(const float* __restrict__ sW1k, in
 }
 
 // (a): hidden layer 1 of one conditioner for this thread's row -> TMEM A operand (hi at kColAhi, lo at kColAlo)
-template <int DM>
+template <int DM, int HP = 64>
 __device__ __forceinline__ void layer1_to_tmem(const float* __restrict__ sW1k, int W1S, const float (&xa)[DM], uint32_t lane_addr) {
+    constexpr int kColAhi = 0, kColAlo = HP;        // TMEM columns of an HP-wide conditioner: A hi | A lo | D2 | D3
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < HP / 16; ++c) {
         uint32_t hi[16], lo[16];
         if constexpr (DM <= 4) {
 #pragma unroll
@@ -111,25 +112,30 @@ __device__ __forceinline__ void layer1_to_tmem(const float* __restrict__ sW1k, i
     }
 }
 
-// (c): D2 + b2 -> ReLU -> split -> A operand.  All four 16-column loads are issued before the single wait.
+// (c): D2 + b2 -> ReLU -> split -> A operand.  Four 16-column loads are issued before each wait (64 columns at a time).
+template <int HP = 64>
 __device__ __forceinline__ void hidden2_to_tmem(const float* __restrict__ sb2, uint32_t lane_addr) {
-    uint32_t v[4][16];
+    constexpr int kColAhi = 0, kColAlo = HP, kColD2 = 2 * HP;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tc::tmem_ld16(lane_addr + kColD2 + c * 16, v[c]);
-    tc::wait_ld();
+    for (int cg = 0; cg < HP / 64; ++cg) {
+        uint32_t v[4][16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint32_t hi[16], lo[16];
+        for (int c = 0; c < 4; ++c) tc::tmem_ld16(lane_addr + kColD2 + (cg * 4 + c) * 16, v[c]);
+        tc::wait_ld();
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(sb2 + c * 16 + j4 * 4);
-            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 0]), __uint_as_float(v[c][j4 * 4 + 1])), make_float2(b.x, b.y));
-            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 2]), __uint_as_float(v[c][j4 * 4 + 3])), make_float2(b.z, b.w));
-            tc::split_tf32_x2(relu_keepnan(s0.x), relu_keepnan(s0.y), hi[j4 * 4 + 0], hi[j4 * 4 + 1], lo[j4 * 4 + 0], lo[j4 * 4 + 1]);
-            tc::split_tf32_x2(relu_keepnan(s1.x), relu_keepnan(s1.y), hi[j4 * 4 + 2], hi[j4 * 4 + 3], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = *reinterpret_cast<const float4*>(sb2 + (cg * 4 + c) * 16 + j4 * 4);
+                const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 0]), __uint_as_float(v[c][j4 * 4 + 1])), make_float2(b.x, b.y));
+                const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(v[c][j4 * 4 + 2]), __uint_as_float(v[c][j4 * 4 + 3])), make_float2(b.z, b.w));
+                tc::split_tf32_x2(relu_keepnan(s0.x), relu_keepnan(s0.y), hi[j4 * 4 + 0], hi[j4 * 4 + 1], lo[j4 * 4 + 0], lo[j4 * 4 + 1]);
+                tc::split_tf32_x2(relu_keepnan(s1.x), relu_keepnan(s1.y), hi[j4 * 4 + 2], hi[j4 * 4 + 3], lo[j4 * 4 + 2], lo[j4 * 4 + 3]);
+            }
+            tc::tmem_st16(lane_addr + kColAhi + (cg * 4 + c) * 16, hi);
+            tc::tmem_st16(lane_addr + kColAlo + (cg * 4 + c) * 16, lo);
         }
-        tc::tmem_st16(lane_addr + kColAhi + c * 16, hi);
-        tc::tmem_st16(lane_addr + kColAlo + c * 16, lo);
     }
 }
 
@@ -169,12 +175,13 @@ struct BlkOff { int w1k, b2, b3, w2hi, w2lo, w3hi, w3lo, net_words; };
 __host__ __device__ inline int pad256(int x) { return (x + 255) & ~255; }
 // nets conditioner blocks follow the 80-word layer header; every block is a multiple of 256 words so that the
 // weight images stay 1024-byte aligned
-__host__ __device__ inline BlkOff blk_offsets(int W1S, int NO3) {
+// HP: hidden units padded to 64 (every kernel here) or 128 (the affine coupling stack with hidden_dim in (64, 128])
+__host__ __device__ inline BlkOff blk_offsets(int W1S, int NO3, int HP = 64) {
     BlkOff o;
-    o.w1k = 0; o.b2 = 64 * W1S; o.b3 = o.b2 + 64;
+    o.w1k = 0; o.b2 = HP * W1S; o.b3 = o.b2 + HP;
     o.w2hi = pad256(NF_LAYER_HDR + o.b3 + NO3) - NF_LAYER_HDR;       // first net: header shares the leading pad
-    o.w2lo = o.w2hi + 4096; o.w3hi = o.w2lo + 4096; o.w3lo = o.w3hi + NO3 * 64;
-    o.net_words = o.w3lo + NO3 * 64;
+    o.w2lo = o.w2hi + HP * HP; o.w3hi = o.w2lo + HP * HP; o.w3lo = o.w3hi + NO3 * HP;
+    o.net_words = o.w3lo + NO3 * HP;
     return o;
 }
 
@@ -289,7 +296,7 @@ spline_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict
                 tc::mbar_wait(&bar, phase); phase ^= 1;
                 tc::fence_after_sync();
                 NF_TICK(1);
-                hidden2_to_tmem(net + off.b2, lane_addr);
+                hidden2_to_tmem<64>(net + off.b2, lane_addr);
                 tc::wait_st();
                 tc::fence_before_sync();
                 __syncthreads();
@@ -657,22 +664,29 @@ spline_stack_tc2_kernel(const float* __restrict__ packed, const float* __restric
 //   TMEM regions; the staging unit is one NET block (header lead + W1k | b2 | b3 | W2 hi/lo | W3 hi/lo, ~43 KB), double
 //   buffered: while net b computes, the next layer's net s arrives.  Head: D outputs padded to 16 columns.
 // ------------------------------------------------------------------------------------------------
-template <int DM>
-__global__ void __launch_bounds__(kTcThreads, 2)
+// HP = 128 (hidden_dim in (64, 128], e.g. the reference's published RealNVP(2, 10, 128)): A hi / lo 2 x 128 TMEM columns,
+//   D2 128, D3 16 = all 512 columns of the SM, so ONE CTA per SM; a net block is ~151 KB (W2 hi / lo images alone 128 KB)
+//   and is single buffered -- the next block is requested when every thread is done with the current one (~1 us of a
+//   ~16 us net pass per tile).  Same code otherwise: K = 128 is 16 k-steps per pass, the head reads 4 K atoms.
+template <int DM, int HP>
+__global__ void __launch_bounds__(kTcThreads, HP == 64 ? 2 : 1)
 coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
-                         float* __restrict__ ld, int64_t B, int flags) {
+                         float* __restrict__ ld, int64_t B, int flags, int nsub) {     // nsub <= kTcSub sub-tiles per weight staging
+    constexpr int NBUF = (HP == 64) ? 2 : 1;
+    constexpr int kColAhi = 0, kColAlo = HP, kColD2 = 2 * HP, kColD3 = 3 * HP;
+    constexpr int kTmemCols = (HP == 64) ? 256 : 512;
     const int inverse = flags & NF_STACK_INVERSE;
     extern __shared__ __align__(1024) float sbuf[];
     const TcHdr hd = read_tc_hdr(packed);
     const int D = hd.D, L = hd.L, W1S = hd.W1S, NO3 = hd.NO3, NBW = hd.blk_words;       // NBW: words per net block
-    float* sx = sbuf + (size_t)2 * NBW;                          // [kTcSub][DM+1][128] row state
+    float* sx = sbuf + (size_t)NBUF * NBW;                       // [kTcSub][DM+1][128] row state
     float* sraw = sx + kTcSub * (DM + 1) * kTcThreads;           // [kTcSub][DM][128] raw s_net outputs
     float* shdr = sraw + kTcSub * DM * kTcThreads;               // [80] layer header (outlives the net-s buffer)
     uint64_t* bars = reinterpret_cast<uint64_t*>(shdr + NF_LAYER_HDR);
     uint64_t& bar = bars[0];
     uint64_t* wbar = bars + 1;
     uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 3);
-    const BlkOff off = blk_offsets(W1S, NO3);
+    const BlkOff off = blk_offsets(W1S, NO3, HP);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
@@ -684,20 +698,19 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
     const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0, wphase = 0u;
 
-    constexpr int ROWS = kTcThreads * kTcSub;
+    const int ROWS = kTcThreads * nsub;
     const int64_t ntiles = (B + ROWS - 1) / ROWS;
     const float* blocks = packed + NF_STACK_HDR;
     const int NQ = 2 * L;                                         // net blocks per pass, order: layer (direction-aware), net
     auto block_of = [&](int q) { const int li = q >> 1; return (size_t)(2 * (inverse ? L - 1 - li : li) + (q & 1)) * NBW; };
 
     int buf = 0;
-    if (tid == 0 && (int64_t)blockIdx.x < ntiles) {
+    if (NBUF == 2 && tid == 0 && (int64_t)blockIdx.x < ntiles) {
         tc::mbar_arrive_expect_tx(&wbar[0], (uint32_t)NBW * 4u);
         tc::bulk_g2s(sbuf, blocks + block_of(0), (uint32_t)NBW * 4u, &wbar[0]);
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll
-        for (int s = 0; s < kTcSub; ++s) {
+        for (int s = 0; s < nsub; ++s) {
             const int64_t r = tile * ROWS + s * kTcThreads + tid;
 #pragma unroll
             for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = (d < D && r < B) ? ld_stream(x + r * D + d) : 0.f;
@@ -708,10 +721,15 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
             tc::fence_proxy_async_smem();
             __syncthreads();                                      // everyone is done with the other buffer
             if (tid == 0) {
-                const bool last = (q == NQ - 1);
-                if (!last || (tile + gridDim.x < ntiles)) {
-                    tc::mbar_arrive_expect_tx(&wbar[buf ^ 1], (uint32_t)NBW * 4u);
-                    tc::bulk_g2s(sbuf + (size_t)(buf ^ 1) * NBW, blocks + block_of(last ? 0 : q + 1), (uint32_t)NBW * 4u, &wbar[buf ^ 1]);
+                if (NBUF == 2) {
+                    const bool last = (q == NQ - 1);
+                    if (!last || (tile + gridDim.x < ntiles)) {
+                        tc::mbar_arrive_expect_tx(&wbar[buf ^ 1], (uint32_t)NBW * 4u);
+                        tc::bulk_g2s(sbuf + (size_t)(buf ^ 1) * NBW, blocks + block_of(last ? 0 : q + 1), (uint32_t)NBW * 4u, &wbar[buf ^ 1]);
+                    }
+                } else {                                          // single buffer: this net's block, now that everyone left the last one
+                    tc::mbar_arrive_expect_tx(&wbar[0], (uint32_t)NBW * 4u);
+                    tc::bulk_g2s(sbuf, blocks + block_of(q), (uint32_t)NBW * 4u, &wbar[0]);
                 }
             }
             tc::mbar_wait(&wbar[buf], (wphase >> buf) & 1u);
@@ -728,7 +746,7 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
             const uint32_t w2hi = tc::smem_u32(nb + off.w2hi), w2lo = tc::smem_u32(nb + off.w2lo);
             const uint32_t w3hi = tc::smem_u32(nb + off.w3hi), w3lo = tc::smem_u32(nb + off.w3lo);
 #pragma unroll 1
-            for (int s = 0; s < kTcSub; ++s) {
+            for (int s = 0; s < nsub; ++s) {
                 float xv[DM], tot;
 #pragma unroll
                 for (int d = 0; d < DM; ++d) xv[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
@@ -742,18 +760,26 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
                 float xa[DM];
 #pragma unroll
                 for (int d = 0; d < DM; ++d) xa[d] = (d < D) ? xv[d] * mask[d] : 0.f;
-                layer1_to_tmem<DM>(nb + off.w1k, W1S, xa, lane_addr);
+                layer1_to_tmem<DM, HP>(nb + off.w1k, W1S, xa, lane_addr);
                 tc::wait_st();
                 tc::fence_before_sync();
                 __syncthreads();
-                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, 64u, &bar); }
+                if (warp == 0) {
+                    tc::fence_after_sync();
+                    if (HP == 64) tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, 64u, &bar);
+                    else tc::warp_issue_gemm_krange_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, (uint32_t)HP, 0, HP / 8, 0u, &bar);
+                }
                 tc::mbar_wait(&bar, phase); phase ^= 1;
                 tc::fence_after_sync();
-                hidden2_to_tmem(nb + off.b2, lane_addr);
+                hidden2_to_tmem<HP>(nb + off.b2, lane_addr);
                 tc::wait_st();
                 tc::fence_before_sync();
                 __syncthreads();
-                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD3, kColAhi, kColAlo, w3hi, w3lo, (uint32_t)NO3, &bar); }
+                if (warp == 0) {
+                    tc::fence_after_sync();
+                    if (HP == 64) tc::warp_issue_gemm_k64_3xtf32(tb, kColD3, kColAhi, kColAlo, w3hi, w3lo, (uint32_t)NO3, &bar);
+                    else tc::warp_issue_gemm_krange_3xtf32(tb, kColD3, kColAhi, kColAlo, w3hi, w3lo, (uint32_t)NO3, 0, HP / 8, 0u, &bar);
+                }
                 tc::mbar_wait(&bar, phase); phase ^= 1;
                 tc::fence_after_sync();
                 uint32_t p[8];
@@ -781,10 +807,9 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
                     sx[(s * (DM + 1) + DM) * kTcThreads + tid] = tot;
                 }
             }
-            buf ^= 1;
+            if (NBUF == 2) buf ^= 1;
         }
-#pragma unroll
-        for (int s = 0; s < kTcSub; ++s) {
+        for (int s = 0; s < nsub; ++s) {
             const int64_t r = tile * ROWS + s * kTcThreads + tid;
             if (r < B) {
                 float zr[DM];
@@ -891,6 +916,10 @@ extern "C" int64_t nf_coupling_stack_tc_block_words(int D) {
     if (D < 1 || D > NF_STACK_DMAX) return -1;
     return NF_LAYER_HDR + blk_offsets(nf_stack_w1s(D), 16).net_words;      // words per NET block (2 per layer)
 }
+extern "C" int64_t nf_coupling_stack_tc_block_words_hidden(int D, int H) {  // hidden units padded to 64 or 128
+    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 128) return -1;
+    return NF_LAYER_HDR + blk_offsets(nf_stack_w1s(D), 16, H <= 64 ? 64 : 128).net_words;
+}
 
 extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
                                             void* y, void* ld, int64_t B, int inverse, nf_stream_t stream) {
@@ -903,27 +932,35 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
     const int32_t* h = (const int32_t*)hdr_host;
     if (h[0] != NF_STACK_MAGIC_AFFINE_TC) return NF_ERR_BAD_SHAPE;
     const int D = h[1], H = h[2], L = h[5], W1S = h[6], NO3 = h[7], NBW = h[8];
-    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 64 || L < 1 || NO3 != 16) return NF_ERR_UNSUPPORTED;
-    if (W1S != nf_stack_w1s(D) || NBW != NF_LAYER_HDR + blk_offsets(W1S, NO3).net_words) return NF_ERR_BAD_SHAPE;
+    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 128 || L < 1 || NO3 != 16) return NF_ERR_UNSUPPORTED;
+    const int HP = H <= 64 ? 64 : 128;
+    if (W1S != nf_stack_w1s(D) || NBW != NF_LAYER_HDR + blk_offsets(W1S, NO3, HP).net_words) return NF_ERR_BAD_SHAPE;
     if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)2 * L * NBW)) return NF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
-    const size_t smem = sizeof(float) * ((size_t)2 * NBW + (size_t)kTcSub * (2 * DMh + 1) * kTcThreads + NF_LAYER_HDR + 8);
+    const int nbuf = HP == 64 ? 2 : 1, tmem_cols = HP == 64 ? 256 : 512;
+    const size_t smem = sizeof(float) * ((size_t)nbuf * NBW + (size_t)kTcSub * (2 * DMh + 1) * kTcThreads + NF_LAYER_HDR + 8);
     if (smem > 227 * 1024) return NF_ERR_UNSUPPORTED;
-    const int64_t ntiles = cdiv(B, kTcThreads * kTcSub);
-#define NF_CTC(DMv)                                                                                                  \
+    // small batches: fewer sub-tiles per weight staging so that every SM gets rows (4 000 rows on eight 512-row tiles
+    // left 140 SMs idle); from kTcSub sub-tiles per resident CTA on, the staging is shared by kTcSub sub-tiles
+    const int res_ctas = kNumSMs * (512 / tmem_cols);
+    int nsub = (int)cdiv(cdiv(B, kTcThreads), res_ctas);
+    nsub = nsub < 1 ? 1 : (nsub > kTcSub ? kTcSub : nsub);
+    const int64_t ntiles = cdiv(B, kTcThreads * nsub);
+#define NF_CTC(DMv, HPv)                                                                                                  \
     do {                                                                                                             \
-        auto kern = coupling_stack_tc_kernel<DMv>;                                                                   \
+        auto kern = coupling_stack_tc_kernel<DMv, HPv>;                                                                   \
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
         int per_sm = (int)((227 * 1024) / (smem + 1024));                                                            \
         if (per_sm < 1) return NF_ERR_UNSUPPORTED;                                                                   \
-        if (per_sm > 512 / kTmemCols) per_sm = 512 / kTmemCols;                                                      \
+        if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;                                                      \
         const int64_t cap = (int64_t)kNumSMs * per_sm;                                                               \
         const int grid = (int)(ntiles < cap ? ntiles : cap);                                                         \
-        kern<<<grid, kTcThreads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, inverse); \
+        kern<<<grid, kTcThreads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, inverse, nsub); \
     } while (0)
-    if (D <= 2) NF_CTC(2); else if (D <= 3) NF_CTC(4); else NF_CTC(8);
+    if (HP == 64) { if (D <= 2) NF_CTC(2, 64); else if (D <= 3) NF_CTC(4, 64); else NF_CTC(8, 64); }
+    else          { if (D <= 2) NF_CTC(2, 128); else if (D <= 3) NF_CTC(4, 128); else NF_CTC(8, 128); }
 #undef NF_CTC
     count_launch();
     NF_LAUNCH_CHECK();

@@ -182,9 +182,10 @@ def _tc_mlp(v, layers):
 
 
 WIDE_TC_MIN_ROWS = 256
-# hidden_dim in (64, 128] is outside the tcgen05 stack kernels; the FP32-pipe stack kernels hold the layer's weights in
-# shared memory at one 4-warp CTA per SM there (RealNVP(2, 10, 128), the reference's first published config: 57 ms per
-# 2^20 rows, profiles/r02v_published.jsonl) -- from this many rows on the GEMM route is several times faster
+# hidden_dim in (64, 128] is outside the tcgen05 SPLINE stack kernels (the affine coupling stack has a 128-wide variant);
+# the FP32-pipe stack kernels hold the layer's weights in shared memory at one 4-warp CTA per SM there (RealNVP(2, 10,
+# 128), the reference's first published config: 57 ms per 2^20 rows, profiles/r02v_published_before.jsonl) -- from this
+# many rows on the GEMM route is several times faster
 WIDE_OVER_STACK_MIN_ROWS = 16384
 
 
@@ -300,8 +301,8 @@ class CouplingLayer(Flow):
 
     def fusable(self, v):
         H = self.s_net[0].out_features
-        if H > 64 and v.shape[0] >= WIDE_OVER_STACK_MIN_ROWS and USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM:
-            return False
+        if H > 64 and v.shape[0] >= WIDE_OVER_STACK_MIN_ROWS and not USE_TENSOR_CORES and ops.USE_TENSOR_CORE_GEMM:
+            return False                              # no tcgen05 stack kernel: see WIDE_OVER_STACK_MIN_ROWS
         return (not self.training and v.dtype == torch.float32 and self.s_net[0].weight.dtype == torch.float32
                 and self.data_dim <= packing.DMAX and H <= 128)
 

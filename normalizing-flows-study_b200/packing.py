@@ -438,24 +438,25 @@ def _pad256(n):
     return (n + 255) & ~255
 
 
-def _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, lead_words):
+def _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, lead_words, HP=64):
     """One conditioner block of the tensor-core stack layout (csrc/stack_tc.cu: blk_offsets):
-    W1k[64][W1S] (W1S == 4: pair-interleaved, see below) | b2[64] | b3[NO3] | pad to a 256-word boundary (counting `lead_words` in front) |
-    W2 hi image | W2 lo image | W3 hi image | W3 lo image.  W3rows/b3rows: [NO3, H] / [NO3] already in head-column order."""
-    w1k = np.zeros((64, W1S))
+    W1k[HP][W1S] (W1S == 4: pair-interleaved, see below) | b2[HP] | b3[NO3] | pad to a 256-word boundary (counting `lead_words` in front) |
+    W2 hi image | W2 lo image | W3 hi image | W3 lo image.  W3rows/b3rows: [NO3, H] / [NO3] already in head-column order.
+    HP: hidden units padded to 64, or 128 for the affine coupling stack with hidden_dim in (64, 128]."""
+    w1k = np.zeros((HP, W1S))
     w1k[:H, :D] = W1
     w1k[:H, W1S - 1] = b1
     if W1S == 4:
         # data_dim <= 3: units are stored in PAIRS, [w0a w0b | w1a w1b | w2a w2b | ba bb] per pair (a = unit 2p, b = 2p+1),
         # so that the kernel's packed-fp32 FMAs (FFMA2) find both units' operands in adjacent registers
-        w1k = w1k.reshape(32, 2, 4).transpose(0, 2, 1).reshape(64, 4)
-    b2p = np.zeros(64)
+        w1k = w1k.reshape(HP // 2, 2, 4).transpose(0, 2, 1).reshape(HP, 4)
+    b2p = np.zeros(HP)
     b2p[:H] = b2
     small = np.concatenate([w1k.ravel(), b2p, b3rows]).astype(np.float32)
     pad = _pad256(lead_words + small.size) - lead_words - small.size
-    w2 = np.zeros((64, 64), dtype=np.float32)
+    w2 = np.zeros((HP, HP), dtype=np.float32)
     w2[:H, :H] = W2
-    w3 = np.zeros((NO3, 64), dtype=np.float32)
+    w3 = np.zeros((NO3, HP), dtype=np.float32)
     w3[:, :H] = W3rows
     return np.concatenate([small, np.zeros(pad, dtype=np.float32), umma_sw128_images(w2), umma_sw128_images(w3)])
 
@@ -513,18 +514,19 @@ def pack_spline_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
 
 
 def pack_coupling_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
-    """Tensor-core layout of an eval-mode affine coupling stack (hidden_dim <= 64, data_dim <= 8): per layer two
-    net blocks (s_net then b_net), each `lead (80 words: the layer header for s_net, zeros for b_net) | W1k | b2 | b3 |
-    pad | W2 hi/lo images | W3 hi/lo images`, conditioner BatchNorm folded into the Linears."""
+    """Tensor-core layout of an eval-mode affine coupling stack (hidden_dim <= 128, padded to 64 or 128; data_dim <= 8):
+    per layer two net blocks (s_net then b_net), each `lead (80 words: the layer header for s_net, zeros for b_net) |
+    W1k | b2 | b3 | pad | W2 hi/lo images | W3 hi/lo images`, conditioner BatchNorm folded into the Linears."""
     l0 = layers[0]
     D = l0.data_dim
     H = l0.s_net[0].out_features
     for l in layers:
         if l.data_dim != D or l.s_net[0].out_features != H:
             return None
-    if D > DMAX or H > 64 or l0.s_net[0].weight.dtype != torch.float32:
+    if D > DMAX or H > 128 or l0.s_net[0].weight.dtype != torch.float32:
         return None
-    nbw = L.lib().nf_coupling_stack_tc_block_words(D)
+    HP = 64 if H <= 64 else 128
+    nbw = L.lib().nf_coupling_stack_tc_block_words_hidden(D, H)
     if nbw < 0:
         return None
     W1S, NO3 = _w1s(D), 16
@@ -543,7 +545,7 @@ def pack_coupling_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
             b3rows = np.zeros(NO3)
             W3rows[:D] = _np(net[6].weight)
             b3rows[:D] = _np(net[6].bias)
-            blk = _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, LAYER_HDR)
+            blk = _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, LAYER_HDR, HP)
             words += [ld, blk]
     flat = np.concatenate(words).astype(np.float32)
     assert flat.size == HDR + 2 * len(layers) * nbw, (flat.size, nbw)

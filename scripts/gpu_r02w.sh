@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r02w}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_published.py -q -x -p no:cacheprovider --timeout=120 -s > gpurun_out/pytest_pub_$TAG.log 2>&1; echo "published tests rc=$?"; grep "published\]\|passed\|failed\|Error" gpurun_out/pytest_pub_$TAG.log | tail -30
+timeout 300 python -m pytest tests/test_gpu_published.py -q -p no:cacheprovider --timeout=120 -s > gpurun_out/pytest_pub_$TAG.log 2>&1; echo "published tests rc=$?"; grep "published\]\|passed\|failed\|Error" gpurun_out/pytest_pub_$TAG.log | tail -30
 timeout 300 python scripts/published_target.py --n 1048576 > gpurun_out/published_$TAG.jsonl 2> gpurun_out/published_$TAG.err; echo "rc=$?"
 timeout 300 python scripts/published_target.py --n 4000 --reps 20 >> gpurun_out/published_$TAG.jsonl 2>> gpurun_out/published_$TAG.err; echo "rc=$?"
 cat gpurun_out/published_$TAG.jsonl

@@ -35,21 +35,36 @@ def _perturbed(model, seed):
     return model.eval()
 
 
+@pytest.mark.parametrize("route", ["tc_stack", "gemm"])
 @pytest.mark.parametrize("bn_between", [False, True])
-def test_realnvp_hidden_128_large_batch_route(bn_between):
+@pytest.mark.parametrize("D,hidden,rows", [(2, 128, ROWS), (2, 128, 700), (3, 100, ROWS), (6, 96, 5000)])
+def test_realnvp_hidden_up_to_128(bn_between, route, D, hidden, rows, monkeypatch):
+    """route tc_stack: the 128-wide variant of the tcgen05 coupling stack kernel (one launch for the whole stack);
+    route gemm: what runs without it at large batch -- folded tensor-core GEMMs + streaming first / last layers."""
+    from nfb200 import flows as F
+    if route == "gemm":
+        if rows < F.WIDE_OVER_STACK_MIN_ROWS:
+            pytest.skip("the GEMM route starts at WIDE_OVER_STACK_MIN_ROWS")
+        monkeypatch.setattr(F, "USE_TENSOR_CORES", False)
     torch.manual_seed(0)
-    model = _perturbed(N.RealNVP(2, 10, 128, batch_norm_between_layers=bn_between), 1)
+    L = 10 if D == 2 else 4
+    model = _perturbed(N.RealNVP(D, L, hidden, batch_norm_between_layers=bn_between), 1)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
-    specs = [dict(kind="coupling")] * 10
+    specs = [dict(kind="coupling")] * L
     model.to(DEV)
-    x = torch.randn(ROWS, 2) * 1.5
-    assert not model.flow.flows[0].fusable(x.to(DEV))
+    x = torch.randn(rows, D) * 1.5
+    x[3, 0] = float("nan")
+    x[5, D - 1] = float("inf")
+    assert model.flow.flows[0].fusable(x.to(DEV)) == (route == "tc_stack")
+    launches = N._lib.launch_count()
     with torch.no_grad():
         for inverse in (False, True):
             ry, rld = O.flow_model(sd, "flow.", specs, x, inverse, bn_between=bn_between)
             y, ld = model.inverse(x.to(DEV)) if inverse else model.forward(x.to(DEV))
-            _compare(f"RealNVP(2,10,128) bn={bn_between} inv={inverse} z", y, ry, 1e-5, 1e-5)
-            _compare(f"RealNVP(2,10,128) bn={bn_between} inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+            _compare(f"RealNVP({D},{L},{hidden}) {route} bn={bn_between} inv={inverse} z", y, ry, 1e-5, 1e-5)
+            _compare(f"RealNVP({D},{L},{hidden}) {route} bn={bn_between} inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+    if route == "tc_stack":
+        assert N._lib.launch_count() - launches == 2, "one launch per direction expected"
 
 
 def test_spline_hidden_128_large_batch_route():
