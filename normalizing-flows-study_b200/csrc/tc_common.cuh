@@ -27,6 +27,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t ok;
     do {
+        // (a suspend-time hint on the try_wait makes no difference: profiles/r02z_mbar_hint_ab.txt)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     } while (!ok);
