@@ -370,14 +370,20 @@ static int stream_launch_g(const SplineStreamArgs& a, bool bwd, int inverse, cud
     const bool wide = (G == 32 && a.Dt > 32);
     const int nwc = 4;
     const size_t smem = (size_t)nwc * (bwd ? 3 : 2) * 32 * P * sizeof(float) + (size_t)nwc * 2 * sizeof(uint64_t);
-    const int per_sm = bwd ? 5 : 8;
     const int64_t nitems = cdiv(a.B, RPW);
     const int64_t ctas = cdiv(nitems, nwc);
-    const int grid = (int)(ctas < (int64_t)kNumSMs * per_sm ? ctas : (int64_t)kNumSMs * per_sm);
+    // persistent warps: exactly one wave of resident CTAs (registers: 8 / 5 per SM; shared memory: 7 / 4 with 10 bins --
+    // a grid of 8 / 5 per SM there ran a second, quarter-full wave: 57 % instead of 66 % of HBM at D = 16, K = 10)
 #define NF_SS(KERN, INV, MODE)                                                                                         \
     do {                                                                                                               \
         auto kern = KERN<KMAX, G, INV, MODE>;                                                                          \
-        if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        int per_sm = 0;                                                                                                \
+        NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * nwc, smem));                         \
+        if (per_sm < 1) return NF_ERR_UNSUPPORTED;                                                                     \
+        const int64_t cap = (int64_t)kNumSMs * per_sm;                                                                 \
+        const int grid = (int)(ctas < cap ? ctas : cap);                                                               \
         kern<<<grid, 32 * nwc, smem, st>>>(a);                                                                         \
     } while (0)
 #define NF_SS_DIR(KERN, MODE) do { if (inverse) NF_SS(KERN, true, MODE); else NF_SS(KERN, false, MODE); } while (0)
