@@ -19,6 +19,11 @@ BUILD = {
     "spline": lambda: N.RealNVPSpline(2, 8, 64),
     "maf": lambda: N.NormalizingFlowModel([N.MaskedAutoregressiveFlow(2, 64) for _ in range(6)]),
     "iaf": lambda: N.NormalizingFlowModel([N.InverseAutoregressiveFlow(2, 64) for _ in range(6)]),
+    # the reference's notebooks (1_Basics_Coupling_Flow, 2_Autoregressive_Flows, 4_Neural_Spline_Flows; plots/fig_gif.py)
+    "nb_realnvp256": lambda: N.RealNVP(2, 8, 256),
+    "nb_maf128": lambda: N.NormalizingFlowModel([N.MaskedAutoregressiveFlow(2, 128) for _ in range(8)]),
+    "nb_iaf128": lambda: N.NormalizingFlowModel([N.InverseAutoregressiveFlow(2, 128) for _ in range(8)]),
+    "nb_spline128": lambda: N.RealNVPSpline(2, 8, 128),
 }
 
 
@@ -29,7 +34,7 @@ def main():
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    for name in [k for k in BUILD if not a.only or k in a.only.split(",")]:
+    for name in [k for k in BUILD if (k in a.only.split(",") if a.only else not k.startswith("nb_"))]:
         torch.manual_seed(0)
         m = BUILD[name]()
         with torch.no_grad():
