@@ -145,6 +145,112 @@ skinny_n_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict
     }
 }
 
+// ---- float32, 128-bit versions of the two forward kernels ---------------------------------------------------------------
+// skinny_k above writes 16 bytes per thread between two dependent broadcast loads and skinny_n reads 4 bytes per lane and
+// iteration: 2.5 TB/s = 38 % of HBM on [2^20, 2] x [2, 256] and [2^20, 256] x [256, 2] (the first / last Linear of
+// RealNVP(2, 8, 256), profiles/r02ag_nb_realnvp256_launch_summary.txt).  Here a thread of the K <= 8 kernel owns FOUR
+// columns and EIGHT rows per pass (eight 128-bit stores per thread behind one round of row loads), and a lane of the
+// N <= 8 kernel reads 16 bytes per load with every load of its row slice in flight before the first FMA.
+template <int KS>
+__global__ void __launch_bounds__(256)
+skinny_k_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
+                     const float* __restrict__ bias, int64_t M, int N, int K, int64_t sam, int64_t sbk, int64_t sbn, int64_t ldc,
+                     int relu, int tx) {
+    extern __shared__ __align__(16) unsigned char skinny_smem[];
+    float* ws = reinterpret_cast<float*>(skinny_smem);           // [K][N] then bias [N]
+    float* bs = ws + (size_t)K * N;
+    for (int i = threadIdx.x; i < K * N; i += 256) { const int k = i / N, n = i - k * N; ws[i] = Bm[k * sbk + n * sbn]; }
+    for (int i = threadIdx.x; i < N; i += 256) bs[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    constexpr int R = 8;
+    const int ty = 256 / tx;                                     // tx: power of two >= min(N / 4, 256)
+    const int cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int N4 = N >> 2;
+    for (int64_t m0 = ((int64_t)blockIdx.x * ty + ry) * R; m0 < M; m0 += (int64_t)gridDim.x * ty * R) {
+        float a[R][KS];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int64_t m = (m0 + i < M) ? m0 + i : M - 1;    // rows beyond the end recompute the last row (not stored)
+#pragma unroll
+            for (int k = 0; k < KS; ++k) a[i][k] = (k < K) ? __ldg(A + m * sam + k) : 0.f;
+        }
+        for (int n4 = cx; n4 < N4; n4 += tx) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * n4);
+            float4 c[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) c[i] = b4;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) if (k < K) {
+                const float4 w = *reinterpret_cast<const float4*>(ws + (size_t)k * N + 4 * n4);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    c[i].x += a[i][k] * w.x; c[i].y += a[i][k] * w.y; c[i].z += a[i][k] * w.z; c[i].w += a[i][k] * w.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i) if (m0 + i < M) {
+                float4 v = c[i];
+                if (relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
+                *reinterpret_cast<float4*>(C + (m0 + i) * ldc + 4 * n4) = v;
+            }
+        }
+    }
+}
+
+// C[m, n < N <= NS] = act(A[m, :] . W[:, n] + bias[n]): 8 lanes per row, weights transposed in shared memory ([n][K], one
+// 128-bit broadcast-free read per lane and output), U 16-byte row loads in flight per lane
+template <int NS>
+__global__ void __launch_bounds__(256)
+skinny_n_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
+                     const float* __restrict__ bias, int64_t M, int N, int K, int64_t sam, int64_t sbk, int64_t sbn, int64_t ldc,
+                     int relu, int accumulate) {
+    extern __shared__ __align__(16) unsigned char skinny_smem[];
+    float* wt = reinterpret_cast<float*>(skinny_smem);           // [NS][K]
+    for (int i = threadIdx.x; i < NS * K; i += 256) { const int n = i / K, k = i - n * K; wt[i] = (n < N) ? Bm[k * sbk + n * sbn] : 0.f; }
+    __syncthreads();
+    constexpr int U = 4;
+    const int sub = threadIdx.x & 7;
+    const int K4 = K >> 2;
+    const int64_t rows_per_pass = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t m0 = (((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 3); m0 < M; m0 += rows_per_pass) {
+        const int64_t m = m0 + ((threadIdx.x & 31) >> 3);
+        float acc[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) acc[n] = 0.f;
+        if (m < M) {
+            const float4* ar = reinterpret_cast<const float4*>(A + m * sam);
+            for (int c0 = sub; c0 < K4; c0 += 8 * U) {
+                float4 av[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { const int c = c0 + 8 * u; av[u] = (c < K4) ? __ldcs(ar + c) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + 8 * u;
+                    if (c < K4) {
+#pragma unroll
+                        for (int n = 0; n < NS; ++n) {
+                            const float4 w = *reinterpret_cast<const float4*>(wt + (size_t)n * K + 4 * c);
+                            acc[n] += av[u].x * w.x; acc[n] += av[u].y * w.y; acc[n] += av[u].z * w.z; acc[n] += av[u].w * w.w;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) acc[n] = group_sum<float, 8>(acc[n]);
+        if (m < M && sub == 0) {
+#pragma unroll
+            for (int n = 0; n < NS; ++n) if (n < N) {
+                float v = acc[n] + (bias ? __ldg(bias + n) : 0.f);
+                float* cp = C + m * ldc + n;
+                if (accumulate) v += *cp;
+                if (relu) v = relu_nan(v);
+                *cp = v;
+            }
+        }
+    }
+}
+
 // column sums of a[rows, cols], cols <= CM: every thread walks whole rows with `cols` accumulators (a warp reads 32
 // consecutive rows = one contiguous run); block reduction, then atomics across blocks (out zeroed by the host)
 template <typename T, int CM>
@@ -222,6 +328,23 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
         return 1;
     }
     // (2) small reduction dimension, contiguous A rows: a thread per output column, 4 rows per pass
+    if constexpr (sizeof(T) == 4) {
+        if (K >= 1 && K <= 8 && sak == 1 && M >= 64 && !accumulate && (N % 4) == 0 && (ldc % 4) == 0 && aligned16(C) &&
+            (size_t)(K + 1) * N * sizeof(T) <= 40 * 1024) {
+            int tx = 1;
+            while (tx < N / 4 && tx < 256) tx <<= 1;
+            const int ty = 256 / tx;
+            int64_t g = cdiv(M, (int64_t)ty * 8 * 2), cap = (int64_t)kNumSMs * 8;
+            if (g < 1) g = 1;
+            const size_t smem = (size_t)(K + 1) * N * sizeof(T);
+            const int grid = (int)(g < cap ? g : cap);
+#define NF_SKV(KSv) skinny_k_vec4_kernel<KSv><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, (const float*)bias, \
+                                                                        M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, tx)
+            if (K <= 2) NF_SKV(2); else if (K <= 4) NF_SKV(4); else NF_SKV(8);
+#undef NF_SKV
+            return 1;
+        }
+    }
     if (K >= 1 && K <= 32 && sak == 1 && M >= 64 && (K <= 8 || (K % 4) != 0) && (size_t)(K + 1) * N * sizeof(T) <= 40 * 1024) {
         int tx = 1;
         while (tx < N && tx < 256) tx <<= 1;
@@ -237,6 +360,17 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
     if (N <= 8 && sak == 1 && M >= 64 && K >= 16) {
         int64_t g = cdiv(M * 8, 256), cap = (int64_t)kNumSMs * 16;
         const int grid = (int)(g < cap ? g : cap);
+        if constexpr (sizeof(T) == 4) {
+            if ((K % 4) == 0 && (sam % 4) == 0 && aligned16(A) && (size_t)8 * K * sizeof(T) <= 48 * 1024) {
+                const int NSv = N <= 2 ? 2 : (N <= 4 ? 4 : 8);
+                const size_t smem = (size_t)NSv * K * sizeof(T);
+#define NF_SNV(NS) skinny_n_vec4_kernel<NS><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, (const float*)bias, \
+                                                                      M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, accumulate)
+                if (N <= 2) NF_SNV(2); else if (N <= 4) NF_SNV(4); else NF_SNV(8);
+#undef NF_SNV
+                return 1;
+            }
+        }
 #define NF_SN(NS) skinny_n_kernel<T, NS><<<grid, 256, 0, st>>>((const T*)A, (const T*)Bm, (T*)C, (const T*)bias, M, (int)N, (int)K, \
                                                              sam, sbk, sbn, ldc, relu, accumulate)
         if (N <= 2) NF_SN(2); else if (N <= 4) NF_SN(4); else NF_SN(8);

@@ -293,8 +293,23 @@ def bench_spline_tf_ncu():
     print("spline_tf_ncu: done")
 
 
+def bench_skinny():
+    """first / last Linear of a 2-D conditioner (RealNVP(2, 8, 256), RealNVP(2, 10, 128), MADE(2, 64)): streaming kernels"""
+    for (B, H, D) in ((1 << 20, 256, 2), (1 << 20, 128, 2), (1 << 20, 64, 2)):
+        x = torch.randn(B, D, device=DEV)
+        h = torch.randn(B, H, device=DEV)
+        w1, b1 = torch.randn(H, D, device=DEV), torch.randn(H, device=DEV)
+        w3, b3 = torch.randn(2 * D, H, device=DEV), torch.randn(2 * D, device=DEV)
+        with torch.no_grad():
+            report(f"skinny first Linear [{B} x {D}] -> {H} (+bias, ReLU)", timeit(lambda: ops.linear_raw(x, w1, b1, relu=True)),
+                   B * 4 * (D + H))
+            report(f"skinny last Linear [{B} x {H}] -> {2 * D} (+bias)", timeit(lambda: ops.linear_raw(h, w3, b3)),
+                   B * 4 * (H + 2 * D))
+        del x, h
+
+
 ALL = {"peaks": bench_peaks, "rqs": bench_rqs, "spline_tf": bench_spline_tf, "affine": bench_affine, "bn": bench_bn, "gemm": bench_gemm,
-       "stacks": bench_stacks, "spline_tf_ncu": bench_spline_tf_ncu}
+       "stacks": bench_stacks, "skinny": bench_skinny, "spline_tf_ncu": bench_spline_tf_ncu}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -133,7 +133,7 @@ def test_col_sum_matches_float64(rows, cols):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,H,D", [(5000, 64, 2), (300, 64, 2), (70000, 128, 3), (4096, 40, 8), (1000, 16, 1), (30000, 64, 23),
-                                   (9000, 300, 29), (2000, 64, 17)])
+                                   (9000, 300, 29), (2000, 64, 17), (1001, 256, 2), (777, 128, 4), (67, 1024, 6), (4099, 100, 5)])
 def test_skinny_products_match_float64(B, H, D, dtype):
     """nf_gemm's skinny routes (one dimension <= 8): first / last Linear of a low-dimensional conditioner, forward,
     input gradient and weight gradient, against float64 products."""
