@@ -29,7 +29,27 @@ skinny_reduce_kernel(const T* __restrict__ Wd, const T* __restrict__ Sk, T* __re
     for (int j = 0; j < JW; ++j)
 #pragma unroll
         for (int s = 0; s < S; ++s) acc[j][s] = T(0);
-    for (int64_t r = r0 + warp; r < r1; r += 8) {
+    // four rows per warp in flight when the accumulators leave room (one row per iteration: 36 % of HBM on the
+    // [2^20, 64]^T x [2^20, 2] weight gradient of a 2-D conditioner's first Linear); same order of additions per row
+    constexpr int U = (JW * S <= 16) ? 4 : 1;
+    int64_t r = r0 + warp;
+    for (; r + (U - 1) * 8 < r1; r += U * 8) {
+        T sk[U][S], v[U][JW];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) sk[u][s] = (s < s_live) ? Sk[(r + u * 8) * lds + s] : T(0);
+#pragma unroll
+            for (int j = 0; j < JW; ++j) { const int c = c0 + lane + 32 * j; v[u][j] = (c < W) ? Wd[(r + u * 8) * ldw + c] : T(0); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < JW; ++j)
+#pragma unroll
+                for (int s = 0; s < S; ++s) acc[j][s] += v[u][j] * sk[u][s];
+    }
+    for (; r < r1; r += 8) {
         T sk[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) sk[s] = (s < s_live) ? Sk[r * lds + s] : T(0);
@@ -151,7 +171,7 @@ skinny_n_kernel(const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict
 // RealNVP(2, 8, 256), profiles/r02ag_nb_realnvp256_launch_summary.txt).  Here a thread of the K <= 8 kernel owns FOUR
 // columns and EIGHT rows per pass (eight 128-bit stores per thread behind one round of row loads), and a lane of the
 // N <= 8 kernel reads 16 bytes per load with every load of its row slice in flight before the first FMA.
-template <int KS>
+template <int KS, int R>
 __global__ void __launch_bounds__(256)
 skinny_k_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
                      const float* __restrict__ bias, int64_t M, int N, int K, int64_t sam, int64_t sbk, int64_t sbn, int64_t ldc,
@@ -162,7 +182,6 @@ skinny_k_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
     for (int i = threadIdx.x; i < K * N; i += 256) { const int k = i / N, n = i - k * N; ws[i] = Bm[k * sbk + n * sbn]; }
     for (int i = threadIdx.x; i < N; i += 256) bs[i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    constexpr int R = 8;
     const int ty = 256 / tx;                                     // tx: power of two >= min(N / 4, 256)
     const int cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
     const int N4 = N >> 2;
@@ -183,8 +202,11 @@ skinny_k_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
             for (int k = 0; k < KS; ++k) if (k < K) {
                 const float4 w = *reinterpret_cast<const float4*>(ws + (size_t)k * N + 4 * n4);
 #pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    c[i].x += a[i][k] * w.x; c[i].y += a[i][k] * w.y; c[i].z += a[i][k] * w.z; c[i].w += a[i][k] * w.w;
+                for (int i = 0; i < R; ++i) {                    // two packed FMAs per row and k (same operations)
+                    const float2 aa = make_float2(a[i][k], a[i][k]);
+                    const float2 lo = __ffma2_rn(aa, make_float2(w.x, w.y), make_float2(c[i].x, c[i].y));
+                    const float2 hi = __ffma2_rn(aa, make_float2(w.z, w.w), make_float2(c[i].z, c[i].w));
+                    c[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
                 }
             }
 #pragma unroll
@@ -192,6 +214,76 @@ skinny_k_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
                 float4 v = c[i];
                 if (relu) { v.x = relu_nan(v.x); v.y = relu_nan(v.y); v.z = relu_nan(v.z); v.w = relu_nan(v.w); }
                 *reinterpret_cast<float4*>(C + (m0 + i) * ldc + 4 * n4) = v;
+            }
+        }
+    }
+}
+
+// K in (8, 32] (the input gradient of a 23 / 29-wide spline head: dX[B, 64] = dY[B, 23] W): a thread owns ONE ROW -- its K
+// values sit in registers, the weights arrive as warp-uniform 128-bit broadcasts from shared memory, and the row leaves as
+// full 32-byte sectors.  (A thread per four columns needs 4 x K row values per thread: one CTA per SM with ~6 KB of loads
+// in flight, 20 % of HBM.)  Columns in blocks of NT.
+template <int KS, int NT>
+__global__ void __launch_bounds__(256, 2)
+skinny_k_rows_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
+                     const float* __restrict__ bias, int64_t M, int N, int K, int64_t sbk, int64_t sbn, int64_t ldc, int relu,
+                     int wide_st) {
+    extern __shared__ __align__(16) unsigned char skinny_smem[];
+    float* ws = reinterpret_cast<float*>(skinny_smem);           // [K][N], bias [N], then the CTA's 256 rows of A [256][K]
+    float* bs = ws + (size_t)K * N;
+    float* sA = bs + N;
+    for (int i = threadIdx.x; i < K * N; i += 256) { const int k = i / N, n = i - k * N; ws[i] = Bm[k * sbk + n * sbn]; }
+    for (int i = threadIdx.x; i < N; i += 256) bs[i] = bias ? bias[i] : 0.f;
+    for (int64_t m0 = (int64_t)blockIdx.x * 256; m0 < M; m0 += (int64_t)gridDim.x * 256) {
+        __syncthreads();                                         // weights staged / the previous rows are consumed
+        // the block's rows are one contiguous run of A (row pitch == K): coalesced copy, 128-bit when the run allows
+        const int nrow = (int)((M - m0) < 256 ? (M - m0) : 256);
+        const int nfl = nrow * K;
+        const float* src = A + m0 * K;
+        if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(nfl * 4)) & 15) == 0) {
+            for (int i = threadIdx.x * 4; i < nfl; i += 1024)
+                *reinterpret_cast<float4*>(sA + i) = __ldcs(reinterpret_cast<const float4*>(src + i));
+        } else {
+            for (int i = threadIdx.x; i < nfl; i += 256) sA[i] = __ldcs(src + i);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x >= nrow) continue;
+        float a[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) a[k] = (k < K) ? sA[threadIdx.x * K + k] : 0.f;     // pitch K: odd or not, <= 2-way
+        float* crow = C + (m0 + threadIdx.x) * ldc;
+        for (int n0 = 0; n0 < N; n0 += NT) {                     // N % NT == 0 (launcher)
+            float2 c[NT / 2];
+#pragma unroll
+            for (int j = 0; j < NT / 4; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + n0 + 4 * j);
+                c[2 * j] = make_float2(b4.x, b4.y); c[2 * j + 1] = make_float2(b4.z, b4.w);
+            }
+#pragma unroll
+            for (int k = 0; k < KS; ++k) if (k < K) {
+                const float2 aa = make_float2(a[k], a[k]);
+                const float* wr = ws + (size_t)k * N + n0;
+#pragma unroll
+                for (int j = 0; j < NT / 4; ++j) {
+                    const float4 w = *reinterpret_cast<const float4*>(wr + 4 * j);
+                    c[2 * j] = __ffma2_rn(aa, make_float2(w.x, w.y), c[2 * j]);
+                    c[2 * j + 1] = __ffma2_rn(aa, make_float2(w.z, w.w), c[2 * j + 1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NT / 8; ++j) {
+                float o[8] = {c[4 * j].x, c[4 * j].y, c[4 * j + 1].x, c[4 * j + 1].y, c[4 * j + 2].x, c[4 * j + 2].y, c[4 * j + 3].x, c[4 * j + 3].y};
+                if (relu) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] = relu_nan(o[q]);
+                }
+                if (wide_st) {                                   // one full 32-byte sector per store
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(crow + n0 + 8 * j), "f"(o[0]), "f"(o[1]),
+                                 "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+                } else {
+                    *reinterpret_cast<float4*>(crow + n0 + 8 * j) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(crow + n0 + 8 * j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                }
             }
         }
     }
@@ -329,18 +421,44 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
     }
     // (2) small reduction dimension, contiguous A rows: a thread per output column, 4 rows per pass
     if constexpr (sizeof(T) == 4) {
+        // K in (8, 32] (the 23 / 29-wide spline heads' input gradient): a row per thread
+        if (K > 8 && K <= 32 && sak == 1 && sam == K && M >= 256 && !accumulate && (N % 32) == 0 && (ldc % 4) == 0 && aligned16(C) &&
+            (size_t)((K + 1) * N + 256 * K) * sizeof(T) <= 96 * 1024) {
+            const size_t smem = (size_t)((K + 1) * N + 256 * K) * sizeof(T);
+            int64_t g = cdiv(M, 256);
+            const int64_t cap = (int64_t)kNumSMs * 2;
+            const int grid = (int)(g < cap ? g : cap);
+            const int wide_st = ((ldc % 8) == 0 && aligned32(C)) ? 1 : 0;
+#define NF_SKR(KSv)                                                                                                           \
+            do {                                                                                                              \
+                if (smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(skinny_k_rows_kernel<KSv, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                skinny_k_rows_kernel<KSv, 32><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, (const float*)bias, \
+                                                                        M, (int)N, (int)K, sbk, sbn, ldc, relu, wide_st);          \
+            } while (0)
+            if (K <= 16) NF_SKR(16); else if (K <= 24) NF_SKR(24); else NF_SKR(32);
+#undef NF_SKR
+            return 1;
+        }
+        // K <= 8: eight rows per thread, four columns
         if (K >= 1 && K <= 8 && sak == 1 && M >= 64 && !accumulate && (N % 4) == 0 && (ldc % 4) == 0 && aligned16(C) &&
             (size_t)(K + 1) * N * sizeof(T) <= 40 * 1024) {
             int tx = 1;
             while (tx < N / 4 && tx < 256) tx <<= 1;
             const int ty = 256 / tx;
-            int64_t g = cdiv(M, (int64_t)ty * 8 * 2), cap = (int64_t)kNumSMs * 8;
+            const int Rv = 8;
+            int64_t g = cdiv(M, (int64_t)ty * Rv * 2);
             if (g < 1) g = 1;
             const size_t smem = (size_t)(K + 1) * N * sizeof(T);
-            const int grid = (int)(g < cap ? g : cap);
-#define NF_SKV(KSv) skinny_k_vec4_kernel<KSv><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, (const float*)bias, \
-                                                                        M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, tx)
-            if (K <= 2) NF_SKV(2); else if (K <= 4) NF_SKV(4); else NF_SKV(8);
+            // one wave of resident CTAs
+#define NF_SKV(KSv, RRv)                                                                                                  \
+            do {                                                                                                          \
+                int per_sm = 0;                                                                                           \
+                NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, skinny_k_vec4_kernel<KSv, RRv>, 256, smem)); \
+                const int64_t cap = (int64_t)kNumSMs * (per_sm < 1 ? 1 : per_sm);                                          \
+                skinny_k_vec4_kernel<KSv, RRv><<<(int)(g < cap ? g : cap), 256, smem, st>>>(                               \
+                    (const float*)A, (const float*)Bm, (float*)C, (const float*)bias, M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, tx); \
+            } while (0)
+            if (K <= 2) NF_SKV(2, 8); else if (K <= 4) NF_SKV(4, 8); else NF_SKV(8, 8);
 #undef NF_SKV
             return 1;
         }

@@ -306,6 +306,16 @@ def bench_skinny():
             report(f"skinny last Linear [{B} x {H}] -> {2 * D} (+bias)", timeit(lambda: ops.linear_raw(h, w3, b3)),
                    B * 4 * (H + 2 * D))
         del x, h
+    # training-side skinny products of a 2-D spline / coupling conditioner (2^20 rows, hidden 64)
+    B, H = 1 << 20, 64
+    gy = torch.randn(B, 23, device=DEV)
+    w = torch.randn(23, H, device=DEV)
+    report(f"skinny input gradient of the spline head dX[{B} x {H}] = dY[. x 23] W", timeit(lambda: ops.gemm(gy, w, B, H, 23, 23, 1, H, 1)),
+           B * 4 * (23 + H))
+    g1, x2 = torch.randn(B, H, device=DEV), torch.randn(B, 2, device=DEV)
+    report(f"skinny weight gradient dW[{H} x 2] = dY[{B} x {H}]^T x", timeit(lambda: ops.gemm(g1, x2, H, 2, B, 1, H, 2, 1)),
+           B * 4 * (H + 2))
+    del gy, g1, x2
 
 
 ALL = {"peaks": bench_peaks, "rqs": bench_rqs, "spline_tf": bench_spline_tf, "affine": bench_affine, "bn": bench_bn, "gemm": bench_gemm,
