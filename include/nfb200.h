@@ -263,6 +263,15 @@ NF_API int64_t nf_coupling_stack_tc_block_words(int D);
 NF_API int64_t nf_coupling_stack_tc_block_words_hidden(int D, int H);
 /* words per layer block of that layout (-1 if the configuration is not supported) */
 NF_API int64_t nf_spline_stack_tc_block_words(int D, int K, int max_dt);
+/* eval-mode stack of MaskedAutoregressiveFlow / InverseAutoregressiveFlow layers on the tensor cores (hidden_dim <= 64,
+ * data_dim <= 8; masked_autoregressive_flow.py:18-78, inverse_autoregressive_flow.py:30-103 around made.py:81-140) in ONE
+ * launch: `packed` = magic 'NFM2', one block per layer of mask-folded weights (csrc/stack_tc.cu).  flags: the stack flag
+ * word (NF_STACK_INVERSE walks the layers backwards, NF_STACK_LOG_PROB_HEAD / NF_STACK_SKIP_Y as above); mode: the
+ * per-layer transform, NF_AR_MAF_INVERSE / NF_AR_IAF_FORWARD (parallel) for any data_dim, NF_AR_MAF_FORWARD /
+ * NF_AR_IAF_INVERSE (the sequential directions) for data_dim == 2 only. */
+NF_API int nf_made_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x, void* y,
+                             void* ld, int64_t B, int flags, int mode, nf_stream_t stream);
+NF_API int64_t nf_made_stack_tc_block_words(int D);
 
 /* ---- a8/a10 and the conditioner MLPs on the tensor cores: y[M,N] = relu?(x[M,K] * W[N,K]^T + bias) ---------
  * fp32 in / fp32 out, 3xTF32 on tcgen05 (fp32-accurate), TMA-fed, accumulators in TMEM (csrc/gemm_tc.cu).

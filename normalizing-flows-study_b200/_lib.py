@@ -74,6 +74,8 @@ _SIGNATURES = {
     "nf_coupling_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
     "nf_coupling_stack_tc_block_words": [_I],
     "nf_coupling_stack_tc_block_words_hidden": [_I, _I],
+    "nf_made_stack_tc_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _I, _P],
+    "nf_made_stack_tc_block_words": [_I],
     "nf_made_chain_bf16_forward": [_P] * 9 + [_P, _P, _P, _L, _I, _I, _I, _I, _P],
     "nf_batchnorm_forward_staged": [_P] * 9 + [_L, _I, _D, _D, _I, _I, _L, _I, _P],
     "nf_batchnorm_backward_staged": [_P] * 10 + [_L, _I, _I, _I, _L, _I, _P],
@@ -88,6 +90,7 @@ _RESTYPES = {
     "nf_ar_blocked_workspace_floats": _L,
     "nf_coupling_stack_tc_block_words": _L,
     "nf_coupling_stack_tc_block_words_hidden": _L,
+    "nf_made_stack_tc_block_words": _L,
     "nf_linear_wgrad_tc_workspace": _L,
 }
 

@@ -291,7 +291,7 @@ skinny_k_rows_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 
 // C[m, n < N <= NS] = act(A[m, :] . W[:, n] + bias[n]): 8 lanes per row, weights transposed in shared memory ([n][K], one
 // 128-bit broadcast-free read per lane and output), U 16-byte row loads in flight per lane
-template <int NS>
+template <int NS, int LPR>          // LPR lanes per row: 8, or 4 for short rows (K <= 64: keeps four loads per lane in flight)
 __global__ void __launch_bounds__(256)
 skinny_n_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
                      const float* __restrict__ bias, int64_t M, int N, int K, int64_t sam, int64_t sbk, int64_t sbn, int64_t ldc,
@@ -301,23 +301,24 @@ skinny_n_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
     for (int i = threadIdx.x; i < NS * K; i += 256) { const int n = i / K, k = i - n * K; wt[i] = (n < N) ? Bm[k * sbk + n * sbn] : 0.f; }
     __syncthreads();
     constexpr int U = 4;
-    const int sub = threadIdx.x & 7;
+    constexpr int SH = (LPR == 8) ? 3 : 2;
+    const int sub = threadIdx.x & (LPR - 1);
     const int K4 = K >> 2;
-    const int64_t rows_per_pass = ((int64_t)gridDim.x * blockDim.x) >> 3;
-    for (int64_t m0 = (((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 3); m0 < M; m0 += rows_per_pass) {
-        const int64_t m = m0 + ((threadIdx.x & 31) >> 3);
+    const int64_t rows_per_pass = ((int64_t)gridDim.x * blockDim.x) >> SH;
+    for (int64_t m0 = (((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> SH); m0 < M; m0 += rows_per_pass) {
+        const int64_t m = m0 + ((threadIdx.x & 31) >> SH);
         float acc[NS];
 #pragma unroll
         for (int n = 0; n < NS; ++n) acc[n] = 0.f;
         if (m < M) {
             const float4* ar = reinterpret_cast<const float4*>(A + m * sam);
-            for (int c0 = sub; c0 < K4; c0 += 8 * U) {
+            for (int c0 = sub; c0 < K4; c0 += LPR * U) {
                 float4 av[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { const int c = c0 + 8 * u; av[u] = (c < K4) ? __ldcs(ar + c) : make_float4(0.f, 0.f, 0.f, 0.f); }
+                for (int u = 0; u < U; ++u) { const int c = c0 + LPR * u; av[u] = (c < K4) ? __ldcs(ar + c) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int c = c0 + 8 * u;
+                    const int c = c0 + LPR * u;
                     if (c < K4) {
 #pragma unroll
                         for (int n = 0; n < NS; ++n) {
@@ -329,7 +330,7 @@ skinny_n_vec4_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
             }
         }
 #pragma unroll
-        for (int n = 0; n < NS; ++n) acc[n] = group_sum<float, 8>(acc[n]);
+        for (int n = 0; n < NS; ++n) acc[n] = group_sum<float, LPR>(acc[n]);
         if (m < M && sub == 0) {
 #pragma unroll
             for (int n = 0; n < NS; ++n) if (n < N) {
@@ -482,8 +483,15 @@ int skinny_gemm_try(const void* A, const void* Bm, void* C, const void* bias, in
             if ((K % 4) == 0 && (sam % 4) == 0 && aligned16(A) && (size_t)8 * K * sizeof(T) <= 48 * 1024) {
                 const int NSv = N <= 2 ? 2 : (N <= 4 ? 4 : 8);
                 const size_t smem = (size_t)NSv * K * sizeof(T);
-#define NF_SNV(NS) skinny_n_vec4_kernel<NS><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, (const float*)bias, \
-                                                                      M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, accumulate)
+                const int64_t g4 = cdiv(M * 4, 256);
+                const int grid4 = (int)(g4 < cap ? g4 : cap);
+#define NF_SNV(NS)                                                                                                            \
+                do {                                                                                                          \
+                    if (K <= 64) skinny_n_vec4_kernel<NS, 4><<<grid4, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C, \
+                                     (const float*)bias, M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, accumulate);             \
+                    else skinny_n_vec4_kernel<NS, 8><<<grid, 256, smem, st>>>((const float*)A, (const float*)Bm, (float*)C,     \
+                                     (const float*)bias, M, (int)N, (int)K, sam, sbk, sbn, ldc, relu, accumulate);             \
+                } while (0)
                 if (N <= 2) NF_SNV(2); else if (N <= 4) NF_SNV(4); else NF_SNV(8);
 #undef NF_SNV
                 return 1;

@@ -26,6 +26,7 @@
 #define NF_STACK_MAGIC_AFFINE 0x4e464131  /* 'NFA1' */
 #define NF_STACK_MAGIC_SPLINE_TC 0x4e465332  /* 'NFS2': tensor-core layout, see stack_tc.cu */
 #define NF_STACK_MAGIC_AFFINE_TC 0x4e464132  /* 'NFA2' */
+#define NF_STACK_MAGIC_MADE_TC 0x4e464d32    /* 'NFM2': MADE / MAF / IAF stack on the tensor cores, see stack_tc.cu */
 #define NF_STACK_HDR 16
 #define NF_LAYER_HDR 80
 #define NF_STACK_DMAX 8

@@ -829,6 +829,177 @@ coupling_stack_tc_kernel(const float* __restrict__ packed, const float* __restri
     if (warp == 0) tc::tmem_dealloc(tb, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// MADE / MAF / IAF stack (eval mode, hidden_dim <= 64, data_dim <= 8; masks and eval-mode BatchNorm folded at pack time)
+//   One block per layer: lead (80-word layer header) | W1k | b2 | b3 | b4[16] | pad | W2 hi/lo | W3 hi/lo | W4 hi/lo images
+//   (73 KB, single buffered: two CTAs per SM keep their 2 x 256 TMEM columns).  The conditioner of made.py:81-140 is
+//   in -> H (FP32 pipe, K = data_dim) -> H -> H (two 64 x 64 tensor-core layers through the same TMEM regions) -> 2 D
+//   (head, 16 columns: [mu_0.. | alpha_0..]).  PARALLEL modes (MAF.inverse, IAF.forward: masked_autoregressive_flow.py:
+//   18-44, inverse_autoregressive_flow.py:30-63): one conditioner pass on the row, then the affine transform of every
+//   dim.  SEQUENTIAL modes for data_dim == 2 (MAF.forward, IAF.inverse: :46-78 / :65-103): the reference's loop evaluates
+//   MADE twice; on zeros the outputs of dim 0 are exactly its output biases (their masked weight rows are all zero), so
+//   dim 0 comes from b4 and the ONE conditioner pass on (out_0, 0) yields dim 1 -- NaN / Inf in out_0 reaches dim 1
+//   through the dense layers as in the reference.  Per-layer scrubs and log-det clamps as nf_affine_ar_forward /
+//   nf_ar_finish_forward.  The reference's published 6 x MAF(2, 64) / 6 x IAF(2, 64) (plots/_common.py:165-167) are one
+//   launch per direction.
+// ------------------------------------------------------------------------------------------------
+struct MadeBlkOff { int w1k, b2, b3, b4, w2hi, w2lo, w3hi, w3lo, w4hi, w4lo, words; };
+__host__ __device__ inline MadeBlkOff made_blk_offsets(int W1S) {
+    MadeBlkOff o;
+    o.w1k = 0; o.b2 = 64 * W1S; o.b3 = o.b2 + 64; o.b4 = o.b3 + 64;
+    o.w2hi = pad256(NF_LAYER_HDR + o.b4 + 16) - NF_LAYER_HDR;
+    o.w2lo = o.w2hi + 4096; o.w3hi = o.w2lo + 4096; o.w3lo = o.w3hi + 4096; o.w4hi = o.w3lo + 4096; o.w4lo = o.w4hi + 16 * 64;
+    o.words = o.w4lo + 16 * 64;
+    return o;
+}
+
+template <int DM>
+__global__ void __launch_bounds__(kTcThreads, 2)
+made_stack_tc_kernel(const float* __restrict__ packed, const float* __restrict__ x, float* __restrict__ y,
+                     float* __restrict__ ld, int64_t B, int flags, int nsub, int mode) {
+    const int inverse = flags & NF_STACK_INVERSE;
+    extern __shared__ __align__(1024) float sbuf[];
+    const TcHdr hd = read_tc_hdr(packed);
+    const int D = hd.D, L = hd.L, W1S = hd.W1S, NBW = hd.blk_words;
+    float* sx = sbuf + (size_t)NBW;                              // [kTcSub][DM+1][128] row state
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sx + kTcSub * (DM + 1) * kTcThreads);
+    uint64_t& bar = bars[0];
+    uint64_t& wbar = bars[1];
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(bars + 2);
+    const MadeBlkOff off = made_blk_offsets(W1S);
+    const bool sequential = (mode == AR_MAF_FWD || mode == AR_IAF_INV);
+    const bool iaf = (mode == AR_IAF_FWD || mode == AR_IAF_INV);
+    const float lim = iaf ? 50.f : 100.f;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemCols);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_init(&wbar, 1); tc::fence_mbar_init(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tb = tmem_base_s;
+    const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0, wphase = 0u;
+
+    const int ROWS = kTcThreads * nsub;
+    const int64_t ntiles = (B + ROWS - 1) / ROWS;
+    const float* blocks = packed + NF_STACK_HDR;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int s = 0; s < nsub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+#pragma unroll
+            for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = (d < D && r < B) ? ld_stream(x + r * D + d) : 0.f;
+            sx[(s * (DM + 1) + DM) * kTcThreads + tid] = 0.f;
+        }
+        for (int li = 0; li < L; ++li) {
+            const int layer = inverse ? L - 1 - li : li;
+            tc::fence_proxy_async_smem();
+            __syncthreads();                                      // everyone is done with the previous layer's block
+            if (tid == 0) {
+                tc::mbar_arrive_expect_tx(&wbar, (uint32_t)NBW * 4u);
+                tc::bulk_g2s(sbuf, blocks + (size_t)layer * NBW, (uint32_t)NBW * 4u, &wbar);
+            }
+            tc::mbar_wait(&wbar, wphase); wphase ^= 1u;
+            const float* shdr = sbuf;
+            const float* nb = sbuf + NF_LAYER_HDR;
+            const int* meta = reinterpret_cast<const int*>(shdr + 16);
+            const bool bn_on = meta[2] != 0;
+            const uint32_t w2hi = tc::smem_u32(nb + off.w2hi), w2lo = tc::smem_u32(nb + off.w2lo);
+            const uint32_t w3hi = tc::smem_u32(nb + off.w3hi), w3lo = tc::smem_u32(nb + off.w3lo);
+            const uint32_t w4hi = tc::smem_u32(nb + off.w4hi), w4lo = tc::smem_u32(nb + off.w4lo);
+            const float* b4 = nb + off.b4;
+#pragma unroll 1
+            for (int s = 0; s < nsub; ++s) {
+                float xv[DM], tot;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xv[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                if (inverse && bn_on) bn_between_tc<DM>(shdr, D, true, xv, tot);
+                // conditioner input: the row itself (parallel), or (out_0, 0) with out_0 from the output biases (sequential, D == 2)
+                float xa[DM], c0 = 0.f, t0 = 0.f;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) xa[d] = (d < D) ? xv[d] : 0.f;
+                if (sequential) {
+                    affine_ar_elem<float>(mode, xv[0], b4[0], b4[D], c0, t0);
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) xa[d] = 0.f;
+                    xa[0] = c0;
+                }
+                layer1_to_tmem<DM, 64>(nb + off.w1k, W1S, xa, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w2hi, w2lo, 64u, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                hidden2_to_tmem<64>(nb + off.b2, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD2, kColAhi, kColAlo, w3hi, w3lo, 64u, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                hidden2_to_tmem<64>(nb + off.b3, lane_addr);
+                tc::wait_st();
+                tc::fence_before_sync();
+                __syncthreads();
+                if (warp == 0) { tc::fence_after_sync(); tc::warp_issue_gemm_k64_3xtf32(tb, kColD3, kColAhi, kColAlo, w4hi, w4lo, 16u, &bar); }
+                tc::mbar_wait(&bar, phase); phase ^= 1;
+                tc::fence_after_sync();
+                uint32_t p[16];
+                tc::tmem_ld16(lane_addr + kColD3, p);
+                tc::wait_ld();
+                tc::fence_before_sync();                          // D3 / A reads precede the next sub-tile's writes
+                float lsum = 0.f;
+                if (!sequential) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) {
+                        float mu = 0.f, al = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) { if (q == d) mu = __uint_as_float(p[q]) + b4[q]; if (q == D + d) al = __uint_as_float(p[q]) + b4[q]; }
+                        float o, t;
+                        affine_ar_elem<float>(mode, xv[d], mu, al, o, t);
+                        if (!is_finite(o)) o = iaf ? xv[d] : 0.f;
+                        xv[d] = o;
+                        lsum += t;
+                    }
+                } else {
+                    float mu = 0.f, al = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { if (q == 1) mu = __uint_as_float(p[q]) + b4[q]; if (q == D + 1) al = __uint_as_float(p[q]) + b4[q]; }
+                    float c1, t1;
+                    affine_ar_elem<float>(mode, xv[1], mu, al, c1, t1);
+                    lsum = t0 + t1;
+                    xv[0] = is_finite(c0) ? c0 : (iaf ? xv[0] : 0.f);
+                    xv[1] = is_finite(c1) ? c1 : (iaf ? xv[1] : 0.f);
+                }
+                tot += clamp_mm(scrub0(lsum), -lim, lim);
+                if (!inverse && bn_on) bn_between_tc<DM>(shdr, D, false, xv, tot);
+#pragma unroll
+                for (int d = 0; d < DM; ++d) sx[(s * (DM + 1) + d) * kTcThreads + tid] = xv[d];
+                sx[(s * (DM + 1) + DM) * kTcThreads + tid] = tot;
+            }
+        }
+        for (int s = 0; s < nsub; ++s) {
+            const int64_t r = tile * ROWS + s * kTcThreads + tid;
+            if (r < B) {
+                float zr[DM];
+#pragma unroll
+                for (int d = 0; d < DM; ++d) zr[d] = sx[(s * (DM + 1) + d) * kTcThreads + tid];
+                if (!(flags & NF_STACK_SKIP_Y)) {
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) if (d < D) st_stream(y + r * D + d, zr[d]);
+                }
+                const float tot = sx[(s * (DM + 1) + DM) * kTcThreads + tid];
+                st_stream(ld + r, (flags & NF_STACK_LOG_PROB_HEAD) ? nf_stack_row_head<DM>(zr, D, tot) : tot);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tb, kTmemCols);
+}
+
 }  // namespace nf
 
 using namespace nf;
@@ -962,6 +1133,50 @@ extern "C" int nf_coupling_stack_tc_forward(const void* packed, const void* hdr_
     if (HP == 64) { if (D <= 2) NF_CTC(2, 64); else if (D <= 3) NF_CTC(4, 64); else NF_CTC(8, 64); }
     else          { if (D <= 2) NF_CTC(2, 128); else if (D <= 3) NF_CTC(4, 128); else NF_CTC(8, 128); }
 #undef NF_CTC
+    count_launch();
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+}
+
+extern "C" int64_t nf_made_stack_tc_block_words(int D) {
+    if (D < 1 || D > NF_STACK_DMAX) return -1;
+    return NF_LAYER_HDR + made_blk_offsets(nf_stack_w1s(D)).words;           // words per layer block
+}
+
+extern "C" int nf_made_stack_tc_forward(const void* packed, const void* hdr_host, int64_t packed_bytes, const void* x,
+                                        void* y, void* ld, int64_t B, int flags, int mode, nf_stream_t stream) {
+    if (B < 0) return NF_ERR_BAD_SHAPE;
+    NF_REQ(hdr_host);
+    if (B == 0) return NF_OK;
+    NF_REQ(packed); NF_REQ(x); NF_REQ(ld);
+    if (!(flags & NF_STACK_SKIP_Y)) NF_REQ(y);
+    if (!aligned16(packed)) return NF_ERR_MISALIGNED;
+    const int32_t* h = (const int32_t*)hdr_host;
+    if (h[0] != NF_STACK_MAGIC_MADE_TC) return NF_ERR_BAD_SHAPE;
+    const int D = h[1], H = h[2], L = h[5], W1S = h[6], NBW = h[8];
+    if (D < 1 || D > NF_STACK_DMAX || H < 1 || H > 64 || L < 1) return NF_ERR_UNSUPPORTED;
+    if (mode < NF_AR_MAF_INVERSE || mode > NF_AR_IAF_INVERSE) return NF_ERR_UNSUPPORTED;
+    if ((mode == NF_AR_MAF_FORWARD || mode == NF_AR_IAF_INVERSE) && D != 2) return NF_ERR_UNSUPPORTED;   // sequential: 2-D only
+    if (W1S != nf_stack_w1s(D) || NBW != NF_LAYER_HDR + made_blk_offsets(W1S).words) return NF_ERR_BAD_SHAPE;
+    if (packed_bytes < (int64_t)sizeof(float) * (NF_STACK_HDR + (int64_t)L * NBW)) return NF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int DMh = D <= 2 ? 2 : (D <= 3 ? 4 : 8);
+    const size_t smem = sizeof(float) * ((size_t)NBW + (size_t)kTcSub * (DMh + 1) * kTcThreads + 8);
+    if (smem > 113 * 1024) return NF_ERR_UNSUPPORTED;             // two CTAs per SM
+    const int res_ctas = kNumSMs * 2;
+    int nsub = (int)cdiv(cdiv(B, kTcThreads), res_ctas);
+    nsub = nsub < 1 ? 1 : (nsub > kTcSub ? kTcSub : nsub);
+    const int64_t ntiles = cdiv(B, kTcThreads * nsub);
+    const int grid = (int)(ntiles < res_ctas ? ntiles : res_ctas);
+#define NF_MTC(DMv)                                                                                                  \
+    do {                                                                                                             \
+        auto kern = made_stack_tc_kernel<DMv>;                                                                       \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        kern<<<grid, kTcThreads, smem, st>>>((const float*)packed, (const float*)x, (float*)y, (float*)ld, B, flags, nsub, mode); \
+    } while (0)
+    if (D <= 2) NF_MTC(2); else if (D <= 3) NF_MTC(4); else NF_MTC(8);
+#undef NF_MTC
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;

@@ -749,6 +749,8 @@ class ChainPlan:
         if bns is not None and training:          # train mode moves the running statistics layer by layer
             return None
         kind = type(flows[0])
+        if kind in (MaskedAutoregressiveFlow, InverseAutoregressiveFlow):
+            return self._run_made_stack(flows, bns, v, inverse, head)
         if kind not in (CouplingLayer, SplineCouplingLayer) or any(type(f) is not kind for f in flows):
             return None
         if not all(f.fusable(v) for f in flows):
@@ -760,3 +762,31 @@ class ChainPlan:
         if kind is CouplingLayer:
             return run_coupling_stack(self._pack, tensors, flows, bns, v, inverse, head)
         return run_spline_stack(self._pack, tensors, flows, bns, v, inverse, head)
+
+    def _run_made_stack(self, flows, bns, v, inverse, head):
+        """Homogeneous MAF / IAF stack, hidden_dim <= 64, data_dim <= 8 (the sequential direction: data_dim == 2):
+        one tcgen05 launch (made_stack_tc_kernel).  None -> the layers run one by one."""
+        kind = type(flows[0])
+        if not USE_TENSOR_CORES or any(type(f) is not kind for f in flows) or v.dtype != torch.float32:
+            return None
+        f0 = flows[0]
+        D, H = f0.dim, f0.conditioner.hidden_dim
+        if D > packing.DMAX or H > 64 or v.shape[1] != D:
+            return None
+        if any(f.dim != D or f.conditioner.hidden_dim != H or (f.conditioner.use_batch_norm and f.training)
+               or f.conditioner.output_dim_multiplier != 2 for f in flows):
+            return None
+        parallel = (inverse == (kind is MaskedAutoregressiveFlow))      # MAF: density is the parallel pass; IAF: sampling
+        if not parallel and D != 2:
+            return None
+        if head and not inverse:
+            return None
+        mods = flows + (list(bns) if bns is not None else [])
+        tensors = self._pack.tensors_of(mods)
+        if torch.is_grad_enabled() and (v.requires_grad or any(t.requires_grad for t in tensors)):
+            return None
+        pk = self._pack.get(tensors, lambda: packing.pack_made_stack_tc(flows, bns), extra=("made_tc",))
+        if pk is None:
+            return None
+        mode = f0._mode_parallel if parallel else f0._mode_sequential
+        return ops.made_stack_tc(pk[0], pk[1], v, inverse, mode, head)

@@ -717,6 +717,17 @@ def coupling_stack_tc(packed, hdr_host, x, inverse, head=False):
     return (y, ld) if ok else None
 
 
+def made_stack_tc(packed, hdr_host, x, inverse, mode, head=False):
+    """Whole MAF / IAF stack in one tcgen05 launch (csrc/stack_tc.cu: made_stack_tc_kernel); None if unsupported."""
+    x = _c(x)
+    B, D = x.shape
+    y = None if head else torch.empty_like(x)
+    ld = torch.empty(B, dtype=x.dtype, device=x.device)
+    ok = L.try_call("nf_made_stack_tc_forward", ptr(packed), hdr_host.ctypes.data, packed.numel() * 4, ptr(x), ptr(y),
+                    ptr(ld), B, _stack_flags(inverse, head), mode, stream())
+    return (y, ld) if ok else None
+
+
 def coupling_stack(packed, hdr_host, x, inverse, head=False):
     x = _c(x)
     B, D = x.shape

@@ -20,6 +20,7 @@ MAGIC_SPLINE = 0x4E465331
 MAGIC_AFFINE = 0x4E464131
 MAGIC_SPLINE_TC = 0x4E465332
 MAGIC_AFFINE_TC = 0x4E464132
+MAGIC_MADE_TC = 0x4E464D32
 HDR, LAYER_HDR, DMAX = 16, 80, 8
 
 
@@ -459,6 +460,50 @@ def _tc_net_block(W1, b1, W2, b2, W3rows, b3rows, D, H, W1S, NO3, lead_words, HP
     w3 = np.zeros((NO3, HP), dtype=np.float32)
     w3[:, :H] = W3rows
     return np.concatenate([small, np.zeros(pad, dtype=np.float32), umma_sw128_images(w2), umma_sw128_images(w3)])
+
+
+def pack_made_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):
+    """Tensor-core layout of an eval-mode stack of MaskedAutoregressiveFlow / InverseAutoregressiveFlow layers (hidden_dim
+    <= 64, data_dim <= 8): per layer `lead (80-word header) | W1k | b2 | b3 | b4[16] | pad | W2 hi/lo | W3 hi/lo | W4 hi/lo`
+    from the mask-folded weights (packing.fold_made: eval-mode conditioner BatchNorm folded in; the degree sort of the
+    hidden units is a consistent permutation of rows / columns and changes nothing).  Head rows: [mu_0.. | alpha_0..]."""
+    l0 = layers[0]
+    D = l0.dim
+    folded = [l.conditioner.folded() for l in layers]
+    if any(f is None for f in folded):
+        return None
+    H = folded[0].H
+    if D > DMAX or H > 64 or any(f.D != D or f.H != H for f in folded) or folded[0].w[0].dtype != torch.float32:
+        return None
+    nbw = L.lib().nf_made_stack_tc_block_words(D)
+    if nbw < 0:
+        return None
+    W1S, NO = _w1s(D), 16
+    hdr = np.zeros(HDR, dtype=np.float32)
+    hdr.view(np.int32)[0:10] = [MAGIC_MADE_TC, D, H, 1, 0, len(layers), W1S, NO, nbw, int(bns is not None)]
+    words = [hdr]
+    for i, f in enumerate(folded):
+        bn = _bn_between_consts(bns[i]) if (bns is not None and i < len(layers) - 1) else None
+        lead = _layer_header(np.zeros(D, dtype=np.float32), [], None, bn)
+        W = [_np(t) for t in f.w]
+        b = [_np(t) for t in f.b]
+        w1k = np.zeros((64, W1S))
+        w1k[:H, :D] = W[0]
+        w1k[:H, W1S - 1] = b[0]
+        if W1S == 4:
+            w1k = w1k.reshape(32, 2, 4).transpose(0, 2, 1).reshape(64, 4)
+        b2p, b3p, b4p = np.zeros(64), np.zeros(64), np.zeros(NO)
+        b2p[:H], b3p[:H], b4p[:2 * D] = b[1], b[2], b[3]
+        small = np.concatenate([w1k.ravel(), b2p, b3p, b4p]).astype(np.float32)
+        pad = _pad256(LAYER_HDR + small.size) - LAYER_HDR - small.size
+        w2 = np.zeros((64, 64), dtype=np.float32); w2[:H, :H] = W[1]
+        w3 = np.zeros((64, 64), dtype=np.float32); w3[:H, :H] = W[2]
+        w4 = np.zeros((NO, 64), dtype=np.float32); w4[:2 * D, :H] = W[3]
+        words += [lead, small, np.zeros(pad, dtype=np.float32), umma_sw128_images(w2), umma_sw128_images(w3), umma_sw128_images(w4)]
+    flat = np.concatenate(words).astype(np.float32)
+    assert flat.size == HDR + len(layers) * nbw, (flat.size, nbw)
+    dev = folded[0].w[0].device
+    return torch.from_numpy(flat).to(dev), flat[:HDR].copy().view(np.int32)
 
 
 def pack_spline_stack_tc(layers, bns: Optional[List[torch.nn.BatchNorm1d]]):

@@ -107,3 +107,43 @@ def test_six_layer_autoregressive_2d_large_batch(kind, hidden):
             y, ld = model.inverse(x.to(DEV)) if inverse else model.forward(x.to(DEV))
             _compare(f"6 x {kind}(2,{hidden}) inv={inverse} z", y, ry, 1e-5, 1e-5)
             _compare(f"6 x {kind}(2,{hidden}) inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize("kind,D,H,L,bn_between,use_bn,rows", [
+    ("maf", 2, 64, 6, False, False, 4000), ("iaf", 2, 64, 6, True, False, 4000),      # published configs at the published n
+    ("maf", 3, 40, 3, False, False, 1500), ("iaf", 5, 64, 4, True, False, 20000),     # data_dim > 2: parallel direction only
+    ("maf", 8, 48, 2, False, True, 777), ("iaf", 2, 32, 5, False, True, 130),         # conditioner BatchNorm (eval), small H
+])
+def test_made_stack_tensor_core_kernel(kind, D, H, L, bn_between, use_bn, rows):
+    """Homogeneous MAF / IAF stacks through the containers: ONE made_stack_tc_kernel launch per direction (both directions
+    for data_dim == 2, the parallel one otherwise) against the CPU oracle, incl. NaN / Inf rows, between-layer BatchNorm,
+    eval-mode conditioner BatchNorm and the fused log-prob head."""
+    torch.manual_seed(0)
+    cls = N.MaskedAutoregressiveFlow if kind == "maf" else N.InverseAutoregressiveFlow
+    model = _perturbed(N.NormalizingFlowModel([cls(D, H, use_batch_norm=use_bn) for _ in range(L)],
+                                              batch_norm_between_layers=bn_between), 7)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    specs = [dict(kind=kind)] * L
+    model.to(DEV)
+    x = torch.randn(rows, D) * 1.5
+    x[3, 0] = float("nan")
+    x[5, D - 1] = float("inf")
+    x[7, 0] = -float("inf")
+    x[9, :] = 1e8
+    parallel_inverse = (kind == "maf")
+    with torch.no_grad():
+        for inverse in (False, True):
+            ry, rld = O.flow_model(sd, "", specs, x, inverse, bn_between=bn_between)
+            xd = x.to(DEV)
+            model.inverse(xd) if inverse else model.forward(xd)          # builds the pack (weight folding launches)
+            before = N._lib.launch_count()
+            y, ld = model.inverse(xd) if inverse else model.forward(xd)
+            launches = N._lib.launch_count() - before
+            if D == 2 or inverse == parallel_inverse:
+                assert launches == 1, f"{kind} D={D} inverse={inverse}: {launches} launches"
+            _compare(f"{L} x {kind}({D},{H}) bn={bn_between}/{use_bn} inv={inverse} z", y, ry, 1e-5, 1e-5)
+            _compare(f"{L} x {kind}({D},{H}) bn={bn_between}/{use_bn} inv={inverse} log_det", ld, rld, 1e-4, 1e-5)
+        # fused head: log N(z; 0, I) + log_det in the same launch, z not stored
+        rz, rld = O.flow_model(sd, "", specs, x, True, bn_between=bn_between)
+        lp = model.log_prob(x.to(DEV))
+        _compare(f"{L} x {kind}({D},{H}) log_prob", lp, O.std_normal_log_prob(rz) + rld, 2e-4, 1e-5)
