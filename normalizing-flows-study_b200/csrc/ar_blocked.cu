@@ -512,7 +512,377 @@ ar_block_warp_kernel(const float* __restrict__ vin, float* __restrict__ xcur, co
     }
 }
 
-int g_ar_block_variant = 1;          // nf_set_option(3, v): 0 = first in-block kernel (CTA barriers), 1 = warp-private tiles
+// ------------------------------------------------------------------------------------------------------------------
+// Third version of the in-block kernel: the dependent in-block steps on the tensor cores.
+//   The step of degree g multiplies a [rows x K] activation slice (K = the block's units of degree <= g: 8..80) into the
+//   8 or 9 units of that degree -- M x 8 x K products on a dependent chain.  tcgen05 wants M = 128 tiles, operands in
+//   shared memory / TMEM and an mbarrier round trip per dependent product; the register-level mma.sync.m16n8k8 (TF32,
+//   measured here at a 20-cycle dependent latency and 0.5 MMA / clk / SM, profiles/r02ap_mma_sync_probe.txt) takes the
+//   accumulator fragment straight back as the next epilogue's input, so this kernel uses it: a warp owns 32 rows (two
+//   m16 tiles) for the whole block, as in the second version, with no CTA barrier after the weight staging.
+//   * fp32 parity as everywhere else: 3xTF32 (a_lo b_hi + a_hi b_lo into a correction accumulator, a_hi b_hi into the main
+//     one; both operands split on the fly with cvt.rna, two ALU operations per element).
+//   * activation tiles are ROW-major [32][pitch], pitch = 4 (mod 8): the four k columns x eight rows of an A fragment
+//     load hit 32 different banks, fills / drains are 16-byte cp.async / stores of row-contiguous global segments.
+//   * every degree occupies whole 8-unit tiles in shared memory (a 9-unit degree: two tiles); dead slots hold zeros.  The
+//     weights are staged once per CTA as B fragments ([pair][lane] float2: the lane's two k rows of its n column), one
+//     LDS.64 per (k-tile, n-tile) pair and warp -- against one LDS.128 per four FMAs-per-lane in the FP32 version, which
+//     kept that kernel at the shared-memory wavefront limit (one per clock and SM) rather than at the FMA rate.
+//   * layer-3 units go straight to global memory (later blocks' pulls) and through a 2-tile scratch into the output
+//     layer's PUSH products, accumulated in C fragments (`par`: (mu, alpha) of the block's dims, 16 columns).
+//   * the affine step of dim g runs in the lane quad's owner of that column pair (lane % 4 == g % 4); NaN / Inf poison
+//     flags are shared over the quad with one shuffle per step; log-det terms are summed per owner lane and reduced over
+//     the quad in a fixed order at the end.  The MADE input of a step is x with zeros in the dims not yet produced (the
+//     reference's loop, masked_autoregressive_flow.py:46-78), so the noise v stays in registers and the x tile starts at 0.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMmaMaxTiles = 16;     // 8-unit tiles per block (8 degrees of <= 16 units)
+constexpr int kSxPitch = 12;         // x tile: 8 dims + 4
+constexpr int kH3Pitch = 20;         // layer-3 scratch: 2 tiles + 4
+
+// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the magnitude and clear the low 13
+// bits -- two integer operations; cvt.rna.tf32.f32 compiles to a ~6-instruction sequence on sm_100a and was a third of
+// this kernel's instruction stream), lo = x - hi exactly; the tensor core ignores lo's low 13 bits (<= 2^-21 |x|).
+__device__ __forceinline__ void split_tf32_reg(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct MmaBlockGeom { int NT, P; };
+// tiles / (k-tile, n-tile) pairs of the block [g0, g1): every degree takes ceil(count / 8) tiles; the n-tiles of degree g
+// see the k-tiles of all degrees <= g of the block
+static inline MmaBlockGeom mma_block_geom(const int32_t* gstart, int g0, int g1) {
+    MmaBlockGeom m{0, 0};
+    for (int g = g0; g < g1; ++g) {
+        const int ntl = (gstart[g + 1] - gstart[g] + 7) / 8;
+        m.NT += ntl;
+        m.P += ntl * m.NT;
+    }
+    return m;
+}
+
+// A fragments of the warp's m16 tiles from a row-major tile, split hi / lo: p0 = the lane's element (row rq, column q) of
+// m-tile 0 in the k-tile, p8 = 8 * pitch
+template <int MT>
+__device__ __forceinline__ void mma_load_a(const float* __restrict__ p0, int p8, uint32_t (&ah)[MT][4], uint32_t (&al)[MT][4]) {
+    float x[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const float* p = p0 + mt * 2 * p8;
+        x[mt][0] = p[0]; x[mt][1] = p[p8]; x[mt][2] = p[4]; x[mt][3] = p[p8 + 4];
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32_reg(x[mt][i], ah[mt][i], al[mt][i]);
+}
+// acc (main / correction) += A (k-tile) x B fragment, 3xTF32, both m16 tiles
+template <int MT>
+__device__ __forceinline__ void mma_step(float (&am)[MT][4], float (&ac)[MT][4], const uint32_t (&ah)[MT][4], const uint32_t (&al)[MT][4],
+                                         float2 b) {
+    uint32_t bh0, bl0, bh1, bl1;
+    split_tf32_reg(b.x, bh0, bl0);
+    split_tf32_reg(b.y, bh1, bl1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) mma_tf32_16x8x8(ac[mt], al[mt], bh0, bh1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) mma_tf32_16x8x8(am[mt], ah[mt], bh0, bh1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) mma_tf32_16x8x8(ac[mt], ah[mt], bl0, bl1);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(MT == 1 ? 512 : 256)
+ar_block_mma_kernel(const float* __restrict__ vin, float* __restrict__ xcur, const float* __restrict__ pre1,
+                    const float* __restrict__ pre2, const float* __restrict__ pre3, const float* __restrict__ preo,
+                    float* __restrict__ act1, float* __restrict__ act2, float* __restrict__ act3,
+                    const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                    const float* __restrict__ w3, const float* __restrict__ b3, const int32_t* __restrict__ gstart,
+                    float* __restrict__ ldacc, int* __restrict__ bad, int64_t B, int D, int H, int g0, int g1, int u0,
+                    int mode, int NT, int P) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int R = 16 * MT;                                   // rows per warp
+    const int nd = g1 - g0, NU8 = NT * 8, AP = NU8 + 4;
+    float2* Bf0 = reinterpret_cast<float2*>(sm);                 // [NT][32]       input layer: k-tile = the block's dims
+    float2* Bf1 = Bf0 + NT * 32;                                 // [P][32]        hidden -> hidden
+    float2* Bf2 = Bf1 + P * 32;                                  // [P][32]
+    float2* Bf3 = Bf2 + P * 32;                                  // [NT][2][32]    output layer: 16 columns (mu, alpha) x 8 dims
+    float* bs = reinterpret_cast<float*>(Bf3 + NT * 64);         // [3][NU8]       biases by shared-memory slot
+    float* b3s = bs + 3 * NU8;                                   // [16]
+    int* Tt = reinterpret_cast<int*>(b3s + 16);                  // [12]  first tile of the block's degree gi
+    int* kmax = Tt + 12;                                         // [16]  k-tiles an n-tile sees
+    int* pb = kmax + 16;                                         // [16]  first pair of an n-tile
+    int* gsl = pb + 16;                                          // [8]   first unit of degree gi, relative to u0
+    int* cnt = gsl + 8;                                          // [8]   units of degree gi (padded layout: multiple of 4)
+    int* gmap = cnt + 8;                                         // [NU8] global unit of a slot, -1 for dead slots
+    int* ctab = gmap + NU8;                                      // [NU8 / 2]  16-byte chunks of a tile row: (global column - u0, slot)
+    float* tiles = reinterpret_cast<float*>(ctab + NU8 / 2);
+    __shared__ int nch_s;
+    if (threadIdx.x == 0) {
+        int t = 0, nch = 0, pairs = 0;
+        for (int gi = 0; gi < nd; ++gi) {
+            const int gs = gstart[g0 + gi] - u0, c = gstart[g0 + gi + 1] - gstart[g0 + gi];
+            const int ntl = (c + 7) >> 3;
+            Tt[gi] = t; gsl[gi] = gs; cnt[gi] = c;
+            for (int j = 0; j < ntl; ++j) { kmax[t + j] = t + ntl; pb[t + j] = pairs; pairs += t + ntl; }
+            for (int s = 0; s < ntl * 8; ++s) gmap[t * 8 + s] = s < c ? u0 + gs + s : -1;
+            for (int c4 = 0; c4 < c; c4 += 4) { ctab[2 * nch] = gs + c4; ctab[2 * nch + 1] = t * 8 + c4; ++nch; }
+            t += ntl;
+        }
+        Tt[nd] = t;
+        nch_s = nch;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < NT * 32; idx += blockDim.x) {
+        const int nt = idx >> 5, l = idx & 31, n = gmap[nt * 8 + (l >> 2)], k0 = l & 3, k1 = k0 + 4;
+        Bf0[idx] = make_float2((n >= 0 && k0 < nd) ? w0[(size_t)n * D + g0 + k0] : 0.f, (n >= 0 && k1 < nd) ? w0[(size_t)n * D + g0 + k1] : 0.f);
+    }
+    for (int nt = 0; nt < NT; ++nt) {
+        const int base = pb[nt] * 32;
+        for (int i = threadIdx.x; i < kmax[nt] * 32; i += blockDim.x) {
+            const int kt = i >> 5, l = i & 31, n = gmap[nt * 8 + (l >> 2)], ka = gmap[kt * 8 + (l & 3)], kb = gmap[kt * 8 + (l & 3) + 4];
+            Bf1[base + i] = make_float2((n >= 0 && ka >= 0) ? w1[(size_t)n * H + ka] : 0.f, (n >= 0 && kb >= 0) ? w1[(size_t)n * H + kb] : 0.f);
+            Bf2[base + i] = make_float2((n >= 0 && ka >= 0) ? w2[(size_t)n * H + ka] : 0.f, (n >= 0 && kb >= 0) ? w2[(size_t)n * H + kb] : 0.f);
+        }
+    }
+    for (int idx = threadIdx.x; idx < NT * 64; idx += blockDim.x) {
+        const int kt = idx >> 6, n2 = (idx >> 5) & 1, l = idx & 31, col = n2 * 8 + (l >> 2), d = col >> 1, e = col & 1;
+        const int ka = gmap[kt * 8 + (l & 3)], kb = gmap[kt * 8 + (l & 3) + 4];
+        const float* wr = w3 + (size_t)(e * D + g0 + d) * H;
+        Bf3[idx] = make_float2((d < nd && ka >= 0) ? wr[ka] : 0.f, (d < nd && kb >= 0) ? wr[kb] : 0.f);
+    }
+    for (int s = threadIdx.x; s < NU8; s += blockDim.x) {
+        const int n = gmap[s];
+        bs[s] = n >= 0 ? b0[n] : 0.f; bs[NU8 + s] = n >= 0 ? b1[n] : 0.f; bs[2 * NU8 + s] = n >= 0 ? b2[n] : 0.f;
+    }
+    if (threadIdx.x < 16) {
+        const int d = threadIdx.x >> 1, e = threadIdx.x & 1;
+        b3s[threadIdx.x] = d < nd ? b3[e * D + g0 + d] : 0.f;
+    }
+    __syncthreads();                                 // tables and fragments staged; no CTA barrier below
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int q = lane & 3, rq = lane >> 2, nch = nch_s;
+    const bool first = (g0 == 0);
+    const int tile_floats = R * (kSxPitch + 2 * AP + kH3Pitch);
+    float* sx = tiles + (size_t)warp * tile_floats;
+    float* a1 = sx + R * kSxPitch;
+    float* a2 = a1 + R * AP;
+    float* h3s = a2 + R * AP;
+    // the lane's A-fragment origins (row rq, column q) in both m16 tiles of each tile array
+    const float* sx0 = sx + rq * kSxPitch + q;
+    const float* a10 = a1 + rq * AP + q;
+    const float* a20 = a2 + rq * AP + q;
+    const float* h30 = h3s + rq * kH3Pitch + q;
+    // 16-byte chunk of a tile row this lane moves in the fills / drains (a row has nch <= 32 chunks)
+    const bool has_chunk = lane < nch;
+    const int gc = has_chunk ? ctab[2 * lane] : 0, sc = has_chunk ? ctab[2 * lane + 1] : 0;
+    const int64_t ntiles = (B + R - 1) / R;
+    for (int64_t tile = (int64_t)blockIdx.x * nwarps + warp; tile < ntiles; tile += (int64_t)gridDim.x * nwarps) {
+        const int64_t r0 = tile * R;
+        const int nrow = (int)((B - r0) < R ? (B - r0) : R);
+        // ---- fill: x tile zeroed, pre1 / pre2 slices of the block's units by 16-byte cp.async (zeros without a previous block)
+        for (int i = lane; i < R * kSxPitch / 4; i += 32) reinterpret_cast<float4*>(sx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!pre1 || nrow < R) for (int i = lane; i < R * AP / 4; i += 32) reinterpret_cast<float4*>(a1)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!pre2 || nrow < R) for (int i = lane; i < R * AP / 4; i += 32) reinterpret_cast<float4*>(a2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        if (has_chunk && (pre1 || pre2)) {
+            const int64_t gofs = r0 * (int64_t)H + u0 + gc;
+            const unsigned s1 = static_cast<unsigned>(__cvta_generic_to_shared(a1 + sc)), s2 = static_cast<unsigned>(__cvta_generic_to_shared(a2 + sc));
+            const float* g1p = pre1 ? pre1 + gofs : nullptr;
+            const float* g2p = pre2 ? pre2 + gofs : nullptr;
+#pragma unroll 4
+            for (int r = 0; r < nrow; ++r) {
+                if (g1p) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s1 + 4u * (unsigned)(r * AP)), "l"(g1p + (int64_t)r * H));
+                if (g2p) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s2 + 4u * (unsigned)(r * AP)), "l"(g2p + (int64_t)r * H));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        // ---- per-lane row state: rows mt * 16 + rq + 8 * h; the quad's lane q owns dims q and q + 4 of the block
+        float vreg[MT][2][2], par[MT][2][4], ldv[MT][2];
+        int pois[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = mt * 16 + rq + 8 * h;
+                const bool ok = r < nrow;
+                const float* vr = vin + (r0 + r) * (int64_t)D + g0;
+                vreg[mt][h][0] = (ok && q < nd) ? vr[q] : 0.f;
+                vreg[mt][h][1] = (ok && q + 4 < nd) ? vr[q + 4] : 0.f;
+                const float* prow = preo + (r0 + r) * 2 * (int64_t)D + 2 * g0;
+#pragma unroll
+                for (int n2 = 0; n2 < 2; ++n2) {
+                    const float2 pv = (preo && ok && n2 * 4 + q < nd) ? *reinterpret_cast<const float2*>(prow + 2 * (n2 * 4 + q)) : make_float2(0.f, 0.f);
+                    par[mt][n2][2 * h] = pv.x; par[mt][n2][2 * h + 1] = pv.y;
+                }
+                ldv[mt][h] = (!first && ok && q == 0) ? ldacc[r0 + r] : 0.f;
+                pois[mt][h] = (!first && ok) ? bad[r0 + r] : 0;
+            }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+
+        for (int g = g0; g < g1; ++g) {
+            const int gi = g - g0;
+            // (A) dim g: parameters = bias + previous blocks (preo) + pushes of the in-block layer-3 units of lower degree
+            {
+                const bool owner = (q == (gi & 3));
+                const float bmu = b3s[2 * gi], bal = b3s[2 * gi + 1];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float pm = (gi & 4) ? par[mt][1][2 * h] : par[mt][0][2 * h];
+                        const float pa = (gi & 4) ? par[mt][1][2 * h + 1] : par[mt][0][2 * h + 1];
+                        const float xv = (gi & 4) ? vreg[mt][h][1] : vreg[mt][h][0];
+                        float o, t;
+                        affine_ar_elem<float>(mode, xv, bmu + pm, bal + pa, o, t);
+                        if (pois[mt][h]) { o = __int_as_float(0x7fc00000); t = o; }
+                        int nb = is_finite(o) ? 0 : 1;
+                        nb = __shfl_sync(0xffffffffu, nb, (lane & ~3) | (gi & 3));
+                        if (owner) { sx[(mt * 16 + rq + 8 * h) * kSxPitch + gi] = o; ldv[mt][h] += t; }
+                        pois[mt][h] |= nb;           // 0 * NaN of the dense reference poisons every later dim
+                    }
+            }
+            if (g == D - 1) break;
+            __syncwarp();
+            const int t0 = Tt[gi], t1 = Tt[gi + 1], cg = cnt[gi];
+            uint32_t ah[MT][4], al[MT][4];
+            // previous blocks' share of this degree's layer-3 pre-activations: requested now, used two layers later (in the
+            // layer-3 loop the load sat on the critical path of every step: 6 % of the stall samples, profiles/r02as)
+            float2 pv3[2][MT][2];
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = mt * 16 + rq + 8 * h, j = tt * 8 + 2 * q;
+                        pv3[tt][mt][h] = (pre3 && (tt == 0 || t1 - t0 > 1) && j < cg && r < nrow) ? *reinterpret_cast<const float2*>(pre3 + (r0 + r) * (int64_t)H + u0 + gsl[gi] + j)
+                                                                       : make_float2(0.f, 0.f);
+                    }
+            // (B) hidden units of degree g, layer by layer
+            for (int nt = t0; nt < t1; ++nt) {               // layer 1: one k-tile (the block's dims; later dims are still zero)
+                float am[MT][4] = {}, ac[MT][4] = {};
+                mma_load_a<MT>(sx0, 8 * kSxPitch, ah, al);
+                mma_step<MT>(am, ac, ah, al, Bf0[nt * 32 + lane]);
+                const int j = (nt - t0) * 8 + 2 * q;
+                const bool live = j < cg;
+                const float2 bb = *reinterpret_cast<const float2*>(bs + nt * 8 + 2 * q);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float2* dst = reinterpret_cast<float2*>(a1 + (mt * 16 + rq + 8 * h) * AP + nt * 8 + 2 * q);
+                        const float2 pv = *dst;
+                        *dst = live ? make_float2(relu_nan(pv.x + bb.x + (am[mt][2 * h] + ac[mt][2 * h])),
+                                                  relu_nan(pv.y + bb.y + (am[mt][2 * h + 1] + ac[mt][2 * h + 1]))) : make_float2(0.f, 0.f);
+                    }
+            }
+            __syncwarp();
+            for (int nt = t0; nt < t1; ++nt) {               // layer 2
+                float am[MT][4] = {}, ac[MT][4] = {};
+                const float2* bp = Bf1 + pb[nt] * 32 + lane;
+                const int nk = kmax[nt];
+                for (int kt = 0; kt < nk; ++kt) {
+                    mma_load_a<MT>(a10 + kt * 8, 8 * AP, ah, al);
+                    mma_step<MT>(am, ac, ah, al, bp[kt * 32]);
+                }
+                const int j = (nt - t0) * 8 + 2 * q;
+                const bool live = j < cg;
+                const float2 bb = *reinterpret_cast<const float2*>(bs + NU8 + nt * 8 + 2 * q);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float2* dst = reinterpret_cast<float2*>(a2 + (mt * 16 + rq + 8 * h) * AP + nt * 8 + 2 * q);
+                        const float2 pv = *dst;
+                        *dst = live ? make_float2(relu_nan(pv.x + bb.x + (am[mt][2 * h] + ac[mt][2 * h])),
+                                                  relu_nan(pv.y + bb.y + (am[mt][2 * h + 1] + ac[mt][2 * h + 1]))) : make_float2(0.f, 0.f);
+                    }
+            }
+            __syncwarp();
+            for (int nt = t0; nt < t1; ++nt) {               // layer 3: to global memory and the push scratch, never to a tile
+                const int j = (nt - t0) * 8 + 2 * q;
+                const bool live = j < cg;
+                float am[MT][4] = {}, ac[MT][4] = {};
+                const float2* bp = Bf2 + pb[nt] * 32 + lane;
+                const int nk = kmax[nt];
+                for (int kt = 0; kt < nk; ++kt) {
+                    mma_load_a<MT>(a20 + kt * 8, 8 * AP, ah, al);
+                    mma_step<MT>(am, ac, ah, al, bp[kt * 32]);
+                }
+                const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * NU8 + nt * 8 + 2 * q);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = mt * 16 + rq + 8 * h;
+                        const float2 pvv = (nt == t0) ? pv3[0][mt][h] : pv3[1][mt][h];
+                        const float2 hv = live ? make_float2(relu_nan(pvv.x + bb.x + (am[mt][2 * h] + ac[mt][2 * h])),
+                                                             relu_nan(pvv.y + bb.y + (am[mt][2 * h + 1] + ac[mt][2 * h + 1]))) : make_float2(0.f, 0.f);
+                        *reinterpret_cast<float2*>(h3s + r * kH3Pitch + j) = hv;
+                        if (g1 < D && live && r < nrow) *reinterpret_cast<float2*>(act3 + (r0 + r) * (int64_t)H + u0 + gsl[gi] + j) = hv;
+                    }
+            }
+            __syncwarp();
+            if (gi + 1 < nd) {                               // push into the parameters of the block's later dims
+                for (int kt = 0; kt < t1 - t0; ++kt) {
+                    mma_load_a<MT>(h30 + kt * 8, 8 * kH3Pitch, ah, al);
+#pragma unroll
+                    for (int n2 = 0; n2 < 2; ++n2) {
+                        if (n2 * 4 + 3 <= gi || n2 * 4 >= nd) continue;          // all four dims of this half are done / beyond the block
+                        const float2 b = Bf3[((t0 + kt) * 2 + n2) * 32 + lane];
+                        uint32_t bh0, bl0, bh1, bl1;
+                        split_tf32_reg(b.x, bh0, bl0);
+                        split_tf32_reg(b.y, bh1, bl1);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            mma_tf32_16x8x8(par[mt][n2], al[mt], bh0, bh1);
+                            mma_tf32_16x8x8(par[mt][n2], ah[mt], bl0, bl1);
+                            mma_tf32_16x8x8(par[mt][n2], ah[mt], bh0, bh1);
+                        }
+                    }
+                }
+                __syncwarp();                                // the scratch is rewritten by the next step's layer 3
+            }
+        }
+        __syncwarp();
+        // ---- drain: x, layer-1 / layer-2 activations (for the later blocks' pulls), log-det sums and poison flags
+        if (lane < nrow)
+            for (int c = 0; c < nd; c += 4)
+                *reinterpret_cast<float4*>(xcur + (r0 + lane) * (int64_t)D + g0 + c) = *reinterpret_cast<const float4*>(sx + lane * kSxPitch + c);
+        if (g1 < D && has_chunk) {
+            float* d1 = act1 + r0 * (int64_t)H + u0 + gc;
+            float* d2 = act2 + r0 * (int64_t)H + u0 + gc;
+#pragma unroll 4
+            for (int r = 0; r < nrow; ++r) {
+                *reinterpret_cast<float4*>(d1 + (int64_t)r * H) = *reinterpret_cast<const float4*>(a1 + r * AP + sc);
+                *reinterpret_cast<float4*>(d2 + (int64_t)r * H) = *reinterpret_cast<const float4*>(a2 + r * AP + sc);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float s = ldv[mt][h];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const int r = mt * 16 + rq + 8 * h;
+                if (q == 0 && r < nrow) { ldacc[r0 + r] = s; bad[r0 + r] = pois[mt][h]; }
+            }
+        __syncwarp();                                // the drain's reads of the tiles are done before the next fill lands
+    }
+}
+
+int g_ar_block_variant = 3;          // nf_set_option(3, v): 0 = first in-block kernel (CTA barriers), 1 = warp-private tiles (FP32 pipe),
+                                     // 2 / 3 = tensor-core in-block steps (mma.sync 3xTF32) with 32 / 16 rows per warp; they fall back
+                                     // to 1 where the layout does not allow them.  Measured at C3: 4.97 / 4.65 / 4.39 ms per pass (1 / 2 / 3)
 
 }  // namespace nf
 
@@ -576,7 +946,40 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
         const bool hp = prev && u0 > 0;
         const bool have_preo = pushed;               // some earlier block pushed into preo (it covers every later dim)
         bool launched = false;
-        {
+        if (g_ar_block_variant >= 2 && nu > 0 && nd <= kBlkMaxDeg && (nd % 4) == 0) {
+            // tensor-core variant (mma.sync): every degree of the block 4-aligned (per-degree padded layout) and <= 16 units
+            bool ok = true;
+            for (int g = g0; g < g1; ++g)
+                if ((gstart_host[g] % 4) != 0 || gstart_host[g + 1] - gstart_host[g] > 16) ok = false;
+            const MmaBlockGeom mg = mma_block_geom(gstart_host, g0, g1);
+            const int NU8 = mg.NT * 8, AP = NU8 + 4;
+            const size_t wfl = (size_t)mg.NT * 64 + 2 * (size_t)mg.P * 64 + (size_t)mg.NT * 128 + 3 * (size_t)NU8 + 16 + 60 + NU8 + NU8 / 2;
+            const int MT = g_ar_block_variant == 3 ? 1 : 2;                             // m16 tiles (16 rows) per warp
+            const int R = 16 * MT, maxw = MT == 1 ? 16 : 8;
+            const size_t tfl = (size_t)R * (size_t)(kSxPitch + 2 * AP + kH3Pitch);
+            int nw = (ok && mg.NT >= 1 && mg.NT <= kMmaMaxTiles && wfl * sizeof(float) < 180 * 1024)
+                         ? (int)((226 * 1024 / sizeof(float) - wfl) / tfl) : 0;
+            if (nw > maxw) nw = maxw;
+            if (nw >= 2) {
+                const size_t smem2 = sizeof(float) * (wfl + (size_t)nw * tfl);
+                const int64_t ctas = cdiv(cdiv(B, (int64_t)R), (int64_t)nw);
+                const int grid2 = (int)(ctas < kNumSMs ? ctas : kNumSMs);              // persistent: one CTA per SM
+#define NF_ABM(MTV)                                                                                                           \
+                do {                                                                                                          \
+                    NF_CUDA(cudaFuncSetAttribute(ar_block_mma_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+                    ar_block_mma_kernel<MTV><<<grid2, 32 * nw, smem2, st>>>(                                                   \
+                        (const float*)v, xcur, prev ? pre1 : nullptr, hp ? pre2 : nullptr, hp ? pre3 : nullptr,                \
+                        have_preo ? preo : nullptr, act1, act2, act3, w0, (const float*)b[0], w1, (const float*)b[1], w2,      \
+                        (const float*)b[2], w3, (const float*)b[3], gstart_dev, ldacc, bad, B, D, H, g0, g1, u0, mode, mg.NT, mg.P); \
+                } while (0)
+                if (MT == 1) NF_ABM(1); else NF_ABM(2);
+#undef NF_ABM
+                count_launch();
+                NF_LAUNCH_CHECK();
+                launched = true;
+            }
+        }
+        if (!launched) {
             // warp-private variant: shared transposed weights + one tile per warp; as many warps as fit in 220 KB
             const int need = ((nu + 3) & ~3) + 4 * kWarpChunks;
             const int nup = need <= 48 ? 48 : (need <= 80 ? 80 : (need <= 96 ? 96 : 160));   // compile-time pitches of ar_block_warp_kernel
@@ -584,7 +987,7 @@ extern "C" int nf_ar_blocked_forward(const void* v, const void* const* w, const 
             const size_t tfl = (size_t)(nd + 2 * nu) * kBlkPad;
             int nw = wfl * sizeof(float) < 200 * 1024 ? (int)((220 * 1024 / sizeof(float) - wfl) / tfl) : 0;
             if (nw > 8) nw = 8;
-            if (g_ar_block_variant == 1 && nw >= 2 && need <= 160 && nd <= kBlkMaxDeg && (nd % 4) == 0) {
+            if (g_ar_block_variant >= 1 && nw >= 2 && need <= 160 && nd <= kBlkMaxDeg && (nd % 4) == 0) {
                 const size_t smem2 = sizeof(float) * (wfl + (size_t)nw * tfl);
                 const int64_t ctas = cdiv(cdiv(B, (int64_t)kBlkRows), (int64_t)nw);
                 const int grid2 = (int)(ctas < kNumSMs ? ctas : kNumSMs);              // persistent: one CTA per SM

@@ -1192,7 +1192,7 @@ namespace nf { int g_wgrad_max_kb = 64; extern int g_ar_block_variant; extern in
 extern "C" int nf_set_option(int key, int value) {
     if (key == 1) { nf::g_tc_two_warpgroups = value != 0; return NF_OK; }
     if (key == 2) { if (value < 1) return NF_ERR_BAD_SHAPE; nf::g_wgrad_max_kb = value; return NF_OK; }
-    if (key == 3) { nf::g_ar_block_variant = value != 0; return NF_OK; }
+    if (key == 3) { if (value < 0 || value > 3) return NF_ERR_UNSUPPORTED; nf::g_ar_block_variant = value; return NF_OK; }
     if (key == 5) { nf::g_gemm_tc_variant = value != 0; return NF_OK; }
     if (key == 6) { nf::g_gemm_tc_small_k = value != 0; return NF_OK; }
     if (key == 10) { nf::g_gemm_tc2_ss = value != 0; return NF_OK; }

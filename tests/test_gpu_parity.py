@@ -357,6 +357,17 @@ def test_blocked_sequential_direction_matches_oracle(kind, D, H, B):
         y64, ld64 = (O.maf_forward(sd64, "", v.double())) if kind == "maf" else O.iaf_inverse(sd64, "", v.double())
         _within(blocked[0].cpu(), ref_y, y64, Z_ATOL, Z_RTOL, f"blocked {kind} z")
         _within(blocked[1].cpu(), ref_ld, ld64, LD_ATOL, LD_RTOL, f"blocked {kind} ld")
+        # the in-block kernel's other variants (nf_set_option(3, v): 1 = FP32 pipe, 2 = mma.sync with 32 rows per warp;
+        # the default, 3, is mma.sync with 16 rows per warp) compute the same recurrence
+        try:
+            for variant in (1, 2):
+                assert N._lib.lib().nf_set_option(3, variant) == 0
+                alt = N.ops.ar_sequential_blocked(v.to(_dev()), folded, mode)
+                _within(alt[0].cpu(), ref_y, y64, Z_ATOL, Z_RTOL, f"blocked {kind} z, in-block variant {variant}")
+                _within(alt[1].cpu(), ref_ld, ld64, LD_ATOL, LD_RTOL, f"blocked {kind} ld, in-block variant {variant}")
+                assert torch.equal(torch.isnan(alt[0]), torch.isnan(blocked[0]))
+        finally:
+            assert N._lib.lib().nf_set_option(3, 3) == 0
         # module entry point takes the blocked route at this size
         before = N._lib.launch_count()
         y2, ld2 = m.forward(v.to(_dev())) if kind == "maf" else m.inverse(v.to(_dev()))
