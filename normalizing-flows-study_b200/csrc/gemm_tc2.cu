@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(DIRECT ? k2ThreadsDirect : k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_wh,
                 const __grid_constant__ CUtensorMap tm_wl, float* __restrict__ Y, const float* __restrict__ bias,
                 int M, int N, int K, int64_t ldc, int relu, const int32_t* __restrict__ k_extent,
-                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec, int ss, int accumulate) {
+                const int32_t* __restrict__ k_begin, int num_tiles, int passes, int vec, int ss, int accumulate, int w_box_rows) {
     // accumulate (DIRECT + vec only, checked on the host): Y += X W^T instead of Y = ... (the blocked sampler's push of a
     // finished block of layer-3 units into the output-layer pre-activations of all later dims)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -137,6 +137,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             // stage index / round parity kept incrementally (n_stages is a run-time value: no div / mod per K block)
+            // narrow outputs (N < 128, one column tile): the W boxes hold only the live rows (w_box_rows), see gemm_tc2_launch
+            const uint32_t tx_bytes = k2XBytes + (passes == 1 ? 1u : 2u) * (uint32_t)w_box_rows * (k2BK * 4);
             int s = 0;
             uint32_t ph = 0;
             bool first_round = true;
@@ -148,7 +150,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (!first_round) tc::mbar_wait(&empty[s], ph ^ 1u);
                     uint8_t* st = smem + s * stage_bytes;
-                    tc::mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    tc::mbar_arrive_expect_tx(&full[s], tx_bytes);
                     tma2_load_2d(st, &tm_x, (kb_first + kb) * k2BK, m0, &full[s]);
                     tma2_load_2d(st + k2XBytes, &tm_wh, (kb_first + kb) * k2BK, n0, &full[s]);
                     if (passes != 1) tma2_load_2d(st + k2XBytes + k2WBytes, &tm_wl, (kb_first + kb) * k2BK, n0, &full[s]);
@@ -445,7 +447,11 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
                     int64_t ldx, int64_t ldw, int64_t ldy, int relu, const int32_t* k_begin, const int32_t* k_extent,
                     cudaStream_t st, int accumulate) {
     alignas(64) CUtensorMap tx, twh, twl;
-    if (!make_map2(&tx, x, M, K, ldx, k2BM) || !make_map2(&twh, w_hi, N, K, ldw, k2BN) || !make_map2(&twl, w_lo, N, K, ldw, k2BN))
+    // W boxes: 128 rows, or only the live rows of a narrow output (rounded up to the MMA's N granularity).  A 128-row box
+    // over a tensor of fewer than 64 rows -- more than half of it out-of-bounds fill -- cost the column-slice GEMMs of the
+    // blocked sampler 35-40 % (K = 448: N = 56 / 60 167 / 171 us against 124 us at N = 64, profiles/r02aw_slice_gemm.jsonl)
+    const int wbox = N >= k2BN ? k2BN : (int)((N + 15) & ~15);
+    if (!make_map2(&tx, x, M, K, ldx, k2BM) || !make_map2(&twh, w_hi, N, K, ldw, wbox) || !make_map2(&twl, w_lo, N, K, ldw, wbox))
         return NF_ERR_UNSUPPORTED;
     const int64_t tiles = cdiv(N, k2BN) * cdiv(M, k2BM);
     if (tiles > 2147483647LL) return NF_ERR_BAD_SHAPE;
@@ -458,17 +464,17 @@ int gemm_tc2_launch(const void* x, const void* w_hi, const void* w_lo, const voi
         const size_t smem = (size_t)k2Stages * k2StageBytes + 2 * k2TbufBytes + 256;
         NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<true, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc2_kernel<true, k2NAcc><<<grid, k2ThreadsDirect, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K,
-                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
+                                                                   ldy, relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate, wbox);
     } else {
         const size_t smem = (size_t)k2Stages * k2StageBytes + k2TbufBytes + 256;
         if (g_gemm_tc2_nacc == 2) {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, 2><<<grid, k2Threads, smem, st>>>((tx), twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
+                                                                     relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate, wbox);
         } else {
             NF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<false, k2NAcc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gemm_tc2_kernel<false, k2NAcc><<<grid, k2Threads, smem, st>>>(tx, twh, twl, (float*)y, (const float*)bias, (int)M, (int)N, (int)K, ldy,
-                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate);
+                                                                          relu, k_extent, k_begin, (int)tiles, g_tc_passes, vec, ss, accumulate, wbox);
         }
     }
     return NF_OK;

@@ -307,21 +307,34 @@ class BlockedMadePack:
 
 def blocked_layout(gstart: np.ndarray, block_degrees: int, align: int = 4):
     """(pos, pgstart, Hp): padded index of every sorted unit, padded degree boundaries, padded width.  Blocks always
-    start at a multiple of `align`; when it costs at most 10 % more units every DEGREE does (the in-block kernel then
-    evaluates a degree's units in exact 4-unit chunks instead of the chunks straddling its neighbours)."""
+    start at a multiple of `align`; when it costs at most 10 % more units every DEGREE does (the in-block kernels then
+    evaluate a degree's units in exact 4-unit chunks / whole 8-unit tensor-core tiles instead of chunks straddling its
+    neighbours).  In that per-degree layout every BLOCK is also padded to a multiple of 2 * align units, the extra `align`
+    dead units going to a degree whose padded count is an odd multiple of `align` (it occupies the same number of 8-unit
+    tiles afterwards): the slice GEMMs of the blocked route then never see a contraction length K = 4 (mod 32) -- a TMA
+    box with 4 live columns out of 32 costs ~25 us per product at 262 144 rows (K = 64: 54 us, K = 68: 79 us,
+    profiles/r02az_slice_gemm.jsonl) -- and every output slice starts 32-byte aligned (256-bit row stores)."""
     D = len(gstart) - 1
     H = int(gstart[D])
     counts = np.diff(gstart).astype(np.int64)
     per_degree = int(((counts + align - 1) // align * align).sum()) <= 1.10 * H
+    padded = counts.copy()
+    if per_degree:
+        padded = (counts + align - 1) // align * align
+        for g0 in range(0, D, block_degrees):
+            g1 = min(g0 + block_degrees, D)
+            if int(padded[g0:g1].sum()) % (2 * align) == align:
+                odd = [g for g in range(g0, g1) if padded[g] % (2 * align) == align]
+                padded[odd[-1]] += align
     pos = np.zeros(H, dtype=np.int64)
     pgstart = np.zeros(D + 1, dtype=np.int32)
     at = 0
     for g in range(D):
-        if g % block_degrees == 0 or per_degree:
+        if g % block_degrees == 0 and not per_degree:
             at = (at + align - 1) // align * align
         pgstart[g] = at
         pos[gstart[g]:gstart[g + 1]] = at + np.arange(counts[g])
-        at += int(counts[g])
+        at += int(padded[g])
     at = (at + align - 1) // align * align
     pgstart[D] = at
     # a degree's dead units are the gap up to the next degree's start

@@ -135,9 +135,9 @@ def test_gemm_precision_switch_is_host_only_and_validated():
 @pytest.mark.parametrize("D,H,gb", [(64, 512, 8), (16, 128, 8), (12, 100, 4), (784, 1024, 8), (8, 16, 8)])
 def test_blocked_sampler_layout_pads_blocks_to_aligned_starts(D, H, gb):
     """packing.blocked_layout (host logic of the blocked sequential direction, csrc/ar_blocked.cu): every block of `gb`
-    degrees starts at a multiple of 4 units, the sorted order of the live units is kept, the dead units sit at the end of
-    their block (counted with its last degree), and the padded boundaries delimit exactly the live units of each degree
-    except there."""
+    degrees starts at a multiple of 4 units (8 in the per-degree layout), the sorted order of the live units is kept, the
+    dead units sit behind the live units of their degree, and the padded boundaries delimit exactly the live units of each
+    degree plus its dead ones."""
     import numpy as np
     from nfb200 import packing
     deg = np.sort(np.arange(H) % (D - 1) + 1)                      # made.py:31-33 hidden degrees, sorted
@@ -149,6 +149,10 @@ def test_blocked_sampler_layout_pads_blocks_to_aligned_starts(D, H, gb):
     for g in range(D):
         n = gstart[g + 1] - gstart[g]
         assert np.array_equal(pos[gstart[g]:gstart[g + 1]], pg[g] + np.arange(n))
-        assert 0 <= pg[g + 1] - pg[g] - n < 4                     # dead units behind the degree's live ones
+        assert 0 <= pg[g + 1] - pg[g] - n < 8                     # dead units behind the degree's live ones
         if g % gb == 0:
             assert pg[g] % 4 == 0
+    # per-degree layout (every degree 4-aligned): blocks are padded to multiples of 8 units, so no slice GEMM of the route
+    # contracts over K = 4 (mod 32) and every output slice is 32-byte aligned
+    if all(pg[g] % 4 == 0 for g in range(D)):
+        assert all(pg[g] % 8 == 0 for g in range(0, D, gb)) and Hp % 8 == 0
