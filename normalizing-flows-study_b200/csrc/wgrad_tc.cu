@@ -78,6 +78,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         tc::fence_mbar_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_slot, kWgTmemCols);
+    // 32-float-wide boxes that hold live columns of dY / X.  Boxes entirely past N / K are never requested (narrow layers:
+    // the 64-wide conditioners of the 2-D flows had half of their TMA boxes filled with out-of-bounds zeros, and
+    // out-of-bounds fill is slow, profiles/r02az_slice_gemm.jsonl); their shared-memory chunks are zeroed once here.
+    const int ng = min(4, (N - n0 + 31) / 32), nx = min(4, (K - k0 + 31) / 32);
+    if (nloc > 0) {
+        for (int s = 0; s < kWgStages; ++s) {
+            uint8_t* st = smem + s * kWgStageBytes;
+            for (int j = ng; j < 4; ++j)
+                for (int i = tid; i < (int)(kWgChunkBytes / 16); i += kWgThreads) reinterpret_cast<uint4*>(st + j * kWgChunkBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int j = nx; j < 4; ++j)
+                for (int i = tid; i < (int)(kWgChunkBytes / 16); i += kWgThreads) reinterpret_cast<uint4*>(st + kWgTileBytes + j * kWgChunkBytes)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        tc::fence_proxy_async_smem();
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -86,22 +100,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)((dy_direct ? 0 : ng) + nx) * kWgChunkBytes;
             for (int i = 0; i < nloc; ++i) {
                 const int s = i % kWgStages;
                 if (i >= kWgStages) tc::mbar_wait(&empty[s], ((i / kWgStages) - 1) & 1);
                 uint8_t* st = smem + s * kWgStageBytes;
                 const int b0 = (kb0 + i) * kWgBK;
-                tc::mbar_arrive_expect_tx(&full[s], dy_direct ? kWgTileBytes : 2 * kWgTileBytes);
+                tc::mbar_arrive_expect_tx(&full[s], tx_bytes);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (!dy_direct) wg_tma_load_2d(st + j * kWgChunkBytes, &tm_g, n0 + 32 * j, b0, &full[s]);
-                    wg_tma_load_2d(st + kWgTileBytes + j * kWgChunkBytes, &tm_x, k0 + 32 * j, b0, &full[s]);
+                    if (!dy_direct && j < ng) wg_tma_load_2d(st + j * kWgChunkBytes, &tm_g, n0 + 32 * j, b0, &full[s]);
+                    if (j < nx) wg_tma_load_2d(st + kWgTileBytes + j * kWgChunkBytes, &tm_x, k0 + 32 * j, b0, &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (whole warp, convergent; one elected lane issues) ----------------
-        const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)kWgBN) | (1u << 16);       // B operand MN-major
+        const uint32_t idesc = tc::idesc_tf32_m128((uint32_t)(nx * 32)) | (1u << 16);   // B operand MN-major; only the live X columns
         const bool leader = tc::elect_one();
         for (int i = 0; i < nloc; ++i) {
             const int s = i % kWgStages;
@@ -140,7 +155,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
             // dY column n = 32q + lane: element (b, n) sits at chunk q, row b, 16-byte slot ((lane/4) ^ (b%8))
             const uint8_t* gcol = st + q * kWgChunkBytes + (lane & 3) * 4;
             uint32_t hi[32], lo[32];
-            if (dy_direct) {
+            const bool dy_live = dy_direct != nullptr || q < ng;       // warp-uniform: this quadrant's 32 dY columns exist
+            if (!dy_live) {
+                // dW rows past N: never stored, their A rows may hold anything
+            } else if (dy_direct) {
                 // dY rows whose pitch TMA cannot take (N % 4 != 0, e.g. the 3K-1 = 23 / 29 wide spline heads): the converter
                 // thread fetches its column straight from global memory (a warp reads 32 consecutive floats per row)
                 const int n = n0 + q * 32 + lane;
@@ -159,7 +177,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
                 }
             }
             const uint32_t a_hi = lane_addr + kWgColA + s * 64, a_lo = a_hi + 32;
-            {
+            if (dy_live) {
                 uint32_t t0[16], t1[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) { t0[j] = hi[j]; t1[j] = hi[16 + j]; }
@@ -175,6 +193,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
             uint8_t* xl = st + 2 * kWgTileBytes;
 #pragma unroll
             for (int j = 0; j < (int)(kWgTileBytes / 16 / 128); ++j) {
+                if (j >= 2 * nx) break;                          // two 2 KB slabs per 32-column chunk; dead chunks stay zero
                 const uint32_t off = (uint32_t)(j * 128 + ct) * 16u;
                 const float4 v = *reinterpret_cast<const float4*>(xh + off);
                 uint4 h, l;
@@ -200,6 +219,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant_
         float* tbuf = reinterpret_cast<float*>(smem) + (size_t)q * 32 * 33;      // stage memory is free once d_full has fired
 #pragma unroll
         for (int c = 0; c < kWgBN / 32; ++c) {
+            if (c >= nx) break;                                  // columns past K: neither accumulated nor stored
             uint32_t v0[16], v1[16];
             if (nloc > 0) {
                 tc::tmem_ld16(lane_addr + kWgColD + c * 32, v0);
@@ -229,6 +249,41 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
         float acc = 0.f;
         for (int s = 0; s < splits; ++s) acc += part[s * split_stride + i];
         dw[(i / K) * ld_dw + (i % K)] = acc;
+    }
+}
+
+// Small outputs with many splits (the 64 x 64 layers of the 2-D flows at 2^20 rows: 296 partial tiles for 4096 sums): the
+// kernel above leaves 4096 threads walking 296 strided values each (40 us).  Here a block owns 32 consecutive outputs, warp
+// w sums the splits w, w + 8, ... (coalesced 128-byte rows, four loads in flight) and the eight partial sums are added in
+// warp order -- still a fixed order, so still deterministic.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_wide_kernel(const float* __restrict__ part, float* __restrict__ dw, int N, int K, int64_t ld_dw, int splits,
+                         int64_t split_stride) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t total = (int64_t)N * K;
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+        const int64_t i = base + lane;
+        float acc = 0.f;
+        if (i < total) {
+            const float* p = part + i;
+            int sp = warp;
+            for (; sp + 24 < splits; sp += 32) {
+                const float v0 = p[sp * split_stride], v1 = p[(sp + 8) * split_stride], v2 = p[(sp + 16) * split_stride],
+                            v3 = p[(sp + 24) * split_stride];
+                acc += v0; acc += v1; acc += v2; acc += v3;
+            }
+            for (; sp < splits; sp += 8) acc += p[sp * split_stride];
+        }
+        red[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && i < total) {
+            float t = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) t += red[w][lane];
+            dw[(i / K) * ld_dw + (i % K)] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -346,6 +401,9 @@ extern "C" int nf_linear_wgrad_tc_masked(const void* dy, const void* x, void* dw
     count_launch();
     NF_LAUNCH_CHECK();
     if (splits > 1) {
+        if (splits >= 16 && N * K <= 65536)
+            wgrad_reduce_wide_kernel<<<(unsigned)cdiv(N * K, 32), 256, 0, st>>>((const float*)workspace, (float*)dw, (int)N, (int)K, ld_dw, splits, (int64_t)N * K);
+        else
         wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>((const float*)workspace, (float*)dw, (int)N, (int)K, ld_dw, splits, (int64_t)N * K);
         count_launch();
         NF_LAUNCH_CHECK();

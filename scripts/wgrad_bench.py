@@ -15,7 +15,8 @@ def t(fn, n=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-for B, Nn, K in [(262144, 512, 512), (262144, 512, 64), (262144, 128, 512), (65536, 512, 512), (65536, 1024, 1024),
+SHAPES = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]]
+for B, Nn, K in SHAPES or [(262144, 512, 512), (262144, 512, 64), (262144, 128, 512), (65536, 512, 512), (65536, 1024, 1024),
                  (65536, 512, 256), (4096, 1024, 1024), (4096, 11368, 1024), (4096, 1024, 784)]:
     g = torch.randn(B, Nn, device="cuda"); x = torch.randn(B, K, device="cuda")
     a = t(lambda: N.ops.linear_wgrad_tc(g, x))
