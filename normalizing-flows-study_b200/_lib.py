@@ -42,7 +42,7 @@ _SIGNATURES = {
     "nf_relu_backward": [_P, _P, _P, _L, _I, _P],
     "nf_col_sum": [_P, _P, _L, _L, _I, _P],
     "nf_batchnorm_forward": [_P] * 9 + [_L, _I, _I, _D, _D, _I, _I, _P],
-    "nf_batchnorm_backward": [_P] * 10 + [_L, _I, _I, _I, _I, _P],
+    "nf_batchnorm_backward": [_P] * 10 + [_L, _I, _I, _I, _I, _P, _P],
     "nf_spline_stack_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
     "nf_coupling_stack_forward": [_P, _P, _L, _P, _P, _P, _L, _I, _P],
     "nf_spline_stack_packed_floats": [_I, _I, _I, _I],
@@ -78,7 +78,7 @@ _SIGNATURES = {
     "nf_made_stack_tc_block_words": [_I],
     "nf_made_chain_bf16_forward": [_P] * 9 + [_P, _P, _P, _L, _I, _I, _I, _I, _P],
     "nf_batchnorm_forward_staged": [_P] * 9 + [_L, _I, _D, _D, _I, _I, _L, _I, _P],
-    "nf_batchnorm_backward_staged": [_P] * 10 + [_L, _I, _I, _I, _L, _I, _P],
+    "nf_batchnorm_backward_staged": [_P] * 10 + [_L, _I, _I, _I, _L, _I, _P, _P],
 }
 _RESTYPES = {
     "nf_status_string": _c.c_char_p,

@@ -355,6 +355,16 @@ __global__ void bn_eval_stats_kernel(const T* __restrict__ running_mean, const T
     if (c < H) { save_mean[c] = running_mean[c]; save_rstd[c] = (T)(1.0 / sqrt((double)running_var[c] + eps)); }
 }
 
+// y = (x - mean) * rstd * gamma + beta with a fixed operation order (no compiler-chosen contraction): the 128-bit backward
+// kernels re-derive the ReLU mask from x with this same function instead of reading y, so it has to be bit-identical in
+// every forward variant
+__device__ __forceinline__ float bn_affine(float x, float mu, float rs, float ga, float be) {
+    return __fmaf_rn(__fmul_rn(__fsub_rn(x, mu), rs), ga, be);
+}
+__device__ __forceinline__ double bn_affine(double x, double mu, double rs, double ga, double be) {
+    return (x - mu) * rs * ga + be;
+}
+
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta,
                                 const T* __restrict__ mean, const T* __restrict__ rstd, T* __restrict__ y, int64_t B,
@@ -362,7 +372,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ g
     const int64_t n = B * H, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = (int)(i % H);
-        T v = (x[i] - mean[c]) * rstd[c] * gamma[c] + beta[c];
+        T v = bn_affine(x[i], mean[c], rstd[c], gamma[c], beta[c]);
         y[i] = relu ? relu_nan(v) : v;
     }
 }
@@ -507,8 +517,8 @@ bn_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     for (int64_t r = r0 + ry; r < r1; r += ty) {
         const float4 v = __ldcs(reinterpret_cast<const float4*>(p + r * H));
         float4 w;
-        w.x = (v.x - mu.x) * rs.x * ga.x + be.x; w.y = (v.y - mu.y) * rs.y * ga.y + be.y;
-        w.z = (v.z - mu.z) * rs.z * ga.z + be.z; w.w = (v.w - mu.w) * rs.w * ga.w + be.w;
+        w.x = bn_affine(v.x, mu.x, rs.x, ga.x, be.x); w.y = bn_affine(v.y, mu.y, rs.y, ga.y, be.y);
+        w.z = bn_affine(v.z, mu.z, rs.z, ga.z, be.z); w.w = bn_affine(v.w, mu.w, rs.w, ga.w, be.w);
         if (relu) { w.x = relu_nan(w.x); w.y = relu_nan(w.y); w.z = relu_nan(w.z); w.w = relu_nan(w.w); }
         *reinterpret_cast<float4*>(o + r * H) = w;
     }
@@ -517,7 +527,10 @@ bn_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 __global__ void __launch_bounds__(256)
 bn_bwd_partial_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ mean,
                            const float* __restrict__ rstd, const float* __restrict__ gy, double* __restrict__ acc, int64_t B,
-                           int H, int relu, int64_t rpc, int tx) {
+                           int H, int relu, int64_t rpc, int tx, const float* __restrict__ gamma_m,
+                           const float* __restrict__ beta_m) {
+    // gamma_m / beta_m != nullptr: the ReLU mask comes from bn_affine(x) (what the forward computed before its ReLU), y is
+    // not read -- a third less traffic for this pass
     extern __shared__ double bn_red[];
     const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
     const int col = (blockIdx.x * tx + cx) * 4;
@@ -526,13 +539,20 @@ bn_bwd_partial_vec4_kernel(const float* __restrict__ x, const float* __restrict_
     if (col < H) {
         const float4 mu4 = ld4(mean + col), rs4 = ld4(rstd + col);
         const double mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+        const bool remask = relu && gamma_m != nullptr;
+        const float4 ga4 = remask ? ld4(gamma_m + col) : make_float4(0.f, 0.f, 0.f, 0.f), be4 = remask ? ld4(beta_m + col) : ga4;
+        const float muf[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rsf[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+        const float gaf[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, bef[4] = {be4.x, be4.y, be4.z, be4.w};
 #pragma unroll 2
         for (int64_t r = r0 + ry; r < r1; r += ty) {
             const int64_t off = r * H + col;
             const float4 g4 = ld4(gy + off), x4 = ld4(x + off);
             float g[4] = {g4.x, g4.y, g4.z, g4.w};
             const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-            if (relu) {
+            if (remask) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (!(bn_affine(xv[j], muf[j], rsf[j], gaf[j], bef[j]) > 0.f)) g[j] = 0.f;
+            } else if (relu) {
                 const float4 y4 = ld4(y + off);
                 if (!(y4.x > 0.f)) g[0] = 0.f;
                 if (!(y4.y > 0.f)) g[1] = 0.f;
@@ -562,7 +582,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gy,
                          const float* __restrict__ ggamma, const float* __restrict__ gbeta, float* __restrict__ gx, int64_t B,
-                         int H, int relu, int training, int64_t rpc, int tx, int64_t count, const double* __restrict__ count_dev) {
+                         int H, int relu, int training, int64_t rpc, int tx, int64_t count, const double* __restrict__ count_dev,
+                         const float* __restrict__ beta_m) {
     const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
     const int col = (blockIdx.x * tx + cx) * 4;
     if (col >= H) return;
@@ -571,12 +592,21 @@ bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ 
     const float gg[4] = {gg4.x, gg4.y, gg4.z, gg4.w}, gb[4] = {gb4.x, gb4.y, gb4.z, gb4.w};
     const float invB = count_dev ? (float)(1.0 / *count_dev) : 1.0f / (float)count;
     const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+    const bool remask = relu && beta_m != nullptr;            // ReLU mask from bn_affine(x) instead of y (see the partial kernel)
+    const float4 be4 = remask ? ld4(beta_m + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float be[4] = {be4.x, be4.y, be4.z, be4.w};
 #pragma unroll 2
     for (int64_t r = r0 + ry; r < r1; r += ty) {
         const int64_t off = r * H + col;
         const float4 g4 = __ldcs(reinterpret_cast<const float4*>(gy + off));
         float g[4] = {g4.x, g4.y, g4.z, g4.w};
-        if (relu) {
+        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (training || remask) x4 = __ldcs(reinterpret_cast<const float4*>(x + off));
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+        if (remask) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (!(bn_affine(xv[j], mu[j], rs[j], ga[j], be[j]) > 0.f)) g[j] = 0.f;
+        } else if (relu) {
             const float4 y4 = __ldcs(reinterpret_cast<const float4*>(y + off));
             if (!(y4.x > 0.f)) g[0] = 0.f;
             if (!(y4.y > 0.f)) g[1] = 0.f;
@@ -585,8 +615,6 @@ bn_bwd_apply_vec4_kernel(const float* __restrict__ x, const float* __restrict__ 
         }
         float o[4];
         if (training) {
-            const float4 x4 = __ldcs(reinterpret_cast<const float4*>(x + off));
-            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float xhat = (xv[j] - mu[j]) * rs[j];
@@ -663,12 +691,15 @@ template <typename T>
 // all-reduced sums in ws over `count` rows (gg / gb receive the GLOBAL sums as a by-product).
 static int bn_backward(const void* x, const void* y, const void* gamma, const void* sm, const void* sr, const void* gy,
                        void* gx, void* gg, void* gb, void* ws, int64_t B, int H, int relu, int training, cudaStream_t st,
-                       int stage = 0, int64_t count = 0) {
+                       int stage = 0, int64_t count = 0, const void* beta = nullptr) {
     int chunks; int64_t rpc;
     bn_chunking(B, H, chunks, rpc);
     dim3 grid((unsigned)((H + 31) / 32), (unsigned)chunks);
     const bool vec = sizeof(T) == 4 && bn_vec_ok(H, x, gy, y, gx ? gx : x) && aligned16(sm) && aligned16(sr) &&
                      (gamma == nullptr || aligned16(gamma)) && (gg == nullptr || aligned16(gg)) && (gb == nullptr || aligned16(gb));
+    // mask parameters of the 128-bit kernels (nullptr: read y)
+    const float* gamma_m = (relu && gamma && beta && aligned16(beta) && aligned16(gamma)) ? (const float*)gamma : nullptr;
+    const float* beta_m = gamma_m ? (const float*)beta : nullptr;
     const BnVecGeom vg = bn_vec_geom(B, H);
     const double* count_dev = (stage == 2 && count < 0) ? (const double*)ws + 2 * H : nullptr;
     if (count <= 0) count = B;
@@ -676,7 +707,7 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
         NF_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * H, st));
         if (vec)
             bn_bwd_partial_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 8, st>>>(
-                (const float*)x, (const float*)y, (const float*)sm, (const float*)sr, (const float*)gy, (double*)ws, B, H, relu, vg.rpc, vg.tx);
+                (const float*)x, (const float*)y, (const float*)sm, (const float*)sr, (const float*)gy, (double*)ws, B, H, relu, vg.rpc, vg.tx, gamma_m, beta_m);
         else
             bn_bwd_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)x, (const T*)y, (const T*)sm, (const T*)sr, (const T*)gy,
                                                            (double*)ws, B, H, relu, rpc);
@@ -690,7 +721,7 @@ static int bn_backward(const void* x, const void* y, const void* gamma, const vo
     if (vec)
         bn_bwd_apply_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, 0, st>>>(
             (const float*)x, (const float*)y, (const float*)gamma, (const float*)sm, (const float*)sr, (const float*)gy,
-            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx, count, count_dev);
+            (const float*)gg, (const float*)gb, (float*)gx, B, H, relu, training, vg.rpc, vg.tx, count, count_dev, beta_m);
     else
     bn_bwd_apply_kernel<T><<<ew_grid(B * H), 256, 0, st>>>((const T*)x, (const T*)y, (const T*)gamma, (const T*)sm,
                                                            (const T*)sr, (const T*)gy, (const T*)gg, (const T*)gb,
@@ -837,7 +868,7 @@ extern "C" int nf_batchnorm_forward_staged(const void* x, const void* gamma, con
 extern "C" int nf_batchnorm_backward_staged(const void* x, const void* y, const void* gamma, const void* save_mean,
                                             const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
                                             void* workspace, int64_t B, int H, int relu, int stage, int64_t count, int dtype,
-                                            nf_stream_t stream) {
+                                            const void* beta, nf_stream_t stream) {
     if (B < 0 || H < 1 || (stage != 1 && stage != 2)) return NF_ERR_BAD_SHAPE;
     NF_REQ(workspace); NF_REQ(save_mean); NF_REQ(save_rstd);
     cudaStream_t st = (cudaStream_t)stream;
@@ -852,7 +883,7 @@ extern "C" int nf_batchnorm_backward_staged(const void* x, const void* y, const 
     NF_REQ(x); NF_REQ(y); NF_REQ(gy);
     if (stage == 2) NF_REQ(gx);
     if (dtype == NF_F32)
-        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, 1, st, stage, count);
+        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, 1, st, stage, count, beta);
     if (dtype == NF_F64)
         return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, 1, st, stage, count);
     return NF_ERR_UNSUPPORTED;
@@ -861,13 +892,13 @@ extern "C" int nf_batchnorm_backward_staged(const void* x, const void* y, const 
 extern "C" int nf_batchnorm_backward(const void* x, const void* y, const void* gamma, const void* save_mean,
                                      const void* save_rstd, const void* gy, void* gx, void* ggamma, void* gbeta,
                                      void* workspace, int64_t B, int H, int relu, int training, int dtype,
-                                     nf_stream_t stream) {
+                                     const void* beta, nf_stream_t stream) {
     if (B < 0 || H < 1) return NF_ERR_BAD_SHAPE;
     if (B == 0) return NF_OK;
     NF_REQ(x); NF_REQ(y); NF_REQ(gamma); NF_REQ(save_mean); NF_REQ(save_rstd); NF_REQ(gy); NF_REQ(gx); NF_REQ(ggamma); NF_REQ(gbeta); NF_REQ(workspace);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NF_F32)
-        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, training, st);
+        return bn_backward<float>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, training, st, 0, 0, beta);
     if (dtype == NF_F64)
         return bn_backward<double>(x, y, gamma, save_mean, save_rstd, gy, gx, ggamma, gbeta, workspace, B, H, relu, training, st);
     return NF_ERR_UNSUPPORTED;

@@ -249,21 +249,21 @@ class _BatchNormFn(Function):
              ptr(y), ptr(sm), ptr(sr), ptr(ws), B, H, int(training), float(momentum), float(eps), int(relu),
              L.dtype_code(x), stream())
         ctx.relu, ctx.training = relu, training
-        ctx.save_for_backward(x, y, gamma, sm, sr)
+        ctx.save_for_backward(x, y, gamma, sm, sr, beta)
         ctx.mark_non_differentiable(sm, sr)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, y, gamma, sm, sr = ctx.saved_tensors
+        x, y, gamma, sm, sr, beta = ctx.saved_tensors
         B, H = x.shape
         gx = torch.empty_like(x)
         gg = torch.empty_like(sm)
         gb = torch.empty_like(sm)
         ws = torch.empty(2 * H, dtype=torch.float64, device=x.device)
         call("nf_batchnorm_backward", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(_c(gy)), ptr(gx), ptr(gg),
-             ptr(gb), ptr(ws), B, H, int(ctx.relu), int(ctx.training), L.dtype_code(x), stream())
+             ptr(gb), ptr(ws), B, H, int(ctx.relu), int(ctx.training), L.dtype_code(x), ptr(_c(beta)), stream())
         return gx, gg, gb, None, None, None, None, None, None
 
 
@@ -319,21 +319,21 @@ class _SyncBatchNormFn(Function):
         call("nf_batchnorm_forward_staged", ptr(x), ptr(_c(gamma)), ptr(_c(beta)), ptr(running_mean), ptr(running_var),
              ptr(y), ptr(sm), ptr(sr), ptr(packed), B, H, float(momentum), float(eps), int(relu), 2, -1, code, stream())
         ctx.relu, ctx.group = relu, group
-        ctx.save_for_backward(x, y, gamma, sm, sr, packed[2 * H:])
+        ctx.save_for_backward(x, y, gamma, sm, sr, packed[2 * H:], beta)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
         import torch.distributed as dist
-        x, y, gamma, sm, sr, count = ctx.saved_tensors
+        x, y, gamma, sm, sr, count, beta = ctx.saved_tensors
         B, H = x.shape
         code = L.dtype_code(x)
         gy = _c(gy)
         gx = torch.empty_like(x)
         glob = torch.empty(2 * H + 1, dtype=torch.float64, device=x.device)
-        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), None, ptr(sm), ptr(sr), ptr(gy), None, None, None, ptr(glob), B, H,
-             int(ctx.relu), 1, 0, code, stream())
+        call("nf_batchnorm_backward_staged", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(gy), None, None, None, ptr(glob),
+             B, H, int(ctx.relu), 1, 0, code, ptr(_c(beta)), stream())
         gg = glob[:H].to(x.dtype)                         # this shard's ggamma / gbeta: the gradient all-reduce sums them
         gb = glob[H:2 * H].to(x.dtype)
         dist.all_reduce(glob[:2 * H], op=dist.ReduceOp.SUM, group=ctx.group)
@@ -341,7 +341,7 @@ class _SyncBatchNormFn(Function):
         gg_g = torch.empty(H, dtype=x.dtype, device=x.device)
         gb_g = torch.empty(H, dtype=x.dtype, device=x.device)
         call("nf_batchnorm_backward_staged", ptr(x), ptr(y), ptr(_c(gamma)), ptr(sm), ptr(sr), ptr(gy), ptr(gx), ptr(gg_g),
-             ptr(gb_g), ptr(glob), B, H, int(ctx.relu), 2, -1, code, stream())
+             ptr(gb_g), ptr(glob), B, H, int(ctx.relu), 2, -1, code, ptr(_c(beta)), stream())
         return gx, gg, gb, None, None, None, None, None, None
 
 

@@ -403,8 +403,10 @@ def test_staged_batchnorm_on_two_shards_equals_one_batch(H, relu):
     assert torch.allclose(rvs[0], bn_ref.running_var, rtol=1e-6, atol=1e-7)
     wsb = [torch.empty(2 * H, dtype=torch.float64, device=DEV) for _ in shards]
     for xs, y, g, w in zip(shards, ys, gys, wsb):
-        call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), None, ptr(sms[0]), ptr(srs[0]), ptr(g), None, None, None, ptr(w),
-             xs.shape[0], H, int(relu), 1, 0, 0, stream())
+        # first shard: ReLU mask re-derived from x (gamma / beta given); second shard: mask read from y
+        first = xs is shards[0]
+        call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), ptr(bn.weight) if first else None, ptr(sms[0]), ptr(srs[0]), ptr(g),
+             None, None, None, ptr(w), xs.shape[0], H, int(relu), 1, 0, 0, ptr(bn.bias) if first else None, stream())
     globb = wsb[0] + wsb[1]
     gxs = []
     for si, (xs, y, g) in enumerate(zip(shards, ys, gys)):
@@ -412,7 +414,7 @@ def test_staged_batchnorm_on_two_shards_equals_one_batch(H, relu):
         gg, gb = torch.empty(H, device=DEV), torch.empty(H, device=DEV)
         wsg = torch.cat([globb, globb.new_tensor([float(B)])])
         call("nf_batchnorm_backward_staged", ptr(xs), ptr(y), ptr(bn.weight), ptr(sms[0]), ptr(srs[0]), ptr(g), ptr(gx), ptr(gg),
-             ptr(gb), ptr(wsg), xs.shape[0], H, int(relu), 2, B if si == 0 else -1, 0, stream())
+             ptr(gb), ptr(wsg), xs.shape[0], H, int(relu), 2, B if si == 0 else -1, 0, ptr(bn.bias) if si == 0 else None, stream())
         gxs.append(gx)
     assert torch.allclose(torch.cat(gxs), xr.grad, rtol=1e-5, atol=1e-6)
     assert torch.allclose(globb[:H].float(), bn_ref.weight.grad, rtol=1e-5, atol=1e-5)
