@@ -109,6 +109,19 @@ def test_product_does_not_import_oracle():
             assert "import oracle" not in src and "from oracle" not in src
 
 
+def test_library_options_from_the_environment():
+    """NFB200_OPTIONS="key:value,..." (the A/B knob of the measurement scripts) is applied through nf_set_option when the
+    library is loaded; a refused value fails the load loudly.  The in-block kernel selector (key 3) takes 0..3."""
+    import subprocess, sys
+    code = "import nfb200; l = nfb200._lib.lib(); print(l.nf_set_option(3, 3), l.nf_set_option(3, 4))"
+    env = dict(os.environ, NFB200_OPTIONS="3:1,7:3")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.split() == ["0", str(N._lib.lib().nf_set_option(3, 4))], r.stderr[-400:]
+    assert N._lib.lib().nf_set_option(3, 4) != 0 and N._lib.lib().nf_set_option(3, 3) == 0
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, NFB200_OPTIONS="3:9"), cwd=ROOT)
+    assert r.returncode != 0 and "refused" in r.stderr
+
+
 def test_gemm_precision_switch_is_host_only_and_validated():
     """set_gemm_precision maps onto nf_set_option(7, passes); no device is needed to flip it, unknown modes and pass
     counts are rejected, and the default is the fp32-parity mode."""
