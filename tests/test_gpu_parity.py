@@ -334,7 +334,8 @@ def test_spline_transform_large_batch(D, K, B, compact):
                 lambda: noise()[1].reshape(B, Dt).sum(1), terms=Dt)
 
 
-@pytest.mark.parametrize("kind,D,H,B", [("maf", 64, 512, 2048), ("iaf", 32, 256, 1500), ("maf", 20, 128, 1024)])
+@pytest.mark.parametrize("kind,D,H,B", [("maf", 64, 512, 2048), ("iaf", 32, 256, 1500), ("maf", 20, 128, 1024),
+                                       ("maf", 36, 288, 1001), ("iaf", 12, 96, 777)])     # last block of 4 degrees; ragged row tiles
 def test_blocked_sequential_direction_matches_oracle(kind, D, H, B):
     """MAF.forward / IAF.inverse through the blocked tensor-core evaluation (ar_blocked.cu) against the oracle's
     D-step loop and against the one-launch incremental kernel."""
@@ -371,8 +372,12 @@ def test_blocked_sequential_direction_matches_oracle(kind, D, H, B):
         # module entry point takes the blocked route at this size
         before = N._lib.launch_count()
         y2, ld2 = m.forward(v.to(_dev())) if kind == "maf" else m.inverse(v.to(_dev()))
-        assert N._lib.launch_count() - before > 8
-        assert torch.equal(torch.isnan(y2), torch.isnan(blocked[0])) and torch.allclose(y2.nan_to_num(), blocked[0].nan_to_num())
+        assert torch.equal(torch.isnan(y2), torch.isnan(blocked[0]))
+        if (D, H) in ((64, 512), (32, 256), (20, 128)):
+            assert N._lib.launch_count() - before > 8
+            assert torch.allclose(y2.nan_to_num(), blocked[0].nan_to_num())
+        else:                          # the added shapes are too small for the module's blocked route: the one-launch kernel
+            _within(y2.cpu(), ref_y, y64, Z_ATOL, Z_RTOL, f"module route {kind} z")
 
 
 def _randomised(m, seed, sigma):
