@@ -301,10 +301,11 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
-def load_traffic(wl):
+def load_traffic(wl, precision="fp32"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed cold-cache
-    (`--cache-control all`) ncu capture, read at run time; None when no capture of this round is committed."""
-    path = os.path.join(ROOT, "profiles", f"r02_{wl}_traffic.json")
+    (`--cache-control all`) ncu capture, read at run time; None when no capture of this round is committed (the file is
+    per workload and precision mode: `r02_<workload>_traffic.json` / `r02_<workload>_<mode>_traffic.json`)."""
+    path = os.path.join(ROOT, "profiles", f"r02_{wl}_traffic.json" if precision == "fp32" else f"r02_{wl}_{precision}_traffic.json")
     try:
         t = json.load(open(path))
         return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t.get("source")
@@ -451,7 +452,7 @@ def roofline_for(wl, r, precision):
     which = "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback 1.59 PFLOP/s"
     ms_dom = 0.5 * (r["ms_log_prob"] + r["ms_sample"]) if wl == "c2" else r["ms_log_prob"]
     achieved = FLOPS_DENSE[wl] * rows / (ms_dom * 1e-3) / 1e12
-    traffic, traffic_src = load_traffic(wl)
+    traffic, traffic_src = load_traffic(wl, precision)
     if wl == "c2":
         kernel = ("spline_stack_tc2_kernel: one launch = all 8 layers of one direction (+ the N(0,I) log-prob head in the "
                   "log_prob pass); layer-2 and head GEMMs on tcgen05 (3xTF32, A operand in TMEM), layer 1 + spline on the "
