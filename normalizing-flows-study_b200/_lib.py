@@ -126,8 +126,11 @@ def lib():
             raise RuntimeError("libnfb200.so ABI version mismatch")
         # A/B knob for measurement scripts: NFB200_OPTIONS="key:value,..." -> nf_set_option(key, value) at load time
         for kv in filter(None, os.environ.get("NFB200_OPTIONS", "").split(",")):
-            k, v = kv.split(":")
-            if l.nf_set_option(int(k), int(v)) != 0:
+            try:
+                k, v = (int(t) for t in kv.split(":"))
+            except ValueError:
+                raise RuntimeError(f"NFB200_OPTIONS: expected 'key:value' integers, got {kv!r}") from None
+            if l.nf_set_option(k, v) != 0:
                 raise RuntimeError(f"NFB200_OPTIONS: nf_set_option({k}, {v}) was refused")
         _lib = l
     return _lib
