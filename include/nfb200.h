@@ -138,6 +138,11 @@ NF_API int nf_gemm(const void* A, const void* Bm, void* C, const void* bias, int
 NF_API int nf_mul_rows(const void* a, const void* b, void* out, int64_t rows, int64_t cols, int64_t b_rows, int dtype,
                 nf_stream_t stream);
 NF_API int nf_relu_backward(const void* y, const void* gy, void* gx, int64_t n, int dtype, nf_stream_t stream);
+/* ReLU backward of a Linear(+ReLU) fused with that Linear's bias gradient (torch.relu's backward followed by the
+ * grad_output.sum(0) of F.linear): gx[rows, cols] = gy where y > 0 else 0, colsum[cols] = column sums of gx; one pass
+ * over y and gy instead of writing gx and reading it again.  colsum is overwritten. */
+NF_API int nf_relu_backward_colsum(const void* y, const void* gy, void* gx, void* colsum, int64_t rows, int64_t cols,
+                            int dtype, nf_stream_t stream);
 NF_API int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, int dtype, nf_stream_t stream);
 
 /* nn.BatchNorm1d inside the coupling conditioners (coupling_layer.py:20,23), fused with the following ReLU.

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "nf_gemm": [_P, _P, _P, _P, _L, _L, _L, _L, _L, _L, _L, _L, _I, _I, _P, _I, _P],
     "nf_mul_rows": [_P, _P, _P, _L, _L, _L, _I, _P],
     "nf_relu_backward": [_P, _P, _P, _L, _I, _P],
+    "nf_relu_backward_colsum": [_P, _P, _P, _P, _L, _L, _I, _P],
     "nf_col_sum": [_P, _P, _L, _L, _I, _P],
     "nf_batchnorm_forward": [_P] * 9 + [_L, _I, _I, _D, _D, _I, _I, _P],
     "nf_batchnorm_backward": [_P] * 10 + [_L, _I, _I, _I, _I, _P, _P],

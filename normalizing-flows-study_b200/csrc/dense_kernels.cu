@@ -632,6 +632,53 @@ static inline bool bn_vec_ok(int H, const void* a, const void* b, const void* c,
     return H % 4 == 0 && H >= 16 && aligned16(a) && aligned16(b) && (!c || aligned16(c)) && (!d || aligned16(d));
 }
 
+// ReLU backward fused with the column sums of its result (the bias gradient of the Linear the ReLU belongs to): gx = gy
+// where y > 0, out[c] += sum_rows gx[:, c].  As two kernels the [B, H] gradient was written by relu_bwd_kernel and read
+// again by col_sum_vec4_kernel (16 x 62 us per training step of the 2-D spline stack at 2^20 rows).  float32, H % 4 == 0,
+// 16-byte aligned; `out` must be zero on entry; per-thread float sums, chunk sums in double, one float atomic per column and
+// chunk (like col_sum_vec4_kernel).
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_vec4_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx,
+                            float* __restrict__ out, int64_t B, int H, int64_t rpc, int tx) {
+    extern __shared__ double bn_red[];                          // [ty][tx][4]
+    const int ty = 256 / tx, cx = threadIdx.x & (tx - 1), ry = threadIdx.x / tx;
+    const int col = (blockIdx.x * tx + cx) * 4;
+    const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = (B < r0 + rpc) ? B : r0 + rpc;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (col < H) {
+        int64_t r = r0 + ry;
+        for (; r + ty < r1; r += 2 * ty) {
+            const int64_t o0 = r * H + col, o1 = (r + ty) * H + col;
+            const float4 ga = __ldcs(reinterpret_cast<const float4*>(gy + o0)), ya = __ldcs(reinterpret_cast<const float4*>(y + o0));
+            const float4 gb = __ldcs(reinterpret_cast<const float4*>(gy + o1)), yb = __ldcs(reinterpret_cast<const float4*>(y + o1));
+            const float4 a = make_float4(ya.x > 0.f ? ga.x : 0.f, ya.y > 0.f ? ga.y : 0.f, ya.z > 0.f ? ga.z : 0.f, ya.w > 0.f ? ga.w : 0.f);
+            const float4 b = make_float4(yb.x > 0.f ? gb.x : 0.f, yb.y > 0.f ? gb.y : 0.f, yb.z > 0.f ? gb.z : 0.f, yb.w > 0.f ? gb.w : 0.f);
+            *reinterpret_cast<float4*>(gx + o0) = a;
+            *reinterpret_cast<float4*>(gx + o1) = b;
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+        }
+        for (; r < r1; r += ty) {
+            const int64_t o0 = r * H + col;
+            const float4 ga = __ldcs(reinterpret_cast<const float4*>(gy + o0)), ya = __ldcs(reinterpret_cast<const float4*>(y + o0));
+            const float4 a = make_float4(ya.x > 0.f ? ga.x : 0.f, ya.y > 0.f ? ga.y : 0.f, ya.z > 0.f ? ga.z : 0.f, ya.w > 0.f ? ga.w : 0.f);
+            *reinterpret_cast<float4*>(gx + o0) = a;
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+    }
+    double* mine = bn_red + ((size_t)ry * tx + cx) * 4;
+    mine[0] = (double)s0.x + s1.x; mine[1] = (double)s0.y + s1.y; mine[2] = (double)s0.z + s1.z; mine[3] = (double)s0.w + s1.w;
+    __syncthreads();
+    if (ry == 0 && col < H) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double t = 0.0;
+            for (int i = 0; i < ty; ++i) t += bn_red[((size_t)i * tx + cx) * 4 + j];
+            atomicAdd(out + col + j, (float)t);
+        }
+    }
+}
+
 static inline int ew_grid(int64_t n) {
     int64_t need = cdiv(n, 256);
     int64_t cap = (int64_t)kNumSMs * 16;
@@ -765,6 +812,31 @@ extern "C" int nf_mul_rows(const void* a, const void* b, void* out, int64_t rows
     count_launch();
     NF_LAUNCH_CHECK();
     return NF_OK;
+}
+
+extern "C" int nf_col_sum(const void* a, void* out, int64_t rows, int64_t cols, int dtype, nf_stream_t stream);
+extern "C" int nf_relu_backward(const void* y, const void* gy, void* gx, int64_t n, int dtype, nf_stream_t stream);
+
+// gx = gy * (y > 0) and colsum[c] = sum_rows gx[:, c] (the ReLU backward of a Linear(+ReLU) and its bias gradient) in one pass
+extern "C" int nf_relu_backward_colsum(const void* y, const void* gy, void* gx, void* colsum, int64_t rows, int64_t cols,
+                                       int dtype, nf_stream_t stream) {
+    if (rows < 0 || cols < 0) return NF_ERR_BAD_SHAPE;
+    if (cols == 0) return NF_OK;
+    NF_REQ(colsum);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NF_F32 && rows >= 1024 && cols >= 16 && cols <= 2147483647LL && bn_vec_ok((int)cols, y, gy, gx, colsum)) {
+        NF_REQ(y); NF_REQ(gy); NF_REQ(gx);
+        const BnVecGeom vg = bn_vec_geom(rows, (int)cols);
+        NF_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, st));
+        relu_bwd_colsum_vec4_kernel<<<dim3((unsigned)vg.col_blocks, (unsigned)vg.chunks), 256, sizeof(double) * 256 * 4, st>>>(
+            (const float*)y, (const float*)gy, (float*)gx, (float*)colsum, rows, (int)cols, vg.rpc, vg.tx);
+        count_launch();
+        NF_LAUNCH_CHECK();
+        return NF_OK;
+    }
+    const int rc = nf_relu_backward(y, gy, gx, rows * cols, dtype, stream);
+    if (rc != NF_OK) return rc;
+    return nf_col_sum(gx, colsum, rows, cols, dtype, stream);
 }
 
 extern "C" int nf_relu_backward(const void* y, const void* gy, void* gx, int64_t n, int dtype, nf_stream_t stream) {

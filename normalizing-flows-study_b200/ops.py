@@ -169,6 +169,14 @@ def relu_backward(y, gy):
     return gx
 
 
+def relu_backward_colsum(y, gy):
+    """(gy * (y > 0), its column sums) in one pass: the ReLU backward of a Linear(+ReLU) and that Linear's bias gradient."""
+    gx = torch.empty_like(gy)
+    cs = torch.empty(gy.shape[1], dtype=gy.dtype, device=gy.device)
+    call("nf_relu_backward_colsum", ptr(y), ptr(gy), ptr(gx), ptr(cs), gy.shape[0], gy.shape[1], L.dtype_code(gy), stream())
+    return gx, cs
+
+
 # --------------------------------------------------------------------------------------------
 # Linear (+ optional weight mask, + optional fused ReLU)
 # --------------------------------------------------------------------------------------------
@@ -204,8 +212,12 @@ class _LinearFn(Function):
     def backward(ctx, gy):
         x, w_eff, mask, y = ctx.saved_tensors
         g = _c(gy)
+        gb_fused = None
         if ctx.relu:
-            g = relu_backward(y, g)
+            if ctx.has_bias and ctx.needs_input_grad[2] and g.dim() == 2:
+                g, gb_fused = relu_backward_colsum(y, g)      # the bias gradient comes out of the same pass
+            else:
+                g = relu_backward(y, g)
         M, K = x.shape
         N = w_eff.shape[0]
         gx = gw = gb = None
@@ -223,7 +235,7 @@ class _LinearFn(Function):
             if mask is not None:
                 gw = mul_rows(gw, mask)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = col_sum(g)
+            gb = gb_fused if gb_fused is not None else col_sum(g)
         return gx, gw, gb, None, None
 
 

@@ -131,6 +131,26 @@ def test_col_sum_matches_float64(rows, cols):
     assert ((got - ref).abs() / scale).max().item() < 1e-6
 
 
+@pytest.mark.parametrize("rows,cols,dtype", [(5, 8, torch.float32), (1500, 132, torch.float32), (65536, 64, torch.float32),
+                                             (70001, 512, torch.float32), (4096, 1024, torch.float32), (3000, 23, torch.float32),
+                                             (2048, 64, torch.float64), (0, 16, torch.float32)])
+def test_relu_backward_colsum_matches_the_two_pass_result(rows, cols, dtype):
+    """nf_relu_backward_colsum (ReLU backward of a Linear(+ReLU) fused with that Linear's bias gradient): gx is exactly
+    gy masked by y > 0 (NaN in y masks like torch.relu's backward: NaN > 0 is false), the column sums match float64; the
+    fused 128-bit kernel and the fallback (two kernels) are both covered."""
+    gen = torch.Generator().manual_seed(rows * 7 + cols)
+    y = torch.relu(torch.randn(rows, cols, generator=gen, dtype=dtype))
+    gy = torch.randn(rows, cols, generator=gen, dtype=dtype) + 0.1
+    if rows > 4:
+        y[3, 1] = float("nan")
+    gx, cs = N_.ops.relu_backward_colsum(y.cuda(), gy.cuda())
+    ref = torch.where(y > 0, gy, torch.zeros_like(gy))
+    assert torch.equal(gx.cpu(), ref)
+    ref_cs = ref.double().sum(0)
+    scale = ref.double().abs().sum(0) + 1e-30
+    assert ((cs.cpu().double() - ref_cs).abs() / scale).max().item() < (1e-6 if dtype == torch.float32 else 1e-13) if cols else True
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("B,H,D", [(5000, 64, 2), (300, 64, 2), (70000, 128, 3), (4096, 40, 8), (1000, 16, 1), (30000, 64, 23),
                                    (9000, 300, 29), (2000, 64, 17), (1001, 256, 2), (777, 128, 4), (67, 1024, 6), (4099, 100, 5)])
