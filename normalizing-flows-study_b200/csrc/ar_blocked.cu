@@ -6,9 +6,11 @@
 //   * contributions of all PREVIOUS blocks to the block's pre-activations are plain dense products over the whole
 //     batch -> nf_linear_tc (tcgen05, 3xTF32, TMA) on column slices of the activation buffers:
 //         pre_l[:, blk] = act_{l-1}[:, :u0] * W_l[blk, :u0]^T        (l = 1..3),   preo[:, dims] = act3[:, :u0] * W3[dims, :u0]^T
-//   * the IN-BLOCK part (gb dependent steps over <= ~72 units per layer) runs in ar_block_warp_kernel (below: a warp
-//     owns 32 rows for the whole block, no CTA barrier); ar_block_kernel is the first version (32 rows per CTA, four
-//     __syncthreads per degree), kept as the fallback for blocks whose weights do not fit in shared memory.
+//   * the IN-BLOCK part (gb dependent steps over <= ~72 units per layer) runs in ar_block_mma_kernel (third version, below:
+//     the steps as register-level mma.sync m16n8k8 3xTF32 products, a warp owns 16 rows for the whole block, no CTA
+//     barrier); ar_block_warp_kernel is the second version (FP32 pipe, a warp owns 32 rows), the fallback where the unit
+//     layout does not give whole 8-unit tiles per degree; ar_block_kernel is the first version (32 rows per CTA, four
+//     __syncthreads per degree), kept for blocks whose weights do not fit in shared memory.
 // Every hidden unit is still evaluated exactly once (total work = one masked MADE pass), ~75 % of it on the tensor pipe.
 #include "nf_common.cuh"
 
